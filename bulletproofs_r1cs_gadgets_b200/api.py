@@ -1,0 +1,432 @@
+"""Python host layer over the C-ABI (include/bp_b200.h).
+
+Mirrors the surface the reference's gadgets are written against -- `Prover`, `Verifier`,
+`LinearCombination`, `Variable`, `PedersenGens`/`BulletproofGens` (one `Gens` object here) -- plus the
+batched `Circuit` API that is the reason this library exists.  Everything numeric happens in
+`libbp_b200.so` (CUDA, sm_100a); this module only marshals bytes.  If the shared library is missing
+the import of any symbol raises: there is no Python or CPU fallback.
+
+Reference call sites mirrored (paths under /root/reference/src): gadget_mimc.rs:99-169 (prove/verify
+flow), gadget_poseidon.rs:554-608 (statics), gadget_vsmt_2.rs:171-209,289-395, gadget_bound_check.rs:49-116.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+L = 2 ** 252 + 27742317777372353535851937790883648493
+
+BP_OK = 0
+ERRORS = {
+    1: "InvalidGeneratorsLength", 2: "FormatError", 3: "VerificationError", 4: "MissingAssignment", 5: "GadgetError",
+    6: "InvalidArgument", 7: "NoDevice", 8: "CudaError", 9: "OutOfMemory",
+}
+SBOX_CUBE, SBOX_INVERSE = 0, 1
+VAR_COMMITTED, VAR_MULT_LEFT, VAR_MULT_RIGHT, VAR_MULT_OUT, VAR_ONE = 0, 1, 2, 3, 4
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_SO = os.path.join(_PKG, "libbp_b200.so")
+
+
+class R1CSError(Exception):
+    def __init__(self, code, where=""):
+        self.code = code
+        super().__init__("%s (%d) %s" % (ERRORS.get(code, "Unknown"), code, where))
+
+
+class bp_var(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("index", C.c_uint32)]
+
+
+class bp_term(C.Structure):
+    _fields_ = [("var", bp_var), ("coeff", C.c_uint8 * 32)]
+
+
+u8p = C.POINTER(C.c_uint8)
+_lib = None
+
+
+def load(path=None):
+    """Load the shared library (once).  `path` is for the test-only emulation build."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or DEFAULT_SO
+    if not os.path.exists(path):
+        raise RuntimeError("bp_b200: %s not found -- build it with `python -c 'import __graft_entry__ as g; g.build()'`; "
+                           "there is no CPU fallback" % path)
+    lib = C.CDLL(path)
+    lib.bp_launch_count.restype = C.c_int64
+    lib.bp_cs_num_constraints.restype = C.c_uint64
+    lib.bp_cs_num_multipliers.restype = C.c_uint64
+    lib.bp_cs_num_commitments.restype = C.c_uint64
+    lib.bp_cs_proof_len.restype = C.c_size_t
+    lib.bp_circuit_proof_len.restype = C.c_size_t
+    for f in ("bp_gens_capacity", "bp_circuit_num_multipliers", "bp_circuit_num_constraints", "bp_circuit_num_commitments", "bp_circuit_num_aux"):
+        getattr(lib, f).restype = C.c_uint32
+    lib.bp_gens_free.restype = None
+    lib.bp_cs_free.restype = None
+    lib.bp_circuit_free.restype = None
+    lib.bp_poseidon_params_free.restype = None
+    _lib = lib
+    return lib
+
+
+def _check(rc, where=""):
+    if rc != BP_OK:
+        raise R1CSError(rc, where)
+
+
+def scalar_bytes(x):
+    if isinstance(x, (bytes, bytearray)):
+        assert len(x) == 32
+        return bytes(x)
+    return (int(x) % L).to_bytes(32, "little")
+
+
+def _buf(b):
+    return (C.c_uint8 * len(b)).from_buffer_copy(bytes(b))
+
+
+def _np_u8(a):
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def scalars_to_array(vals):
+    """iterable of ints -> uint8 [len][32]"""
+    vals = list(vals)
+    if not vals:
+        return np.zeros((0, 32), dtype=np.uint8)
+    return np.frombuffer(b"".join(scalar_bytes(v) for v in vals), dtype=np.uint8).reshape(-1, 32).copy()
+
+
+class Variable:
+    __slots__ = ("kind", "index")
+
+    def __init__(self, kind, index=0):
+        self.kind, self.index = kind, index
+
+    @staticmethod
+    def One():
+        return Variable(VAR_ONE, 0)
+
+    def __eq__(self, o):
+        return isinstance(o, Variable) and (self.kind, self.index) == (o.kind, o.index)
+
+    def __hash__(self):
+        return hash((self.kind, self.index))
+
+    def __repr__(self):
+        return "Variable(%d,%d)" % (self.kind, self.index)
+
+    def _c(self):
+        return bp_var(self.kind, self.index)
+
+    # arithmetic promotes to LinearCombination, as in the reference
+    def __add__(self, o):
+        return LinearCombination.of(self) + o
+
+    def __sub__(self, o):
+        return LinearCombination.of(self) - o
+
+    def __rsub__(self, o):
+        return LinearCombination.of(o) - self
+
+    def __radd__(self, o):
+        return LinearCombination.of(o) + self
+
+    def __mul__(self, s):
+        return LinearCombination.of(self) * s
+
+
+class LinearCombination:
+    """list of (Variable, int coefficient); duplicates allowed (reference LinearCombination)."""
+
+    def __init__(self, terms=None):
+        self.terms = list(terms) if terms else []
+
+    @staticmethod
+    def of(x):
+        if isinstance(x, LinearCombination):
+            return x
+        if isinstance(x, Variable):
+            return LinearCombination([(x, 1)])
+        return LinearCombination([(Variable.One(), int(x) % L)])
+
+    def __add__(self, o):
+        return LinearCombination(self.terms + LinearCombination.of(o).terms)
+
+    __radd__ = __add__
+
+    def __sub__(self, o):
+        return LinearCombination(self.terms + [(v, (-c) % L) for v, c in LinearCombination.of(o).terms])
+
+    def __rsub__(self, o):
+        return LinearCombination.of(o) - self
+
+    def __neg__(self):
+        return LinearCombination([(v, (-c) % L) for v, c in self.terms])
+
+    def __mul__(self, s):
+        return LinearCombination([(v, c * int(s) % L) for v, c in self.terms])
+
+    def get_terms(self):
+        return list(self.terms)
+
+    def _c(self):
+        n = len(self.terms)
+        arr = (bp_term * max(n, 1))()
+        for i, (v, c) in enumerate(self.terms):
+            arr[i].var.kind, arr[i].var.index = v.kind, v.index
+            C.memmove(arr[i].coeff, scalar_bytes(c), 32)
+        return arr, n
+
+
+class PoseidonParams:
+    """PoseidonParams::new(width, full_b, full_e, partial) over the reference's constants (gadget_poseidon.rs:27-94)."""
+
+    def __init__(self, width=6, full_rounds_beginning=4, full_rounds_end=4, partial_rounds=140, constants=None):
+        if constants is None:
+            constants = open(os.path.join(_PKG, "data", "poseidon_constants.bin"), "rb").read()
+        self.width, self.full_rounds_beginning, self.full_rounds_end, self.partial_rounds = width, full_rounds_beginning, full_rounds_end, partial_rounds
+        self._h = C.c_void_p()
+        _check(load().bp_poseidon_params_new(_buf(constants), C.c_size_t(len(constants) // 32), width, full_rounds_beginning, full_rounds_end,
+                                             partial_rounds, C.byref(self._h)), "poseidon_params_new")
+
+    def __del__(self):
+        if _lib is not None and getattr(self, "_h", None):
+            _lib.bp_poseidon_params_free(self._h)
+            self._h = None
+
+    def hash_2(self, xl, xr, sbox):
+        out = (C.c_uint8 * 32)()
+        _check(load().bp_poseidon_hash_2(self._h, _buf(scalar_bytes(xl)), _buf(scalar_bytes(xr)), sbox, out))
+        return int.from_bytes(bytes(out), "little")
+
+
+class Gens:
+    """PedersenGens::default() + BulletproofGens::new(capacity, 1), resident on the device."""
+
+    def __init__(self, capacity):
+        self._h = C.c_void_p()
+        _check(load().bp_gens_new(C.c_uint32(capacity), C.byref(self._h)), "gens_new")
+        self.capacity = capacity
+
+    def __del__(self):
+        if _lib is not None and getattr(self, "_h", None):
+            _lib.bp_gens_free(self._h)
+            self._h = None
+
+    def pedersen(self):
+        B, Bb = (C.c_uint8 * 32)(), (C.c_uint8 * 32)()
+        _check(load().bp_gens_pedersen(self._h, B, Bb))
+        return bytes(B), bytes(Bb)
+
+    def export(self, which, count):
+        out = np.zeros((count, 32), dtype=np.uint8)
+        _check(load().bp_gens_export(self._h, which, C.c_uint32(count), out.ctypes.data_as(u8p)))
+        return out
+
+    def commit(self, v, r):
+        """pc_gens.commit(v, r).compress()"""
+        out = (C.c_uint8 * 32)()
+        _check(load().bp_pc_commit(self._h, 1, _buf(scalar_bytes(v)), _buf(scalar_bytes(r)), out))
+        return bytes(out)
+
+
+def _vars3(arr):
+    return tuple(Variable(arr[i].kind, arr[i].index) for i in range(3))
+
+
+class ConstraintSystem:
+    def __init__(self, gens, label, prover):
+        self.gens = gens
+        self._h = C.c_void_p()
+        fn = load().bp_prover_new if prover else load().bp_verifier_new
+        _check(fn(gens._h, _buf(label) if label else None, C.c_size_t(len(label)), C.byref(self._h)))
+        self.is_prover = prover
+
+    def __del__(self):
+        if _lib is not None and getattr(self, "_h", None):
+            _lib.bp_cs_free(self._h)
+            self._h = None
+
+    def multiply(self, left, right):
+        l, nl = LinearCombination.of(left)._c()
+        r, nr = LinearCombination.of(right)._c()
+        out = (bp_var * 3)()
+        _check(load().bp_cs_multiply(self._h, l, C.c_size_t(nl), r, C.c_size_t(nr), out), "multiply")
+        return _vars3(out)
+
+    def allocate_multiplier(self, assignment):
+        out = (bp_var * 3)()
+        if assignment is None:
+            rc = load().bp_cs_allocate_multiplier(self._h, None, None, out)
+        else:
+            rc = load().bp_cs_allocate_multiplier(self._h, _buf(scalar_bytes(assignment[0])), _buf(scalar_bytes(assignment[1])), out)
+        _check(rc, "allocate_multiplier")
+        return _vars3(out)
+
+    def allocate_single(self, assignment):
+        var, ov, has = bp_var(), bp_var(), C.c_int32(0)
+        val = None if assignment is None else _buf(scalar_bytes(assignment))
+        _check(load().bp_cs_allocate_single(self._h, val, C.byref(var), C.byref(ov), C.byref(has)), "allocate_single")
+        return Variable(var.kind, var.index), (Variable(ov.kind, ov.index) if has.value else None)
+
+    def evaluate_lc(self, lc):
+        arr, n = LinearCombination.of(lc)._c()
+        out = (C.c_uint8 * 32)()
+        rc = load().bp_cs_evaluate_lc(self._h, arr, C.c_size_t(n), out)
+        if rc == 4:
+            return None
+        _check(rc, "evaluate_lc")
+        return int.from_bytes(bytes(out), "little")
+
+    def constrain(self, lc):
+        arr, n = LinearCombination.of(lc)._c()
+        _check(load().bp_cs_constrain(self._h, arr, C.c_size_t(n)), "constrain")
+
+    def num_constraints(self):
+        return int(load().bp_cs_num_constraints(self._h))
+
+    def num_multipliers(self):
+        return int(load().bp_cs_num_multipliers(self._h))
+
+    def num_commitments(self):
+        return int(load().bp_cs_num_commitments(self._h))
+
+    # ---- the reference's gadgets, executed by the library's host layer against this constraint system
+    def allocate_statics(self, num_statics):
+        out = (bp_var * num_statics)()
+        _check(load().bp_gadget_allocate_statics(self._h, C.c_uint32(num_statics), out), "allocate_statics")
+        return [Variable(o.kind, o.index) for o in out]
+
+    def poseidon_hash_2_gadget(self, params, xl, xr, statics, sbox, expected):
+        st = (bp_var * len(statics))(*[s._c() for s in statics])
+        _check(load().bp_gadget_poseidon_hash_2(self._h, params._h, xl._c(), xr._c(), st, C.c_uint32(len(statics)), sbox,
+                                                _buf(scalar_bytes(expected))), "poseidon_hash_2_gadget")
+
+    def vsmt2_verif_gadget(self, params, depth, root, leaf, bits, nodes, statics):
+        b = (bp_var * depth)(*[x._c() for x in bits])
+        nd = (bp_var * depth)(*[x._c() for x in nodes])
+        st = (bp_var * len(statics))(*[s._c() for s in statics])
+        _check(load().bp_gadget_vsmt2_verif(self._h, params._h, C.c_uint32(depth), _buf(scalar_bytes(root)), leaf._c(), b, nd, st,
+                                            C.c_uint32(len(statics))), "vsmt2_verif_gadget")
+
+    def mimc_gadget(self, left, right, constants, image):
+        cb = b"".join(scalar_bytes(c) for c in constants)
+        _check(load().bp_gadget_mimc(self._h, left._c(), right._c(), C.c_uint32(len(constants)), _buf(cb), _buf(scalar_bytes(image))), "mimc_gadget")
+
+    def bound_check_gadget(self, v, a, b, vmax, vmin, bit_size, values=None):
+        has = values is not None
+        vv, av, bv = values if has else (0, 0, 0)
+        _check(load().bp_gadget_bound_check(self._h, v._c(), a._c(), b._c(), int(has), C.c_uint64(vv), C.c_uint64(av), C.c_uint64(bv),
+                                            C.c_uint64(vmax), C.c_uint64(vmin), C.c_uint32(bit_size)), "bound_check_gadget")
+
+    def compile(self):
+        return Circuit._from_cs(self)
+
+
+class Prover(ConstraintSystem):
+    """Transcript::new(label); Prover::new(&pc_gens, &mut transcript)"""
+
+    def __init__(self, gens, label):
+        super().__init__(gens, label, True)
+
+    def commit(self, v, v_blinding):
+        V, var = (C.c_uint8 * 32)(), bp_var()
+        _check(load().bp_prover_commit(self._h, _buf(scalar_bytes(v)), _buf(scalar_bytes(v_blinding)), V, C.byref(var)), "commit")
+        return bytes(V), Variable(var.kind, var.index)
+
+    def prove(self, entropy):
+        """prover.prove(&bp_gens); `entropy` = the 32 bytes the reference takes from thread_rng()"""
+        plen = load().bp_cs_proof_len(self._h)
+        out = (C.c_uint8 * plen)()
+        n = C.c_size_t(plen)
+        _check(load().bp_prover_prove(self._h, _buf(entropy), out, C.byref(n)), "prove")
+        return bytes(out[: n.value])
+
+
+class Verifier(ConstraintSystem):
+    """Transcript::new(label); Verifier::new(&mut transcript)"""
+
+    def __init__(self, gens, label):
+        super().__init__(gens, label, False)
+
+    def commit(self, V):
+        var = bp_var()
+        _check(load().bp_verifier_commit(self._h, _buf(V), C.byref(var)), "commit")
+        return Variable(var.kind, var.index)
+
+    def verify(self, proof, entropy):
+        """verifier.verify(&proof, &pc_gens, &bp_gens) -> raises R1CSError on failure"""
+        _check(load().bp_verifier_verify(self._h, _buf(proof), C.c_size_t(len(proof)), _buf(entropy)), "verify")
+        return True
+
+
+class Circuit:
+    """A compiled constraint system shared by every proof of a batch."""
+
+    def __init__(self):
+        self._h = C.c_void_p()
+
+    @staticmethod
+    def _from_cs(cs):
+        c = Circuit()
+        _check(load().bp_circuit_compile(cs._h, C.byref(c._h)), "circuit_compile")
+        c._sizes()
+        return c
+
+    @staticmethod
+    def from_arrays(n, m, cons_ptr, kind, idx, coeff):
+        c = Circuit()
+        cons_ptr = np.ascontiguousarray(cons_ptr, dtype=np.uint32)
+        kind, idx, coeff = _np_u8(kind), np.ascontiguousarray(idx, dtype=np.uint32), _np_u8(coeff)
+        _check(load().bp_circuit_from_arrays(C.c_uint32(n), C.c_uint32(m), C.c_uint32(len(cons_ptr) - 1), cons_ptr.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                             kind.ctypes.data_as(u8p), idx.ctypes.data_as(C.POINTER(C.c_uint32)), coeff.ctypes.data_as(u8p),
+                                             C.byref(c._h)), "circuit_from_arrays")
+        c._sizes()
+        return c
+
+    def _sizes(self):
+        l = load()
+        self.n = l.bp_circuit_num_multipliers(self._h)
+        self.q = l.bp_circuit_num_constraints(self._h)
+        self.m = l.bp_circuit_num_commitments(self._h)
+        self.num_aux = l.bp_circuit_num_aux(self._h)
+        self.has_witness_program = bool(l.bp_circuit_has_witness_program(self._h))
+        self.proof_len = l.bp_circuit_proof_len(self._h)
+
+    def __del__(self):
+        if _lib is not None and getattr(self, "_h", None):
+            _lib.bp_circuit_free(self._h)
+            self._h = None
+
+    def prove_batch(self, gens, label, v, v_blinding, entropy, aux=None, witness=None):
+        """v, v_blinding: uint8 [B][m][32]; entropy [B][32]; aux [B][num_aux][32]; witness = (aL,aR,aO) each [B][n][32] or None.
+        Returns (V [B][m][32], proofs [B][proof_len], status [B]).  Host buffers in, host buffers out."""
+        v, v_blinding, entropy = _np_u8(v), _np_u8(v_blinding), _np_u8(entropy)
+        B = entropy.shape[0]
+        V = np.zeros((B, self.m, 32), dtype=np.uint8)
+        proofs = np.zeros((B, self.proof_len), dtype=np.uint8)
+        status = np.zeros(B, dtype=np.int32)
+        p = lambda a: a.ctypes.data_as(u8p) if a is not None else None
+        aux = _np_u8(aux) if aux is not None else None
+        wl = [_np_u8(w) for w in witness] if witness is not None else [None, None, None]
+        _check(load().bp_prove_batch(gens._h, self._h, C.c_uint32(B), _buf(label) if label else None, C.c_size_t(len(label)), p(v), p(v_blinding),
+                                     p(entropy), p(aux), p(wl[0]), p(wl[1]), p(wl[2]), p(V), p(proofs), status.ctypes.data_as(C.POINTER(C.c_int32))),
+               "prove_batch")
+        return V, proofs, status
+
+    def verify_batch(self, gens, label, V, proofs, entropy):
+        V, proofs, entropy = _np_u8(V), _np_u8(proofs), _np_u8(entropy)
+        B = entropy.shape[0]
+        status = np.zeros(B, dtype=np.int32)
+        _check(load().bp_verify_batch(gens._h, self._h, C.c_uint32(B), _buf(label) if label else None, C.c_size_t(len(label)), V.ctypes.data_as(u8p),
+                                      proofs.ctypes.data_as(u8p), entropy.ctypes.data_as(u8p), status.ctypes.data_as(C.POINTER(C.c_int32))),
+               "verify_batch")
+        return status
+
+
+def launch_count():
+    return int(load().bp_launch_count())

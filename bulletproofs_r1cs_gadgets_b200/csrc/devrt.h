@@ -1,0 +1,57 @@
+// Launch / memory shim.  Product build: CUDA runtime on the caller's stream, every kernel is a
+// named instantiation run_kernel<Functor> (that is the name ncu shows).  Emulation build
+// (-DBP_HOST_EMUL, tests/emul only): the same functor bodies run in a host loop so kernel-body
+// unit tests work in the CPU-only container.  There is no runtime switch between the two.
+#pragma once
+#include "hd.h"
+#include <stdio.h>
+#include <stdlib.h>
+
+#ifndef BP_HOST_EMUL
+#include <cuda_runtime.h>
+typedef cudaStream_t dev_stream;
+
+template <class K>
+__global__ void __launch_bounds__(K::kBlock, K::kMinBlocks) run_kernel(long n, K k) {
+  long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid < n) k(tid);
+}
+extern long g_launch_count;
+template <class K>
+inline int launch(long n, dev_stream s, const K &k) {
+  if (n <= 0) return 0;
+  long blocks = (n + K::kBlock - 1) / K::kBlock;
+  run_kernel<K><<<(unsigned)blocks, K::kBlock, 0, s>>>(n, k);
+  g_launch_count++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { fprintf(stderr, "bp_b200: launch failed: %s\n", cudaGetErrorString(e)); return 1; }
+  return 0;
+}
+inline int dev_malloc(void **p, size_t n) { return cudaMalloc(p, n ? n : 16) != cudaSuccess; }
+inline void dev_free(void *p) { if (p) cudaFree(p); }
+inline int dev_h2d(void *d, const void *h, size_t n, dev_stream s) { return n ? cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s) != cudaSuccess : 0; }
+inline int dev_d2h(void *h, const void *d, size_t n, dev_stream s) { return n ? cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s) != cudaSuccess : 0; }
+inline int dev_d2d(void *d, const void *s_, size_t n, dev_stream s) { return n ? cudaMemcpyAsync(d, s_, n, cudaMemcpyDeviceToDevice, s) != cudaSuccess : 0; }
+inline int dev_memset(void *d, int v, size_t n, dev_stream s) { return n ? cudaMemsetAsync(d, v, n, s) != cudaSuccess : 0; }
+inline int dev_sync(dev_stream s) {
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) { fprintf(stderr, "bp_b200: stream sync failed: %s\n", cudaGetErrorString(e)); return 1; }
+  return 0;
+}
+#else
+typedef int dev_stream;
+extern long g_launch_count;
+template <class K>
+inline int launch(long n, dev_stream, const K &k) {
+  for (long t = 0; t < n; t++) k(t);
+  g_launch_count++;
+  return 0;
+}
+inline int dev_malloc(void **p, size_t n) { *p = malloc(n ? n : 16); return *p == NULL; }
+inline void dev_free(void *p) { free(p); }
+inline int dev_h2d(void *d, const void *h, size_t n, dev_stream) { if (n) memcpy(d, h, n); return 0; }
+inline int dev_d2h(void *h, const void *d, size_t n, dev_stream) { if (n) memcpy(h, d, n); return 0; }
+inline int dev_d2d(void *d, const void *s_, size_t n, dev_stream) { if (n) memcpy(d, s_, n); return 0; }
+inline int dev_memset(void *d, int v, size_t n, dev_stream) { if (n) memset(d, v, n); return 0; }
+inline int dev_sync(dev_stream) { return 0; }
+#endif

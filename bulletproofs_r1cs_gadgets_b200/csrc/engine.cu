@@ -1,0 +1,385 @@
+// Batched prover / verifier pipelines.  See engine.h and kernels.h.
+#include "engine.h"
+#include <algorithm>
+#include <mutex>
+
+long g_launch_count = 0;
+long engine_launch_count() { return g_launch_count; }
+
+#define CK(x) do { int _e = (x); if (_e) { fprintf(stderr, "bp_b200: %s failed at %s:%d\n", #x, __FILE__, __LINE__); return BP_ERR_CUDA; } } while (0)
+
+static const uint8_t BASEPOINT_C[32] = {0xe2, 0xf2, 0xae, 0x0a, 0x6a, 0xbc, 0x4e, 0x71, 0xa8, 0x84, 0xa9, 0x61, 0xc5, 0x00, 0x51, 0x5f,
+                                        0x58, 0xe3, 0x0b, 0x6a, 0xa5, 0x82, 0xdd, 0x8d, 0xb6, 0xa6, 0x59, 0x45, 0xe0, 0x8d, 0x2d, 0x76};
+
+int bp_device_init() {
+#ifndef BP_HOST_EMUL
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    fprintf(stderr, "bp_b200: no CUDA device (%s); this library has no CPU path\n", e == cudaSuccess ? "count 0" : cudaGetErrorString(e));
+    return BP_ERR_NO_DEVICE;
+  }
+#endif
+  return BP_OK;
+}
+
+template <class T>
+static int dalloc(T **p, size_t count) { return dev_malloc((void **)p, count * sizeof(T)); }
+
+struct Workspace {
+  int B = 0;
+  scm *v = 0, *vbl = 0, *aux = 0, *wit = 0, *rand1 = 0, *w_all = 0, *zpow = 0, *ypow = 0, *yinvpow = 0, *a = 0, *b = 0, *chal = 0, *t = 0, *tb = 0,
+      *clr = 0, *part = 0;
+  strobe128 *ts = 0, *rng = 0;
+  int8_t *dig = 0; size_t dig_bytes = 0;
+  ge_p3 *buckets = 0; size_t bucket_slots = 0;
+  ge_p3 *wsum = 0, *Q = 0, *Gt = 0, *Ht = 0, *pts = 0;
+  int8_t *naf = 0; int *naf_top = 0;
+  void release() {
+    void *ps[] = {v, vbl, aux, wit, rand1, w_all, zpow, ypow, yinvpow, a, b, chal, t, tb, clr, part, ts, rng, dig, buckets, wsum, Q, Gt, Ht, pts, naf, naf_top};
+    for (void *p : ps) dev_free(p);
+    *this = Workspace();
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ generators
+int gens_create(uint32_t capacity, BpGens **out) {
+  int rc = bp_device_init();
+  if (rc) return rc;
+  if (capacity == 0) capacity = 1;
+  BpGens *g = new BpGens();
+  memset(g, 0, sizeof *g);
+  g->capacity = capacity;
+  dev_stream s = 0;
+  if (dalloc(&g->G_p3, capacity) || dalloc(&g->H_p3, capacity) || dalloc(&g->G_n, capacity) || dalloc(&g->H_n, capacity) ||
+      dalloc(&g->pc, 2) || dalloc(&g->pc_niels, 2) || dalloc(&g->pc_table, 2 * 64 * 16)) { gens_free(g); return BP_ERR_OOM; }
+  // generator chains: SHAKE256("GeneratorsChain" || label) with label = 'G'/'H' || u32le(party 0)
+  std::vector<uint8_t> uni((size_t)capacity * 64);
+  uint8_t *d_uni = nullptr, *d_small = nullptr; int *d_ok = nullptr;
+  CK(dalloc(&d_uni, (size_t)capacity * 64)); CK(dalloc(&d_small, 256)); CK(dalloc(&d_ok, 1));
+  for (int which = 0; which < 2; which++) {
+    uint8_t seed[20]; memcpy(seed, "GeneratorsChain", 15); seed[15] = which ? 'H' : 'G'; seed[16] = seed[17] = seed[18] = seed[19] = 0;
+    keccak_xof k; shake256_init(k, seed, 20);
+    keccak_squeeze(k, uni.data(), uni.size());
+    CK(dev_h2d(d_uni, uni.data(), uni.size(), s));
+    CK(launch(capacity, s, KGensFromUniform{d_uni, which ? g->H_p3 : g->G_p3, which ? g->H_n : g->G_n}));
+    CK(dev_sync(s));
+  }
+  // Pedersen bases
+  uint8_t small[96 + 64]; memcpy(small, BASEPOINT_C, 32); sha3_512(small + 32, BASEPOINT_C, 32);
+  int ok = 1;
+  CK(dev_h2d(d_small, small, 96, s)); CK(dev_h2d(d_ok, &ok, sizeof ok, s));
+  CK(launch(2, s, KPcBases{d_small, d_small + 32, g->pc, g->pc_niels, d_small + 96, d_ok}));
+  CK(launch(128, s, KPcTable{g->pc, g->pc_table}));
+  CK(dev_d2h(g->pc_c, d_small + 96, 64, s)); CK(dev_d2h(&ok, d_ok, sizeof ok, s));
+  CK(dev_sync(s));
+  dev_free(d_uni); dev_free(d_small); dev_free(d_ok);
+  if (!ok) { gens_free(g); return BP_ERR_CUDA; }
+  *out = g;
+  return BP_OK;
+}
+void gens_free(BpGens *g) {
+  if (!g) return;
+  if (g->msm_ws) { g->msm_ws->release(); delete g->msm_ws; }
+  dev_free(g->G_p3); dev_free(g->H_p3); dev_free(g->G_n); dev_free(g->H_n); dev_free(g->pc); dev_free(g->pc_niels); dev_free(g->pc_table);
+  delete g;
+}
+int gens_export(const BpGens *g, int which, uint32_t count, uint8_t *out) {
+  if (count > g->capacity) return BP_ERR_INVALID_GENERATORS_LENGTH;
+  uint8_t *d = nullptr; CK(dalloc(&d, (size_t)count * 32));
+  CK(launch(count, 0, KEncodePoints{which ? g->H_p3 : g->G_p3, d}));
+  CK(dev_d2h(out, d, (size_t)count * 32, 0)); CK(dev_sync(0));
+  dev_free(d);
+  return BP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ circuits
+static uint32_t next_pow2(uint32_t n) { uint32_t N = 1; while (N < n) N <<= 1; return N; }
+static uint32_t ilog2(uint32_t N) { uint32_t k = 0; while ((1u << k) < N) k++; return k; }
+
+size_t circuit_proof_len(const BpCircuit *c) { return 32 * (size_t)(14 + 2 * c->k + 2); }
+
+int circuit_create(uint32_t n, uint32_t m, uint32_t q, const uint32_t *cons_ptr, const uint8_t *kind, const uint32_t *idx,
+                   const scm *coeff, const TapeOp *tape, uint32_t naux, uint32_t nwlc, const uint32_t *wlc_ptr,
+                   const uint8_t *wkind, const uint32_t *widx, const scm *wcoeff, BpCircuit **out) {
+  int rc = bp_device_init();
+  if (rc) return rc;
+  BpCircuit *c = new BpCircuit();
+  memset(c, 0, sizeof *c);
+  c->n = n; c->m = m; c->q = q; c->N = next_pow2(n ? n : 1); c->k = ilog2(c->N);
+  c->nnz = cons_ptr[q]; c->nslots = 3 * n + m + 1; c->naux = naux;
+  // validate + transpose to slot-major
+  std::vector<uint32_t> slot_cnt(c->nslots + 1, 0);
+  auto slot_of = [&](uint32_t t) -> long {
+    uint32_t i = idx[t];
+    switch (kind[t]) {
+      case 1: return i < n ? (long)i : -1;
+      case 2: return i < n ? (long)n + i : -1;
+      case 3: return i < n ? (long)2 * n + i : -1;
+      case 0: return i < m ? (long)3 * n + i : -1;
+      case 4: return (long)3 * n + m;
+      default: return -1;
+    }
+  };
+  for (uint32_t t = 0; t < c->nnz; t++) { long s = slot_of(t); if (s < 0) { delete c; return BP_ERR_INVALID_ARGUMENT; } slot_cnt[s + 1]++; }
+  for (uint32_t s = 0; s < c->nslots; s++) slot_cnt[s + 1] += slot_cnt[s];
+  std::vector<uint32_t> fill(slot_cnt.begin(), slot_cnt.end() - 1), tq(c->nnz ? c->nnz : 1);
+  std::vector<scm> tc(c->nnz ? c->nnz : 1);
+  for (uint32_t k = 0; k < q; k++)
+    for (uint32_t t = cons_ptr[k]; t < cons_ptr[k + 1]; t++) {
+      long s = slot_of(t); uint32_t at = fill[s]++;
+      tq[at] = k;
+      scm co = coeff[t];
+      if (kind[t] == 0 || kind[t] == 4) co = sc_neg(co);  // wV and wc accumulate with a minus sign (A.3 step 7)
+      tc[at] = co;
+    }
+  dev_stream s = 0;
+  if (dalloc(&c->d_slot_ptr, c->nslots + 1) || dalloc(&c->d_tq, tq.size()) || dalloc(&c->d_tcoeff, tc.size())) { circuit_free(c); return BP_ERR_OOM; }
+  CK(dev_h2d(c->d_slot_ptr, slot_cnt.data(), (c->nslots + 1) * sizeof(uint32_t), s));
+  CK(dev_h2d(c->d_tq, tq.data(), tq.size() * sizeof(uint32_t), s));
+  CK(dev_h2d(c->d_tcoeff, tc.data(), tc.size() * sizeof(scm), s));
+  if (tape) {
+    c->has_tape = 1;
+    uint32_t wn = wlc_ptr[nwlc];
+    for (uint32_t t = 0; t < wn; t++) {
+      uint32_t lim = wkind[t] == 0 ? m : (wkind[t] == 4 ? 1 : n);
+      if (wkind[t] > 4 || widx[t] >= lim) { circuit_free(c); return BP_ERR_INVALID_ARGUMENT; }
+    }
+    for (uint32_t i = 0; i < n; i++) {
+      const TapeOp &op = tape[i];
+      bool okL = (op.opL == W_LC && op.argL < nwlc) || (op.opL == W_AUX && op.argL < naux);
+      bool okR = (op.opR == W_LC && op.argR < nwlc) || (op.opR == W_AUX && op.argR < naux) || op.opR == W_INV_L;
+      if (!okL || !okR) { circuit_free(c); return BP_ERR_INVALID_ARGUMENT; }
+    }
+    if (dalloc(&c->d_tape, n ? n : 1) || dalloc(&c->d_wptr, nwlc + 1) || dalloc(&c->d_wkind, wn ? wn : 1) || dalloc(&c->d_widx, wn ? wn : 1) ||
+        dalloc(&c->d_wcoeff, wn ? wn : 1)) { circuit_free(c); return BP_ERR_OOM; }
+    CK(dev_h2d(c->d_tape, tape, n * sizeof(TapeOp), s));
+    CK(dev_h2d(c->d_wptr, wlc_ptr, (nwlc + 1) * sizeof(uint32_t), s));
+    CK(dev_h2d(c->d_wkind, wkind, wn, s));
+    CK(dev_h2d(c->d_widx, widx, wn * sizeof(uint32_t), s));
+    CK(dev_h2d(c->d_wcoeff, wcoeff, wn * sizeof(scm), s));
+  }
+  CK(dev_sync(s));
+  c->ws = new Workspace();
+  *out = c;
+  return BP_OK;
+}
+void circuit_free(BpCircuit *c) {
+  if (!c) return;
+  dev_free(c->d_slot_ptr); dev_free(c->d_tq); dev_free(c->d_tcoeff); dev_free(c->d_tape); dev_free(c->d_wptr); dev_free(c->d_wkind);
+  dev_free(c->d_widx); dev_free(c->d_wcoeff);
+  if (c->ws) { c->ws->release(); delete c->ws; }
+  delete c;
+}
+
+static const int CH_DOT = 256;  // multipliers per partial-sum thread
+static const int CH_POW = 64;   // exponents per powers thread
+static long msm_target_warps() { return 148L * 8 * 4; }
+
+static int ensure_workspace(BpCircuit *c, int B) {
+  Workspace *w = c->ws;
+  if (w->B >= B) return BP_OK;
+  w->release();
+  const size_t n = c->n, N = c->N, m = c->m, q = c->q, Bz = (size_t)B;
+  const size_t k = c->k;
+  size_t nchunks = (std::max(n, N) + CH_DOT - 1) / CH_DOT + 1;
+  size_t rows_as = (2 * n + 1) + (n + 1) + (2 * n + 1), rows_ipa = 2 * (N + 1), rows_ver = 2 * N + m + 13 + 2 * k + 2;
+  w->dig_bytes = std::max(std::max(rows_as, rows_ipa), rows_ver) * 32 * Bz;
+  // bucket slots: enough for one MSM launch at the largest split the launcher will pick
+  size_t max_warps = (size_t)std::max<long>(msm_target_warps(), 2L * B) + B;
+  w->bucket_slots = max_warps * MSM_WINDOWS * MSM_BUCKETS;
+  int bad = 0;
+  bad |= dalloc(&w->v, (m + 1) * Bz); bad |= dalloc(&w->vbl, (m + 1) * Bz); bad |= dalloc(&w->aux, (size_t)(c->naux + 1) * Bz);
+  bad |= dalloc(&w->wit, 3 * (n + 1) * Bz); bad |= dalloc(&w->rand1, (3 + 2 * n) * Bz); bad |= dalloc(&w->w_all, (size_t)c->nslots * Bz);
+  bad |= dalloc(&w->zpow, (q + 1) * Bz); bad |= dalloc(&w->ypow, N * Bz); bad |= dalloc(&w->yinvpow, N * Bz);
+  bad |= dalloc(&w->a, N * Bz); bad |= dalloc(&w->b, N * Bz); bad |= dalloc(&w->chal, 16 * Bz);
+  bad |= dalloc(&w->t, 6 * Bz); bad |= dalloc(&w->tb, 5 * Bz); bad |= dalloc(&w->clr, 2 * Bz); bad |= dalloc(&w->part, nchunks * 6 * Bz);
+  bad |= dalloc(&w->ts, Bz); bad |= dalloc(&w->rng, Bz);
+  bad |= dalloc(&w->dig, w->dig_bytes); bad |= dalloc(&w->buckets, w->bucket_slots); bad |= dalloc(&w->wsum, max_warps * MSM_WINDOWS);
+  bad |= dalloc(&w->Q, Bz); bad |= dalloc(&w->Gt, (N / 2 + 1) * Bz); bad |= dalloc(&w->Ht, (N / 2 + 1) * Bz);
+  bad |= dalloc(&w->pts, (m + 11 + 2 * k + 1) * Bz);
+  bad |= dalloc(&w->naf, 4 * 256 * Bz); bad |= dalloc(&w->naf_top, 4 * Bz);
+  if (bad) { w->release(); return BP_ERR_OOM; }
+  w->B = B;
+  return BP_OK;
+}
+
+// one MSM launch: ninst instances, shared digit buffer, result handling in KMsmFinish
+static int run_msm(Workspace *w, const MsmSeg *segs, int nseg, long ninst, const int8_t *dig, long dig_inst_stride, uint8_t *out,
+                   long out_stride, int mode, int *status, dev_stream s) {
+  long rows = 0;
+  for (int i = 0; i < nseg; i++) rows += segs[i].count;
+  long S = (msm_target_warps() + ninst - 1) / ninst;
+  long maxS = rows / 256; if (maxS < 1) maxS = 1;
+  if (S > maxS) S = maxS;
+  if (S < 1) S = 1;
+  while ((size_t)(ninst * S) * MSM_WINDOWS * MSM_BUCKETS > w->bucket_slots && S > 1) S--;
+  if ((size_t)(ninst * S) * MSM_WINDOWS * MSM_BUCKETS > w->bucket_slots) return BP_ERR_OOM;
+  KMsmAccumulate k{};
+  for (int i = 0; i < nseg; i++) k.seg[i] = segs[i];
+  k.nseg = nseg; k.S = (int)S; k.dig = dig; k.dig_inst_stride = dig_inst_stride; k.buckets = w->buckets; k.wsum = w->wsum;
+  CK(launch(ninst * S * MSM_WINDOWS, s, k));
+  CK(launch(ninst, s, KMsmFinish{w->wsum, (int)S, out, out_stride, mode, status, BP_ERR_VERIFICATION}));
+  return BP_OK;
+}
+
+static void base_transcript(strobe128 &t, const uint8_t *label, int label_len) {
+  ts_init(t, label, label_len);
+  const uint8_t r1[7] = {'r', '1', 'c', 's', ' ', 'v', '1'};
+  ts_append(t, "dom-sep", r1, 7);
+}
+
+// ------------------------------------------------------------------------------------------------ prover
+int engine_prove(const BpGens *g, BpCircuit *c, const ProveArgs &A, dev_stream s) {
+  const int B = A.B;
+  if (B <= 0) return BP_OK;
+  if (g->capacity < c->n || g->capacity < c->N) return BP_ERR_INVALID_GENERATORS_LENGTH;
+  if (!A.aL && !c->has_tape) return BP_ERR_MISSING_ASSIGNMENT;
+  int rc = ensure_workspace(c, B);
+  if (rc) return rc;
+  Workspace *w = c->ws;
+  const long n = c->n, N = c->N, m = c->m, q = c->q, k = c->k;
+  const long plen = (long)circuit_proof_len(c);
+  scm *aL = w->wit, *aR = w->wit + n * B, *aO = w->wit + 2 * n * B;
+  scm *i_b = w->rand1, *sL = w->rand1 + 3L * B, *sR = w->rand1 + (3 + n) * B;
+  scm *wL = w->w_all, *wR = w->w_all + n * B, *wO = w->w_all + 2 * n * B, *wV = w->w_all + 3 * n * B;
+  scm *ch_y = w->chal, *ch_z = w->chal + B, *ch_yinv = w->chal + 2L * B, *ch_u = w->chal + 3L * B, *ch_x = w->chal + 4L * B,
+      *ch_w = w->chal + 5L * B, *ipa_u = w->chal + 6L * B, *ipa_uinv = w->chal + 7L * B, *alpha = w->chal + 8L * B, *beta = w->chal + 9L * B;
+
+  CK(dev_memset(A.status, 0, sizeof(int) * B, s));
+  CK(dev_memset(A.proofs, 0, (size_t)plen * B, s));
+  // 1. inputs -> Montgomery, commitments V_j = v_j*B + r_j*B_blinding
+  CK(launch(m * B, s, KLoadScalars{A.v, w->v, (int)m, B}));
+  CK(launch(m * B, s, KLoadScalars{A.vbl, w->vbl, (int)m, B}));
+  CK(launch(m * B, s, KCommit{w->v, w->vbl, (int)m, B, g->pc_table, A.V_out, m * 32, 32, nullptr}));
+  // 2. transcript start + transcript RNG, blinding draws (A.3 steps 1-3)
+  strobe128 base; base_transcript(base, A.label, A.label_len);
+  CK(launch(B, s, KTsStart{base, A.V_out, (int)m, B, w->vbl, A.entropy, w->ts, w->rng, 1}));
+  CK(launch(B, s, KRngDraw{w->rng, w->rand1, (int)(3 + 2 * n), B}));
+  // 3. witness
+  if (A.aL) {
+    CK(launch(n * B, s, KLoadScalars{A.aL, aL, (int)n, B}));
+    CK(launch(n * B, s, KLoadScalars{A.aR, aR, (int)n, B}));
+    CK(launch(n * B, s, KLoadScalars{A.aO, aO, (int)n, B}));
+  } else {
+    if (c->naux) CK(launch((long)c->naux * B, s, KLoadScalars{A.aux, w->aux, (int)c->naux, B}));
+    CK(launch(B, s, KWitnessTape{c->d_tape, WitnessLcs{c->d_wptr, c->d_wkind, c->d_widx, c->d_wcoeff}, (int)n, B, w->v, w->aux, aL, aR, aO}));
+  }
+  // 4. A_I1, A_O1, S1 (A.3 step 4)
+  {
+    const long rowsI = 2 * n + 1, rowsO = n + 1;
+    int8_t *dI = w->dig, *dO = dI + rowsI * 32 * B, *dS = dO + rowsO * 32 * B;
+    CK(launch(B, s, KRecode{i_b, nullptr, 1, B, dI, rowsI * 32, 0}));
+    CK(launch(n * B, s, KRecode{aL, nullptr, (int)n, B, dI, rowsI * 32, 1}));
+    CK(launch(n * B, s, KRecode{aR, nullptr, (int)n, B, dI, rowsI * 32, (int)(1 + n)}));
+    CK(launch(B, s, KRecode{i_b + B, nullptr, 1, B, dO, rowsO * 32, 0}));
+    CK(launch(n * B, s, KRecode{aO, nullptr, (int)n, B, dO, rowsO * 32, 1}));
+    CK(launch(B, s, KRecode{i_b + 2L * B, nullptr, 1, B, dS, rowsI * 32, 0}));
+    CK(launch(n * B, s, KRecode{sL, nullptr, (int)n, B, dS, rowsI * 32, 1}));
+    CK(launch(n * B, s, KRecode{sR, nullptr, (int)n, B, dS, rowsI * 32, (int)(1 + n)}));
+    MsmSeg segs[3] = {{g->pc_niels + 1, 0, 0, 1}, {g->G_n, 0, 0, (int)n}, {g->H_n, 0, 0, (int)n}};
+    rc = run_msm(w, segs, 3, B, dI, rowsI * 32, A.proofs + 0, plen, 0, nullptr, s); if (rc) return rc;
+    rc = run_msm(w, segs, 2, B, dO, rowsO * 32, A.proofs + 32, plen, 0, nullptr, s); if (rc) return rc;
+    rc = run_msm(w, segs, 3, B, dS, rowsI * 32, A.proofs + 64, plen, 0, nullptr, s); if (rc) return rc;
+  }
+  // 5. y, z; powers; flattened weights (A.3 steps 5-7)
+  CK(launch(B, s, KTsPhase2{w->ts, A.proofs, plen, ch_y, ch_z, ch_yinv, A.status, 0}));
+  CK(launch(((q + CH_POW - 1) / CH_POW) * B, s, KPowers{ch_z, w->zpow, (int)q, B, 1, CH_POW}));
+  CK(launch(((N + CH_POW - 1) / CH_POW) * B, s, KPowers{ch_y, w->ypow, (int)N, B, 0, CH_POW}));
+  CK(launch(((N + CH_POW - 1) / CH_POW) * B, s, KPowers{ch_yinv, w->yinvpow, (int)N, B, 0, CH_POW}));
+  CK(launch((long)c->nslots * B, s, KFlatten{c->d_slot_ptr, c->d_tq, c->d_tcoeff, w->zpow, w->w_all, B}));
+  // 6. t(x) coefficients, T commitments (A.3 steps 8-10)
+  PolyIn pin{aL, aR, aO, sL, sR, wL, wR, wO, w->ypow, w->yinvpow};
+  {
+    long nch = (n + CH_DOT - 1) / CH_DOT;
+    if (nch == 0) nch = 1;
+    CK(launch(nch * B, s, KPolyT{pin, (int)n, B, CH_DOT, w->part}));
+    CK(launch(6L * B, s, KSumPartials{w->part, (int)nch, 6, B, w->t}));
+  }
+  CK(launch(B, s, KRngDraw{w->rng, w->tb, 5, B}));
+  {
+    // T_1,T_3,T_4,T_5,T_6 use t[0],t[2],t[3],t[4],t[5]: commit rows individually
+    const int tj[5] = {0, 2, 3, 4, 5};
+    for (int j = 0; j < 5; j++)
+      CK(launch(B, s, KCommit{w->t + (long)tj[j] * B, w->tb + (long)j * B, 1, B, g->pc_table, A.proofs + 192 + 32 * j, plen, 0, nullptr}));
+  }
+  CK(launch(B, s, KTsPhase3{w->ts, A.proofs, plen, ch_u, ch_x, A.status, 0}));
+  // 7. evaluate l, r at x; scalars of the proof (A.3 steps 11-13); w and Q (step 14)
+  CK(launch(N * B, s, KPolyEval{pin, (int)n, B, ch_x, w->a, w->b}));
+  CK(launch(B, s, KProverScalars{w->t, w->tb, i_b, wV, w->vbl, (int)m, B, ch_x, A.proofs, plen}));
+  CK(launch(B, s, KTsPhase4{w->ts, A.proofs, plen, ch_w, (unsigned)N}));
+  CK(launch(B, s, KCommit{ch_w, nullptr, 1, B, g->pc_table, nullptr, 0, 0, w->Q}));
+  // 8. inner-product argument (A.4)
+  CK(launch(2L * B, s, KFillScalar{alpha, sc_one()}));  // alpha, beta are adjacent
+  long len = N;
+  for (int round = 0; round < k; round++) {
+    const long h = len / 2;
+    long nch = (h + CH_DOT - 1) / CH_DOT;
+    CK(launch(nch * B, s, KIpaDots{w->a, w->b, (int)h, B, CH_DOT, w->part}));
+    CK(launch(2L * B, s, KSumPartials{w->part, (int)nch, 2, B, w->clr}));
+    const long rows = 2 * h + 1;
+    int8_t *dL = w->dig, *dR = w->dig + rows * 32 * B;
+    CK(launch(h * B, s, KRecodeIpa{w->a, w->b, alpha, beta, w->yinvpow, ch_u, w->clr, (int)h, B, (int)n, round, dL, dR, rows * 32}));
+    MsmSeg sL_[3], sR_[3];
+    if (round == 0) {
+      sL_[0] = {g->G_n + h, 0, 0, (int)h}; sL_[1] = {g->H_n, 0, 0, (int)h};
+      sR_[0] = {g->G_n, 0, 0, (int)h};     sR_[1] = {g->H_n + h, 0, 0, (int)h};
+    } else {
+      const long gs = N / 2 + 1;
+      sL_[0] = {w->Gt + h, gs, 1, (int)h}; sL_[1] = {w->Ht, gs, 1, (int)h};
+      sR_[0] = {w->Gt, gs, 1, (int)h};     sR_[1] = {w->Ht + h, gs, 1, (int)h};
+    }
+    sL_[2] = {w->Q, 1, 1, 1}; sR_[2] = sL_[2];
+    rc = run_msm(w, sL_, 3, B, dL, rows * 32, A.proofs + 448 + 64 * round, plen, 0, nullptr, s); if (rc) return rc;
+    rc = run_msm(w, sR_, 3, B, dR, rows * 32, A.proofs + 448 + 64 * round + 32, plen, 0, nullptr, s); if (rc) return rc;
+    CK(launch(B, s, KTsIpaRound{w->ts, A.proofs, plen, round, B, (int)h, w->yinvpow, ch_u, ipa_u, ipa_uinv, alpha, beta, w->naf, w->naf_top,
+                               A.status, 0}));
+    CK(launch(h * B, s, KFoldAB{w->a, w->b, ipa_u, ipa_uinv, (int)h, B}));
+    if (h > 1) {
+      const long gs = N / 2 + 1;
+      if (round == 0) CK(launch(2 * h * B, s, KFoldGens{g->G_p3, g->H_p3, 0, w->Gt, w->Ht, gs, w->naf, w->naf_top, (int)h, (int)n, round}));
+      else CK(launch(2 * h * B, s, KFoldGens{w->Gt, w->Ht, gs, w->Gt, w->Ht, gs, w->naf, w->naf_top, (int)h, (int)n, round}));
+    }
+    len = h;
+  }
+  CK(launch(B, s, KStoreAB{w->a, w->b, A.proofs, plen, 448 + 64 * k}));
+  return BP_OK;
+}
+
+int engine_commit(const BpGens *g, int count, const uint8_t *v, const uint8_t *r, uint8_t *out) {
+  if (count <= 0) return BP_OK;
+  uint8_t *d_in = nullptr, *d_out = nullptr; scm *d_s = nullptr;
+  CK(dalloc(&d_in, (size_t)count * 64)); CK(dalloc(&d_out, (size_t)count * 32)); CK(dalloc(&d_s, (size_t)count * 2));
+  dev_stream s = 0;
+  CK(dev_h2d(d_in, v, (size_t)count * 32, s)); CK(dev_h2d(d_in + (size_t)count * 32, r, (size_t)count * 32, s));
+  // treat as B = count proofs with one commitment each
+  CK(launch(count, s, KLoadScalars{d_in, d_s, 1, count}));
+  CK(launch(count, s, KLoadScalars{d_in + (size_t)count * 32, d_s + count, 1, count}));
+  CK(launch(count, s, KCommit{d_s, d_s + count, 1, count, g->pc_table, d_out, 32, 0, nullptr}));
+  CK(dev_d2h(out, d_out, (size_t)count * 32, s)); CK(dev_sync(s));
+  dev_free(d_in); dev_free(d_out); dev_free(d_s);
+  return BP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ MSM microbenchmark entry
+int engine_msm_gens(BpGens *g, uint32_t n, const uint8_t *d_scalars, uint8_t *d_out, dev_stream s) {
+  if (n == 0 || n > g->capacity) return BP_ERR_INVALID_GENERATORS_LENGTH;
+  if (!g->msm_ws || g->msm_ws_n < n) {
+    if (g->msm_ws) { g->msm_ws->release(); delete g->msm_ws; }
+    Workspace *w = g->msm_ws = new Workspace();
+    size_t max_warps = (size_t)msm_target_warps() + 1;
+    w->bucket_slots = max_warps * MSM_WINDOWS * MSM_BUCKETS;
+    if (dalloc(&w->a, n) || dalloc(&w->dig, (size_t)n * 32) || dalloc(&w->buckets, w->bucket_slots) || dalloc(&w->wsum, max_warps * MSM_WINDOWS)) {
+      w->release(); return BP_ERR_OOM;
+    }
+    g->msm_ws_n = n;
+  }
+  Workspace *w = g->msm_ws;
+  CK(launch(n, s, KLoadScalars{d_scalars, w->a, (int)n, 1}));
+  CK(launch(n, s, KRecode{w->a, nullptr, (int)n, 1, w->dig, (long)n * 32, 0}));
+  MsmSeg seg[1] = {{g->G_n, 0, 0, (int)n}};
+  return run_msm(w, seg, 1, 1, w->dig, (long)n * 32, d_out, 32, 0, nullptr, s);
+}
+
+// ------------------------------------------------------------------------------------------------ verifier (placeholder until kernels land)
+int engine_verify(const BpGens *, BpCircuit *, const VerifyArgs &, dev_stream) { return BP_ERR_INVALID_ARGUMENT; }

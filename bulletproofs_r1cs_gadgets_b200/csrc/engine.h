@@ -1,0 +1,73 @@
+// Host-side engine: device generator tables, compiled circuits, and the batched prover/verifier
+// pipelines that string the kernels of kernels.h together on one CUDA stream per engine call.
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+#include <vector>
+#include "kernels.h"
+#include "devrt.h"
+
+#include "../../include/bp_b200.h"  // status codes
+
+struct BpGens {
+  uint32_t capacity;
+  ge_p3 *G_p3, *H_p3;
+  ge_niels *G_n, *H_n;
+  ge_p3 *pc;            // B, B_blinding
+  ge_niels *pc_niels;
+  ge_niels *pc_table;   // [2][64][16]
+  uint8_t pc_c[64];     // compressed B, B_blinding (host copy)
+  struct Workspace *msm_ws; uint32_t msm_ws_n;  // scratch of the MSM microbenchmark entry
+};
+
+struct HostTerm { uint8_t kind; uint32_t idx; uint8_t coeff[32]; };  // kind: 0 committed,1 left,2 right,3 output,4 one
+
+struct Workspace;
+struct BpCircuit {
+  uint32_t n, N, k, m, q, nnz, nslots, naux;
+  uint32_t *d_slot_ptr, *d_tq; scm *d_tcoeff;
+  int has_tape;
+  TapeOp *d_tape; uint32_t *d_wptr; uint8_t *d_wkind; uint32_t *d_widx; scm *d_wcoeff;
+  Workspace *ws;
+};
+
+int bp_device_init();
+int gens_create(uint32_t capacity, BpGens **out);
+void gens_free(BpGens *g);
+int gens_export(const BpGens *g, int which, uint32_t count, uint8_t *out);  // which: 0 G, 1 H -> compressed
+
+// cons_ptr[q+1], terms in constraint order, coefficients in Montgomery form (host).  tape (optional, n entries) + witness LCs.
+int circuit_create(uint32_t n, uint32_t m, uint32_t q, const uint32_t *cons_ptr, const uint8_t *kind, const uint32_t *idx,
+                   const scm *coeff, const TapeOp *tape, uint32_t naux, uint32_t nwlc, const uint32_t *wlc_ptr,
+                   const uint8_t *wkind, const uint32_t *widx, const scm *wcoeff, BpCircuit **out);
+void circuit_free(BpCircuit *c);
+size_t circuit_proof_len(const BpCircuit *c);
+
+struct ProveArgs {
+  int B;
+  const uint8_t *label; int label_len;
+  // all pointers are DEVICE pointers, layouts [B][count][32]
+  const uint8_t *v, *vbl, *entropy;
+  const uint8_t *aL, *aR, *aO;   // explicit witness, or all NULL to run the circuit's witness tape
+  const uint8_t *aux;            // [B][naux][32] tape inputs
+  uint8_t *V_out;                // [B][m][32]
+  uint8_t *proofs;               // [B][proof_len]
+  int *status;                   // [B]
+};
+int engine_prove(const BpGens *g, BpCircuit *c, const ProveArgs &a, dev_stream s);
+
+struct VerifyArgs {
+  int B;
+  const uint8_t *label; int label_len;
+  const uint8_t *V;        // [B][m][32] device
+  const uint8_t *proofs;   // [B][proof_len] device
+  const uint8_t *entropy;  // [B][32] device
+  int *status;             // [B] device
+};
+int engine_verify(const BpGens *g, BpCircuit *c, const VerifyArgs &a, dev_stream s);
+
+// one-off helper: commitments a*B + b*B_blinding for host scalars
+int engine_commit(const BpGens *g, int count, const uint8_t *v, const uint8_t *r, uint8_t *out);
+long engine_launch_count();
+// sum_i scalars[i] * G[i] over the first n generators; d_scalars [n][32] canonical bytes, d_out 32 bytes (device)
+int engine_msm_gens(BpGens *g, uint32_t n, const uint8_t *d_scalars, uint8_t *d_out, dev_stream s);

@@ -1,0 +1,253 @@
+// Host-side recorder methods and the C++ restatement of the reference's gadget layer.
+// Each function cites the reference file:line it mirrors (paths relative to /root/reference/src).
+#include "recorder.h"
+#include <unordered_map>
+
+LC LC::simplified() const {  // gadget_poseidon.rs:99-112
+  LC out;
+  std::unordered_map<uint64_t, size_t> pos;
+  pos.reserve(terms.size() * 2);
+  for (const Term &t : terms) {
+    uint64_t key = ((uint64_t)t.var.kind << 32) | t.var.index;
+    auto it = pos.find(key);
+    if (it == pos.end()) { pos.emplace(key, out.terms.size()); out.terms.push_back(t); }
+    else out.terms[it->second].coeff = sc_add(out.terms[it->second].coeff, t.coeff);
+  }
+  return out;
+}
+
+bool bp_cs::eval(const LC &lc, scm &out) const {
+  if (!is_prover) return false;
+  scm acc = sc_zero();
+  for (const Term &t : lc.terms) {
+    scm val;
+    switch (t.var.kind) {
+      case BP_VAR_COMMITTED: val = v[t.var.index]; break;
+      case BP_VAR_MULT_LEFT: val = aL[t.var.index]; break;
+      case BP_VAR_MULT_RIGHT: val = aR[t.var.index]; break;
+      case BP_VAR_MULT_OUT: val = aO[t.var.index]; break;
+      default: val = sc_one(); break;
+    }
+    acc = sc_add(acc, sc_mul(t.coeff, val));
+  }
+  out = acc;
+  return true;
+}
+
+// cs.multiply: allocates one multiplier, evaluates both sides on the prover, adds `left - l = 0`, `right - r = 0`
+void bp_cs::multiply(const LC &l, const LC &r, bp_var out[3]) {
+  uint32_t i = num_mult++;
+  if (is_prover) { scm lv, rv; eval(l, lv); eval(r, rv); aL.push_back(lv); aR.push_back(rv); aO.push_back(sc_mul(lv, rv)); }
+  TapeOp op{}; op.opL = W_LC; op.opR = W_LC; op.argL = add_wlc(l); op.argR = add_wlc(r);
+  tape.push_back(op);
+  out[0] = bp_var{BP_VAR_MULT_LEFT, i}; out[1] = bp_var{BP_VAR_MULT_RIGHT, i}; out[2] = bp_var{BP_VAR_MULT_OUT, i};
+  LC lc = l; lc -= LC(out[0]); constrain(lc);
+  LC rc = r; rc -= LC(out[1]); constrain(rc);
+}
+
+int bp_cs::allocate_multiplier(const scm *l, const scm *r, bp_var out[3]) {
+  if (is_prover && (!l || !r)) return BP_ERR_MISSING_ASSIGNMENT;
+  uint32_t i = num_mult++;
+  if (is_prover) { aL.push_back(*l); aR.push_back(*r); aO.push_back(sc_mul(*l, *r)); aux.push_back(*l); aux.push_back(*r); }
+  TapeOp op{}; op.opL = W_AUX; op.opR = W_AUX; op.argL = naux; op.argR = naux + 1; naux += 2;
+  tape.push_back(op);
+  out[0] = bp_var{BP_VAR_MULT_LEFT, i}; out[1] = bp_var{BP_VAR_MULT_RIGHT, i}; out[2] = bp_var{BP_VAR_MULT_OUT, i};
+  return BP_OK;
+}
+
+int bp_cs::allocate_single(int how, const scm *value, const LC *lc, bp_var *var, bp_var *out_var, int *has_out) {
+  scm val = sc_zero();
+  if (is_prover) {
+    if (how == 0) { if (!value) return BP_ERR_MISSING_ASSIGNMENT; val = *value; }
+    else if (how == 1) eval(*lc, val);
+    else { if (pending < 0) return BP_ERR_INVALID_ARGUMENT; val = sc_invert(aL[pending]); }
+  }
+  if (pending < 0) {
+    if (how == 2) return BP_ERR_INVALID_ARGUMENT;
+    uint32_t i = num_mult++;
+    pending = i;
+    if (is_prover) { aL.push_back(val); aR.push_back(sc_zero()); aO.push_back(sc_zero()); }
+    TapeOp op{};
+    if (how == 1) { op.opL = W_LC; op.argL = add_wlc(*lc); } else { op.opL = W_AUX; op.argL = naux++; if (is_prover) aux.push_back(val); }
+    op.opR = W_AUX; op.argR = 0;  // completed by the second call
+    tape.push_back(op);
+    *var = bp_var{BP_VAR_MULT_LEFT, i};
+    if (has_out) *has_out = 0;
+  } else {
+    uint32_t i = (uint32_t)pending;
+    pending = -1;
+    if (is_prover) { aR[i] = val; aO[i] = sc_mul(aL[i], val); }
+    TapeOp &op = tape[i];
+    if (how == 2) { op.opR = W_INV_L; op.argR = 0; }
+    else if (how == 1) { op.opR = W_LC; op.argR = add_wlc(*lc); }
+    else { op.opR = W_AUX; op.argR = naux++; if (is_prover) aux.push_back(val); }
+    *var = bp_var{BP_VAR_MULT_RIGHT, i};
+    if (out_var) *out_var = bp_var{BP_VAR_MULT_OUT, i};
+    if (has_out) *has_out = 1;
+  }
+  return BP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ r1cs_utils / zero_nonzero
+static void constrain_lc_with_scalar(bp_cs &cs, const LC &lc, const scm &s) {  // r1cs_utils.rs:51-53
+  cs.constrain(lc - LC::constant(s));
+}
+static void is_nonzero_gadget(bp_cs &cs, bp_var x, bp_var x_inv) {  // gadget_zero_nonzero.rs:46-66
+  LC x_lc(x), y_lc = LC::constant(sc_one());
+  LC one_minus_y = LC(var_one()) - y_lc;
+  bp_var o[3];
+  cs.multiply(x_lc, one_minus_y, o);
+  cs.constrain(LC(o[2]));
+  cs.multiply(x_lc, LC(x_inv), o);
+  cs.constrain(LC(o[2]) - y_lc);
+}
+
+// ------------------------------------------------------------------------------------------------ Poseidon
+static scm apply_sbox(const scm &x, int sbox) {  // gadget_poseidon.rs:120-125
+  return sbox == BP_SBOX_CUBE ? sc_mul(sc_sqr(x), x) : sc_invert(x);
+}
+void poseidon_permutation(const bp_poseidon_params &p, std::vector<scm> &st, int sbox) {  // gadget_poseidon.rs:189-280
+  const uint32_t w = p.width, total = p.full_rounds_beginning + p.partial_rounds + p.full_rounds_end;
+  size_t off = 0;
+  for (uint32_t rnd = 0; rnd < total; rnd++) {
+    bool full = rnd < p.full_rounds_beginning || rnd >= p.full_rounds_beginning + p.partial_rounds;
+    for (uint32_t i = 0; i < w; i++) {
+      st[i] = sc_add(st[i], p.round_keys[off++]);
+      if (full || i == w - 1) st[i] = apply_sbox(st[i], sbox);
+    }
+    std::vector<scm> nx(w, sc_zero());
+    for (uint32_t i = 0; i < w; i++)
+      for (uint32_t j = 0; j < w; j++) nx[i] = sc_add(nx[i], sc_mul(st[j], p.mds[i][j]));
+    st = nx;
+  }
+}
+scm poseidon_hash_2(const bp_poseidon_params &p, const scm &xl, const scm &xr, int sbox) {  // gadget_poseidon.rs:428-443
+  std::vector<scm> st(p.width, sc_zero());
+  st[1] = xl; st[2] = xr; st[3] = sc_from_u64(101);
+  poseidon_permutation(p, st, sbox);
+  return st[1];
+}
+static int synthesize_sbox(bp_cs &cs, const LC &input, const scm &round_key, int sbox, bp_var &out) {
+  LC inp = input + LC::constant(round_key);
+  if (sbox == BP_SBOX_CUBE) {  // gadget_poseidon.rs:141-150
+    bp_var a[3], b[3];
+    cs.multiply(inp, inp, a);
+    cs.multiply(LC(a[2]), LC(a[0]), b);
+    out = b[2];
+    return BP_OK;
+  }
+  // gadget_poseidon.rs:153-185
+  bp_var var_l, var_r, var_o; int has;
+  int rc = cs.allocate_single(1, nullptr, &inp, &var_l, nullptr, &has); if (rc) return rc;
+  rc = cs.allocate_single(2, nullptr, nullptr, &var_r, &var_o, &has); if (rc) return rc;
+  is_nonzero_gadget(cs, var_l, var_r);
+  constrain_lc_with_scalar(cs, LC(var_o), sc_one());
+  out = var_r;
+  return BP_OK;
+}
+int poseidon_permutation_constraints(bp_cs &cs, const bp_poseidon_params &p, std::vector<LC> &st, int sbox) {  // gadget_poseidon.rs:282-399
+  const uint32_t w = p.width, total = p.full_rounds_beginning + p.partial_rounds + p.full_rounds_end;
+  if (st.size() != w) return BP_ERR_GADGET;
+  size_t off = 0;
+  for (uint32_t rnd = 0; rnd < total; rnd++) {
+    bool full = rnd < p.full_rounds_beginning || rnd >= p.full_rounds_beginning + p.partial_rounds;
+    std::vector<LC> outs(w);
+    for (uint32_t i = 0; i < w; i++) {
+      const scm &rk = p.round_keys[off++];
+      if (full || i == w - 1) { bp_var o; int rc = synthesize_sbox(cs, st[i], rk, sbox, o); if (rc) return rc; outs[i] = LC(o); }
+      else outs[i] = st[i] + LC::constant(rk);
+    }
+    std::vector<LC> nx(w);
+    for (uint32_t j = 0; j < w; j++)
+      for (uint32_t i = 0; i < w; i++) nx[i] += outs[j] * p.mds[i][j];
+    for (uint32_t i = 0; i < w; i++) st[i] = full ? nx[i] : nx[i].simplified();
+  }
+  return BP_OK;
+}
+int poseidon_hash_2_constraints(bp_cs &cs, const bp_poseidon_params &p, const LC &xl, const LC &xr, const std::vector<LC> &statics, int sbox, LC &out) {
+  if (statics.size() != p.width - 2) return BP_ERR_GADGET;  // gadget_poseidon.rs:445-468
+  std::vector<LC> in;
+  in.push_back(statics[0]); in.push_back(xl); in.push_back(xr);
+  for (size_t i = 1; i < statics.size(); i++) in.push_back(statics[i]);
+  int rc = poseidon_permutation_constraints(cs, p, in, sbox);
+  if (rc) return rc;
+  out = in[1];
+  return BP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ VSMT-2
+int vsmt2_verif_gadget(bp_cs &cs, const bp_poseidon_params &p, uint32_t depth, const scm &root, bp_var leaf, const bp_var *bits,
+                       const bp_var *nodes, const bp_var *statics, uint32_t num_statics) {  // gadget_vsmt_2.rs:171-209
+  std::vector<LC> st;
+  for (uint32_t i = 0; i < num_statics; i++) st.push_back(LC(statics[i]));
+  LC prev;
+  for (uint32_t i = 0; i < depth; i++) {
+    LC leaf_lc = i == 0 ? LC(leaf) : prev;
+    LC one_minus = LC(var_one()) - LC(bits[i]);
+    bp_var l1[3], l2[3], r1[3], r2[3];
+    cs.multiply(one_minus, leaf_lc, l1);
+    cs.multiply(LC(bits[i]), LC(nodes[i]), l2);
+    LC left = LC(l1[2]) + LC(l2[2]);
+    cs.multiply(LC(bits[i]), leaf_lc, r1);
+    cs.multiply(one_minus, LC(nodes[i]), r2);
+    LC right = LC(r1[2]) + LC(r2[2]);
+    int rc = poseidon_hash_2_constraints(cs, p, left, right, st, BP_SBOX_INVERSE, prev);
+    if (rc) return rc;
+  }
+  constrain_lc_with_scalar(cs, prev, root);
+  return BP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ MiMC
+scm mimc_native(const scm &xl_, const scm &xr_, uint32_t rounds, const scm *constants) {  // gadget_mimc.rs:19-39
+  scm xl = xl_, xr = xr_;
+  for (uint32_t j = 0; j < rounds; j++) {
+    scm t = sc_add(xl, constants[j]);
+    scm nl = sc_add(sc_mul(sc_sqr(t), t), xr);
+    xr = xl; xl = nl;
+  }
+  return xl;
+}
+int mimc_gadget(bp_cs &cs, bp_var left, bp_var right, uint32_t rounds, const scm *constants, const scm &image) {  // gadget_mimc.rs:41-79
+  LC lv(left), rv(right);
+  for (uint32_t j = 0; j < rounds; j++) {
+    LC lpc = lv + LC::constant(constants[j]);
+    bp_var a[3], b[3];
+    cs.multiply(lpc, lpc, a);
+    cs.multiply(LC(a[2]), LC(a[0]), b);
+    LC tmp = LC(b[2]) + rv;
+    rv = lv; lv = tmp;
+  }
+  constrain_lc_with_scalar(cs, lv, image);
+  return BP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ range / bound check
+int positive_no_gadget(bp_cs &cs, bp_var v, bool has_assignment, uint64_t value, uint32_t bit_size) {  // r1cs_utils.rs:20-48
+  LC cv; cv.terms.push_back(Term{v, sc_neg(sc_one())});
+  scm exp2 = sc_one();
+  for (uint32_t i = 0; i < bit_size; i++) {
+    bp_var o[3]; int rc;
+    if (has_assignment) {
+      uint64_t bit = i < 64 ? (value >> i) & 1 : 0;
+      scm a = sc_from_u64(1 - bit), b = sc_from_u64(bit);
+      rc = cs.allocate_multiplier(&a, &b, o);
+    } else rc = cs.allocate_multiplier(nullptr, nullptr, o);
+    if (rc) return rc;
+    cs.constrain(LC(o[2]));
+    cs.constrain(LC(o[0]) + (LC(o[1]) - LC::from_u64(1)));
+    cv.terms.push_back(Term{o[1], exp2});
+    exp2 = sc_add(exp2, exp2);
+  }
+  cs.constrain(cv);
+  return BP_OK;
+}
+int bound_check_gadget(bp_cs &cs, bp_var v, bp_var a, bp_var b, bool has_assignment, uint64_t vv, uint64_t av, uint64_t bv, uint64_t max,
+                       uint64_t min, uint32_t bit_size) {  // gadget_bound_check.rs:18-45
+  (void)vv;
+  cs.constrain(LC(v) - LC::from_u64(min) - LC(a));
+  cs.constrain(LC::from_u64(max) - LC(v) - LC(b));
+  constrain_lc_with_scalar(cs, LC(a) + LC(b), sc_from_u64(max - min));
+  int rc = positive_no_gadget(cs, a, has_assignment, av, bit_size); if (rc) return rc;
+  return positive_no_gadget(cs, b, has_assignment, bv, bit_size);
+}

@@ -1,0 +1,628 @@
+// Kernel bodies of the batched Bulletproofs R1CS prover/verifier.  Each kernel is a functor
+// whose operator()(tid) is the work of one CUDA thread; devrt.h turns it into the named
+// kernel run_kernel<Functor>.
+//
+// Layout conventions (B = proofs in the chunk):
+//   * per-proof scalar vectors are proof-minor: element i of proof p lives at v[i*B + p], so a warp of
+//     consecutive proofs reads/writes 32 consecutive 32-byte scalars (coalesced);
+//   * scalars are in Montgomery form (sc25519.h) while on the device;
+//   * MSM digit rows are signed radix-256: 32 int8 per scalar, row r of instance q at dig[q*stride + r*32 + w];
+//   * points are ge_p3 (160 B) when per-proof, ge_niels (128 B, affine) when shared generators.
+//
+// Protocol references: SURVEY.md App. A (Prover::prove A.3, InnerProductProof::create A.4,
+// Verifier::verify A.5) -- the reference takes these from the un-vendored `bulletproofs` fork
+// (reference Cargo.toml:22-26; call sites src/gadget_vsmt_2.rs:347,395).
+#pragma once
+#include "ge25519.h"
+#include "sc25519.h"
+#include "keccak.h"
+
+// ------------------------------------------------------------------------------------------------
+// scalars in / out
+// ------------------------------------------------------------------------------------------------
+// bytes [B][cnt][32] -> Montgomery [cnt][B]
+struct KLoadScalars {
+  static constexpr int kBlock = 128, kMinBlocks = 1;
+  const uint8_t *in; scm *out; int cnt, B;
+  HD void operator()(long tid) const {
+    int p = (int)(tid % B); long i = tid / B;
+    out[i * B + p] = sc_from_bytes_mod_order(in + ((long)p * cnt + i) * 32);
+  }
+};
+
+// signed radix-256 digits of a canonical scalar
+HD void sc_recode_bytes(int8_t dig[32], const scm &s) {
+  uint64_t w[4]; sc_to_canonical(w, s);
+  int carry = 0;
+#pragma unroll
+  for (int i = 0; i < 32; i++) {
+    int d = (int)((w[i >> 3] >> (8 * (i & 7))) & 0xff) + carry;
+    carry = d >= 128;  // digits in [-128, 127] fit int8
+    d -= carry << 8;
+    dig[i] = (int8_t)d;
+  }
+}
+HD void store_digits(int8_t *dst, const int8_t dig[32]) {
+#if defined(__CUDA_ARCH__)
+  uint4 a, b;
+  memcpy(&a, dig, 16); memcpy(&b, dig + 16, 16);
+  reinterpret_cast<uint4 *>(dst)[0] = a; reinterpret_cast<uint4 *>(dst)[1] = b;
+#else
+  memcpy(dst, dig, 32);
+#endif
+}
+// src [cnt][B] (optionally times mul[p]) -> digit rows row0.. of each instance
+struct KRecode {
+  static constexpr int kBlock = 128, kMinBlocks = 1;
+  const scm *src; const scm *mul; int cnt, B; int8_t *dig; long inst_stride; int row0;
+  HD void operator()(long tid) const {
+    int p = (int)(tid % B); long i = tid / B;
+    scm s = src[i * B + p];
+    if (mul) s = sc_mul(s, mul[p]);
+    int8_t d[32]; sc_recode_bytes(d, s);
+    store_digits(dig + (long)p * inst_stride + (row0 + i) * 32, d);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Pedersen-style fixed-base commitments  a*B + b*B_blinding  (PedersenGens::commit)
+// table[base][window 0..63][digit 0..15] = digit * 16^window * P  in niels form (digit 0 unused)
+// ------------------------------------------------------------------------------------------------
+struct KCommit {
+  static constexpr int kBlock = 128, kMinBlocks = 1;
+  const scm *a; const scm *b; int cnt, B; const ge_niels *table;
+  uint8_t *out; long out_stride_p, out_stride_j; ge_p3 *out_pt;
+  HD void operator()(long tid) const {
+    int p = (int)(tid % B); long j = tid / B;
+    ge_p3 acc; ge_identity(acc);
+    for (int base = 0; base < 2; base++) {
+      const scm *src = base ? b : a;
+      if (!src) continue;
+      uint64_t w[4]; sc_to_canonical(w, src[j * B + p]);
+      for (int win = 0; win < 64; win++) {
+        int d = (int)((w[win >> 4] >> (4 * (win & 15))) & 15);
+        if (d) { ge_niels q; load_struct(q, &table[(base * 64 + win) * 16 + d]); ge_madd(acc, acc, q, 0); }
+      }
+    }
+    if (out) ristretto_encode(out + (long)p * out_stride_p + j * out_stride_j, acc);
+    if (out_pt) store_struct(&out_pt[j * B + p], acc);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Multi-scalar multiplication: bucket method, one thread per (instance, 8-bit window).
+// A warp is one instance; lane w owns window w and a private set of 128 buckets in global memory
+// (signed digits), reads the same base point as the other 31 lanes (broadcast) and byte w of the
+// shared 32-byte digit row (one sector per warp).  No atomics, no sorting.
+// ------------------------------------------------------------------------------------------------
+struct MsmSeg { const void *bases; long inst_stride; int fmt; int count; };  // fmt 0: shared/strided ge_niels, 1: ge_p3
+#define MSM_WINDOWS 32
+#define MSM_BUCKETS 128
+
+struct KMsmAccumulate {
+  static constexpr int kBlock = 128, kMinBlocks = 1;
+  MsmSeg seg[4]; int nseg; int S;  // S = row-range splits per instance (each split owns its own buckets)
+  const int8_t *dig; long dig_inst_stride; ge_p3 *buckets; ge_p3 *wsum;
+  HD void operator()(long tid) const {
+    long q = tid / MSM_WINDOWS; int w = (int)(tid % MSM_WINDOWS);
+    long inst = q / S; int sp = (int)(q % S);
+    ge_p3 *bk = buckets + tid * MSM_BUCKETS;
+    {
+      ge_p3 id; ge_identity(id);
+      for (int d = 0; d < MSM_BUCKETS; d++) store_struct(&bk[d], id);
+    }
+    long total = 0;
+    for (int s = 0; s < nseg; s++) total += seg[s].count;
+    const long r0 = total * sp / S, r1 = total * (sp + 1) / S;
+    const int8_t *drow = dig + inst * dig_inst_stride + w;
+    long row = 0;
+    for (int s = 0; s < nseg; s++) {
+      const long cnt = seg[s].count;
+      long lo = (r0 > row ? r0 : row) - row, hi = (r1 < row + cnt ? r1 : row + cnt) - row;
+      if (seg[s].fmt == 0) {
+        const ge_niels *bases = (const ge_niels *)seg[s].bases + inst * seg[s].inst_stride;
+        for (long t = lo; t < hi; t++) {
+          int d = drow[(row + t) * 32];
+          if (d != 0) {
+            int neg = d < 0; int idx = (neg ? -d : d) - 1;
+            ge_niels qn; load_struct(qn, &bases[t]);
+            ge_p3 acc; load_struct(acc, &bk[idx]);
+            ge_madd(acc, acc, qn, neg);
+            store_struct(&bk[idx], acc);
+          }
+        }
+      } else {
+        const ge_p3 *bases = (const ge_p3 *)seg[s].bases + inst * seg[s].inst_stride;
+        for (long t = lo; t < hi; t++) {
+          int d = drow[(row + t) * 32];
+          if (d != 0) {
+            int neg = d < 0; int idx = (neg ? -d : d) - 1;
+            ge_p3 qp; load_struct(qp, &bases[t]);
+            ge_cached c; ge_to_cached(c, qp);
+            ge_p3 acc; load_struct(acc, &bk[idx]);
+            ge_add_cached(acc, acc, c, neg);
+            store_struct(&bk[idx], acc);
+          }
+        }
+      }
+      row += cnt;
+    }
+    // window sum = sum_d (d+1) * bucket[d] by the running-sum trick
+    ge_p3 run, tot; ge_identity(run); ge_identity(tot);
+    for (int d = MSM_BUCKETS - 1; d >= 0; d--) {
+      ge_p3 b; load_struct(b, &bk[d]);
+      ge_add(run, run, b);
+      ge_add(tot, tot, run);
+    }
+    store_struct(&wsum[tid], tot);
+  }
+};
+
+// sum the splits, Horner over the 32 window sums, then ristretto-encode (mode 0) or test for the identity (mode 1)
+struct KMsmFinish {
+  static constexpr int kBlock = 64, kMinBlocks = 1;
+  const ge_p3 *wsum; int S; uint8_t *out; long out_stride; int mode; int *status; int fail_code;
+  HD void window(ge_p3 &r, long inst, int w) const {
+    load_struct(r, &wsum[(inst * S) * MSM_WINDOWS + w]);
+    for (int s = 1; s < S; s++) { ge_p3 t; load_struct(t, &wsum[(inst * S + s) * MSM_WINDOWS + w]); ge_add(r, r, t); }
+  }
+  HD void operator()(long inst) const {
+    ge_p3 acc; window(acc, inst, MSM_WINDOWS - 1);
+    for (int w = MSM_WINDOWS - 2; w >= 0; w--) {
+      for (int i = 0; i < 7; i++) ge_dbl_p2(acc, acc);
+      ge_dbl(acc, acc);
+      ge_p3 s; window(s, inst, w);
+      ge_add(acc, acc, s);
+    }
+    if (mode == 0) ristretto_encode(out + inst * out_stride, acc);
+    else if (!ge_is_identity_ristretto(acc)) status[inst] = fail_code;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Merlin transcript phases (one thread per proof)
+// ------------------------------------------------------------------------------------------------
+#define TS_CHALLENGE(t, label, dst) do { uint8_t _b[64]; ts_challenge_bytes(t, label, _b, 64); dst = sc_from_bytes_wide(_b); } while (0)
+
+// base = Transcript::new(label) + "r1cs v1" domain separator (computed once on the host).
+// Appends V_0..V_{m-1} and "m"; then builds the prover's transcript RNG (A.3 step 2).
+struct KTsStart {
+  static constexpr int kBlock = 64, kMinBlocks = 1;
+  strobe128 base; const uint8_t *V; int m, B; const scm *vbl; const uint8_t *entropy; strobe128 *ts; strobe128 *rng; int prover;
+  HD void operator()(long p) const {
+    strobe128 t = base;
+    for (int j = 0; j < m; j++) ts_append(t, "V", V + ((long)p * m + j) * 32, 32);
+    ts_append_u64(t, "m", (uint64_t)m);
+    store_struct(&ts[p], t);
+    if (prover) {
+      for (int j = 0; j < m; j++) { uint8_t b[32]; sc_tobytes(b, vbl[(long)j * B + p]); trng_rekey(t, "v_blinding", b, 32); }
+      trng_finalize(t, entropy + p * 32);
+      store_struct(&rng[p], t);
+    }
+  }
+};
+// draws `count` uniform scalars (64 bytes each, wide reduction) into dst[i*B+p]
+struct KRngDraw {
+  static constexpr int kBlock = 32, kMinBlocks = 1;
+  strobe128 *rng; scm *dst; int count, B;
+  HD void operator()(long p) const {
+    strobe128 r; load_struct(r, &rng[p]);
+    for (int i = 0; i < count; i++) { uint8_t b[64]; trng_fill(r, b, 64); dst[(long)i * B + p] = sc_from_bytes_wide(b); }
+    store_struct(&rng[p], r);
+  }
+};
+// A_I1,A_O1,S1 + one-phase separator + identity A_I2,A_O2,S2 -> y, z ; also y^-1
+struct KTsPhase2 {
+  static constexpr int kBlock = 64, kMinBlocks = 1;
+  strobe128 *ts; const uint8_t *proofs; long proof_stride; scm *y, *z, *yinv; int *status; int verifier;
+  HD void operator()(long p) const {
+    strobe128 t; load_struct(t, &ts[p]);
+    const uint8_t *pf = proofs + p * proof_stride;
+    if (verifier) {
+      for (int j = 0; j < 3; j++) { uint8_t nz = 0; for (int i = 0; i < 32; i++) nz |= pf[32 * j + i]; if (!nz) status[p] = 3; }
+    }
+    ts_append(t, "A_I1", pf, 32); ts_append(t, "A_O1", pf + 32, 32); ts_append(t, "S1", pf + 64, 32);
+    const uint8_t ph[11] = {'r', '1', 'c', 's', '-', '1', 'p', 'h', 'a', 's', 'e'};
+    ts_append(t, "dom-sep", ph, 11);
+    ts_append(t, "A_I2", pf + 96, 32); ts_append(t, "A_O2", pf + 128, 32); ts_append(t, "S2", pf + 160, 32);
+    scm yy, zz;
+    TS_CHALLENGE(t, "y", yy); TS_CHALLENGE(t, "z", zz);
+    y[p] = yy; z[p] = zz; yinv[p] = sc_invert(yy);
+    store_struct(&ts[p], t);
+  }
+};
+// T_1,T_3,T_4,T_5,T_6 -> u, x
+struct KTsPhase3 {
+  static constexpr int kBlock = 64, kMinBlocks = 1;
+  strobe128 *ts; const uint8_t *proofs; long proof_stride; scm *u, *x; int *status; int verifier;
+  HD void operator()(long p) const {
+    strobe128 t; load_struct(t, &ts[p]);
+    const uint8_t *pf = proofs + p * proof_stride + 192;
+    if (verifier) {
+      for (int j = 0; j < 5; j++) { uint8_t nz = 0; for (int i = 0; i < 32; i++) nz |= pf[32 * j + i]; if (!nz) status[p] = 3; }
+    }
+    ts_append(t, "T_1", pf, 32); ts_append(t, "T_3", pf + 32, 32); ts_append(t, "T_4", pf + 64, 32);
+    ts_append(t, "T_5", pf + 96, 32); ts_append(t, "T_6", pf + 128, 32);
+    scm uu, xx;
+    TS_CHALLENGE(t, "u", uu); TS_CHALLENGE(t, "x", xx);
+    u[p] = uu; x[p] = xx;
+    store_struct(&ts[p], t);
+  }
+};
+// t_x, t_x_blinding, e_blinding -> w ; then the inner-product domain separator with n = N
+struct KTsPhase4 {
+  static constexpr int kBlock = 64, kMinBlocks = 1;
+  strobe128 *ts; const uint8_t *proofs; long proof_stride; scm *w; unsigned N;
+  HD void operator()(long p) const {
+    strobe128 t; load_struct(t, &ts[p]);
+    const uint8_t *pf = proofs + p * proof_stride + 352;
+    ts_append(t, "t_x", pf, 32); ts_append(t, "t_x_blinding", pf + 32, 32); ts_append(t, "e_blinding", pf + 64, 32);
+    scm ww; TS_CHALLENGE(t, "w", ww); w[p] = ww;
+    const uint8_t ipp[6] = {'i', 'p', 'p', ' ', 'v', '1'};
+    ts_append(t, "dom-sep", ipp, 6);
+    ts_append_u64(t, "n", (uint64_t)N);
+    store_struct(&ts[p], t);
+  }
+};
+
+// non-adjacent form of a canonical scalar; returns index of the top non-zero digit (or -1)
+HD int sc_naf(int8_t naf[256], const scm &s) {
+  uint64_t k[4]; sc_to_canonical(k, s);
+  int top = -1;
+  for (int i = 0; i < 256; i++) {
+    int8_t z = 0;
+    if (k[0] & 1) {
+      if ((k[0] & 3) == 3) { z = -1; uint64_t c = 1; for (int j = 0; j < 4; j++) { uint64_t t = k[j] + c; c = t < c; k[j] = t; } }
+      else { z = 1; k[0] &= ~(uint64_t)1; }
+      top = i;
+    }
+    naf[i] = z;
+    k[0] = (k[0] >> 1) | (k[1] << 63); k[1] = (k[1] >> 1) | (k[2] << 63); k[2] = (k[2] >> 1) | (k[3] << 63); k[3] >>= 1;
+  }
+  return top;
+}
+
+// One inner-product round, transcript side (A.4): append L,R, draw u; derive everything the
+// scalar fold and the generator fold of this round need.
+//   folded generators are kept un-normalised:  G_true[i] = alpha * Gt[i],  H_true[i] = beta * y^-i * Ht[i]
+//   Gt'[i] = Gt[i] + eG * Gt[h+i],  eG = u^2          (times the G-factor class of index h+i in round 0)
+//   Ht'[i] = Ht[i] + eH * Ht[h+i],  eH = u^-2 * y^-h  (same class factor)
+//   alpha' = alpha * u^-1,  beta' = beta * u
+struct KTsIpaRound {
+  static constexpr int kBlock = 64, kMinBlocks = 1;
+  strobe128 *ts; const uint8_t *proofs; long proof_stride; int round; int B; int h;
+  const scm *yinvpow; const scm *ufac;  // y^-i table [N][B]; the r1cs challenge u (class factor, round 0 only)
+  scm *u, *uinv, *alpha, *beta; int8_t *naf; int *naf_top; int *status; int verifier;
+  HD void operator()(long p) const {
+    strobe128 t; load_struct(t, &ts[p]);
+    const uint8_t *pf = proofs + p * proof_stride + 448 + 64 * round;
+    if (verifier) {
+      for (int j = 0; j < 2; j++) { uint8_t nz = 0; for (int i = 0; i < 32; i++) nz |= pf[32 * j + i]; if (!nz) status[p] = 3; }
+    }
+    ts_append(t, "L", pf, 32); ts_append(t, "R", pf + 32, 32);
+    scm uu; TS_CHALLENGE(t, "u", uu);
+    store_struct(&ts[p], t);
+    scm ui = sc_invert(uu);
+    u[p] = uu; uinv[p] = ui;
+    if (verifier) return;
+    scm eG = sc_sqr(uu), eH = sc_mul(sc_sqr(ui), yinvpow[(long)h * B + p]);
+    int8_t nf[256];
+    int8_t *dst = naf + p * 4 * 256;
+    int top;
+    top = sc_naf(nf, eG); for (int i = 0; i < 256; i++) dst[i] = nf[i]; naf_top[p * 4 + 0] = top;
+    top = sc_naf(nf, eH); for (int i = 0; i < 256; i++) dst[512 + i] = nf[i]; naf_top[p * 4 + 2] = top;
+    if (round == 0) {
+      scm f = ufac[p];
+      top = sc_naf(nf, sc_mul(eG, f)); for (int i = 0; i < 256; i++) dst[256 + i] = nf[i]; naf_top[p * 4 + 1] = top;
+      top = sc_naf(nf, sc_mul(eH, f)); for (int i = 0; i < 256; i++) dst[768 + i] = nf[i]; naf_top[p * 4 + 3] = top;
+    }
+    alpha[p] = sc_mul(alpha[p], ui); beta[p] = sc_mul(beta[p], uu);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// scalar-vector kernels
+// ------------------------------------------------------------------------------------------------
+// out[i][p] = base[p]^(i + exp0), i < len; one thread per (chunk of CH exponents, proof)
+struct KPowers {
+  static constexpr int kBlock = 128, kMinBlocks = 1;
+  const scm *base; scm *out; int len, B, exp0, CH;
+  HD void operator()(long tid) const {
+    int p = (int)(tid % B); int c = (int)(tid / B);
+    int i0 = c * CH, i1 = i0 + CH < len ? i0 + CH : len;
+    scm b = base[p];
+    scm cur = sc_pow_u32(b, (uint32_t)(i0 + exp0));
+    for (int i = i0; i < i1; i++) { out[(long)i * B + p] = cur; cur = sc_mul(cur, b); }
+  }
+};
+HD void fill_scalar(scm *dst, long n, const scm &v) { for (long i = 0; i < n; i++) dst[i] = v; }
+struct KFillScalar {
+  static constexpr int kBlock = 128, kMinBlocks = 1;
+  scm *dst; scm v;
+  HD void operator()(long tid) const { dst[tid] = v; }
+};
+
+// flattened constraint weights (A.3 step 7) from the slot-major transpose of the constraint matrix:
+// slot s in [0,3n+m+1) = wL | wR | wO | wV | wc;  w[s][p] = sum_t coeff_t * z^(q_t+1)   (signs folded into coeff)
+struct KFlatten {
+  static constexpr int kBlock = 128, kMinBlocks = 1;
+  const uint32_t *slot_ptr; const uint32_t *t_q; const scm *t_coeff; const scm *zpow; scm *w; int B;
+  HD void operator()(long tid) const {
+    int p = (int)(tid % B); long s = tid / B;
+    scm acc = sc_zero();
+    for (uint32_t t = slot_ptr[s]; t < slot_ptr[s + 1]; t++) acc = sc_add(acc, sc_mul(t_coeff[t], zpow[(long)t_q[t] * B + p]));
+    w[s * B + p] = acc;
+  }
+};
+
+struct PolyIn { const scm *aL, *aR, *aO, *sL, *sR, *wL, *wR, *wO, *ypow, *yinvpow; };
+struct PolyCoef { scm l1, l2, l3, r0, r1, r3; };
+HD void poly_coef(PolyCoef &c, const PolyIn &in, long at) {
+  scm ey = in.ypow[at];
+  c.l1 = sc_add(in.aL[at], sc_mul(in.yinvpow[at], in.wR[at]));
+  c.l2 = in.aO[at];
+  c.l3 = in.sL[at];
+  c.r0 = sc_sub(in.wO[at], ey);
+  c.r1 = sc_add(sc_mul(ey, in.aR[at]), in.wL[at]);
+  c.r3 = sc_mul(ey, in.sR[at]);
+}
+// partial sums of t_1..t_6 (A.3 step 9) over a chunk of multipliers
+struct KPolyT {
+  static constexpr int kBlock = 128, kMinBlocks = 1;
+  PolyIn in; int n, B, CH; scm *part;  // part[(c*6 + j)*B + p]
+  HD void operator()(long tid) const {
+    int p = (int)(tid % B); int c = (int)(tid / B);
+    int i0 = c * CH, i1 = i0 + CH < n ? i0 + CH : n;
+    scm t1 = sc_zero(), t2 = t1, t3 = t1, t4 = t1, t5 = t1, t6 = t1;
+    for (int i = i0; i < i1; i++) {
+      PolyCoef k; poly_coef(k, in, (long)i * B + p);
+      t1 = sc_add(t1, sc_mul(k.l1, k.r0));
+      t2 = sc_add(t2, sc_add(sc_mul(k.l1, k.r1), sc_mul(k.l2, k.r0)));
+      t3 = sc_add(t3, sc_add(sc_mul(k.l2, k.r1), sc_mul(k.l3, k.r0)));
+      t4 = sc_add(t4, sc_add(sc_mul(k.l1, k.r3), sc_mul(k.l3, k.r1)));
+      t5 = sc_add(t5, sc_mul(k.l2, k.r3));
+      t6 = sc_add(t6, sc_mul(k.l3, k.r3));
+    }
+    scm *o = part + ((long)c * 6) * B + p;
+    o[0] = t1; o[B] = t2; o[2L * B] = t3; o[3L * B] = t4; o[4L * B] = t5; o[5L * B] = t6;
+  }
+};
+// out[j][p] = sum_c part[(c*nv + j)*B + p]
+struct KSumPartials {
+  static constexpr int kBlock = 128, kMinBlocks = 1;
+  const scm *part; int nchunks, nv, B; scm *out;
+  HD void operator()(long tid) const {
+    int p = (int)(tid % B); int j = (int)(tid / B);
+    scm acc = sc_zero();
+    for (int c = 0; c < nchunks; c++) acc = sc_add(acc, part[((long)c * nv + j) * B + p]);
+    out[(long)j * B + p] = acc;
+  }
+};
+// l(x), r(x) padded to N (A.3 step 12) -> the a, b vectors of the inner-product argument
+struct KPolyEval {
+  static constexpr int kBlock = 128, kMinBlocks = 1;
+  PolyIn in; int n, B; const scm *x; scm *a, *b;
+  HD void operator()(long tid) const {
+    int p = (int)(tid % B); long i = tid / B; long at = i * B + p;
+    if (i < n) {
+      PolyCoef k; poly_coef(k, in, at);
+      scm xx = x[p], x2 = sc_sqr(xx), x3 = sc_mul(x2, xx);
+      a[at] = sc_add(sc_add(sc_mul(k.l1, xx), sc_mul(k.l2, x2)), sc_mul(k.l3, x3));
+      b[at] = sc_add(sc_add(k.r0, sc_mul(k.r1, xx)), sc_mul(k.r3, x3));
+    } else {
+      a[at] = sc_zero();
+      b[at] = sc_neg(in.ypow[at]);
+    }
+  }
+};
+// t_x, t_x_blinding, e_blinding (A.3 steps 11-13) -> proof bytes 352..447
+struct KProverScalars {
+  static constexpr int kBlock = 64, kMinBlocks = 1;
+  const scm *t;      // [6][B]: t1..t6
+  const scm *tb;     // [5][B]: blindings of T_1,T_3,T_4,T_5,T_6
+  const scm *blind;  // [3][B]: i,o,s blindings
+  const scm *wV, *vbl; int m, B; const scm *x; uint8_t *proofs; long proof_stride;
+  HD void operator()(long p) const {
+    scm xx = x[p];
+    scm t2b = sc_zero();
+    for (int j = 0; j < m; j++) t2b = sc_add(t2b, sc_mul(wV[(long)j * B + p], vbl[(long)j * B + p]));
+    scm xp = xx, tx = sc_zero(), txb = sc_zero();
+    const int bidx[6] = {0, -1, 1, 2, 3, 4};
+    for (int j = 0; j < 6; j++) {
+      tx = sc_add(tx, sc_mul(t[(long)j * B + p], xp));
+      scm bl = bidx[j] < 0 ? t2b : tb[(long)bidx[j] * B + p];
+      txb = sc_add(txb, sc_mul(bl, xp));
+      xp = sc_mul(xp, xx);
+    }
+    scm e = sc_mul(xx, sc_add(blind[p], sc_mul(xx, sc_add(blind[B + p], sc_mul(xx, blind[2L * B + p])))));
+    uint8_t *pf = proofs + p * proof_stride + 352;
+    sc_tobytes(pf, tx); sc_tobytes(pf + 32, txb); sc_tobytes(pf + 64, e);
+  }
+};
+
+// c_L = <a_lo, b_hi>, c_R = <a_hi, b_lo> partials
+struct KIpaDots {
+  static constexpr int kBlock = 128, kMinBlocks = 1;
+  const scm *a, *b; int h, B, CH; scm *part;  // part[(c*2+j)*B+p]
+  HD void operator()(long tid) const {
+    int p = (int)(tid % B); int c = (int)(tid / B);
+    int i0 = c * CH, i1 = i0 + CH < h ? i0 + CH : h;
+    scm cl = sc_zero(), cr = cl;
+    for (int i = i0; i < i1; i++) {
+      long lo = (long)i * B + p, hi = (long)(h + i) * B + p;
+      cl = sc_add(cl, sc_mul(a[lo], b[hi]));
+      cr = sc_add(cr, sc_mul(a[hi], b[lo]));
+    }
+    part[((long)c * 2) * B + p] = cl; part[((long)c * 2 + 1) * B + p] = cr;
+  }
+};
+// digit rows of the L and R multiscalar multiplications of one round (see KTsIpaRound for the scaling)
+//   L rows: [0,h) alpha*a[i]*gf(h+i) on Gt[h+i];  [h,2h) beta*y^-i*b[h+i]*gf(i) on Ht[i];  row 2h: c_L on Q
+//   R rows: [0,h) alpha*a[h+i]*gf(i) on Gt[i];    [h,2h) beta*y^-(h+i)*b[i]*gf(h+i) on Ht[h+i]; row 2h: c_R on Q
+struct KRecodeIpa {
+  static constexpr int kBlock = 128, kMinBlocks = 1;
+  const scm *a, *b, *alpha, *beta, *yinvpow, *ufac, *clr; int h, B, n, round;
+  int8_t *digL, *digR; long inst_stride;
+  HD void operator()(long tid) const {
+    int p = (int)(tid % B); int i = (int)(tid / B);
+    long lo = (long)i * B + p, hi = (long)(h + i) * B + p;
+    scm al = alpha[p], be = beta[p];
+    scm gf_lo = sc_one(), gf_hi = sc_one();
+    if (round == 0) { if (i >= n) gf_lo = ufac[p]; if (h + i >= n) gf_hi = ufac[p]; }
+    int8_t d[32];
+    int8_t *L = digL + (long)p * inst_stride, *R = digR + (long)p * inst_stride;
+    sc_recode_bytes(d, sc_mul(sc_mul(al, a[lo]), gf_hi)); store_digits(L + (long)i * 32, d);
+    sc_recode_bytes(d, sc_mul(sc_mul(sc_mul(be, yinvpow[lo]), b[hi]), gf_lo)); store_digits(L + (long)(h + i) * 32, d);
+    sc_recode_bytes(d, sc_mul(sc_mul(al, a[hi]), gf_lo)); store_digits(R + (long)i * 32, d);
+    sc_recode_bytes(d, sc_mul(sc_mul(sc_mul(be, yinvpow[hi]), b[lo]), gf_hi)); store_digits(R + (long)(h + i) * 32, d);
+    if (i == 0) {
+      sc_recode_bytes(d, clr[p]); store_digits(L + (long)2 * h * 32, d);
+      sc_recode_bytes(d, clr[B + p]); store_digits(R + (long)2 * h * 32, d);
+    }
+  }
+};
+// a' = a_lo*u + a_hi*u^-1 ; b' = b_lo*u^-1 + b_hi*u   (in place on the low halves)
+struct KFoldAB {
+  static constexpr int kBlock = 128, kMinBlocks = 1;
+  scm *a, *b; const scm *u, *uinv; int h, B;
+  HD void operator()(long tid) const {
+    int p = (int)(tid % B); int i = (int)(tid / B);
+    long lo = (long)i * B + p, hi = (long)(h + i) * B + p;
+    scm uu = u[p], ui = uinv[p];
+    a[lo] = sc_add(sc_mul(a[lo], uu), sc_mul(a[hi], ui));
+    b[lo] = sc_add(sc_mul(b[lo], ui), sc_mul(b[hi], uu));
+  }
+};
+struct KStoreAB {
+  static constexpr int kBlock = 64, kMinBlocks = 1;
+  const scm *a, *b; uint8_t *proofs; long proof_stride; long off;
+  HD void operator()(long p) const { uint8_t *pf = proofs + p * proof_stride + off; sc_tobytes(pf, a[p]); sc_tobytes(pf + 32, b[p]); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// generator fold: dst[p][i] = lo[i] + e * hi[i],  e given in NAF (shared by all i of a proof and class)
+// thread order is proof-major so a warp walks one NAF (uniform branches).
+// ------------------------------------------------------------------------------------------------
+struct KFoldGens {
+  static constexpr int kBlock = 128, kMinBlocks = 1;
+  const ge_p3 *srcG, *srcH; long src_stride;  // round 0: shared generators (stride 0); later: per-proof
+  ge_p3 *dstG, *dstH; long dst_stride;
+  const int8_t *naf; const int *naf_top; int h, n, round;
+  HD void operator()(long tid) const {
+    long p = tid / (2 * h); int r = (int)(tid % (2 * h)); int which = r / h; int i = r % h;
+    const ge_p3 *src = (which ? srcH : srcG) + p * src_stride;
+    ge_p3 *dst = (which ? dstH : dstG) + p * dst_stride;
+    int cls = (round == 0 && h + i >= n) ? 1 : 0;
+    const int8_t *nf = naf + (p * 4 + which * 2 + cls) * 256;
+    int top = naf_top[p * 4 + which * 2 + cls];
+    ge_p3 lo, hi; load_struct(lo, &src[i]); load_struct(hi, &src[h + i]);
+    ge_p3 acc;
+    if (top < 0) { acc = lo; }
+    else {
+      ge_cached c; ge_to_cached(c, hi);
+      if (nf[top] > 0) acc = hi; else ge_neg(acc, hi);
+      for (int bit = top - 1; bit >= 0; bit--) {
+        int d = nf[bit];
+        // T is only needed when an addition follows (a digit here, or the final + lo)
+        if (d != 0 || bit == 0) ge_dbl(acc, acc); else ge_dbl_p2(acc, acc);
+        if (d != 0) ge_add_cached(acc, acc, c, d < 0);
+      }
+      ge_cached cl; ge_to_cached(cl, lo);
+      ge_add_cached(acc, acc, cl, 0);
+    }
+    store_struct(&dst[i], acc);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// set-up kernels (BulletproofGens::new / PedersenGens::default; outside any timed region)
+// ------------------------------------------------------------------------------------------------
+// 64 uniform bytes per generator (SHAKE256 stream squeezed on the host) -> ristretto one-way map
+struct KGensFromUniform {
+  static constexpr int kBlock = 64, kMinBlocks = 1;
+  const uint8_t *uniform; ge_p3 *out_p3; ge_niels *out_niels;
+  HD void operator()(long i) const {
+    ge_p3 p, q; ristretto_from_uniform(p, uniform + i * 64);
+    ge_normalize(q, p);
+    store_struct(&out_p3[i], q);
+    ge_niels nl; ge_to_niels(nl, q);
+    store_struct(&out_niels[i], nl);
+  }
+};
+// pc[0] = B (decoded from the canonical basepoint encoding), pc[1] = B_blinding (from uniform bytes)
+struct KPcBases {
+  static constexpr int kBlock = 32, kMinBlocks = 1;
+  const uint8_t *basepoint_c; const uint8_t *bb_uniform; ge_p3 *pc; ge_niels *pc_niels; uint8_t *pc_c; int *ok;
+  HD void operator()(long i) const {
+    ge_p3 p, q;
+    if (i == 0) { if (!ristretto_decode(p, basepoint_c)) *ok = 0; }
+    else ristretto_from_uniform(p, bb_uniform);
+    ge_normalize(q, p);
+    store_struct(&pc[i], q);
+    ge_niels nl; ge_to_niels(nl, q); store_struct(&pc_niels[i], nl);
+    ristretto_encode(pc_c + 32 * i, q);
+  }
+};
+// table[(base*64 + win)*16 + d] = d * 16^win * pc[base]
+struct KPcTable {
+  static constexpr int kBlock = 32, kMinBlocks = 1;
+  const ge_p3 *pc; ge_niels *table;
+  HD void operator()(long tid) const {
+    int base = (int)(tid / 64), win = (int)(tid % 64);
+    ge_p3 P; load_struct(P, &pc[base]);
+    for (int i = 0; i < 4 * win; i++) ge_dbl(P, P);
+    ge_p3 acc = P;
+    ge_niels id; ge_niels_identity(id);
+    store_struct(&table[(base * 64 + win) * 16], id);
+    for (int d = 1; d < 16; d++) {
+      ge_niels nl; ge_to_niels(nl, acc); store_struct(&table[(base * 64 + win) * 16 + d], nl);
+      ge_add(acc, acc, P);
+    }
+  }
+};
+struct KEncodePoints {
+  static constexpr int kBlock = 64, kMinBlocks = 1;
+  const ge_p3 *pts; uint8_t *out;
+  HD void operator()(long i) const { ge_p3 p; load_struct(p, &pts[i]); ristretto_encode(out + 32 * i, p); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// witness generation: tape interpreter, one thread per proof.
+// Each multiplier i has (opL,argL,opR,argR):  W_LC evaluates witness linear combination #arg over
+// already-assigned variables (cs.multiply / evaluate_lc), W_INV_L takes the inverse of this
+// multiplier's left value (synthesize_inverse_sbox, reference src/gadget_poseidon.rs:160-166),
+// W_AUX reads per-proof auxiliary input #arg (allocate_multiplier with caller-computed values,
+// reference src/r1cs_utils.rs:29-32).
+// ------------------------------------------------------------------------------------------------
+enum { W_LC = 0, W_INV_L = 1, W_AUX = 2 };
+struct TapeOp { uint8_t opL, opR, pad[2]; uint32_t argL, argR; };
+struct WitnessLcs { const uint32_t *ptr; const uint8_t *kind; const uint32_t *idx; const scm *coeff; };
+struct KWitnessTape {
+  static constexpr int kBlock = 32, kMinBlocks = 1;
+  const TapeOp *tape; WitnessLcs lcs; int n, B; const scm *v; const scm *aux; scm *aL, *aR, *aO;
+  HD scm eval(uint32_t lc, int p) const {
+    scm acc = sc_zero();
+    for (uint32_t t = lcs.ptr[lc]; t < lcs.ptr[lc + 1]; t++) {
+      scm c = lcs.coeff[t]; long at = (long)lcs.idx[t] * B + p;
+      switch (lcs.kind[t]) {
+        case 0: acc = sc_add(acc, sc_mul(c, v[at])); break;
+        case 1: acc = sc_add(acc, sc_mul(c, aL[at])); break;
+        case 2: acc = sc_add(acc, sc_mul(c, aR[at])); break;
+        case 3: acc = sc_add(acc, sc_mul(c, aO[at])); break;
+        default: acc = sc_add(acc, c); break;
+      }
+    }
+    return acc;
+  }
+  HD void operator()(long p_) const {
+    int p = (int)p_;
+    for (int i = 0; i < n; i++) {
+      TapeOp op = tape[i];
+      scm l, r;
+      if (op.opL == W_LC) l = eval(op.argL, p); else l = aux[(long)op.argL * B + p];
+      if (op.opR == W_LC) r = eval(op.argR, p); else if (op.opR == W_INV_L) r = sc_invert(l); else r = aux[(long)op.argR * B + p];
+      long at = (long)i * B + p;
+      aL[at] = l; aR[at] = r; aO[at] = sc_mul(l, r);
+    }
+  }
+};

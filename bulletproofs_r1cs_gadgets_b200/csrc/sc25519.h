@@ -1,0 +1,146 @@
+// Scalar field F_l, l = 2^252 + 27742317777372353535851937790883648493, in Montgomery form
+// (R = 2^256) on 4 x 64-bit limbs.  Replaces curve25519-dalek's Scalar (reference
+// Cargo.toml:8; call sites e.g. src/gadget_poseidon.rs:123,162, src/scalar_utils.rs:236).
+// All device-resident scalars are kept in Montgomery form; bytes crossing the C-ABI are
+// canonical 32-byte little-endian.
+#pragma once
+#include "hd.h"
+#include "constants.h"
+
+struct alignas(16) scm { uint64_t v[4]; };  // value * 2^256 mod l, always < l
+
+HD void sc_const_l(uint64_t l[4]) { const uint64_t c[4] = SC_L_LIMBS; l[0] = c[0]; l[1] = c[1]; l[2] = c[2]; l[3] = c[3]; }
+HD scm sc_zero() { scm r; r.v[0] = r.v[1] = r.v[2] = r.v[3] = 0; return r; }
+HD scm sc_one() { const uint64_t c[4] = SC_R_LIMBS; scm r; r.v[0] = c[0]; r.v[1] = c[1]; r.v[2] = c[2]; r.v[3] = c[3]; return r; }
+HD scm sc_r2() { const uint64_t c[4] = SC_R2_LIMBS; scm r; r.v[0] = c[0]; r.v[1] = c[1]; r.v[2] = c[2]; r.v[3] = c[3]; return r; }
+HD scm sc_r3() { const uint64_t c[4] = SC_R3_LIMBS; scm r; r.v[0] = c[0]; r.v[1] = c[1]; r.v[2] = c[2]; r.v[3] = c[3]; return r; }
+
+HD uint64_t addc64(uint64_t a, uint64_t b, uint64_t &carry) {
+  uint64_t s = a + carry; uint64_t c1 = s < carry; uint64_t r = s + b; carry = c1 + (r < b); return r;
+}
+HD uint64_t subb64(uint64_t a, uint64_t b, uint64_t &borrow) {
+  uint64_t d = a - b; uint64_t b1 = a < b; uint64_t r = d - borrow; borrow = b1 + (d < borrow); return r;
+}
+// r = a - l if a >= l else a   (a < 2l)
+HD void sc_cond_sub_l(uint64_t a[4], uint64_t top) {
+  uint64_t l[4]; sc_const_l(l);
+  uint64_t t[4], br = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) t[i] = subb64(a[i], l[i], br);
+  // if top is set or no borrow, take t
+  uint64_t take = (top != 0) | (br == 0);
+  uint64_t m = (uint64_t)0 - take;
+#pragma unroll
+  for (int i = 0; i < 4; i++) a[i] = (a[i] & ~m) | (t[i] & m);
+}
+HD scm sc_add(const scm &a, const scm &b) {
+  scm r; uint64_t c = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) r.v[i] = addc64(a.v[i], b.v[i], c);
+  sc_cond_sub_l(r.v, c);
+  return r;
+}
+HD scm sc_sub(const scm &a, const scm &b) {
+  scm r; uint64_t br = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) r.v[i] = subb64(a.v[i], b.v[i], br);
+  uint64_t l[4]; sc_const_l(l);
+  uint64_t m = (uint64_t)0 - (br != 0), c = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) r.v[i] = addc64(r.v[i], l[i] & m, c);
+  return r;
+}
+HD scm sc_neg(const scm &a) { return sc_sub(sc_zero(), a); }
+HD int sc_is_zero(const scm &a) { return (a.v[0] | a.v[1] | a.v[2] | a.v[3]) == 0; }
+HD int sc_equal(const scm &a, const scm &b) { return ((a.v[0] ^ b.v[0]) | (a.v[1] ^ b.v[1]) | (a.v[2] ^ b.v[2]) | (a.v[3] ^ b.v[3])) == 0; }
+
+// Montgomery product a*b/2^256 mod l (CIOS); a may be any 256-bit value, b < l  ->  result < l
+HD scm sc_montmul(const scm &a, const scm &b) {
+  uint64_t l[4]; sc_const_l(l);
+  uint64_t t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    uint64_t hi, lo, c, k;
+    uint64_t bi = b.v[i];
+    // t += a * b[i]
+    mul64wide(a.v[0], bi, hi, lo); k = 0; t0 = addc64(t0, lo, k); c = hi + k;
+    mul64wide(a.v[1], bi, hi, lo); k = 0; t1 = addc64(t1, lo, k); hi += k; k = 0; t1 = addc64(t1, c, k); c = hi + k;
+    mul64wide(a.v[2], bi, hi, lo); k = 0; t2 = addc64(t2, lo, k); hi += k; k = 0; t2 = addc64(t2, c, k); c = hi + k;
+    mul64wide(a.v[3], bi, hi, lo); k = 0; t3 = addc64(t3, lo, k); hi += k; k = 0; t3 = addc64(t3, c, k); c = hi + k;
+    k = 0; t4 = addc64(t4, c, k); t5 = k;
+    // t += m * l ; t >>= 64
+    uint64_t m = t0 * SC_NINV;
+    mul64wide(m, l[0], hi, lo); k = 0; (void)addc64(t0, lo, k); c = hi + k;
+    mul64wide(m, l[1], hi, lo); k = 0; t0 = addc64(t1, lo, k); hi += k; k = 0; t0 = addc64(t0, c, k); c = hi + k;
+    // l[2] == 0
+    k = 0; t1 = addc64(t2, c, k); c = k;
+    mul64wide(m, l[3], hi, lo); k = 0; t2 = addc64(t3, lo, k); hi += k; k = 0; t2 = addc64(t2, c, k); c = hi + k;
+    k = 0; t3 = addc64(t4, c, k); t4 = t5 + k;
+  }
+  scm r; r.v[0] = t0; r.v[1] = t1; r.v[2] = t2; r.v[3] = t3;
+  sc_cond_sub_l(r.v, t4);
+  sc_cond_sub_l(r.v, 0);
+  return r;
+}
+HD scm sc_mul(const scm &a, const scm &b) { return sc_montmul(a, b); }  // both Montgomery -> Montgomery
+HD scm sc_sqr(const scm &a) { return sc_montmul(a, a); }
+HD scm sc_muladd(const scm &a, const scm &b, const scm &c) { return sc_add(sc_montmul(a, b), c); }
+
+HD void load_le64x4(uint64_t w[4], const uint8_t *s) {
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    uint64_t x = 0;
+#pragma unroll
+    for (int j = 7; j >= 0; j--) x = (x << 8) | s[8 * i + j];
+    w[i] = x;
+  }
+}
+// any 32 bytes (reduced mod l) -> Montgomery
+HD scm sc_from_bytes_mod_order(const uint8_t *s) { scm x; load_le64x4(x.v, s); return sc_montmul(x, sc_r2()); }
+// 64 bytes, wide reduction -> Montgomery:  lo*R + hi*2^256*R = montmul(lo,R^2) + montmul(hi,R^3)
+HD scm sc_from_bytes_wide(const uint8_t *s) {
+  scm lo, hi; load_le64x4(lo.v, s); load_le64x4(hi.v, s + 32);
+  return sc_add(sc_montmul(lo, sc_r2()), sc_montmul(hi, sc_r3()));
+}
+// Montgomery -> canonical integer limbs
+HD void sc_to_canonical(uint64_t w[4], const scm &a) {
+  scm one; one.v[0] = 1; one.v[1] = one.v[2] = one.v[3] = 0;
+  scm r = sc_montmul(a, one);
+  w[0] = r.v[0]; w[1] = r.v[1]; w[2] = r.v[2]; w[3] = r.v[3];
+}
+HD void sc_tobytes(uint8_t *s, const scm &a) {
+  uint64_t w[4]; sc_to_canonical(w, a);
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) s[8 * i + j] = (uint8_t)(w[i] >> (8 * j));
+}
+// canonical check: returns 1 and sets r when the 32 bytes encode an integer < l
+HD int sc_from_canonical_bytes(scm &r, const uint8_t *s) {
+  scm x; load_le64x4(x.v, s);
+  uint64_t l[4]; sc_const_l(l);
+  uint64_t br = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) (void)subb64(x.v[i], l[i], br);
+  r = sc_montmul(x, sc_r2());
+  return br != 0;
+}
+HD scm sc_from_u64(uint64_t x) { scm a; a.v[0] = x; a.v[1] = a.v[2] = a.v[3] = 0; return sc_montmul(a, sc_r2()); }
+
+// a^(l-2); invert(0) == 0 like Scalar::invert on zero in the reference's dependency
+// (reference src/scalar_utils.rs:305-307 relies on it)
+HD scm sc_invert(const scm &a) {
+  const uint64_t e[4] = SC_LM2_LIMBS;
+  // l-2 = 2^252 + c (c < 2^125): top bit, then 127 zero bits where only squarings happen
+  scm acc = a;  // bit 252
+  for (int i = 251; i >= 0; i--) {
+    acc = sc_sqr(acc);
+    if ((e[i >> 6] >> (i & 63)) & 1) acc = sc_montmul(acc, a);
+  }
+  return acc;
+}
+HD scm sc_pow_u32(const scm &a, uint32_t e) {
+  scm acc = sc_one(), base = a;
+  while (e) { if (e & 1) acc = sc_montmul(acc, base); base = sc_sqr(base); e >>= 1; }
+  return acc;
+}

@@ -1,0 +1,176 @@
+/* bp_b200 -- C-ABI of the B200-native Bulletproofs R1CS prover / verifier.
+ *
+ * Drop-in boundary for the gadget crate lovesh/bulletproofs-r1cs-gadgets: every entry point below
+ * replaces one item of the `bulletproofs::r1cs` / `bulletproofs::{PedersenGens,BulletproofGens}` /
+ * `merlin::Transcript` surface the reference's gadgets call (reference Cargo.toml:18,22-26).  The
+ * reference-side call site each one stands in for is cited as file:line under /root/reference.
+ *
+ * Conventions
+ *   - scalars: 32 bytes, little-endian; inputs are reduced mod l, outputs are canonical;
+ *   - points: 32-byte ristretto255 encodings (CompressedRistretto);
+ *   - every function returns an int32 status (BP_OK = 0); nothing throws or aborts across the ABI;
+ *   - the caller owns every buffer; handles are opaque and released by the matching *_free;
+ *   - a handle may be used from one host thread at a time (the reference objects are &mut-exclusive);
+ *   - the 32 bytes of OS entropy that Prover::prove / Verifier::verify draw internally in the reference
+ *     are an explicit argument here, so results are reproducible;
+ *   - all proving / verifying arithmetic runs in CUDA kernels on the current device; without a usable
+ *     device every entry point that needs one returns BP_ERR_NO_DEVICE.  There is no CPU path.
+ *
+ * Proof bytes: the R1CSProof field tuple, 32 bytes each, in order
+ *   A_I1 A_O1 S1 A_I2 A_O2 S2 T_1 T_3 T_4 T_5 T_6 t_x t_x_blinding e_blinding L_0 R_0 .. L_{k-1} R_{k-1} a b
+ * (the reference never serialises a proof; this is the untagged layout).
+ */
+#ifndef BP_B200_H
+#define BP_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* R1CSError (reference src/gadget_poseidon.rs:136, src/gadget_range_proof.rs:28) */
+#define BP_OK 0
+#define BP_ERR_INVALID_GENERATORS_LENGTH 1
+#define BP_ERR_FORMAT 2
+#define BP_ERR_VERIFICATION 3
+#define BP_ERR_MISSING_ASSIGNMENT 4
+#define BP_ERR_GADGET 5
+#define BP_ERR_INVALID_ARGUMENT 6
+#define BP_ERR_NO_DEVICE 7
+#define BP_ERR_CUDA 8
+#define BP_ERR_OOM 9
+
+/* Variable (reference src/gadget_vsmt_2.rs:192 Variable::One(), src/gadget_poseidon.rs:101 HashMap key) */
+#define BP_VAR_COMMITTED 0
+#define BP_VAR_MULT_LEFT 1
+#define BP_VAR_MULT_RIGHT 2
+#define BP_VAR_MULT_OUT 3
+#define BP_VAR_ONE 4
+typedef struct bp_var { uint32_t kind; uint32_t index; } bp_var;
+/* one (Variable, Scalar) term of a LinearCombination (reference src/r1cs_utils.rs:45, get_terms src/gadget_poseidon.rs:102) */
+typedef struct bp_term { bp_var var; uint8_t coeff[32]; } bp_term;
+
+typedef struct bp_gens bp_gens;       /* PedersenGens::default() + BulletproofGens::new(capacity, 1) */
+typedef struct bp_cs bp_cs;           /* a Prover or Verifier with its Transcript */
+typedef struct bp_circuit bp_circuit; /* a compiled constraint system for batched proving */
+
+int32_t bp_version(void);
+/* number of CUDA kernels this library has launched in this process (bench.py reports it) */
+int64_t bp_launch_count(void);
+
+/* ---- generators --------------------------------------------------------------------------------
+ * PedersenGens::default() (reference src/gadget_mimc.rs:99) and BulletproofGens::new(capacity, 1)
+ * (reference src/gadget_vsmt_2.rs:290): derived on the device, deterministic. */
+int32_t bp_gens_new(uint32_t capacity, bp_gens **out);
+void bp_gens_free(bp_gens *g);
+uint32_t bp_gens_capacity(const bp_gens *g);
+/* compressed B and B_blinding */
+int32_t bp_gens_pedersen(const bp_gens *g, uint8_t B[32], uint8_t B_blinding[32]);
+/* first `count` generators of chain G (which = 0) or H (which = 1), party 0, compressed */
+int32_t bp_gens_export(const bp_gens *g, int32_t which, uint32_t count, uint8_t *out);
+/* pc_gens.commit(v, r).compress() (reference src/gadget_poseidon.rs:584-587), `count` at once */
+int32_t bp_pc_commit(const bp_gens *g, uint32_t count, const uint8_t *v, const uint8_t *r, uint8_t *out);
+
+/* ---- tier 1: one constraint system at a time (semantic mirror) ----------------------------------
+ * Transcript::new(label) + Prover::new(&pc_gens, &mut transcript)   (reference src/gadget_mimc.rs:113-114) */
+int32_t bp_prover_new(const bp_gens *g, const uint8_t *label, size_t label_len, bp_cs **out);
+/* Transcript::new(label) + Verifier::new(&mut transcript)           (reference src/gadget_mimc.rs:146-147) */
+int32_t bp_verifier_new(const bp_gens *g, const uint8_t *label, size_t label_len, bp_cs **out);
+void bp_cs_free(bp_cs *cs);
+/* prover.commit(v, v_blinding) -> (CompressedRistretto, Variable)   (reference src/gadget_mimc.rs:117) */
+int32_t bp_prover_commit(bp_cs *cs, const uint8_t v[32], const uint8_t v_blinding[32], uint8_t V_out[32], bp_var *var);
+/* verifier.commit(V) -> Variable                                    (reference src/gadget_mimc.rs:149) */
+int32_t bp_verifier_commit(bp_cs *cs, const uint8_t V[32], bp_var *var);
+/* cs.multiply(left, right) -> (l, r, o)                             (reference src/gadget_mimc.rs:71) */
+int32_t bp_cs_multiply(bp_cs *cs, const bp_term *left, size_t nleft, const bp_term *right, size_t nright, bp_var out[3]);
+/* cs.allocate_multiplier(Some((l, r)) | None) -> (l, r, o)          (reference src/r1cs_utils.rs:29) ; l == NULL means None */
+int32_t bp_cs_allocate_multiplier(bp_cs *cs, const uint8_t *l, const uint8_t *r, bp_var out[3]);
+/* fork API cs.allocate_single(Option<Scalar>) -> (Variable, Option<Variable>)   (reference src/gadget_poseidon.rs:165-166) */
+int32_t bp_cs_allocate_single(bp_cs *cs, const uint8_t *value, bp_var *var, bp_var *out_var, int32_t *has_out);
+/* fork API cs.evaluate_lc(&lc) -> Option<Scalar>                    (reference src/gadget_poseidon.rs:160); BP_ERR_MISSING_ASSIGNMENT = None */
+int32_t bp_cs_evaluate_lc(bp_cs *cs, const bp_term *lc, size_t n, uint8_t out[32]);
+/* cs.constrain(lc)                                                  (reference src/r1cs_utils.rs:35) */
+int32_t bp_cs_constrain(bp_cs *cs, const bp_term *lc, size_t n);
+/* fork API num_constraints / num_multipliers                       (reference src/gadget_vsmt_2.rs:345) */
+uint64_t bp_cs_num_constraints(const bp_cs *cs);
+uint64_t bp_cs_num_multipliers(const bp_cs *cs);
+uint64_t bp_cs_num_commitments(const bp_cs *cs);
+size_t bp_cs_proof_len(const bp_cs *cs);
+/* prover.prove(&bp_gens) -> R1CSProof                               (reference src/gadget_vsmt_2.rs:347) */
+int32_t bp_prover_prove(bp_cs *cs, const uint8_t entropy[32], uint8_t *proof, size_t *proof_len);
+/* verifier.verify(&proof, &pc_gens, &bp_gens)                       (reference src/gadget_vsmt_2.rs:395) */
+int32_t bp_verifier_verify(bp_cs *cs, const uint8_t *proof, size_t proof_len, const uint8_t entropy[32]);
+
+/* ---- gadgets of the reference, run against a bp_cs (host side of the hot path) -------------------
+ * Scalar assignments are prover-only; pass NULL on the verifier side (AllocatedScalar.assignment = None,
+ * reference src/r1cs_utils.rs:8-11). */
+typedef struct bp_poseidon_params bp_poseidon_params; /* PoseidonParams (reference src/gadget_poseidon.rs:27-94) */
+#define BP_SBOX_CUBE 0
+#define BP_SBOX_INVERSE 1
+/* PoseidonParams::new(width, full_b, full_e, partial) with the constants of src/poseidon_constants.rs;
+ * `constants` = 36 MDS entries then round keys, 32-byte LE as loaded by get_scalar_from_hex (src/scalar_utils.rs:232-237) */
+int32_t bp_poseidon_params_new(const uint8_t *constants, size_t nconstants, uint32_t width, uint32_t full_rounds_beginning,
+                               uint32_t full_rounds_end, uint32_t partial_rounds, bp_poseidon_params **out);
+void bp_poseidon_params_free(bp_poseidon_params *p);
+/* Poseidon_permutation (src/gadget_poseidon.rs:189-280) and Poseidon_hash_2 (:428-443), evaluated natively */
+int32_t bp_poseidon_hash_2(const bp_poseidon_params *p, const uint8_t xl[32], const uint8_t xr[32], int32_t sbox, uint8_t out[32]);
+/* allocate_statics_for_prover / _for_verifier (src/gadget_poseidon.rs:554-608) */
+int32_t bp_gadget_allocate_statics(bp_cs *cs, uint32_t num_statics, bp_var *out_vars);
+/* Poseidon_hash_2_gadget (src/gadget_poseidon.rs:470-486) */
+int32_t bp_gadget_poseidon_hash_2(bp_cs *cs, const bp_poseidon_params *p, bp_var xl, bp_var xr, const bp_var *statics,
+                                  uint32_t num_statics, int32_t sbox, const uint8_t expected_hash[32]);
+/* vanilla_merkle_merkle_tree_verif_gadget (src/gadget_vsmt_2.rs:171-209) */
+int32_t bp_gadget_vsmt2_verif(bp_cs *cs, const bp_poseidon_params *p, uint32_t depth, const uint8_t root[32], bp_var leaf,
+                              const bp_var *leaf_index_bits, const bp_var *proof_nodes, const bp_var *statics, uint32_t num_statics);
+/* mimc_gadget (src/gadget_mimc.rs:41-79) */
+int32_t bp_gadget_mimc(bp_cs *cs, bp_var left, bp_var right, uint32_t rounds, const uint8_t *constants, const uint8_t image[32]);
+/* mimc (src/gadget_mimc.rs:19-39), evaluated natively */
+int32_t bp_mimc(const uint8_t xl[32], const uint8_t xr[32], uint32_t rounds, const uint8_t *constants, uint8_t out[32]);
+/* bound_check_gadget (src/gadget_bound_check.rs:18-45); v/a/b assignments as u64, has_assignment = 0 on the verifier */
+int32_t bp_gadget_bound_check(bp_cs *cs, bp_var v, bp_var a, bp_var b, int32_t has_assignment, uint64_t v_val, uint64_t a_val,
+                              uint64_t b_val, uint64_t max, uint64_t min, uint32_t bit_size);
+
+/* ---- tier 2: batched proving over a compiled circuit (what the GPU is for) -----------------------
+ * A circuit is the constraint system a gadget recorded on a Verifier-side bp_cs (no assignments) plus the
+ * witness program the recorder derived: how each multiplier's (left, right) follows from the committed
+ * values -- cs.multiply evaluates its two linear combinations, the inverse S-box inverts its left value,
+ * allocate_multiplier reads a caller-supplied auxiliary input.  Every proof of a batch shares it. */
+int32_t bp_circuit_compile(const bp_cs *recorded, bp_circuit **out);
+/* same, from flat arrays: constraint q holds terms cons_ptr[q]..cons_ptr[q+1] (kinds BP_VAR_*); no witness program */
+int32_t bp_circuit_from_arrays(uint32_t n_multipliers, uint32_t n_commitments, uint32_t n_constraints, const uint32_t *cons_ptr,
+                               const uint8_t *kind, const uint32_t *idx, const uint8_t *coeff, bp_circuit **out);
+void bp_circuit_free(bp_circuit *c);
+uint32_t bp_circuit_num_multipliers(const bp_circuit *c);
+uint32_t bp_circuit_num_constraints(const bp_circuit *c);
+uint32_t bp_circuit_num_commitments(const bp_circuit *c);
+uint32_t bp_circuit_num_aux(const bp_circuit *c);
+int32_t bp_circuit_has_witness_program(const bp_circuit *c);
+size_t bp_circuit_proof_len(const bp_circuit *c);
+
+/* B independent proofs.  HOST buffers: v, v_blinding [B][m][32]; entropy [B][32]; aux [B][num_aux][32] (may be
+ * NULL when num_aux == 0); witness aL/aR/aO [B][n][32] or all NULL to run the witness program on the device.
+ * Outputs: V [B][m][32], proofs [B][proof_len], status [B].  Copies host<->device inside the call. */
+int32_t bp_prove_batch(const bp_gens *g, bp_circuit *c, uint32_t B, const uint8_t *label, size_t label_len, const uint8_t *v,
+                       const uint8_t *v_blinding, const uint8_t *entropy, const uint8_t *aux, const uint8_t *aL,
+                       const uint8_t *aR, const uint8_t *aO, uint8_t *V_out, uint8_t *proofs, int32_t *status);
+/* same with every buffer already resident in device memory (cudaMalloc'ed by the caller), on `stream`
+ * (a cudaStream_t cast to void*; NULL = default stream).  Returns after enqueueing; the caller synchronises. */
+int32_t bp_prove_batch_device(const bp_gens *g, bp_circuit *c, uint32_t B, const uint8_t *label, size_t label_len,
+                              const uint8_t *d_v, const uint8_t *d_v_blinding, const uint8_t *d_entropy, const uint8_t *d_aux,
+                              const uint8_t *d_aL, const uint8_t *d_aR, const uint8_t *d_aO, uint8_t *d_V_out,
+                              uint8_t *d_proofs, int32_t *d_status, void *stream);
+/* B independent verifications of proofs over the same circuit; status[p] = BP_OK or BP_ERR_VERIFICATION / BP_ERR_FORMAT */
+int32_t bp_verify_batch(const bp_gens *g, bp_circuit *c, uint32_t B, const uint8_t *label, size_t label_len, const uint8_t *V,
+                        const uint8_t *proofs, const uint8_t *entropy, int32_t *status);
+int32_t bp_verify_batch_device(const bp_gens *g, bp_circuit *c, uint32_t B, const uint8_t *label, size_t label_len,
+                               const uint8_t *d_V, const uint8_t *d_proofs, const uint8_t *d_entropy, int32_t *d_status, void *stream);
+
+/* ---- MSM microbenchmark entry (BASELINE.json config 3) -------------------------------------------
+ * result = sum_i scalars[i] * points[i] over ristretto255; points are the first n generators of chain G.
+ * d_scalars: device, [n][32] canonical LE.  out: device, 32 bytes. */
+int32_t bp_msm_gens_device(const bp_gens *g, uint32_t n, const uint8_t *d_scalars, uint8_t *d_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
