@@ -410,4 +410,35 @@ int32_t bp_msm_gens_device(const bp_gens *g, uint32_t n, const uint8_t *d_scalar
   return engine_msm_gens(g->g, n, d_scalars, d_out, s);
 }
 
+// primitive self-test on the device (tests only); host buffers
+int32_t bp_selftest_device(int32_t which, const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len) {
+  int rc = bp_device_init();
+  if (rc) return rc;
+  DevBuf di, dout;
+  if (di.alloc(in_len + 16) || dout.alloc(out_len + 16)) return BP_ERR_OOM;
+  dev_stream s = 0;
+  if (dev_h2d(di.p, in, in_len, s) || dev_memset(dout.p, 0, out_len, s)) return BP_ERR_CUDA;
+  if (launch(1, s, KSelfTest{which, di.p, (int)in_len, dout.p, (int)out_len})) return BP_ERR_CUDA;
+  if (dev_d2h(out, dout.p, out_len, s) || dev_sync(s)) return BP_ERR_CUDA;
+  return BP_OK;
+}
+
+// runs the real KLoadScalars + KTsStart kernels on crafted inputs (m commitments): in = V[m][32] | vbl[m][32] | entropy[32] | label
+// out = ts state (208 B) | rng state (208 B)
+int32_t bp_selftest_tsstart(uint32_t m, const uint8_t *in, const uint8_t *label, size_t label_len, uint8_t *out) {
+  int rc = bp_device_init();
+  if (rc) return rc;
+  DevBuf di, dts, drng, dvbl;
+  if (di.alloc(64 * m + 32) || dts.alloc(sizeof(strobe128)) || drng.alloc(sizeof(strobe128)) || dvbl.alloc(32 * m + 32)) return BP_ERR_OOM;
+  dev_stream s = 0;
+  if (dev_h2d(di.p, in, 64 * m + 32, s)) return BP_ERR_CUDA;
+  if (launch(m, s, KLoadScalars{di.p + 32 * m, (scm *)dvbl.p, (int)m, 1})) return BP_ERR_CUDA;
+  strobe128 base; ts_init(base, label, (int)label_len);
+  const uint8_t r1[7] = {'r', '1', 'c', 's', ' ', 'v', '1'};
+  ts_append(base, "dom-sep", r1, 7);
+  if (launch(1, s, KTsStart{base, di.p, (int)m, 1, (const scm *)dvbl.p, di.p + 64 * m, (strobe128 *)dts.p, (strobe128 *)drng.p, 1})) return BP_ERR_CUDA;
+  if (dev_d2h(out, dts.p, sizeof(strobe128), s) || dev_d2h(out + sizeof(strobe128), drng.p, sizeof(strobe128), s) || dev_sync(s)) return BP_ERR_CUDA;
+  return BP_OK;
+}
+
 }  // extern "C"

@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(K::kBlock, K::kMinBlocks) run_kernel(long n, K
 }
 extern long g_launch_count;
 template <class K>
-inline int launch(long n, dev_stream s, const K &k) {
+int launch(long n, dev_stream s, const K &k) {
   if (n <= 0) return 0;
   long blocks = (n + K::kBlock - 1) / K::kBlock;
   run_kernel<K><<<(unsigned)blocks, K::kBlock, 0, s>>>(n, k);
@@ -42,7 +42,7 @@ inline int dev_sync(dev_stream s) {
 typedef int dev_stream;
 extern long g_launch_count;
 template <class K>
-inline int launch(long n, dev_stream, const K &k) {
+int launch(long n, dev_stream, const K &k) {
   for (long t = 0; t < n; t++) k(t);
   g_launch_count++;
   return 0;

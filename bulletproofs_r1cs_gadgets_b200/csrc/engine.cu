@@ -255,6 +255,13 @@ int engine_prove(const BpGens *g, BpCircuit *c, const ProveArgs &A, dev_stream s
   // 2. transcript start + transcript RNG, blinding draws (A.3 steps 1-3)
   strobe128 base; base_transcript(base, A.label, A.label_len);
   CK(launch(B, s, KTsStart{base, A.V_out, (int)m, B, w->vbl, A.entropy, w->ts, w->rng, 1}));
+  std::vector<uint8_t> dbg_states;
+  if (getenv("BP_B200_DEBUG_DUMP")) {
+    dbg_states.resize(2 * sizeof(strobe128) + 32 * m);
+    CK(dev_d2h(dbg_states.data(), w->ts, sizeof(strobe128), s)); CK(dev_d2h(dbg_states.data() + sizeof(strobe128), w->rng, sizeof(strobe128), s));
+    CK(dev_d2h(dbg_states.data() + 2 * sizeof(strobe128), A.V_out, 32 * m, s));
+    CK(dev_sync(s));
+  }
   CK(launch(B, s, KRngDraw{w->rng, w->rand1, (int)(3 + 2 * n), B}));
   // 3. witness
   if (A.aL) {
@@ -343,6 +350,22 @@ int engine_prove(const BpGens *g, BpCircuit *c, const ProveArgs &A, dev_stream s
     len = h;
   }
   CK(launch(B, s, KStoreAB{w->a, w->b, A.proofs, plen, 448 + 64 * k}));
+  if (const char *dump = getenv("BP_B200_DEBUG_DUMP")) {  // developer aid: raw Montgomery scalars of proof 0..B-1
+    CK(dev_sync(s));
+    FILE *f = fopen(dump, "wb");
+    if (f) {
+      auto put = [&](const char *name, const scm *d, long count) {
+        std::vector<scm> h(count); dev_d2h(h.data(), d, count * sizeof(scm), s); dev_sync(s);
+        std::vector<uint8_t> b(count * 32); for (long i = 0; i < count; i++) sc_tobytes(b.data() + 32 * i, h[i]);
+        char hdr[32] = {0}; snprintf(hdr, sizeof hdr, "%s", name); fwrite(hdr, 1, 24, f); uint64_t c = count; fwrite(&c, 8, 1, f); fwrite(b.data(), 1, b.size(), f);
+      };
+      put("rand1", w->rand1, (3 + 2 * n) * B); put("chal", w->chal, 10L * B); put("t", w->t, 6L * B); put("tb", w->tb, 5L * B);
+      put("wit", w->wit, 3 * n * B); put("w_all", w->w_all, (long)c->nslots * B); put("v", w->v, m * B); put("vbl", w->vbl, m * B);
+      { char hdr[32] = {0}; snprintf(hdr, sizeof hdr, "raw_states"); fwrite(hdr, 1, 24, f); uint64_t cnt = 0; fwrite(&cnt, 8, 1, f); }
+      fwrite(dbg_states.data(), 1, dbg_states.size(), f);
+      fclose(f);
+    }
+  }
   return BP_OK;
 }
 

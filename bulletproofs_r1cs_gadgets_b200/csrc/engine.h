@@ -4,8 +4,7 @@
 #include <stdint.h>
 #include <stddef.h>
 #include <vector>
-#include "kernels.h"
-#include "devrt.h"
+#include "kernel_groups.h"
 
 #include "../../include/bp_b200.h"  // status codes
 

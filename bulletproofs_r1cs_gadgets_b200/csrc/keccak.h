@@ -7,7 +7,14 @@
 
 HD uint64_t rol64(uint64_t x, int n) { return (x << n) | (x >> (64 - n)); }
 
+// Not inlined on the device: with the permutation inlined into the byte-addressed STROBE code nvcc 12.9
+// -O3 produced a wrong transcript-RNG state in KTsStart (caught by the oracle parity test; -G and this
+// form are both correct).  A call boundary also keeps every transcript kernel small.
+#if defined(__CUDACC__)
+static __host__ __device__ __noinline__ void keccak_f1600(uint64_t st[25]) {
+#else
 HD void keccak_f1600(uint64_t st[25]) {
+#endif
   const uint64_t RC[24] = {
       0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808AULL, 0x8000000080008000ULL,
       0x000000000000808BULL, 0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL,
@@ -105,6 +112,18 @@ HD void strobe_init(strobe128 &s, const uint8_t *label, int n) {
   keccak_f1600(s.st);
   s.pos = 0; s.pos_begin = 0; s.cur_flags = 0;
   strobe_meta_ad(s, label, n, 0);
+}
+
+// global <-> local copies, member by member (no type punning on the mixed u64/u8 struct)
+HD void strobe_load(strobe128 &d, const strobe128 *src) {
+#pragma unroll
+  for (int i = 0; i < 25; i++) d.st[i] = src->st[i];
+  d.pos = src->pos; d.pos_begin = src->pos_begin; d.cur_flags = src->cur_flags;
+}
+HD void strobe_store(strobe128 *dst, const strobe128 &s) {
+#pragma unroll
+  for (int i = 0; i < 25; i++) dst->st[i] = s.st[i];
+  dst->pos = s.pos; dst->pos_begin = s.pos_begin; dst->cur_flags = s.cur_flags;
 }
 
 // ---------------------------------------------------------------- Merlin transcript

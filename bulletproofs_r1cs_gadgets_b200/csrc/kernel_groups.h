@@ -1,0 +1,24 @@
+// Kernel instantiation groups: each k_*.cu explicitly instantiates launch<K> (and with it the
+// __global__ run_kernel<K>) for one group so the heavy kernels compile in parallel; every other
+// translation unit sees them as extern templates.
+#pragma once
+#include "kernels.h"
+#include "devrt.h"
+
+#define KGROUP_MSM(X) X(KMsmAccumulate) X(KMsmFinish)
+#define KGROUP_FOLD(X) X(KFoldGens)
+#define KGROUP_POINTS(X) X(KCommit) X(KGensFromUniform) X(KPcBases) X(KPcTable) X(KEncodePoints)
+#define KGROUP_TRANSCRIPT(X) X(KTsStart) X(KRngDraw) X(KTsPhase2) X(KTsPhase3) X(KTsPhase4) X(KTsIpaRound) X(KSelfTest)
+#define KGROUP_SCALAR(X) X(KLoadScalars) X(KRecode) X(KPowers) X(KFillScalar) X(KFlatten) X(KPolyT) X(KSumPartials) X(KPolyEval) \
+  X(KProverScalars) X(KIpaDots) X(KRecodeIpa) X(KFoldAB) X(KStoreAB) X(KWitnessTape)
+
+#define KDECL_EXTERN(K) extern template int launch<K>(long, dev_stream, const K &);
+#define KDEFINE(K) template int launch<K>(long, dev_stream, const K &);
+
+#ifndef KGROUP_DEFINING
+KGROUP_MSM(KDECL_EXTERN)
+KGROUP_FOLD(KDECL_EXTERN)
+KGROUP_POINTS(KDECL_EXTERN)
+KGROUP_TRANSCRIPT(KDECL_EXTERN)
+KGROUP_SCALAR(KDECL_EXTERN)
+#endif

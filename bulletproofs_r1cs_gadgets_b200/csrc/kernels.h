@@ -190,14 +190,14 @@ struct KTsStart {
   static constexpr int kBlock = 64, kMinBlocks = 1;
   strobe128 base; const uint8_t *V; int m, B; const scm *vbl; const uint8_t *entropy; strobe128 *ts; strobe128 *rng; int prover;
   HD void operator()(long p) const {
-    strobe128 t = base;
+    strobe128 t; strobe_load(t, &base);
     for (int j = 0; j < m; j++) ts_append(t, "V", V + ((long)p * m + j) * 32, 32);
     ts_append_u64(t, "m", (uint64_t)m);
-    store_struct(&ts[p], t);
+    strobe_store(&ts[p], t);
     if (prover) {
       for (int j = 0; j < m; j++) { uint8_t b[32]; sc_tobytes(b, vbl[(long)j * B + p]); trng_rekey(t, "v_blinding", b, 32); }
       trng_finalize(t, entropy + p * 32);
-      store_struct(&rng[p], t);
+      strobe_store(&rng[p], t);
     }
   }
 };
@@ -206,9 +206,9 @@ struct KRngDraw {
   static constexpr int kBlock = 32, kMinBlocks = 1;
   strobe128 *rng; scm *dst; int count, B;
   HD void operator()(long p) const {
-    strobe128 r; load_struct(r, &rng[p]);
+    strobe128 r; strobe_load(r, &rng[p]);
     for (int i = 0; i < count; i++) { uint8_t b[64]; trng_fill(r, b, 64); dst[(long)i * B + p] = sc_from_bytes_wide(b); }
-    store_struct(&rng[p], r);
+    strobe_store(&rng[p], r);
   }
 };
 // A_I1,A_O1,S1 + one-phase separator + identity A_I2,A_O2,S2 -> y, z ; also y^-1
@@ -216,7 +216,7 @@ struct KTsPhase2 {
   static constexpr int kBlock = 64, kMinBlocks = 1;
   strobe128 *ts; const uint8_t *proofs; long proof_stride; scm *y, *z, *yinv; int *status; int verifier;
   HD void operator()(long p) const {
-    strobe128 t; load_struct(t, &ts[p]);
+    strobe128 t; strobe_load(t, &ts[p]);
     const uint8_t *pf = proofs + p * proof_stride;
     if (verifier) {
       for (int j = 0; j < 3; j++) { uint8_t nz = 0; for (int i = 0; i < 32; i++) nz |= pf[32 * j + i]; if (!nz) status[p] = 3; }
@@ -228,7 +228,7 @@ struct KTsPhase2 {
     scm yy, zz;
     TS_CHALLENGE(t, "y", yy); TS_CHALLENGE(t, "z", zz);
     y[p] = yy; z[p] = zz; yinv[p] = sc_invert(yy);
-    store_struct(&ts[p], t);
+    strobe_store(&ts[p], t);
   }
 };
 // T_1,T_3,T_4,T_5,T_6 -> u, x
@@ -236,7 +236,7 @@ struct KTsPhase3 {
   static constexpr int kBlock = 64, kMinBlocks = 1;
   strobe128 *ts; const uint8_t *proofs; long proof_stride; scm *u, *x; int *status; int verifier;
   HD void operator()(long p) const {
-    strobe128 t; load_struct(t, &ts[p]);
+    strobe128 t; strobe_load(t, &ts[p]);
     const uint8_t *pf = proofs + p * proof_stride + 192;
     if (verifier) {
       for (int j = 0; j < 5; j++) { uint8_t nz = 0; for (int i = 0; i < 32; i++) nz |= pf[32 * j + i]; if (!nz) status[p] = 3; }
@@ -246,7 +246,7 @@ struct KTsPhase3 {
     scm uu, xx;
     TS_CHALLENGE(t, "u", uu); TS_CHALLENGE(t, "x", xx);
     u[p] = uu; x[p] = xx;
-    store_struct(&ts[p], t);
+    strobe_store(&ts[p], t);
   }
 };
 // t_x, t_x_blinding, e_blinding -> w ; then the inner-product domain separator with n = N
@@ -254,14 +254,14 @@ struct KTsPhase4 {
   static constexpr int kBlock = 64, kMinBlocks = 1;
   strobe128 *ts; const uint8_t *proofs; long proof_stride; scm *w; unsigned N;
   HD void operator()(long p) const {
-    strobe128 t; load_struct(t, &ts[p]);
+    strobe128 t; strobe_load(t, &ts[p]);
     const uint8_t *pf = proofs + p * proof_stride + 352;
     ts_append(t, "t_x", pf, 32); ts_append(t, "t_x_blinding", pf + 32, 32); ts_append(t, "e_blinding", pf + 64, 32);
     scm ww; TS_CHALLENGE(t, "w", ww); w[p] = ww;
     const uint8_t ipp[6] = {'i', 'p', 'p', ' ', 'v', '1'};
     ts_append(t, "dom-sep", ipp, 6);
     ts_append_u64(t, "n", (uint64_t)N);
-    store_struct(&ts[p], t);
+    strobe_store(&ts[p], t);
   }
 };
 
@@ -294,14 +294,14 @@ struct KTsIpaRound {
   const scm *yinvpow; const scm *ufac;  // y^-i table [N][B]; the r1cs challenge u (class factor, round 0 only)
   scm *u, *uinv, *alpha, *beta; int8_t *naf; int *naf_top; int *status; int verifier;
   HD void operator()(long p) const {
-    strobe128 t; load_struct(t, &ts[p]);
+    strobe128 t; strobe_load(t, &ts[p]);
     const uint8_t *pf = proofs + p * proof_stride + 448 + 64 * round;
     if (verifier) {
       for (int j = 0; j < 2; j++) { uint8_t nz = 0; for (int i = 0; i < 32; i++) nz |= pf[32 * j + i]; if (!nz) status[p] = 3; }
     }
     ts_append(t, "L", pf, 32); ts_append(t, "R", pf + 32, 32);
     scm uu; TS_CHALLENGE(t, "u", uu);
-    store_struct(&ts[p], t);
+    strobe_store(&ts[p], t);
     scm ui = sc_invert(uu);
     u[p] = uu; uinv[p] = ui;
     if (verifier) return;
@@ -623,6 +623,63 @@ struct KWitnessTape {
       if (op.opR == W_LC) r = eval(op.argR, p); else if (op.opR == W_INV_L) r = sc_invert(l); else r = aux[(long)op.argR * B + p];
       long at = (long)i * B + p;
       aL[at] = l; aR[at] = r; aO[at] = sc_mul(l, r);
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// primitive self-tests: run one primitive on the device so the test-suite can compare it with the
+// oracle through the C-ABI (bp_selftest_device).  in/out are small device byte buffers.
+// ------------------------------------------------------------------------------------------------
+enum { ST_MERLIN = 0, ST_SC_INVERT = 1, ST_SC_WIDE = 2, ST_RISTRETTO_ROUNDTRIP = 3, ST_SC_MUL = 4, ST_FROM_UNIFORM = 5, ST_RNG = 6, ST_KECCAK = 7, ST_TSSTART = 8 };
+struct KSelfTest {
+  static constexpr int kBlock = 32, kMinBlocks = 1;
+  int which; const uint8_t *in; int in_len; uint8_t *out; int out_len;
+  HD void operator()(long) const {
+    switch (which) {
+      case ST_MERLIN: {  // Transcript::new(in[0..a)); append_message("some label", in[a..)); challenge_bytes("challenge", out)
+        int a = in[0];
+        strobe128 t; ts_init(t, in + 1, a);
+        ts_append(t, "some label", in + 1 + a, in_len - 1 - a);
+        ts_challenge_bytes(t, "challenge", out, out_len);
+        break;
+      }
+      case ST_SC_INVERT: sc_tobytes(out, sc_invert(sc_from_bytes_mod_order(in))); break;
+      case ST_SC_WIDE: sc_tobytes(out, sc_from_bytes_wide(in)); break;
+      case ST_RISTRETTO_ROUNDTRIP: { ge_p3 p; int ok = ristretto_decode(p, in); out[32] = (uint8_t)ok; if (ok) { ge_p3 d; ge_dbl(d, p); ge_sub(d, d, p); ristretto_encode(out, d); } break; }
+      case ST_SC_MUL: sc_tobytes(out, sc_mul(sc_from_bytes_mod_order(in), sc_from_bytes_mod_order(in + 32))); break;
+      case ST_FROM_UNIFORM: { ge_p3 p; ristretto_from_uniform(p, in); ristretto_encode(out, p); break; }
+      case ST_RNG: {  // transcript "rngtest" -> build rng with witness in[0..32), entropy in[32..64) -> out_len/32 scalars
+        const uint8_t lbl[7] = {'r', 'n', 'g', 't', 'e', 's', 't'};
+        strobe128 t; ts_init(t, lbl, 7);
+        trng_rekey(t, "v_blinding", in, 32); trng_finalize(t, in + 32);
+        for (int i = 0; i < out_len / 32; i++) { uint8_t b[64]; trng_fill(t, b, 64); sc_tobytes(out + 32 * i, sc_from_bytes_wide(b)); }
+        break;
+      }
+      case ST_KECCAK: {  // keccak-f on 200 bytes
+        uint64_t st[25];
+        for (int i = 0; i < 25; i++) { uint64_t x = 0; for (int j = 7; j >= 0; j--) x = (x << 8) | in[8 * i + j]; st[i] = x; }
+        keccak_f1600(st);
+        for (int i = 0; i < 200; i++) out[i] = st_get(st, i);
+        break;
+      }
+      case ST_TSSTART: {  // replica of KTsStart for m = 2: in = V0 V1 vbl0 vbl1 entropy (5 x 32); out = ts state (208) | rng state (208) | 2 draws
+        const uint8_t lbl[4] = {'M', 'i', 'M', 'C'};
+        strobe128 t; ts_init(t, lbl, 4);
+        const uint8_t r1[7] = {'r', '1', 'c', 's', ' ', 'v', '1'};
+        ts_append(t, "dom-sep", r1, 7);
+        for (int j = 0; j < 2; j++) ts_append(t, "V", in + 32 * j, 32);
+        ts_append_u64(t, "m", 2);
+        for (int i = 0; i < 200; i++) out[i] = st_get(t.st, i);
+        out[200] = t.pos; out[201] = t.pos_begin; out[202] = t.cur_flags;
+        for (int j = 0; j < 2; j++) { uint8_t b[32]; sc_tobytes(b, sc_from_bytes_mod_order(in + 64 + 32 * j)); trng_rekey(t, "v_blinding", b, 32); }
+        trng_finalize(t, in + 128);
+        for (int i = 0; i < 200; i++) out[208 + i] = st_get(t.st, i);
+        out[408] = t.pos; out[409] = t.pos_begin; out[410] = t.cur_flags;
+        for (int i = 0; i < 2; i++) { uint8_t b[64]; trng_fill(t, b, 64); sc_tobytes(out + 416 + 32 * i, sc_from_bytes_wide(b)); }
+        break;
+      }
+      default: break;
     }
   }
 };

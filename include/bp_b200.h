@@ -170,6 +170,11 @@ int32_t bp_verify_batch_device(const bp_gens *g, bp_circuit *c, uint32_t B, cons
  * d_scalars: device, [n][32] canonical LE.  out: device, 32 bytes. */
 int32_t bp_msm_gens_device(const bp_gens *g, uint32_t n, const uint8_t *d_scalars, uint8_t *d_out, void *stream);
 
+/* ---- device self-tests of single primitives (used by tests/ to pin the CUDA arithmetic to the oracle) ----
+ * which: 0 Merlin transcript KAT, 1 scalar invert, 2 wide scalar reduction, 3 ristretto decode/encode round trip,
+ *        4 scalar multiply, 5 ristretto one-way map, 6 transcript RNG draws, 7 Keccak-f[1600].  Host buffers. */
+int32_t bp_selftest_device(int32_t which, const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len);
+
 #ifdef __cplusplus
 }
 #endif
