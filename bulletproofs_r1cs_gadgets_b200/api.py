@@ -22,7 +22,7 @@ ERRORS = {
     6: "InvalidArgument", 7: "NoDevice", 8: "CudaError", 9: "OutOfMemory",
 }
 SBOX_CUBE, SBOX_INVERSE = 0, 1
-VAR_COMMITTED, VAR_MULT_LEFT, VAR_MULT_RIGHT, VAR_MULT_OUT, VAR_ONE = 0, 1, 2, 3, 4
+VAR_COMMITTED, VAR_MULT_LEFT, VAR_MULT_RIGHT, VAR_MULT_OUT, VAR_ONE, VAR_PUBLIC = 0, 1, 2, 3, 4, 5
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_SO = os.path.join(_PKG, "libbp_b200.so")
@@ -62,7 +62,7 @@ def load(path=None):
     lib.bp_cs_num_commitments.restype = C.c_uint64
     lib.bp_cs_proof_len.restype = C.c_size_t
     lib.bp_circuit_proof_len.restype = C.c_size_t
-    for f in ("bp_gens_capacity", "bp_circuit_num_multipliers", "bp_circuit_num_constraints", "bp_circuit_num_commitments", "bp_circuit_num_aux"):
+    for f in ("bp_gens_capacity", "bp_circuit_num_multipliers", "bp_circuit_num_constraints", "bp_circuit_num_commitments", "bp_circuit_num_aux", "bp_circuit_num_public"):
         getattr(lib, f).restype = C.c_uint32
     lib.bp_gens_free.restype = None
     lib.bp_cs_free.restype = None
@@ -282,6 +282,12 @@ class ConstraintSystem:
         _check(rc, "evaluate_lc")
         return int.from_bytes(bytes(out), "little")
 
+    def public_input(self, value=None):
+        """declares the next per-proof public input of a batched circuit (BP_VAR_PUBLIC)"""
+        var = bp_var()
+        _check(load().bp_cs_public_input(self._h, None if value is None else _buf(scalar_bytes(value)), C.byref(var)), "public_input")
+        return Variable(var.kind, var.index)
+
     def constrain(self, lc):
         arr, n = LinearCombination.of(lc)._c()
         _check(load().bp_cs_constrain(self._h, arr, C.c_size_t(n)), "constrain")
@@ -303,6 +309,10 @@ class ConstraintSystem:
 
     def poseidon_hash_2_gadget(self, params, xl, xr, statics, sbox, expected):
         st = (bp_var * len(statics))(*[s._c() for s in statics])
+        if isinstance(expected, Variable):
+            _check(load().bp_gadget_poseidon_hash_2_public(self._h, params._h, xl._c(), xr._c(), st, C.c_uint32(len(statics)), sbox, expected._c()),
+                   "poseidon_hash_2_gadget")
+            return
         _check(load().bp_gadget_poseidon_hash_2(self._h, params._h, xl._c(), xr._c(), st, C.c_uint32(len(statics)), sbox,
                                                 _buf(scalar_bytes(expected))), "poseidon_hash_2_gadget")
 
@@ -310,11 +320,18 @@ class ConstraintSystem:
         b = (bp_var * depth)(*[x._c() for x in bits])
         nd = (bp_var * depth)(*[x._c() for x in nodes])
         st = (bp_var * len(statics))(*[s._c() for s in statics])
+        if isinstance(root, Variable):
+            _check(load().bp_gadget_vsmt2_verif_public(self._h, params._h, C.c_uint32(depth), root._c(), leaf._c(), b, nd, st, C.c_uint32(len(statics))),
+                   "vsmt2_verif_gadget")
+            return
         _check(load().bp_gadget_vsmt2_verif(self._h, params._h, C.c_uint32(depth), _buf(scalar_bytes(root)), leaf._c(), b, nd, st,
                                             C.c_uint32(len(statics))), "vsmt2_verif_gadget")
 
     def mimc_gadget(self, left, right, constants, image):
         cb = b"".join(scalar_bytes(c) for c in constants)
+        if isinstance(image, Variable):
+            _check(load().bp_gadget_mimc_public(self._h, left._c(), right._c(), C.c_uint32(len(constants)), _buf(cb), image._c()), "mimc_gadget")
+            return
         _check(load().bp_gadget_mimc(self._h, left._c(), right._c(), C.c_uint32(len(constants)), _buf(cb), _buf(scalar_bytes(image))), "mimc_gadget")
 
     def bound_check_gadget(self, v, a, b, vmax, vmin, bit_size, values=None):
@@ -394,6 +411,7 @@ class Circuit:
         self.q = l.bp_circuit_num_constraints(self._h)
         self.m = l.bp_circuit_num_commitments(self._h)
         self.num_aux = l.bp_circuit_num_aux(self._h)
+        self.num_public = l.bp_circuit_num_public(self._h)
         self.has_witness_program = bool(l.bp_circuit_has_witness_program(self._h))
         self.proof_len = l.bp_circuit_proof_len(self._h)
 
@@ -402,8 +420,8 @@ class Circuit:
             _lib.bp_circuit_free(self._h)
             self._h = None
 
-    def prove_batch(self, gens, label, v, v_blinding, entropy, aux=None, witness=None):
-        """v, v_blinding: uint8 [B][m][32]; entropy [B][32]; aux [B][num_aux][32]; witness = (aL,aR,aO) each [B][n][32] or None.
+    def prove_batch(self, gens, label, v, v_blinding, entropy, aux=None, pub=None, witness=None):
+        """v, v_blinding: uint8 [B][m][32]; entropy [B][32]; aux [B][num_aux][32]; pub [B][num_public][32]; witness = (aL,aR,aO) each [B][n][32] or None.
         Returns (V [B][m][32], proofs [B][proof_len], status [B]).  Host buffers in, host buffers out."""
         v, v_blinding, entropy = _np_u8(v), _np_u8(v_blinding), _np_u8(entropy)
         B = entropy.shape[0]
@@ -412,19 +430,21 @@ class Circuit:
         status = np.zeros(B, dtype=np.int32)
         p = lambda a: a.ctypes.data_as(u8p) if a is not None else None
         aux = _np_u8(aux) if aux is not None else None
+        pub = _np_u8(pub) if pub is not None else None
         wl = [_np_u8(w) for w in witness] if witness is not None else [None, None, None]
         _check(load().bp_prove_batch(gens._h, self._h, C.c_uint32(B), _buf(label) if label else None, C.c_size_t(len(label)), p(v), p(v_blinding),
-                                     p(entropy), p(aux), p(wl[0]), p(wl[1]), p(wl[2]), p(V), p(proofs), status.ctypes.data_as(C.POINTER(C.c_int32))),
+                                     p(entropy), p(aux), p(pub), p(wl[0]), p(wl[1]), p(wl[2]), p(V), p(proofs), status.ctypes.data_as(C.POINTER(C.c_int32))),
                "prove_batch")
         return V, proofs, status
 
-    def verify_batch(self, gens, label, V, proofs, entropy):
+    def verify_batch(self, gens, label, V, proofs, entropy, pub=None):
         V, proofs, entropy = _np_u8(V), _np_u8(proofs), _np_u8(entropy)
+        pub = _np_u8(pub) if pub is not None else None
         B = entropy.shape[0]
         status = np.zeros(B, dtype=np.int32)
         _check(load().bp_verify_batch(gens._h, self._h, C.c_uint32(B), _buf(label) if label else None, C.c_size_t(len(label)), V.ctypes.data_as(u8p),
-                                      proofs.ctypes.data_as(u8p), entropy.ctypes.data_as(u8p), status.ctypes.data_as(C.POINTER(C.c_int32))),
-               "verify_batch")
+                                      proofs.ctypes.data_as(u8p), entropy.ctypes.data_as(u8p), pub.ctypes.data_as(u8p) if pub is not None else None,
+                                      status.ctypes.data_as(C.POINTER(C.c_int32))), "verify_batch")
         return status
 
 

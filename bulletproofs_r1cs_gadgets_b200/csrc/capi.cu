@@ -16,6 +16,7 @@ static bool var_ok(const bp_cs *cs, bp_var v) {
     case BP_VAR_COMMITTED: return v.index < cs->V.size();
     case BP_VAR_MULT_LEFT: case BP_VAR_MULT_RIGHT: case BP_VAR_MULT_OUT: return v.index < cs->num_mult;
     case BP_VAR_ONE: return true;
+    case BP_VAR_PUBLIC: return v.index < cs->pub.size();
     default: return false;
   }
 }
@@ -109,6 +110,12 @@ int32_t bp_cs_evaluate_lc(bp_cs *cs, const bp_term *lc, size_t n, uint8_t out[32
   sc_tobytes(out, v);
   return BP_OK;
 }
+int32_t bp_cs_public_input(bp_cs *cs, const uint8_t *value, bp_var *var) {
+  if (!cs || !var) return BP_ERR_INVALID_ARGUMENT;
+  cs->pub.push_back(value ? load_scalar(value) : sc_zero());
+  *var = bp_var{BP_VAR_PUBLIC, (uint32_t)cs->pub.size() - 1};
+  return BP_OK;
+}
 int32_t bp_cs_constrain(bp_cs *cs, const bp_term *lc, size_t n) {
   if (!cs || !lc_ok(cs, lc, n)) return BP_ERR_INVALID_ARGUMENT;
   cs->constrain(lc_from_terms(lc, n));
@@ -126,12 +133,12 @@ static int32_t compile_cs(const bp_cs *cs, bool with_tape, BpCircuit **out) {
   std::vector<uint8_t> kind(nnz ? nnz : 1); std::vector<uint32_t> idx(nnz ? nnz : 1); std::vector<scm> co(nnz ? nnz : 1);
   for (size_t t = 0; t < nnz; t++) { kind[t] = (uint8_t)cs->terms[t].var.kind; idx[t] = cs->terms[t].var.index; co[t] = cs->terms[t].coeff; }
   if (!with_tape || cs->pending >= 0)
-    return circuit_create(cs->num_mult, (uint32_t)cs->V.size(), (uint32_t)cs->num_constraints(), cs->cons_ptr.data(), kind.data(), idx.data(),
+    return circuit_create(cs->num_mult, (uint32_t)cs->V.size(), (uint32_t)cs->pub.size(), (uint32_t)cs->num_constraints(), cs->cons_ptr.data(), kind.data(), idx.data(),
                           co.data(), nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, out);
   size_t wn = cs->wlc_terms.size();
   std::vector<uint8_t> wkind(wn ? wn : 1); std::vector<uint32_t> widx(wn ? wn : 1); std::vector<scm> wco(wn ? wn : 1);
   for (size_t t = 0; t < wn; t++) { wkind[t] = (uint8_t)cs->wlc_terms[t].var.kind; widx[t] = cs->wlc_terms[t].var.index; wco[t] = cs->wlc_terms[t].coeff; }
-  return circuit_create(cs->num_mult, (uint32_t)cs->V.size(), (uint32_t)cs->num_constraints(), cs->cons_ptr.data(), kind.data(), idx.data(),
+  return circuit_create(cs->num_mult, (uint32_t)cs->V.size(), (uint32_t)cs->pub.size(), (uint32_t)cs->num_constraints(), cs->cons_ptr.data(), kind.data(), idx.data(),
                         co.data(), cs->tape.data(), cs->naux, (uint32_t)cs->wlc_ptr.size() - 1, cs->wlc_ptr.data(), wkind.data(), widx.data(),
                         wco.data(), out);
 }
@@ -187,12 +194,14 @@ int32_t bp_verifier_verify(bp_cs *cs, const uint8_t *proof, size_t proof_len, co
   BpCircuit *c = nullptr;
   int rc = compile_cs(cs, false, &c);
   if (rc) return rc;
-  DevBuf dV, dP, de, dS;
-  if (dV.alloc(m * 32 + 32) || dP.alloc(proof_len) || de.alloc(32) || dS.alloc(sizeof(int))) { circuit_free(c); return BP_ERR_OOM; }
+  DevBuf dV, dP, de, dS, dpub;
+  std::vector<uint8_t> hpub; scalars_to_bytes(hpub, cs->pub);
+  if (dV.alloc(m * 32 + 32) || dP.alloc(proof_len) || de.alloc(32) || dS.alloc(sizeof(int)) || dpub.alloc(hpub.size())) { circuit_free(c); return BP_ERR_OOM; }
   dev_stream s = 0;
+  dev_h2d(dpub.p, hpub.data(), hpub.size(), s);
   for (uint32_t i = 0; i < m; i++) dev_h2d(dV.p + 32 * i, cs->V[i].data(), 32, s);
   dev_h2d(dP.p, proof, proof_len, s); dev_h2d(de.p, entropy, 32, s);
-  VerifyArgs a{}; a.B = 1; a.label = cs->label.data(); a.label_len = (int)cs->label.size(); a.V = dV.p; a.proofs = dP.p; a.entropy = de.p; a.status = (int *)dS.p;
+  VerifyArgs a{}; a.B = 1; a.label = cs->label.data(); a.label_len = (int)cs->label.size(); a.V = dV.p; a.proofs = dP.p; a.entropy = de.p; a.pub = dpub.p; a.status = (int *)dS.p;
   rc = engine_verify(g, c, a, s);
   int st = 0;
   if (!rc) { dev_d2h(&st, dS.p, sizeof st, s); if (dev_sync(s)) rc = BP_ERR_CUDA; }
@@ -241,17 +250,38 @@ int32_t bp_gadget_poseidon_hash_2(bp_cs *cs, const bp_poseidon_params *p, bp_var
   cs->constrain(h - LC::constant(load_scalar(expected)));
   return BP_OK;
 }
+int32_t bp_gadget_poseidon_hash_2_public(bp_cs *cs, const bp_poseidon_params *p, bp_var xl, bp_var xr, const bp_var *statics, uint32_t ns,
+                                         int32_t sbox, bp_var expected) {
+  if (!cs || !p || !statics || !var_ok(cs, expected) || !var_ok(cs, xl) || !var_ok(cs, xr)) return BP_ERR_INVALID_ARGUMENT;
+  std::vector<LC> st; for (uint32_t i = 0; i < ns; i++) { if (!var_ok(cs, statics[i])) return BP_ERR_INVALID_ARGUMENT; st.push_back(LC(statics[i])); }
+  LC h; int rc = poseidon_hash_2_constraints(*cs, *p, LC(xl), LC(xr), st, sbox, h);
+  if (rc) return rc;
+  cs->constrain(h - LC(expected));
+  return BP_OK;
+}
 int32_t bp_gadget_vsmt2_verif(bp_cs *cs, const bp_poseidon_params *p, uint32_t depth, const uint8_t root[32], bp_var leaf,
                               const bp_var *bits, const bp_var *nodes, const bp_var *statics, uint32_t ns) {
   if (!cs || !p || !root || !bits || !nodes || !statics || !var_ok(cs, leaf)) return BP_ERR_INVALID_ARGUMENT;
   for (uint32_t i = 0; i < depth; i++) if (!var_ok(cs, bits[i]) || !var_ok(cs, nodes[i])) return BP_ERR_INVALID_ARGUMENT;
   for (uint32_t i = 0; i < ns; i++) if (!var_ok(cs, statics[i])) return BP_ERR_INVALID_ARGUMENT;
-  return vsmt2_verif_gadget(*cs, *p, depth, load_scalar(root), leaf, bits, nodes, statics, ns);
+  return vsmt2_verif_gadget(*cs, *p, depth, LC::constant(load_scalar(root)), leaf, bits, nodes, statics, ns);
+}
+int32_t bp_gadget_vsmt2_verif_public(bp_cs *cs, const bp_poseidon_params *p, uint32_t depth, bp_var root, bp_var leaf, const bp_var *bits,
+                                     const bp_var *nodes, const bp_var *statics, uint32_t ns) {
+  if (!cs || !p || !bits || !nodes || !statics || !var_ok(cs, leaf) || !var_ok(cs, root)) return BP_ERR_INVALID_ARGUMENT;
+  for (uint32_t i = 0; i < depth; i++) if (!var_ok(cs, bits[i]) || !var_ok(cs, nodes[i])) return BP_ERR_INVALID_ARGUMENT;
+  for (uint32_t i = 0; i < ns; i++) if (!var_ok(cs, statics[i])) return BP_ERR_INVALID_ARGUMENT;
+  return vsmt2_verif_gadget(*cs, *p, depth, LC(root), leaf, bits, nodes, statics, ns);
 }
 int32_t bp_gadget_mimc(bp_cs *cs, bp_var left, bp_var right, uint32_t rounds, const uint8_t *constants, const uint8_t image[32]) {
   if (!cs || !constants || !image || !var_ok(cs, left) || !var_ok(cs, right)) return BP_ERR_INVALID_ARGUMENT;
   std::vector<scm> k(rounds); for (uint32_t i = 0; i < rounds; i++) k[i] = load_scalar(constants + 32 * (size_t)i);
-  return mimc_gadget(*cs, left, right, rounds, k.data(), load_scalar(image));
+  return mimc_gadget(*cs, left, right, rounds, k.data(), LC::constant(load_scalar(image)));
+}
+int32_t bp_gadget_mimc_public(bp_cs *cs, bp_var left, bp_var right, uint32_t rounds, const uint8_t *constants, bp_var image) {
+  if (!cs || !constants || !var_ok(cs, image) || !var_ok(cs, left) || !var_ok(cs, right)) return BP_ERR_INVALID_ARGUMENT;
+  std::vector<scm> k(rounds); for (uint32_t i = 0; i < rounds; i++) k[i] = load_scalar(constants + 32 * (size_t)i);
+  return mimc_gadget(*cs, left, right, rounds, k.data(), LC(image));
 }
 int32_t bp_mimc(const uint8_t xl[32], const uint8_t xr[32], uint32_t rounds, const uint8_t *constants, uint8_t out[32]) {
   if (!xl || !xr || !constants || !out) return BP_ERR_INVALID_ARGUMENT;
@@ -284,7 +314,7 @@ int32_t bp_circuit_from_arrays(uint32_t n, uint32_t m, uint32_t q, const uint32_
   std::vector<scm> co(nnz ? nnz : 1);
   for (uint32_t t = 0; t < nnz; t++) co[t] = load_scalar(coeff + 32 * (size_t)t);
   BpCircuit *c = nullptr;
-  int rc = circuit_create(n, m, q, cons_ptr, kind, idx, co.data(), nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, &c);
+  int rc = circuit_create(n, m, 0, q, cons_ptr, kind, idx, co.data(), nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, &c);
   if (rc) return rc;
   *out = new bp_circuit{c};
   return BP_OK;
@@ -294,6 +324,7 @@ uint32_t bp_circuit_num_multipliers(const bp_circuit *c) { return c ? c->c->n : 
 uint32_t bp_circuit_num_constraints(const bp_circuit *c) { return c ? c->c->q : 0; }
 uint32_t bp_circuit_num_commitments(const bp_circuit *c) { return c ? c->c->m : 0; }
 uint32_t bp_circuit_num_aux(const bp_circuit *c) { return c ? c->c->naux : 0; }
+uint32_t bp_circuit_num_public(const bp_circuit *c) { return c ? c->c->npub : 0; }
 int32_t bp_circuit_has_witness_program(const bp_circuit *c) { return c ? c->c->has_tape : 0; }
 size_t bp_circuit_proof_len(const bp_circuit *c) { return c ? circuit_proof_len(c->c) : 0; }
 
@@ -309,8 +340,8 @@ static uint32_t chunk_size(const BpCircuit *c, uint32_t B) {
 }
 
 int32_t bp_prove_batch_device(const bp_gens *g, bp_circuit *c, uint32_t B, const uint8_t *label, size_t label_len, const uint8_t *d_v,
-                              const uint8_t *d_vb, const uint8_t *d_entropy, const uint8_t *d_aux, const uint8_t *d_aL, const uint8_t *d_aR,
-                              const uint8_t *d_aO, uint8_t *d_V, uint8_t *d_proofs, int32_t *d_status, void *stream) {
+                              const uint8_t *d_vb, const uint8_t *d_entropy, const uint8_t *d_aux, const uint8_t *d_pub, const uint8_t *d_aL,
+                              const uint8_t *d_aR, const uint8_t *d_aO, uint8_t *d_V, uint8_t *d_proofs, int32_t *d_status, void *stream) {
   if (!g || !c || !d_v || !d_vb || !d_entropy || !d_V || !d_proofs || !d_status || (label_len && !label)) return BP_ERR_INVALID_ARGUMENT;
   BpCircuit *cc = c->c;
   if ((d_aL || d_aR || d_aO) && !(d_aL && d_aR && d_aO)) return BP_ERR_INVALID_ARGUMENT;
@@ -328,6 +359,7 @@ int32_t bp_prove_batch_device(const bp_gens *g, bp_circuit *c, uint32_t B, const
     ProveArgs a{}; a.B = (int)bc; a.label = label; a.label_len = (int)label_len;
     a.v = d_v + (size_t)p0 * m * 32; a.vbl = d_vb + (size_t)p0 * m * 32; a.entropy = d_entropy + (size_t)p0 * 32;
     a.aux = d_aux ? d_aux + (size_t)p0 * cc->naux * 32 : nullptr;
+    a.pub = d_pub ? d_pub + (size_t)p0 * cc->npub * 32 : nullptr;
     if (d_aL) { a.aL = d_aL + (size_t)p0 * n * 32; a.aR = d_aR + (size_t)p0 * n * 32; a.aO = d_aO + (size_t)p0 * n * 32; }
     a.V_out = d_V + (size_t)p0 * m * 32; a.proofs = d_proofs + (size_t)p0 * plen; a.status = d_status + p0;
     int rc = engine_prove(g->g, cc, a, s);
@@ -337,16 +369,17 @@ int32_t bp_prove_batch_device(const bp_gens *g, bp_circuit *c, uint32_t B, const
 }
 
 int32_t bp_prove_batch(const bp_gens *g, bp_circuit *c, uint32_t B, const uint8_t *label, size_t label_len, const uint8_t *v, const uint8_t *vb,
-                       const uint8_t *entropy, const uint8_t *aux, const uint8_t *aL, const uint8_t *aR, const uint8_t *aO, uint8_t *V_out,
-                       uint8_t *proofs, int32_t *status) {
+                       const uint8_t *entropy, const uint8_t *aux, const uint8_t *pub, const uint8_t *aL, const uint8_t *aR, const uint8_t *aO,
+                       uint8_t *V_out, uint8_t *proofs, int32_t *status) {
   if (!g || !c || !v || !vb || !entropy || !V_out || !proofs || !status) return BP_ERR_INVALID_ARGUMENT;
   BpCircuit *cc = c->c;
   if ((aL || aR || aO) && !(aL && aR && aO)) return BP_ERR_INVALID_ARGUMENT;
   if (!aL && !cc->has_tape) return BP_ERR_MISSING_ASSIGNMENT;
   if (!aL && cc->naux && !aux) return BP_ERR_MISSING_ASSIGNMENT;
   if (B == 0) return BP_OK;
-  const size_t m = cc->m, n = cc->n, plen = circuit_proof_len(cc), na = cc->naux;
-  DevBuf dv, dvb, de, da, daL, daR, daO, dV, dP, dS;
+  const size_t m = cc->m, n = cc->n, plen = circuit_proof_len(cc), na = cc->naux, np_ = cc->npub;
+  DevBuf dv, dvb, de, da, dpb, daL, daR, daO, dV, dP, dS;
+  if (dpb.alloc(B * np_ * 32 + 32)) return BP_ERR_OOM;
   if (dv.alloc(B * m * 32 + 32) || dvb.alloc(B * m * 32 + 32) || de.alloc((size_t)B * 32) || da.alloc(B * na * 32 + 32) || dV.alloc(B * m * 32 + 32) ||
       dP.alloc(B * plen) || dS.alloc(B * sizeof(int))) return BP_ERR_OOM;
   if (aL && (daL.alloc(B * n * 32 + 32) || daR.alloc(B * n * 32 + 32) || daO.alloc(B * n * 32 + 32))) return BP_ERR_OOM;
@@ -354,9 +387,10 @@ int32_t bp_prove_batch(const bp_gens *g, bp_circuit *c, uint32_t B, const uint8_
   int bad = 0;
   bad |= dev_h2d(dv.p, v, B * m * 32, s); bad |= dev_h2d(dvb.p, vb, B * m * 32, s); bad |= dev_h2d(de.p, entropy, (size_t)B * 32, s);
   if (na && aux) bad |= dev_h2d(da.p, aux, B * na * 32, s);
+  if (np_ && pub) bad |= dev_h2d(dpb.p, pub, B * np_ * 32, s);
   if (aL) { bad |= dev_h2d(daL.p, aL, B * n * 32, s); bad |= dev_h2d(daR.p, aR, B * n * 32, s); bad |= dev_h2d(daO.p, aO, B * n * 32, s); }
   if (bad) return BP_ERR_CUDA;
-  int rc = bp_prove_batch_device(g, c, B, label, label_len, dv.p, dvb.p, de.p, na ? da.p : nullptr, daL.p, daR.p, daO.p, dV.p, dP.p, (int32_t *)dS.p, nullptr);
+  int rc = bp_prove_batch_device(g, c, B, label, label_len, dv.p, dvb.p, de.p, na ? da.p : nullptr, (np_ && pub) ? dpb.p : nullptr, daL.p, daR.p, daO.p, dV.p, dP.p, (int32_t *)dS.p, nullptr);
   if (rc) return rc;
   bad |= dev_d2h(V_out, dV.p, B * m * 32, s); bad |= dev_d2h(proofs, dP.p, B * plen, s); bad |= dev_d2h(status, dS.p, B * sizeof(int), s);
   bad |= dev_sync(s);
@@ -364,7 +398,7 @@ int32_t bp_prove_batch(const bp_gens *g, bp_circuit *c, uint32_t B, const uint8_
 }
 
 int32_t bp_verify_batch_device(const bp_gens *g, bp_circuit *c, uint32_t B, const uint8_t *label, size_t label_len, const uint8_t *d_V,
-                               const uint8_t *d_proofs, const uint8_t *d_entropy, int32_t *d_status, void *stream) {
+                               const uint8_t *d_proofs, const uint8_t *d_entropy, const uint8_t *d_pub, int32_t *d_status, void *stream) {
   if (!g || !c || !d_V || !d_proofs || !d_entropy || !d_status || (label_len && !label)) return BP_ERR_INVALID_ARGUMENT;
   BpCircuit *cc = c->c;
 #ifndef BP_HOST_EMUL
@@ -378,23 +412,27 @@ int32_t bp_verify_batch_device(const bp_gens *g, bp_circuit *c, uint32_t B, cons
     uint32_t bc = std::min(ch, B - p0);
     VerifyArgs a{}; a.B = (int)bc; a.label = label; a.label_len = (int)label_len;
     a.V = d_V + (size_t)p0 * m * 32; a.proofs = d_proofs + (size_t)p0 * plen; a.entropy = d_entropy + (size_t)p0 * 32; a.status = d_status + p0;
+    a.pub = d_pub ? d_pub + (size_t)p0 * cc->npub * 32 : nullptr;
     int rc = engine_verify(g->g, cc, a, s);
     if (rc) return rc;
   }
   return BP_OK;
 }
 int32_t bp_verify_batch(const bp_gens *g, bp_circuit *c, uint32_t B, const uint8_t *label, size_t label_len, const uint8_t *V, const uint8_t *proofs,
-                        const uint8_t *entropy, int32_t *status) {
+                        const uint8_t *entropy, const uint8_t *pub, int32_t *status) {
   if (!g || !c || !V || !proofs || !entropy || !status) return BP_ERR_INVALID_ARGUMENT;
   if (B == 0) return BP_OK;
   BpCircuit *cc = c->c;
   const size_t m = cc->m, plen = circuit_proof_len(cc);
-  DevBuf dV, dP, de, dS;
-  if (dV.alloc(B * m * 32 + 32) || dP.alloc(B * plen) || de.alloc((size_t)B * 32) || dS.alloc(B * sizeof(int))) return BP_ERR_OOM;
+  DevBuf dV, dP, de, dS, dpb;
+  const size_t np_ = cc->npub;
+  if (np_ && !pub) return BP_ERR_MISSING_ASSIGNMENT;
+  if (dV.alloc(B * m * 32 + 32) || dP.alloc(B * plen) || de.alloc((size_t)B * 32) || dS.alloc(B * sizeof(int)) || dpb.alloc(B * np_ * 32 + 32)) return BP_ERR_OOM;
   dev_stream s = 0;
+  if (np_ && dev_h2d(dpb.p, pub, B * np_ * 32, s)) return BP_ERR_CUDA;
   int bad = dev_h2d(dV.p, V, B * m * 32, s) | dev_h2d(dP.p, proofs, B * plen, s) | dev_h2d(de.p, entropy, (size_t)B * 32, s);
   if (bad) return BP_ERR_CUDA;
-  int rc = bp_verify_batch_device(g, c, B, label, label_len, dV.p, dP.p, de.p, (int32_t *)dS.p, nullptr);
+  int rc = bp_verify_batch_device(g, c, B, label, label_len, dV.p, dP.p, de.p, np_ ? dpb.p : nullptr, (int32_t *)dS.p, nullptr);
   if (rc) return rc;
   bad = dev_d2h(status, dS.p, B * sizeof(int), s) | dev_sync(s);
   return bad ? BP_ERR_CUDA : BP_OK;

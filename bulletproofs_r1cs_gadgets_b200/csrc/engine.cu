@@ -28,7 +28,7 @@ static int dalloc(T **p, size_t count) { return dev_malloc((void **)p, count * s
 
 struct Workspace {
   int B = 0;
-  scm *v = 0, *vbl = 0, *aux = 0, *wit = 0, *rand1 = 0, *w_all = 0, *zpow = 0, *ypow = 0, *yinvpow = 0, *a = 0, *b = 0, *chal = 0, *t = 0, *tb = 0,
+  scm *v = 0, *vbl = 0, *aux = 0, *pub = 0, *uj = 0, *wit = 0, *rand1 = 0, *w_all = 0, *zpow = 0, *ypow = 0, *yinvpow = 0, *a = 0, *b = 0, *chal = 0, *t = 0, *tb = 0,
       *clr = 0, *part = 0;
   strobe128 *ts = 0, *rng = 0;
   int8_t *dig = 0; size_t dig_bytes = 0;
@@ -36,7 +36,7 @@ struct Workspace {
   ge_p3 *wsum = 0, *Q = 0, *Gt = 0, *Ht = 0, *pts = 0;
   int8_t *naf = 0; int *naf_top = 0;
   void release() {
-    void *ps[] = {v, vbl, aux, wit, rand1, w_all, zpow, ypow, yinvpow, a, b, chal, t, tb, clr, part, ts, rng, dig, buckets, wsum, Q, Gt, Ht, pts, naf, naf_top};
+    void *ps[] = {pub, uj, v, vbl, aux, wit, rand1, w_all, zpow, ypow, yinvpow, a, b, chal, t, tb, clr, part, ts, rng, dig, buckets, wsum, Q, Gt, Ht, pts, naf, naf_top};
     for (void *p : ps) dev_free(p);
     *this = Workspace();
   }
@@ -99,7 +99,7 @@ static uint32_t ilog2(uint32_t N) { uint32_t k = 0; while ((1u << k) < N) k++; r
 
 size_t circuit_proof_len(const BpCircuit *c) { return 32 * (size_t)(14 + 2 * c->k + 2); }
 
-int circuit_create(uint32_t n, uint32_t m, uint32_t q, const uint32_t *cons_ptr, const uint8_t *kind, const uint32_t *idx,
+int circuit_create(uint32_t n, uint32_t m, uint32_t npub, uint32_t q, const uint32_t *cons_ptr, const uint8_t *kind, const uint32_t *idx,
                    const scm *coeff, const TapeOp *tape, uint32_t naux, uint32_t nwlc, const uint32_t *wlc_ptr,
                    const uint8_t *wkind, const uint32_t *widx, const scm *wcoeff, BpCircuit **out) {
   int rc = bp_device_init();
@@ -107,7 +107,7 @@ int circuit_create(uint32_t n, uint32_t m, uint32_t q, const uint32_t *cons_ptr,
   BpCircuit *c = new BpCircuit();
   memset(c, 0, sizeof *c);
   c->n = n; c->m = m; c->q = q; c->N = next_pow2(n ? n : 1); c->k = ilog2(c->N);
-  c->nnz = cons_ptr[q]; c->nslots = 3 * n + m + 1; c->naux = naux;
+  c->nnz = cons_ptr[q]; c->nslots = 3 * n + m + 1 + npub; c->naux = naux; c->npub = npub;
   // validate + transpose to slot-major
   std::vector<uint32_t> slot_cnt(c->nslots + 1, 0);
   auto slot_of = [&](uint32_t t) -> long {
@@ -118,6 +118,7 @@ int circuit_create(uint32_t n, uint32_t m, uint32_t q, const uint32_t *cons_ptr,
       case 3: return i < n ? (long)2 * n + i : -1;
       case 0: return i < m ? (long)3 * n + i : -1;
       case 4: return (long)3 * n + m;
+      case 5: return i < npub ? (long)3 * n + m + 1 + i : -1;
       default: return -1;
     }
   };
@@ -130,7 +131,7 @@ int circuit_create(uint32_t n, uint32_t m, uint32_t q, const uint32_t *cons_ptr,
       long s = slot_of(t); uint32_t at = fill[s]++;
       tq[at] = k;
       scm co = coeff[t];
-      if (kind[t] == 0 || kind[t] == 4) co = sc_neg(co);  // wV and wc accumulate with a minus sign (A.3 step 7)
+      if (kind[t] == 0 || kind[t] == 4 || kind[t] == 5) co = sc_neg(co);  // wV and wc accumulate with a minus sign (A.3 step 7)
       tc[at] = co;
     }
   dev_stream s = 0;
@@ -142,8 +143,8 @@ int circuit_create(uint32_t n, uint32_t m, uint32_t q, const uint32_t *cons_ptr,
     c->has_tape = 1;
     uint32_t wn = wlc_ptr[nwlc];
     for (uint32_t t = 0; t < wn; t++) {
-      uint32_t lim = wkind[t] == 0 ? m : (wkind[t] == 4 ? 1 : n);
-      if (wkind[t] > 4 || widx[t] >= lim) { circuit_free(c); return BP_ERR_INVALID_ARGUMENT; }
+      uint32_t lim = wkind[t] == 0 ? m : (wkind[t] == 4 ? 1 : (wkind[t] == 5 ? npub : n));
+      if (wkind[t] > 5 || widx[t] >= lim) { circuit_free(c); return BP_ERR_INVALID_ARGUMENT; }
     }
     for (uint32_t i = 0; i < n; i++) {
       const TapeOp &op = tape[i];
@@ -189,7 +190,7 @@ static int ensure_workspace(BpCircuit *c, int B) {
   size_t max_warps = (size_t)std::max<long>(msm_target_warps(), 2L * B) + B;
   w->bucket_slots = max_warps * MSM_WINDOWS * MSM_BUCKETS;
   int bad = 0;
-  bad |= dalloc(&w->v, (m + 1) * Bz); bad |= dalloc(&w->vbl, (m + 1) * Bz); bad |= dalloc(&w->aux, (size_t)(c->naux + 1) * Bz);
+  bad |= dalloc(&w->v, (m + 1) * Bz); bad |= dalloc(&w->vbl, (m + 1) * Bz); bad |= dalloc(&w->aux, (size_t)(c->naux + 1) * Bz); bad |= dalloc(&w->pub, (size_t)(c->npub + 1) * Bz); bad |= dalloc(&w->uj, (2 * k + 2) * Bz);
   bad |= dalloc(&w->wit, 3 * (n + 1) * Bz); bad |= dalloc(&w->rand1, (3 + 2 * n) * Bz); bad |= dalloc(&w->w_all, (size_t)c->nslots * Bz);
   bad |= dalloc(&w->zpow, (q + 1) * Bz); bad |= dalloc(&w->ypow, N * Bz); bad |= dalloc(&w->yinvpow, N * Bz);
   bad |= dalloc(&w->a, N * Bz); bad |= dalloc(&w->b, N * Bz); bad |= dalloc(&w->chal, 16 * Bz);
@@ -270,7 +271,8 @@ int engine_prove(const BpGens *g, BpCircuit *c, const ProveArgs &A, dev_stream s
     CK(launch(n * B, s, KLoadScalars{A.aO, aO, (int)n, B}));
   } else {
     if (c->naux) CK(launch((long)c->naux * B, s, KLoadScalars{A.aux, w->aux, (int)c->naux, B}));
-    CK(launch(B, s, KWitnessTape{c->d_tape, WitnessLcs{c->d_wptr, c->d_wkind, c->d_widx, c->d_wcoeff}, (int)n, B, w->v, w->aux, aL, aR, aO}));
+    if (c->npub && A.pub) CK(launch((long)c->npub * B, s, KLoadScalars{A.pub, w->pub, (int)c->npub, B}));
+    CK(launch(B, s, KWitnessTape{c->d_tape, WitnessLcs{c->d_wptr, c->d_wkind, c->d_widx, c->d_wcoeff}, (int)n, B, w->v, w->aux, w->pub, aL, aR, aO}));
   }
   // 4. A_I1, A_O1, S1 (A.3 step 4)
   {
@@ -404,5 +406,38 @@ int engine_msm_gens(BpGens *g, uint32_t n, const uint8_t *d_scalars, uint8_t *d_
   return run_msm(w, seg, 1, 1, w->dig, (long)n * 32, d_out, 32, 0, nullptr, s);
 }
 
-// ------------------------------------------------------------------------------------------------ verifier (placeholder until kernels land)
-int engine_verify(const BpGens *, BpCircuit *, const VerifyArgs &, dev_stream) { return BP_ERR_INVALID_ARGUMENT; }
+// ------------------------------------------------------------------------------------------------ verifier (A.5)
+int engine_verify(const BpGens *g, BpCircuit *c, const VerifyArgs &A, dev_stream s) {
+  const int B = A.B;
+  if (B <= 0) return BP_OK;
+  if (g->capacity < c->N) return BP_ERR_INVALID_GENERATORS_LENGTH;
+  if (c->npub && !A.pub) return BP_ERR_MISSING_ASSIGNMENT;
+  int rc = ensure_workspace(c, B);
+  if (rc) return rc;
+  Workspace *w = c->ws;
+  const long n = c->n, N = c->N, m = c->m, q = c->q, k = c->k;
+  const long plen = (long)circuit_proof_len(c);
+  scm *wL = w->w_all, *wR = w->w_all + n * B, *wO = w->w_all + 2 * n * B, *wV = w->w_all + 3 * n * B, *wc = w->w_all + (3 * n + m) * B,
+      *wP = w->w_all + (3 * n + m + 1) * B;
+  scm *ch_z = w->chal + B, *ch_yinv = w->chal + 2L * B;
+  scm *uj = w->uj, *ujinv = w->uj + (k + 1) * B;
+  CK(dev_memset(A.status, 0, sizeof(int) * B, s));
+  strobe128 base; base_transcript(base, A.label, A.label_len);
+  CK(launch(B, s, KTsVerify{base, A.V, (int)m, B, (int)k, (unsigned)N, A.proofs, plen, A.entropy, w->chal, uj, ujinv, A.status}));
+  CK(launch(((q + CH_POW - 1) / CH_POW) * B, s, KPowers{ch_z, w->zpow, (int)q, B, 1, CH_POW}));
+  CK(launch(((N + CH_POW - 1) / CH_POW) * B, s, KPowers{ch_yinv, w->yinvpow, (int)N, B, 0, CH_POW}));
+  CK(launch((long)c->nslots * B, s, KFlatten{c->d_slot_ptr, c->d_tq, c->d_tcoeff, w->zpow, w->w_all, B}));
+  if (c->npub) CK(launch((long)c->npub * B, s, KLoadScalars{A.pub, w->pub, (int)c->npub, B}));
+  CK(launch(N * B, s, KVerifyS{uj, ujinv, (int)k, B, w->a}));
+  {
+    long nch = (n + CH_DOT - 1) / CH_DOT; if (nch == 0) nch = 1;
+    CK(launch(nch * B, s, KVerifyDelta{wL, wR, w->yinvpow, (int)n, B, CH_DOT, w->part}));
+    CK(launch(B, s, KSumPartials{w->part, (int)nch, 1, B, w->clr}));
+  }
+  const long npts = 11 + m + 2 * k, rows = 2 + 2 * N + npts;
+  CK(launch(N * B, s, KVerifyGH{wL, wR, wO, w->yinvpow, w->a, w->chal, A.proofs, plen, (int)n, (int)N, (int)k, B, w->dig, rows * 32}));
+  CK(launch(B, s, KVerifyScalars{w->chal, uj, ujinv, wV, wc, wP, w->pub, w->clr, A.proofs, plen, (int)m, (int)c->npub, (int)N, (int)k, B, w->dig, rows * 32}));
+  CK(launch(npts * B, s, KVerifyDecompress{A.V, A.proofs, plen, (int)m, (int)k, B, w->pts, npts, A.status}));
+  MsmSeg segs[4] = {{g->pc_niels, 0, 0, 2}, {g->G_n, 0, 0, (int)N}, {g->H_n, 0, 0, (int)N}, {w->pts, npts, 1, (int)npts}};
+  return run_msm(w, segs, 4, B, w->dig, rows * 32, nullptr, 0, 1, A.status, s);
+}

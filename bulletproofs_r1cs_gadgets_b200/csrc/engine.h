@@ -23,7 +23,7 @@ struct HostTerm { uint8_t kind; uint32_t idx; uint8_t coeff[32]; };  // kind: 0 
 
 struct Workspace;
 struct BpCircuit {
-  uint32_t n, N, k, m, q, nnz, nslots, naux;
+  uint32_t n, N, k, m, q, nnz, nslots, naux, npub;
   uint32_t *d_slot_ptr, *d_tq; scm *d_tcoeff;
   int has_tape;
   TapeOp *d_tape; uint32_t *d_wptr; uint8_t *d_wkind; uint32_t *d_widx; scm *d_wcoeff;
@@ -36,7 +36,7 @@ void gens_free(BpGens *g);
 int gens_export(const BpGens *g, int which, uint32_t count, uint8_t *out);  // which: 0 G, 1 H -> compressed
 
 // cons_ptr[q+1], terms in constraint order, coefficients in Montgomery form (host).  tape (optional, n entries) + witness LCs.
-int circuit_create(uint32_t n, uint32_t m, uint32_t q, const uint32_t *cons_ptr, const uint8_t *kind, const uint32_t *idx,
+int circuit_create(uint32_t n, uint32_t m, uint32_t npub, uint32_t q, const uint32_t *cons_ptr, const uint8_t *kind, const uint32_t *idx,
                    const scm *coeff, const TapeOp *tape, uint32_t naux, uint32_t nwlc, const uint32_t *wlc_ptr,
                    const uint8_t *wkind, const uint32_t *widx, const scm *wcoeff, BpCircuit **out);
 void circuit_free(BpCircuit *c);
@@ -49,6 +49,7 @@ struct ProveArgs {
   const uint8_t *v, *vbl, *entropy;
   const uint8_t *aL, *aR, *aO;   // explicit witness, or all NULL to run the circuit's witness tape
   const uint8_t *aux;            // [B][naux][32] tape inputs
+  const uint8_t *pub;            // [B][npub][32] public inputs (only read by the witness tape on the prover side)
   uint8_t *V_out;                // [B][m][32]
   uint8_t *proofs;               // [B][proof_len]
   int *status;                   // [B]
@@ -61,6 +62,7 @@ struct VerifyArgs {
   const uint8_t *V;        // [B][m][32] device
   const uint8_t *proofs;   // [B][proof_len] device
   const uint8_t *entropy;  // [B][32] device
+  const uint8_t *pub;      // [B][npub][32] device public inputs
   int *status;             // [B] device
 };
 int engine_verify(const BpGens *g, BpCircuit *c, const VerifyArgs &a, dev_stream s);

@@ -26,6 +26,7 @@ bool bp_cs::eval(const LC &lc, scm &out) const {
       case BP_VAR_MULT_LEFT: val = aL[t.var.index]; break;
       case BP_VAR_MULT_RIGHT: val = aR[t.var.index]; break;
       case BP_VAR_MULT_OUT: val = aO[t.var.index]; break;
+      case BP_VAR_PUBLIC: val = pub[t.var.index]; break;
       default: val = sc_one(); break;
     }
     acc = sc_add(acc, sc_mul(t.coeff, val));
@@ -176,7 +177,7 @@ int poseidon_hash_2_constraints(bp_cs &cs, const bp_poseidon_params &p, const LC
 }
 
 // ------------------------------------------------------------------------------------------------ VSMT-2
-int vsmt2_verif_gadget(bp_cs &cs, const bp_poseidon_params &p, uint32_t depth, const scm &root, bp_var leaf, const bp_var *bits,
+int vsmt2_verif_gadget(bp_cs &cs, const bp_poseidon_params &p, uint32_t depth, const LC &root, bp_var leaf, const bp_var *bits,
                        const bp_var *nodes, const bp_var *statics, uint32_t num_statics) {  // gadget_vsmt_2.rs:171-209
   std::vector<LC> st;
   for (uint32_t i = 0; i < num_statics; i++) st.push_back(LC(statics[i]));
@@ -194,7 +195,7 @@ int vsmt2_verif_gadget(bp_cs &cs, const bp_poseidon_params &p, uint32_t depth, c
     int rc = poseidon_hash_2_constraints(cs, p, left, right, st, BP_SBOX_INVERSE, prev);
     if (rc) return rc;
   }
-  constrain_lc_with_scalar(cs, prev, root);
+  cs.constrain(prev - root);  // constrain_lc_with_scalar(cs, prev_hash, root), gadget_vsmt_2.rs:206
   return BP_OK;
 }
 
@@ -208,7 +209,7 @@ scm mimc_native(const scm &xl_, const scm &xr_, uint32_t rounds, const scm *cons
   }
   return xl;
 }
-int mimc_gadget(bp_cs &cs, bp_var left, bp_var right, uint32_t rounds, const scm *constants, const scm &image) {  // gadget_mimc.rs:41-79
+int mimc_gadget(bp_cs &cs, bp_var left, bp_var right, uint32_t rounds, const scm *constants, const LC &image) {  // gadget_mimc.rs:41-79
   LC lv(left), rv(right);
   for (uint32_t j = 0; j < rounds; j++) {
     LC lpc = lv + LC::constant(constants[j]);
@@ -218,7 +219,7 @@ int mimc_gadget(bp_cs &cs, bp_var left, bp_var right, uint32_t rounds, const scm
     LC tmp = LC(b[2]) + rv;
     rv = lv; lv = tmp;
   }
-  constrain_lc_with_scalar(cs, lv, image);
+  cs.constrain(lv - image);  // constrain_lc_with_scalar(cs, res_v, image), gadget_mimc.rs:50
   return BP_OK;
 }
 

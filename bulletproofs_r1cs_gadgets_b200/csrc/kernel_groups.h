@@ -7,10 +7,10 @@
 
 #define KGROUP_MSM(X) X(KMsmAccumulate) X(KMsmFinish)
 #define KGROUP_FOLD(X) X(KFoldGens)
-#define KGROUP_POINTS(X) X(KCommit) X(KGensFromUniform) X(KPcBases) X(KPcTable) X(KEncodePoints)
-#define KGROUP_TRANSCRIPT(X) X(KTsStart) X(KRngDraw) X(KTsPhase2) X(KTsPhase3) X(KTsPhase4) X(KTsIpaRound) X(KSelfTest)
+#define KGROUP_POINTS(X) X(KCommit) X(KGensFromUniform) X(KPcBases) X(KPcTable) X(KEncodePoints) X(KVerifyDecompress)
+#define KGROUP_TRANSCRIPT(X) X(KTsStart) X(KRngDraw) X(KTsPhase2) X(KTsPhase3) X(KTsPhase4) X(KTsIpaRound) X(KSelfTest) X(KTsVerify)
 #define KGROUP_SCALAR(X) X(KLoadScalars) X(KRecode) X(KPowers) X(KFillScalar) X(KFlatten) X(KPolyT) X(KSumPartials) X(KPolyEval) \
-  X(KProverScalars) X(KIpaDots) X(KRecodeIpa) X(KFoldAB) X(KStoreAB) X(KWitnessTape)
+  X(KProverScalars) X(KIpaDots) X(KRecodeIpa) X(KFoldAB) X(KStoreAB) X(KWitnessTape) X(KVerifyS) X(KVerifyDelta) X(KVerifyGH) X(KVerifyScalars)
 
 #define KDECL_EXTERN(K) extern template int launch<K>(long, dev_stream, const K &);
 #define KDEFINE(K) template int launch<K>(long, dev_stream, const K &);

@@ -16,6 +16,8 @@
 #include "ge25519.h"
 #include "sc25519.h"
 #include "keccak.h"
+#define BP_ERR_FORMAT_ 2
+#define BP_ERR_VERIFICATION_ 3
 
 // ------------------------------------------------------------------------------------------------
 // scalars in / out
@@ -175,7 +177,7 @@ struct KMsmFinish {
       ge_add(acc, acc, s);
     }
     if (mode == 0) ristretto_encode(out + inst * out_stride, acc);
-    else if (!ge_is_identity_ristretto(acc)) status[inst] = fail_code;
+    else if (!ge_is_identity_ristretto(acc) && status[inst] == 0) status[inst] = fail_code;
   }
 };
 
@@ -599,7 +601,7 @@ struct TapeOp { uint8_t opL, opR, pad[2]; uint32_t argL, argR; };
 struct WitnessLcs { const uint32_t *ptr; const uint8_t *kind; const uint32_t *idx; const scm *coeff; };
 struct KWitnessTape {
   static constexpr int kBlock = 32, kMinBlocks = 1;
-  const TapeOp *tape; WitnessLcs lcs; int n, B; const scm *v; const scm *aux; scm *aL, *aR, *aO;
+  const TapeOp *tape; WitnessLcs lcs; int n, B; const scm *v; const scm *aux; const scm *pub; scm *aL, *aR, *aO;
   HD scm eval(uint32_t lc, int p) const {
     scm acc = sc_zero();
     for (uint32_t t = lcs.ptr[lc]; t < lcs.ptr[lc + 1]; t++) {
@@ -609,6 +611,7 @@ struct KWitnessTape {
         case 1: acc = sc_add(acc, sc_mul(c, aL[at])); break;
         case 2: acc = sc_add(acc, sc_mul(c, aR[at])); break;
         case 3: acc = sc_add(acc, sc_mul(c, aO[at])); break;
+        case 5: acc = sc_add(acc, sc_mul(c, pub[at])); break;
         default: acc = sc_add(acc, c); break;
       }
     }
@@ -681,5 +684,150 @@ struct KSelfTest {
       }
       default: break;
     }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// verifier: transcript replay, verification scalars, one multiscalar check per proof
+// ------------------------------------------------------------------------------------------------
+// Whole transcript of one verification in one thread: every proof element is known up front.
+// chal layout [..][B]: 0 y, 1 z, 2 y^-1, 3 u, 4 x, 5 w, 6 r ; ipa challenges u_j at uj[j*B+p], inverses at ujinv.
+struct KTsVerify {
+  static constexpr int kBlock = 64, kMinBlocks = 1;
+  strobe128 base; const uint8_t *V; int m, B, k; unsigned N; const uint8_t *proofs; long proof_stride; const uint8_t *entropy;
+  scm *chal; scm *uj, *ujinv; int *status;
+  HD static int is_zero32(const uint8_t *b) { uint8_t nz = 0; for (int i = 0; i < 32; i++) nz |= b[i]; return nz == 0; }
+  HD void operator()(long p) const {
+    strobe128 t; strobe_load(t, &base);
+    int st = 0;
+    for (int j = 0; j < m; j++) ts_append(t, "V", V + ((long)p * m + j) * 32, 32);
+    ts_append_u64(t, "m", (uint64_t)m);
+    const uint8_t *pf = proofs + p * proof_stride;
+    if (is_zero32(pf) || is_zero32(pf + 32) || is_zero32(pf + 64)) st = BP_ERR_VERIFICATION_;
+    ts_append(t, "A_I1", pf, 32); ts_append(t, "A_O1", pf + 32, 32); ts_append(t, "S1", pf + 64, 32);
+    const uint8_t ph[11] = {'r', '1', 'c', 's', '-', '1', 'p', 'h', 'a', 's', 'e'};
+    ts_append(t, "dom-sep", ph, 11);
+    ts_append(t, "A_I2", pf + 96, 32); ts_append(t, "A_O2", pf + 128, 32); ts_append(t, "S2", pf + 160, 32);
+    scm y, z, u, x, w, r;
+    TS_CHALLENGE(t, "y", y); TS_CHALLENGE(t, "z", z);
+    for (int j = 0; j < 5; j++) if (is_zero32(pf + 192 + 32 * j)) st = BP_ERR_VERIFICATION_;
+    ts_append(t, "T_1", pf + 192, 32); ts_append(t, "T_3", pf + 224, 32); ts_append(t, "T_4", pf + 256, 32);
+    ts_append(t, "T_5", pf + 288, 32); ts_append(t, "T_6", pf + 320, 32);
+    TS_CHALLENGE(t, "u", u); TS_CHALLENGE(t, "x", x);
+    ts_append(t, "t_x", pf + 352, 32); ts_append(t, "t_x_blinding", pf + 384, 32); ts_append(t, "e_blinding", pf + 416, 32);
+    TS_CHALLENGE(t, "w", w);
+    const uint8_t ipp[6] = {'i', 'p', 'p', ' ', 'v', '1'};
+    ts_append(t, "dom-sep", ipp, 6);
+    ts_append_u64(t, "n", (uint64_t)N);
+    for (int j = 0; j < k; j++) {
+      const uint8_t *lr = pf + 448 + 64 * j;
+      if (is_zero32(lr) || is_zero32(lr + 32)) st = BP_ERR_VERIFICATION_;
+      ts_append(t, "L", lr, 32); ts_append(t, "R", lr + 32, 32);
+      scm c; TS_CHALLENGE(t, "u", c);
+      uj[(long)j * B + p] = c; ujinv[(long)j * B + p] = sc_invert(c);
+    }
+    // scalars of the proof must be canonical (R1CSProof::from_bytes -> FormatError)
+    scm tmp;
+    if (!sc_from_canonical_bytes(tmp, pf + 352) || !sc_from_canonical_bytes(tmp, pf + 384) || !sc_from_canonical_bytes(tmp, pf + 416) ||
+        !sc_from_canonical_bytes(tmp, pf + 448 + 64 * k) || !sc_from_canonical_bytes(tmp, pf + 480 + 64 * k)) st = BP_ERR_FORMAT_;
+    trng_finalize(t, entropy + p * 32);
+    { uint8_t b[64]; trng_fill(t, b, 64); r = sc_from_bytes_wide(b); }
+    chal[p] = y; chal[B + p] = z; chal[2L * B + p] = sc_invert(y); chal[3L * B + p] = u; chal[4L * B + p] = x; chal[5L * B + p] = w; chal[6L * B + p] = r;
+    if (st) status[p] = st;
+  }
+};
+// s_i = prod_j u_j^(+1 if bit (k-1-j) of i else -1)
+struct KVerifyS {
+  static constexpr int kBlock = 128, kMinBlocks = 1;
+  const scm *uj, *ujinv; int k, B; scm *s;
+  HD void operator()(long tid) const {
+    int p = (int)(tid % B); long i = tid / B;
+    scm acc = sc_one();
+    for (int j = 0; j < k; j++) acc = sc_mul(acc, ((i >> (k - 1 - j)) & 1) ? uj[(long)j * B + p] : ujinv[(long)j * B + p]);
+    s[i * B + p] = acc;
+  }
+};
+// delta partial sums: sum_{i<n} y^-i * wR_i * wL_i
+struct KVerifyDelta {
+  static constexpr int kBlock = 128, kMinBlocks = 1;
+  const scm *wL, *wR, *yinvpow; int n, B, CH; scm *part;
+  HD void operator()(long tid) const {
+    int p = (int)(tid % B); int c = (int)(tid / B);
+    int i0 = c * CH, i1 = i0 + CH < n ? i0 + CH : n;
+    scm acc = sc_zero();
+    for (int i = i0; i < i1; i++) { long at = (long)i * B + p; acc = sc_add(acc, sc_mul(sc_mul(yinvpow[at], wR[at]), wL[at])); }
+    part[(long)c * B + p] = acc;
+  }
+};
+// digit rows of the G and H scalars: rows [2, 2+N) and [2+N, 2+2N)
+struct KVerifyGH {
+  static constexpr int kBlock = 128, kMinBlocks = 1;
+  const scm *wL, *wR, *wO, *yinvpow, *s, *chal; const uint8_t *proofs; long proof_stride; int n, N, k, B; int8_t *dig; long inst_stride;
+  HD void operator()(long tid) const {
+    int p = (int)(tid % B); long i = tid / B; long at = i * B + p;
+    scm x = chal[4L * B + p], u = chal[3L * B + p];
+    const uint8_t *pf = proofs + p * proof_stride + 448 + 64 * k;
+    scm a = sc_from_bytes_mod_order(pf), b = sc_from_bytes_mod_order(pf + 32);
+    scm yi = yinvpow[at];
+    scm g = sc_neg(sc_mul(a, s[at]));
+    scm hh = sc_neg(sc_mul(b, s[(long)(N - 1 - i) * B + p]));
+    if (i < n) {
+      g = sc_add(g, sc_mul(x, sc_mul(yi, wR[at])));
+      hh = sc_add(hh, sc_add(sc_mul(x, wL[at]), wO[at]));
+    }
+    hh = sc_sub(sc_mul(yi, hh), sc_one());
+    if (i >= n) { g = sc_mul(g, u); hh = sc_mul(hh, u); }
+    int8_t d[32];
+    int8_t *row = dig + (long)p * inst_stride;
+    sc_recode_bytes(d, g); store_digits(row + (2 + i) * 32, d);
+    sc_recode_bytes(d, hh); store_digits(row + (2 + N + i) * 32, d);
+  }
+};
+// remaining scalars: rows 0,1 (B, B_blinding) and the per-proof points after the generators:
+// A_I1 A_O1 S1 A_I2 A_O2 S2 | V_0..V_{m-1} | T_1 T_3 T_4 T_5 T_6 | L_0.. | R_0..
+struct KVerifyScalars {
+  static constexpr int kBlock = 64, kMinBlocks = 1;
+  const scm *chal, *uj, *ujinv, *wV, *wc, *wP, *pub, *delta; const uint8_t *proofs; long proof_stride; int m, npub, N, k, B; int8_t *dig; long inst_stride;
+  HD void put(int8_t *row, long r, const scm &v) const { int8_t d[32]; sc_recode_bytes(d, v); store_digits(row + r * 32, d); }
+  HD void operator()(long p) const {
+    const uint8_t *pf = proofs + p * proof_stride;
+    scm u = chal[3L * B + p], x = chal[4L * B + p], w = chal[5L * B + p], r = chal[6L * B + p];
+    scm t_x = sc_from_bytes_mod_order(pf + 352), t_xb = sc_from_bytes_mod_order(pf + 384), e_b = sc_from_bytes_mod_order(pf + 416);
+    scm a = sc_from_bytes_mod_order(pf + 448 + 64 * k), b = sc_from_bytes_mod_order(pf + 480 + 64 * k);
+    scm xx = sc_sqr(x), xxx = sc_mul(xx, x), rxx = sc_mul(r, xx);
+    int8_t *row = dig + (long)p * inst_stride;
+    scm wcv = wc[p];
+    for (int i = 0; i < npub; i++) wcv = sc_add(wcv, sc_mul(wP[(long)i * B + p], pub[(long)i * B + p]));
+    scm bsc = sc_add(sc_mul(w, sc_sub(t_x, sc_mul(a, b))), sc_mul(r, sc_sub(sc_mul(xx, sc_add(wcv, delta[p])), t_x)));
+    put(row, 0, bsc);
+    put(row, 1, sc_neg(sc_add(e_b, sc_mul(r, t_xb))));
+    long o = 2 + 2L * N;
+    put(row, o + 0, x); put(row, o + 1, xx); put(row, o + 2, xxx);
+    put(row, o + 3, sc_mul(u, x)); put(row, o + 4, sc_mul(u, xx)); put(row, o + 5, sc_mul(u, xxx));
+    o += 6;
+    for (int j = 0; j < m; j++) put(row, o + j, sc_mul(wV[(long)j * B + p], rxx));
+    o += m;
+    scm rx = sc_mul(r, x);
+    put(row, o, rx); put(row, o + 1, sc_mul(rxx, x)); put(row, o + 2, sc_mul(rxx, xx)); put(row, o + 3, sc_mul(rxx, xxx)); put(row, o + 4, sc_mul(sc_mul(rxx, xx), xx));
+    o += 5;
+    for (int j = 0; j < k; j++) { put(row, o + j, sc_sqr(uj[(long)j * B + p])); put(row, o + k + j, sc_sqr(ujinv[(long)j * B + p])); }
+  }
+};
+// decompress the per-proof points in the order KVerifyScalars lays their scalars out
+struct KVerifyDecompress {
+  static constexpr int kBlock = 64, kMinBlocks = 1;
+  const uint8_t *V; const uint8_t *proofs; long proof_stride; int m, k, B; ge_p3 *pts; long pts_stride; int *status;
+  HD void operator()(long tid) const {
+    int np = 11 + m + 2 * k;
+    long p = tid / np; int j = (int)(tid % np);
+    const uint8_t *pf = proofs + p * proof_stride, *src;
+    if (j < 6) src = pf + 32 * j;
+    else if (j < 6 + m) src = V + (p * m + (j - 6)) * 32;
+    else if (j < 11 + m) src = pf + 192 + 32 * (j - 6 - m);
+    else if (j < 11 + m + k) src = pf + 448 + 64 * (j - 11 - m);
+    else src = pf + 448 + 64 * (j - 11 - m - k) + 32;
+    ge_p3 pt;
+    if (!ristretto_decode(pt, src)) { status[p] = BP_ERR_VERIFICATION_; ge_identity(pt); }
+    store_struct(&pts[p * pts_stride + j], pt);
   }
 };

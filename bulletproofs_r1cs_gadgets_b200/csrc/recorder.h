@@ -51,6 +51,8 @@ struct bp_cs {
   std::vector<Term> wlc_terms;
   std::vector<scm> aux;                          // prover only: values of the auxiliary inputs
   uint32_t naux = 0;
+  std::vector<scm> pub;                          // public inputs (values for this cs; zero when recording only)
+
 
   uint32_t add_wlc(const LC &lc) {
     wlc_terms.insert(wlc_terms.end(), lc.terms.begin(), lc.terms.end());
@@ -77,9 +79,9 @@ void poseidon_permutation(const bp_poseidon_params &p, std::vector<scm> &state, 
 scm poseidon_hash_2(const bp_poseidon_params &p, const scm &xl, const scm &xr, int sbox);
 int poseidon_permutation_constraints(bp_cs &cs, const bp_poseidon_params &p, std::vector<LC> &state, int sbox);
 int poseidon_hash_2_constraints(bp_cs &cs, const bp_poseidon_params &p, const LC &xl, const LC &xr, const std::vector<LC> &statics, int sbox, LC &out);
-int vsmt2_verif_gadget(bp_cs &cs, const bp_poseidon_params &p, uint32_t depth, const scm &root, bp_var leaf, const bp_var *bits,
+int vsmt2_verif_gadget(bp_cs &cs, const bp_poseidon_params &p, uint32_t depth, const LC &root, bp_var leaf, const bp_var *bits,
                        const bp_var *nodes, const bp_var *statics, uint32_t num_statics);
-int mimc_gadget(bp_cs &cs, bp_var left, bp_var right, uint32_t rounds, const scm *constants, const scm &image);
+int mimc_gadget(bp_cs &cs, bp_var left, bp_var right, uint32_t rounds, const scm *constants, const LC &image);
 scm mimc_native(const scm &xl, const scm &xr, uint32_t rounds, const scm *constants);
 int positive_no_gadget(bp_cs &cs, bp_var v, bool has_assignment, uint64_t value, uint32_t bit_size);
 int bound_check_gadget(bp_cs &cs, bp_var v, bp_var a, bp_var b, bool has_assignment, uint64_t vv, uint64_t av, uint64_t bv, uint64_t max,

@@ -46,6 +46,9 @@ extern "C" {
 #define BP_VAR_MULT_RIGHT 2
 #define BP_VAR_MULT_OUT 3
 #define BP_VAR_ONE 4
+/* a per-proof public input of a compiled circuit (extension for batching: the reference bakes public values such as the
+ * Merkle root into the constraint system as constants, src/gadget_vsmt_2.rs:206; a batch shares one circuit) */
+#define BP_VAR_PUBLIC 5
 typedef struct bp_var { uint32_t kind; uint32_t index; } bp_var;
 /* one (Variable, Scalar) term of a LinearCombination (reference src/r1cs_utils.rs:45, get_terms src/gadget_poseidon.rs:102) */
 typedef struct bp_term { bp_var var; uint8_t coeff[32]; } bp_term;
@@ -89,6 +92,8 @@ int32_t bp_cs_allocate_multiplier(bp_cs *cs, const uint8_t *l, const uint8_t *r,
 int32_t bp_cs_allocate_single(bp_cs *cs, const uint8_t *value, bp_var *var, bp_var *out_var, int32_t *has_out);
 /* fork API cs.evaluate_lc(&lc) -> Option<Scalar>                    (reference src/gadget_poseidon.rs:160); BP_ERR_MISSING_ASSIGNMENT = None */
 int32_t bp_cs_evaluate_lc(bp_cs *cs, const bp_term *lc, size_t n, uint8_t out[32]);
+/* declares the next public input; `value` is its value for this constraint system (may be NULL on a recording-only cs) */
+int32_t bp_cs_public_input(bp_cs *cs, const uint8_t *value, bp_var *var);
 /* cs.constrain(lc)                                                  (reference src/r1cs_utils.rs:35) */
 int32_t bp_cs_constrain(bp_cs *cs, const bp_term *lc, size_t n);
 /* fork API num_constraints / num_multipliers                       (reference src/gadget_vsmt_2.rs:345) */
@@ -119,11 +124,17 @@ int32_t bp_gadget_allocate_statics(bp_cs *cs, uint32_t num_statics, bp_var *out_
 /* Poseidon_hash_2_gadget (src/gadget_poseidon.rs:470-486) */
 int32_t bp_gadget_poseidon_hash_2(bp_cs *cs, const bp_poseidon_params *p, bp_var xl, bp_var xr, const bp_var *statics,
                                   uint32_t num_statics, int32_t sbox, const uint8_t expected_hash[32]);
+int32_t bp_gadget_poseidon_hash_2_public(bp_cs *cs, const bp_poseidon_params *p, bp_var xl, bp_var xr, const bp_var *statics,
+                                         uint32_t num_statics, int32_t sbox, bp_var expected_hash);
 /* vanilla_merkle_merkle_tree_verif_gadget (src/gadget_vsmt_2.rs:171-209) */
 int32_t bp_gadget_vsmt2_verif(bp_cs *cs, const bp_poseidon_params *p, uint32_t depth, const uint8_t root[32], bp_var leaf,
                               const bp_var *leaf_index_bits, const bp_var *proof_nodes, const bp_var *statics, uint32_t num_statics);
+/* same circuit with the root as a public-input variable (BP_VAR_PUBLIC) instead of a baked-in constant */
+int32_t bp_gadget_vsmt2_verif_public(bp_cs *cs, const bp_poseidon_params *p, uint32_t depth, bp_var root, bp_var leaf,
+                                     const bp_var *leaf_index_bits, const bp_var *proof_nodes, const bp_var *statics, uint32_t num_statics);
 /* mimc_gadget (src/gadget_mimc.rs:41-79) */
 int32_t bp_gadget_mimc(bp_cs *cs, bp_var left, bp_var right, uint32_t rounds, const uint8_t *constants, const uint8_t image[32]);
+int32_t bp_gadget_mimc_public(bp_cs *cs, bp_var left, bp_var right, uint32_t rounds, const uint8_t *constants, bp_var image);
 /* mimc (src/gadget_mimc.rs:19-39), evaluated natively */
 int32_t bp_mimc(const uint8_t xl[32], const uint8_t xr[32], uint32_t rounds, const uint8_t *constants, uint8_t out[32]);
 /* bound_check_gadget (src/gadget_bound_check.rs:18-45); v/a/b assignments as u64, has_assignment = 0 on the verifier */
@@ -144,26 +155,28 @@ uint32_t bp_circuit_num_multipliers(const bp_circuit *c);
 uint32_t bp_circuit_num_constraints(const bp_circuit *c);
 uint32_t bp_circuit_num_commitments(const bp_circuit *c);
 uint32_t bp_circuit_num_aux(const bp_circuit *c);
+uint32_t bp_circuit_num_public(const bp_circuit *c);
 int32_t bp_circuit_has_witness_program(const bp_circuit *c);
 size_t bp_circuit_proof_len(const bp_circuit *c);
 
-/* B independent proofs.  HOST buffers: v, v_blinding [B][m][32]; entropy [B][32]; aux [B][num_aux][32] (may be
- * NULL when num_aux == 0); witness aL/aR/aO [B][n][32] or all NULL to run the witness program on the device.
+/* B independent proofs.  HOST buffers: v, v_blinding [B][m][32]; entropy [B][32]; aux [B][num_aux][32] and
+ * pub [B][num_public][32] (NULL when the count is 0); witness aL/aR/aO [B][n][32] or all NULL to run the witness program on the device.
  * Outputs: V [B][m][32], proofs [B][proof_len], status [B].  Copies host<->device inside the call. */
 int32_t bp_prove_batch(const bp_gens *g, bp_circuit *c, uint32_t B, const uint8_t *label, size_t label_len, const uint8_t *v,
-                       const uint8_t *v_blinding, const uint8_t *entropy, const uint8_t *aux, const uint8_t *aL,
+                       const uint8_t *v_blinding, const uint8_t *entropy, const uint8_t *aux, const uint8_t *pub, const uint8_t *aL,
                        const uint8_t *aR, const uint8_t *aO, uint8_t *V_out, uint8_t *proofs, int32_t *status);
 /* same with every buffer already resident in device memory (cudaMalloc'ed by the caller), on `stream`
  * (a cudaStream_t cast to void*; NULL = default stream).  Returns after enqueueing; the caller synchronises. */
 int32_t bp_prove_batch_device(const bp_gens *g, bp_circuit *c, uint32_t B, const uint8_t *label, size_t label_len,
                               const uint8_t *d_v, const uint8_t *d_v_blinding, const uint8_t *d_entropy, const uint8_t *d_aux,
-                              const uint8_t *d_aL, const uint8_t *d_aR, const uint8_t *d_aO, uint8_t *d_V_out,
+                              const uint8_t *d_pub, const uint8_t *d_aL, const uint8_t *d_aR, const uint8_t *d_aO, uint8_t *d_V_out,
                               uint8_t *d_proofs, int32_t *d_status, void *stream);
 /* B independent verifications of proofs over the same circuit; status[p] = BP_OK or BP_ERR_VERIFICATION / BP_ERR_FORMAT */
 int32_t bp_verify_batch(const bp_gens *g, bp_circuit *c, uint32_t B, const uint8_t *label, size_t label_len, const uint8_t *V,
-                        const uint8_t *proofs, const uint8_t *entropy, int32_t *status);
+                        const uint8_t *proofs, const uint8_t *entropy, const uint8_t *pub, int32_t *status);
 int32_t bp_verify_batch_device(const bp_gens *g, bp_circuit *c, uint32_t B, const uint8_t *label, size_t label_len,
-                               const uint8_t *d_V, const uint8_t *d_proofs, const uint8_t *d_entropy, int32_t *d_status, void *stream);
+                               const uint8_t *d_V, const uint8_t *d_proofs, const uint8_t *d_entropy, const uint8_t *d_pub, int32_t *d_status,
+                               void *stream);
 
 /* ---- MSM microbenchmark entry (BASELINE.json config 3) -------------------------------------------
  * result = sum_i scalars[i] * points[i] over ristretto255; points are the first n generators of chain G.
