@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: batched Bulletproofs R1CS proving, Poseidon VSMT-2 depth-32 membership proofs.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference ...                     (the CPU oracle port on all host cores)
+
+A step = one pass of the prover over one batch of `--batch` synthetic proofs per GPU (BASELINE.json
+config 5 shape: depth 32, inverse S-box, n = 18176 multipliers, N = 32768, m = 69 commitments).
+`value` = proofs/s with inputs resident in HBM; `e2e` = the same through the host-buffer C-ABI call
+(bp_prove_batch: H2D of inputs and D2H of commitments + proofs inside the timed region).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+
+METRIC = "R1CS proofs/sec (Poseidon VSMT-2 depth-32)"
+UNIT = "proofs/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("BP_BENCH_BATCH", "256")), help="proofs per GPU per step")
+    ap.add_argument("--depth", type=int, default=32)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="proofs in the cpu_baseline sample (0 = one per host core)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """samples nvidia-smi during the timed region (B200_PROFILING.md clocks line)"""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def oracle_circuit(depth):
+    """constraint system of the VSMT-2 circuit recorded by the independent Python oracle (root value irrelevant to the prover)"""
+    from oracle import bp_pyref as R, gadgets_pyref as G, c_oracle as CO
+    pp = G.PoseidonParams()
+    vf = R.Verifier(R.Transcript(b"VSMT"))
+    vs = [vf.commit(bytes(32)) for _ in range(1 + 2 * depth + 4)]
+    G.vanilla_merkle_tree_verif_gadget(vf, depth, 0, vs[0], vs[1:1 + depth], vs[1 + depth:1 + 2 * depth], vs[1 + 2 * depth:], pp)
+    blob = open(os.path.join(HERE, "bulletproofs_r1cs_gadgets_b200", "data", "poseidon_constants.bin"), "rb").read()
+    CO.poseidon_set_params(blob)
+    return CO.Circuit.from_cs(vf, len(vs))
+
+
+def cpu_prove(circ, depth, inputs, count, nthreads):
+    """times the C oracle (native witness + prove) on `count` proofs over `nthreads` host threads"""
+    from oracle import c_oracle as CO
+    N = 1
+    while N < circ.n:
+        N *= 2
+    CO.lib().bpo_ensure_gens(N)
+    t0 = time.time()
+    status, V, proofs = CO.prove_batch(circ, count, inputs["v"][:count], inputs["v_blinding"][:count], inputs["entropy"][:count], b"VSMT", N, nthreads,
+                                       witness_kind=1, depth=depth)
+    dt = time.time() - t0
+    assert not status.any()
+    return dt, V, proofs
+
+
+def run_reference(args):
+    """--impl reference: the reference itself is Rust with un-vendored crates and cannot be built in this image
+    (no cargo/rustc), so this arm times the oracle's C port of the same algorithm on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from bulletproofs_r1cs_gadgets_b200 import workloads  # input generator only (pure hashlib); no GPU library is loaded
+    cores = os.cpu_count() or 1
+    sample = args.cpu_sample or cores
+    circ = oracle_circuit(args.depth)
+    wl = workloads.Vsmt2.__new__(workloads.Vsmt2)
+    wl.depth, wl.cfg = args.depth, b"vsmt2/%d" % args.depth
+
+    class _M:
+        m = 1 + 2 * args.depth + 4
+    wl.circuit = _M()
+    inputs = wl.inputs(0, sample, with_root=False)
+    times = []
+    for i in range(args.warmup + args.steps):
+        dt, _, _ = cpu_prove(circ, args.depth, inputs, sample, cores)
+        if i >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = sample * len(times) / total
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 (F_l, GF(2^255-19))",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": "gadget_vsmt_2 depth-%d membership proofs, inverse S-box (n=%d, m=%d)" % (args.depth, circ.n, circ.m),
+                       "proofs_per_step": sample, "note": "C port of the reference algorithm (oracle/bp_oracle.c); curve25519-dalek itself is not buildable here"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": "%d proofs per step, one thread per proof" % sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import numpy as np
+    import torch
+    import ctypes as C
+    from bulletproofs_r1cs_gadgets_b200 import api, workloads
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    lib = api.load()
+
+    B = args.batch
+    gens = api.Gens(32768 if args.depth == 32 else 1 << 20)
+    wl = workloads.Vsmt2(gens, depth=args.depth)
+    circ = wl.circuit
+    if gens.capacity < wl.gens_capacity:
+        gens = api.Gens(wl.gens_capacity)
+    # rank r proves proofs [r*B, (r+1)*B): independent statements, no exchange during proving
+    inp = wl.inputs(rank * B, B, with_root=False)
+    pin = {k: torch.from_numpy(v).pin_memory() for k, v in inp.items() if k in ("v", "v_blinding", "entropy")}
+    d = {k: t.to(dev) for k, t in pin.items()}
+    m, plen = circ.m, circ.proof_len
+    d_V = torch.empty((B, m, 32), dtype=torch.uint8, device=dev)
+    d_P = torch.empty((B, plen), dtype=torch.uint8, device=dev)
+    d_S = torch.empty((B,), dtype=torch.int32, device=dev)
+    gathered = torch.empty((world * B, plen), dtype=torch.uint8, device=dev) if world > 1 else None
+    label = b"VSMT"
+    lbuf = api._buf(label)
+
+    def ptr(t):
+        return C.c_void_p(t.data_ptr())
+
+    def step_device():
+        stream = torch.cuda.current_stream().cuda_stream
+        rc = lib.bp_prove_batch_device(gens._h, circ._h, C.c_uint32(B), lbuf, C.c_size_t(len(label)), ptr(d["v"]), ptr(d["v_blinding"]), ptr(d["entropy"]),
+                                       None, None, None, None, None, ptr(d_V), ptr(d_P), ptr(d_S), C.c_void_p(stream))
+        if rc != 0:
+            raise api.R1CSError(rc, "bp_prove_batch_device")
+        if world > 1:  # the one collective of the path: gather the fixed-size proof records
+            dist.all_gather_into_tensor(gathered, d_P)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    api.profile_enable(True)
+    l0 = api.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    api.profile_enable(False)
+    clocks = sampler.stop()
+    launches = api.launch_count() - l0
+    prof = api.profile_report()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    status = d_S.cpu().numpy()
+    assert not status.any(), "prover status %s" % status[:8]
+    value = world * B * args.steps / (ms / 1000.0)
+
+    # ---- e2e: the host-buffer C-ABI call (H2D inputs + D2H outputs inside the timed region) ----
+    e2e = None
+    if not args.no_e2e:
+        hv, hvb, hent = inp["v"], inp["v_blinding"], inp["entropy"]
+        circ.prove_batch(gens, label, hv, hvb, hent)  # warm
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(max(1, args.steps)):
+            V_h, P_h, S_h = circ.prove_batch(gens, label, hv, hvb, hent)
+        f1.record()
+        barrier()
+        ems = f0.elapsed_time(f1)
+        if world > 1:
+            t = torch.tensor([ems], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ems = float(t.item())
+        assert not S_h.any()
+        assert P_h.tobytes() == d_P.cpu().numpy().tobytes(), "host-buffer and device-buffer paths disagree"
+        e2e = {"value": world * B * max(1, args.steps) / (ems / 1000.0), "unit": UNIT,
+               "h2d_bytes_per_step": int(hv.nbytes + hvb.nbytes + hent.nbytes), "d2h_bytes_per_step": int(V_h.nbytes + P_h.nbytes + S_h.nbytes)}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel and of the MSM kernel (algorithmic bytes: DESIGN.md section 4) ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(HERE, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    n, N, k = circ.n, 1 << (circ.n - 1).bit_length(), (circ.n - 1).bit_length()
+    msm_terms_per_proof = (2 * n + 1) + (n + 1) + (2 * n + 1) + sum(2 * (2 * (N >> (j + 1)) + 1) for j in range(k))
+    fold_outputs_per_proof = sum(2 * (N >> (j + 1)) for j in range(k) if (N >> (j + 1)) > 1)
+    alg_bytes = {"KMsmAccumulate": 64.0 * msm_terms_per_proof * B * args.steps, "KFoldGens": 96.0 * fold_outputs_per_proof * B * args.steps}
+    total_kernel_ms = sum(v[1] for v in prof.values()) or 1.0
+    shares = {kname: round(v[1] / total_kernel_ms, 4) for kname, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:8]}
+
+    def roof(kname):
+        if kname not in prof or kname not in alg_bytes:
+            return None
+        launches_k, ms_k, _ = prof[kname]
+        ach = alg_bytes[kname] / (ms_k / 1000.0) / 1e9
+        return {"kernel": kname, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                "peak_source": peak_src, "launches": launches_k, "avg_launch_ms": ms_k / launches_k, "share_of_step": shares.get(kname)}
+    dominant = max(prof.items(), key=lambda kv: kv[1][1])[0] if prof else None
+    roofline = roof(dominant) or roof("KMsmAccumulate")
+
+    # ---- cpu_baseline: the oracle port on a bounded sample of the same workload ----
+    cpu = None
+    if not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        sample = args.cpu_sample or min(cores, B)
+        oc = oracle_circuit(args.depth)
+        dt, V_o, P_o = cpu_prove(oc, args.depth, inp, sample, cores)
+        same = P_o.tobytes() == d_P[:sample].cpu().numpy().tobytes() and V_o.tobytes() == d_V[:sample].cpu().numpy().tobytes()
+        cpu = {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "first %d proofs of the step, one thread per proof (oracle/bp_oracle.c)" % sample, "bit_exact_vs_gpu": bool(same)}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 (F_l Montgomery 4x64, GF(2^255-19) 10x25.5-bit)",
+            "data": "synthetic",
+            "config": {"workload": "gadget_vsmt_2 depth-%d membership proofs, inverse S-box (n=%d, N=%d, m=%d, q=%d)" % (args.depth, circ.n, N, circ.m, circ.q),
+                       "proofs_per_gpu_per_step": B, "global_proofs_per_step": world * B, "parallelism": "proofs sharded over %d GPU(s), NCCL all-gather of proof bytes" % world,
+                       "l2": "per-step working set (GBs of scalars, digits, buckets, folded generators) exceeds the 126 MB L2"},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_msm": roof("KMsmAccumulate"),
+            "kernel_time_shares": shares, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

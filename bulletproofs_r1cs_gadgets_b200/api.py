@@ -450,3 +450,18 @@ class Circuit:
 
 def launch_count():
     return int(load().bp_launch_count())
+
+
+def profile_enable(on=True):
+    load().bp_profile_enable(1 if on else 0)
+
+
+def profile_report():
+    """{kernel: (launches, total_ms, threads)} since the last report; call after a device synchronise"""
+    buf = C.create_string_buffer(1 << 16)
+    n = load().bp_profile_report(buf, C.c_size_t(len(buf)))
+    out = {}
+    for line in buf.raw[:n].decode().splitlines():
+        name, launches, ms, threads = line.split()
+        out[name] = (int(launches), float(ms), float(threads))
+    return out

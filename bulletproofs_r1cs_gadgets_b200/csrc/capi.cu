@@ -30,6 +30,8 @@ extern "C" {
 
 int32_t bp_version(void) { return 1; }
 int64_t bp_launch_count(void) { return engine_launch_count(); }
+void bp_profile_enable(int32_t on) { engine_profile_enable(on); }
+int32_t bp_profile_report(char *buf, size_t cap) { return engine_profile_report(buf, cap); }
 
 // ------------------------------------------------------------------------------------------------ generators
 int32_t bp_gens_new(uint32_t capacity, bp_gens **out) {

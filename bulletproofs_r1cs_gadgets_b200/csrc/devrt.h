@@ -17,11 +17,17 @@ __global__ void __launch_bounds__(K::kBlock, K::kMinBlocks) run_kernel(long n, K
   if (tid < n) k(tid);
 }
 extern long g_launch_count;
+// optional per-kernel timing (bp_profile_*): CUDA events recorded on the launching stream around every kernel
+extern int g_profile_on;
+void profile_begin(const char *name, long threads, dev_stream s);
+void profile_end(dev_stream s);
 template <class K>
 int launch(long n, dev_stream s, const K &k) {
   if (n <= 0) return 0;
   long blocks = (n + K::kBlock - 1) / K::kBlock;
+  if (g_profile_on) profile_begin(K::kName, n, s);
   run_kernel<K><<<(unsigned)blocks, K::kBlock, 0, s>>>(n, k);
+  if (g_profile_on) profile_end(s);
   g_launch_count++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { fprintf(stderr, "bp_b200: launch failed: %s\n", cudaGetErrorString(e)); return 1; }

@@ -6,6 +6,44 @@
 long g_launch_count = 0;
 long engine_launch_count() { return g_launch_count; }
 
+// ------------------------------------------------------------------------------------------------ per-kernel event timing
+#ifndef BP_HOST_EMUL
+#include <map>
+#include <string>
+int g_profile_on = 0;
+struct ProfRec { const char *name; long threads; cudaEvent_t e0, e1; };
+static std::vector<ProfRec> g_prof;
+void profile_begin(const char *name, long threads, dev_stream s) {
+  ProfRec r{name, threads, nullptr, nullptr};
+  cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+  cudaEventRecord(r.e0, s);
+  g_prof.push_back(r);
+}
+void profile_end(dev_stream s) { cudaEventRecord(g_prof.back().e1, s); }
+void engine_profile_enable(int on) { g_profile_on = on; }
+// writes "name launches total_ms threads\n" lines; clears the records.  Caller must have synchronised.
+int engine_profile_report(char *buf, size_t cap) {
+  struct Agg { long launches = 0; double ms = 0; double threads = 0; };
+  std::map<std::string, Agg> agg;
+  for (ProfRec &r : g_prof) {
+    float ms = 0; cudaEventSynchronize(r.e1); cudaEventElapsedTime(&ms, r.e0, r.e1);
+    Agg &a = agg[r.name]; a.launches++; a.ms += ms; a.threads += (double)r.threads;
+    cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+  }
+  g_prof.clear();
+  size_t off = 0;
+  for (auto &kv : agg) {
+    int w = snprintf(buf + off, off < cap ? cap - off : 0, "%s %ld %.6f %.0f\n", kv.first.c_str(), kv.second.launches, kv.second.ms, kv.second.threads);
+    if (w < 0 || off + (size_t)w >= cap) break;
+    off += (size_t)w;
+  }
+  return (int)off;
+}
+#else
+void engine_profile_enable(int) {}
+int engine_profile_report(char *buf, size_t cap) { if (cap) buf[0] = 0; return 0; }
+#endif
+
 #define CK(x) do { int _e = (x); if (_e) { fprintf(stderr, "bp_b200: %s failed at %s:%d\n", #x, __FILE__, __LINE__); return BP_ERR_CUDA; } } while (0)
 
 static const uint8_t BASEPOINT_C[32] = {0xe2, 0xf2, 0xae, 0x0a, 0x6a, 0xbc, 0x4e, 0x71, 0xa8, 0x84, 0xa9, 0x61, 0xc5, 0x00, 0x51, 0x5f,

@@ -70,5 +70,7 @@ int engine_verify(const BpGens *g, BpCircuit *c, const VerifyArgs &a, dev_stream
 // one-off helper: commitments a*B + b*B_blinding for host scalars
 int engine_commit(const BpGens *g, int count, const uint8_t *v, const uint8_t *r, uint8_t *out);
 long engine_launch_count();
+void engine_profile_enable(int on);
+int engine_profile_report(char *buf, size_t cap);
 // sum_i scalars[i] * G[i] over the first n generators; d_scalars [n][32] canonical bytes, d_out 32 bytes (device)
 int engine_msm_gens(BpGens *g, uint32_t n, const uint8_t *d_scalars, uint8_t *d_out, dev_stream s);

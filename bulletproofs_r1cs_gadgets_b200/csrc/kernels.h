@@ -25,6 +25,7 @@
 // bytes [B][cnt][32] -> Montgomery [cnt][B]
 struct KLoadScalars {
   static constexpr int kBlock = 128, kMinBlocks = 1;
+  static constexpr const char *kName = "KLoadScalars";
   const uint8_t *in; scm *out; int cnt, B;
   HD void operator()(long tid) const {
     int p = (int)(tid % B); long i = tid / B;
@@ -56,6 +57,7 @@ HD void store_digits(int8_t *dst, const int8_t dig[32]) {
 // src [cnt][B] (optionally times mul[p]) -> digit rows row0.. of each instance
 struct KRecode {
   static constexpr int kBlock = 128, kMinBlocks = 1;
+  static constexpr const char *kName = "KRecode";
   const scm *src; const scm *mul; int cnt, B; int8_t *dig; long inst_stride; int row0;
   HD void operator()(long tid) const {
     int p = (int)(tid % B); long i = tid / B;
@@ -72,6 +74,7 @@ struct KRecode {
 // ------------------------------------------------------------------------------------------------
 struct KCommit {
   static constexpr int kBlock = 128, kMinBlocks = 1;
+  static constexpr const char *kName = "KCommit";
   const scm *a; const scm *b; int cnt, B; const ge_niels *table;
   uint8_t *out; long out_stride_p, out_stride_j; ge_p3 *out_pt;
   HD void operator()(long tid) const {
@@ -103,6 +106,7 @@ struct MsmSeg { const void *bases; long inst_stride; int fmt; int count; };  // 
 
 struct KMsmAccumulate {
   static constexpr int kBlock = 128, kMinBlocks = 1;
+  static constexpr const char *kName = "KMsmAccumulate";
   MsmSeg seg[4]; int nseg; int S;  // S = row-range splits per instance (each split owns its own buckets)
   const int8_t *dig; long dig_inst_stride; ge_p3 *buckets; ge_p3 *wsum;
   HD void operator()(long tid) const {
@@ -163,6 +167,7 @@ struct KMsmAccumulate {
 // sum the splits, Horner over the 32 window sums, then ristretto-encode (mode 0) or test for the identity (mode 1)
 struct KMsmFinish {
   static constexpr int kBlock = 64, kMinBlocks = 1;
+  static constexpr const char *kName = "KMsmFinish";
   const ge_p3 *wsum; int S; uint8_t *out; long out_stride; int mode; int *status; int fail_code;
   HD void window(ge_p3 &r, long inst, int w) const {
     load_struct(r, &wsum[(inst * S) * MSM_WINDOWS + w]);
@@ -190,6 +195,7 @@ struct KMsmFinish {
 // Appends V_0..V_{m-1} and "m"; then builds the prover's transcript RNG (A.3 step 2).
 struct KTsStart {
   static constexpr int kBlock = 64, kMinBlocks = 1;
+  static constexpr const char *kName = "KTsStart";
   strobe128 base; const uint8_t *V; int m, B; const scm *vbl; const uint8_t *entropy; strobe128 *ts; strobe128 *rng; int prover;
   HD void operator()(long p) const {
     strobe128 t; strobe_load(t, &base);
@@ -206,6 +212,7 @@ struct KTsStart {
 // draws `count` uniform scalars (64 bytes each, wide reduction) into dst[i*B+p]
 struct KRngDraw {
   static constexpr int kBlock = 32, kMinBlocks = 1;
+  static constexpr const char *kName = "KRngDraw";
   strobe128 *rng; scm *dst; int count, B;
   HD void operator()(long p) const {
     strobe128 r; strobe_load(r, &rng[p]);
@@ -216,6 +223,7 @@ struct KRngDraw {
 // A_I1,A_O1,S1 + one-phase separator + identity A_I2,A_O2,S2 -> y, z ; also y^-1
 struct KTsPhase2 {
   static constexpr int kBlock = 64, kMinBlocks = 1;
+  static constexpr const char *kName = "KTsPhase2";
   strobe128 *ts; const uint8_t *proofs; long proof_stride; scm *y, *z, *yinv; int *status; int verifier;
   HD void operator()(long p) const {
     strobe128 t; strobe_load(t, &ts[p]);
@@ -236,6 +244,7 @@ struct KTsPhase2 {
 // T_1,T_3,T_4,T_5,T_6 -> u, x
 struct KTsPhase3 {
   static constexpr int kBlock = 64, kMinBlocks = 1;
+  static constexpr const char *kName = "KTsPhase3";
   strobe128 *ts; const uint8_t *proofs; long proof_stride; scm *u, *x; int *status; int verifier;
   HD void operator()(long p) const {
     strobe128 t; strobe_load(t, &ts[p]);
@@ -254,6 +263,7 @@ struct KTsPhase3 {
 // t_x, t_x_blinding, e_blinding -> w ; then the inner-product domain separator with n = N
 struct KTsPhase4 {
   static constexpr int kBlock = 64, kMinBlocks = 1;
+  static constexpr const char *kName = "KTsPhase4";
   strobe128 *ts; const uint8_t *proofs; long proof_stride; scm *w; unsigned N;
   HD void operator()(long p) const {
     strobe128 t; strobe_load(t, &ts[p]);
@@ -292,6 +302,7 @@ HD int sc_naf(int8_t naf[256], const scm &s) {
 //   alpha' = alpha * u^-1,  beta' = beta * u
 struct KTsIpaRound {
   static constexpr int kBlock = 64, kMinBlocks = 1;
+  static constexpr const char *kName = "KTsIpaRound";
   strobe128 *ts; const uint8_t *proofs; long proof_stride; int round; int B; int h;
   const scm *yinvpow; const scm *ufac;  // y^-i table [N][B]; the r1cs challenge u (class factor, round 0 only)
   scm *u, *uinv, *alpha, *beta; int8_t *naf; int *naf_top; int *status; int verifier;
@@ -328,6 +339,7 @@ struct KTsIpaRound {
 // out[i][p] = base[p]^(i + exp0), i < len; one thread per (chunk of CH exponents, proof)
 struct KPowers {
   static constexpr int kBlock = 128, kMinBlocks = 1;
+  static constexpr const char *kName = "KPowers";
   const scm *base; scm *out; int len, B, exp0, CH;
   HD void operator()(long tid) const {
     int p = (int)(tid % B); int c = (int)(tid / B);
@@ -340,6 +352,7 @@ struct KPowers {
 HD void fill_scalar(scm *dst, long n, const scm &v) { for (long i = 0; i < n; i++) dst[i] = v; }
 struct KFillScalar {
   static constexpr int kBlock = 128, kMinBlocks = 1;
+  static constexpr const char *kName = "KFillScalar";
   scm *dst; scm v;
   HD void operator()(long tid) const { dst[tid] = v; }
 };
@@ -348,6 +361,7 @@ struct KFillScalar {
 // slot s in [0,3n+m+1) = wL | wR | wO | wV | wc;  w[s][p] = sum_t coeff_t * z^(q_t+1)   (signs folded into coeff)
 struct KFlatten {
   static constexpr int kBlock = 128, kMinBlocks = 1;
+  static constexpr const char *kName = "KFlatten";
   const uint32_t *slot_ptr; const uint32_t *t_q; const scm *t_coeff; const scm *zpow; scm *w; int B;
   HD void operator()(long tid) const {
     int p = (int)(tid % B); long s = tid / B;
@@ -371,6 +385,7 @@ HD void poly_coef(PolyCoef &c, const PolyIn &in, long at) {
 // partial sums of t_1..t_6 (A.3 step 9) over a chunk of multipliers
 struct KPolyT {
   static constexpr int kBlock = 128, kMinBlocks = 1;
+  static constexpr const char *kName = "KPolyT";
   PolyIn in; int n, B, CH; scm *part;  // part[(c*6 + j)*B + p]
   HD void operator()(long tid) const {
     int p = (int)(tid % B); int c = (int)(tid / B);
@@ -392,6 +407,7 @@ struct KPolyT {
 // out[j][p] = sum_c part[(c*nv + j)*B + p]
 struct KSumPartials {
   static constexpr int kBlock = 128, kMinBlocks = 1;
+  static constexpr const char *kName = "KSumPartials";
   const scm *part; int nchunks, nv, B; scm *out;
   HD void operator()(long tid) const {
     int p = (int)(tid % B); int j = (int)(tid / B);
@@ -403,6 +419,7 @@ struct KSumPartials {
 // l(x), r(x) padded to N (A.3 step 12) -> the a, b vectors of the inner-product argument
 struct KPolyEval {
   static constexpr int kBlock = 128, kMinBlocks = 1;
+  static constexpr const char *kName = "KPolyEval";
   PolyIn in; int n, B; const scm *x; scm *a, *b;
   HD void operator()(long tid) const {
     int p = (int)(tid % B); long i = tid / B; long at = i * B + p;
@@ -420,6 +437,7 @@ struct KPolyEval {
 // t_x, t_x_blinding, e_blinding (A.3 steps 11-13) -> proof bytes 352..447
 struct KProverScalars {
   static constexpr int kBlock = 64, kMinBlocks = 1;
+  static constexpr const char *kName = "KProverScalars";
   const scm *t;      // [6][B]: t1..t6
   const scm *tb;     // [5][B]: blindings of T_1,T_3,T_4,T_5,T_6
   const scm *blind;  // [3][B]: i,o,s blindings
@@ -445,6 +463,7 @@ struct KProverScalars {
 // c_L = <a_lo, b_hi>, c_R = <a_hi, b_lo> partials
 struct KIpaDots {
   static constexpr int kBlock = 128, kMinBlocks = 1;
+  static constexpr const char *kName = "KIpaDots";
   const scm *a, *b; int h, B, CH; scm *part;  // part[(c*2+j)*B+p]
   HD void operator()(long tid) const {
     int p = (int)(tid % B); int c = (int)(tid / B);
@@ -463,6 +482,7 @@ struct KIpaDots {
 //   R rows: [0,h) alpha*a[h+i]*gf(i) on Gt[i];    [h,2h) beta*y^-(h+i)*b[i]*gf(h+i) on Ht[h+i]; row 2h: c_R on Q
 struct KRecodeIpa {
   static constexpr int kBlock = 128, kMinBlocks = 1;
+  static constexpr const char *kName = "KRecodeIpa";
   const scm *a, *b, *alpha, *beta, *yinvpow, *ufac, *clr; int h, B, n, round;
   int8_t *digL, *digR; long inst_stride;
   HD void operator()(long tid) const {
@@ -486,6 +506,7 @@ struct KRecodeIpa {
 // a' = a_lo*u + a_hi*u^-1 ; b' = b_lo*u^-1 + b_hi*u   (in place on the low halves)
 struct KFoldAB {
   static constexpr int kBlock = 128, kMinBlocks = 1;
+  static constexpr const char *kName = "KFoldAB";
   scm *a, *b; const scm *u, *uinv; int h, B;
   HD void operator()(long tid) const {
     int p = (int)(tid % B); int i = (int)(tid / B);
@@ -497,6 +518,7 @@ struct KFoldAB {
 };
 struct KStoreAB {
   static constexpr int kBlock = 64, kMinBlocks = 1;
+  static constexpr const char *kName = "KStoreAB";
   const scm *a, *b; uint8_t *proofs; long proof_stride; long off;
   HD void operator()(long p) const { uint8_t *pf = proofs + p * proof_stride + off; sc_tobytes(pf, a[p]); sc_tobytes(pf + 32, b[p]); }
 };
@@ -507,6 +529,7 @@ struct KStoreAB {
 // ------------------------------------------------------------------------------------------------
 struct KFoldGens {
   static constexpr int kBlock = 128, kMinBlocks = 1;
+  static constexpr const char *kName = "KFoldGens";
   const ge_p3 *srcG, *srcH; long src_stride;  // round 0: shared generators (stride 0); later: per-proof
   ge_p3 *dstG, *dstH; long dst_stride;
   const int8_t *naf; const int *naf_top; int h, n, round;
@@ -542,6 +565,7 @@ struct KFoldGens {
 // 64 uniform bytes per generator (SHAKE256 stream squeezed on the host) -> ristretto one-way map
 struct KGensFromUniform {
   static constexpr int kBlock = 64, kMinBlocks = 1;
+  static constexpr const char *kName = "KGensFromUniform";
   const uint8_t *uniform; ge_p3 *out_p3; ge_niels *out_niels;
   HD void operator()(long i) const {
     ge_p3 p, q; ristretto_from_uniform(p, uniform + i * 64);
@@ -554,6 +578,7 @@ struct KGensFromUniform {
 // pc[0] = B (decoded from the canonical basepoint encoding), pc[1] = B_blinding (from uniform bytes)
 struct KPcBases {
   static constexpr int kBlock = 32, kMinBlocks = 1;
+  static constexpr const char *kName = "KPcBases";
   const uint8_t *basepoint_c; const uint8_t *bb_uniform; ge_p3 *pc; ge_niels *pc_niels; uint8_t *pc_c; int *ok;
   HD void operator()(long i) const {
     ge_p3 p, q;
@@ -568,6 +593,7 @@ struct KPcBases {
 // table[(base*64 + win)*16 + d] = d * 16^win * pc[base]
 struct KPcTable {
   static constexpr int kBlock = 32, kMinBlocks = 1;
+  static constexpr const char *kName = "KPcTable";
   const ge_p3 *pc; ge_niels *table;
   HD void operator()(long tid) const {
     int base = (int)(tid / 64), win = (int)(tid % 64);
@@ -584,6 +610,7 @@ struct KPcTable {
 };
 struct KEncodePoints {
   static constexpr int kBlock = 64, kMinBlocks = 1;
+  static constexpr const char *kName = "KEncodePoints";
   const ge_p3 *pts; uint8_t *out;
   HD void operator()(long i) const { ge_p3 p; load_struct(p, &pts[i]); ristretto_encode(out + 32 * i, p); }
 };
@@ -601,6 +628,7 @@ struct TapeOp { uint8_t opL, opR, pad[2]; uint32_t argL, argR; };
 struct WitnessLcs { const uint32_t *ptr; const uint8_t *kind; const uint32_t *idx; const scm *coeff; };
 struct KWitnessTape {
   static constexpr int kBlock = 32, kMinBlocks = 1;
+  static constexpr const char *kName = "KWitnessTape";
   const TapeOp *tape; WitnessLcs lcs; int n, B; const scm *v; const scm *aux; const scm *pub; scm *aL, *aR, *aO;
   HD scm eval(uint32_t lc, int p) const {
     scm acc = sc_zero();
@@ -637,6 +665,7 @@ struct KWitnessTape {
 enum { ST_MERLIN = 0, ST_SC_INVERT = 1, ST_SC_WIDE = 2, ST_RISTRETTO_ROUNDTRIP = 3, ST_SC_MUL = 4, ST_FROM_UNIFORM = 5, ST_RNG = 6, ST_KECCAK = 7, ST_TSSTART = 8 };
 struct KSelfTest {
   static constexpr int kBlock = 32, kMinBlocks = 1;
+  static constexpr const char *kName = "KSelfTest";
   int which; const uint8_t *in; int in_len; uint8_t *out; int out_len;
   HD void operator()(long) const {
     switch (which) {
@@ -694,6 +723,7 @@ struct KSelfTest {
 // chal layout [..][B]: 0 y, 1 z, 2 y^-1, 3 u, 4 x, 5 w, 6 r ; ipa challenges u_j at uj[j*B+p], inverses at ujinv.
 struct KTsVerify {
   static constexpr int kBlock = 64, kMinBlocks = 1;
+  static constexpr const char *kName = "KTsVerify";
   strobe128 base; const uint8_t *V; int m, B, k; unsigned N; const uint8_t *proofs; long proof_stride; const uint8_t *entropy;
   scm *chal; scm *uj, *ujinv; int *status;
   HD static int is_zero32(const uint8_t *b) { uint8_t nz = 0; for (int i = 0; i < 32; i++) nz |= b[i]; return nz == 0; }
@@ -739,6 +769,7 @@ struct KTsVerify {
 // s_i = prod_j u_j^(+1 if bit (k-1-j) of i else -1)
 struct KVerifyS {
   static constexpr int kBlock = 128, kMinBlocks = 1;
+  static constexpr const char *kName = "KVerifyS";
   const scm *uj, *ujinv; int k, B; scm *s;
   HD void operator()(long tid) const {
     int p = (int)(tid % B); long i = tid / B;
@@ -750,6 +781,7 @@ struct KVerifyS {
 // delta partial sums: sum_{i<n} y^-i * wR_i * wL_i
 struct KVerifyDelta {
   static constexpr int kBlock = 128, kMinBlocks = 1;
+  static constexpr const char *kName = "KVerifyDelta";
   const scm *wL, *wR, *yinvpow; int n, B, CH; scm *part;
   HD void operator()(long tid) const {
     int p = (int)(tid % B); int c = (int)(tid / B);
@@ -762,6 +794,7 @@ struct KVerifyDelta {
 // digit rows of the G and H scalars: rows [2, 2+N) and [2+N, 2+2N)
 struct KVerifyGH {
   static constexpr int kBlock = 128, kMinBlocks = 1;
+  static constexpr const char *kName = "KVerifyGH";
   const scm *wL, *wR, *wO, *yinvpow, *s, *chal; const uint8_t *proofs; long proof_stride; int n, N, k, B; int8_t *dig; long inst_stride;
   HD void operator()(long tid) const {
     int p = (int)(tid % B); long i = tid / B; long at = i * B + p;
@@ -787,6 +820,7 @@ struct KVerifyGH {
 // A_I1 A_O1 S1 A_I2 A_O2 S2 | V_0..V_{m-1} | T_1 T_3 T_4 T_5 T_6 | L_0.. | R_0..
 struct KVerifyScalars {
   static constexpr int kBlock = 64, kMinBlocks = 1;
+  static constexpr const char *kName = "KVerifyScalars";
   const scm *chal, *uj, *ujinv, *wV, *wc, *wP, *pub, *delta; const uint8_t *proofs; long proof_stride; int m, npub, N, k, B; int8_t *dig; long inst_stride;
   HD void put(int8_t *row, long r, const scm &v) const { int8_t d[32]; sc_recode_bytes(d, v); store_digits(row + r * 32, d); }
   HD void operator()(long p) const {
@@ -816,6 +850,7 @@ struct KVerifyScalars {
 // decompress the per-proof points in the order KVerifyScalars lays their scalars out
 struct KVerifyDecompress {
   static constexpr int kBlock = 64, kMinBlocks = 1;
+  static constexpr const char *kName = "KVerifyDecompress";
   const uint8_t *V; const uint8_t *proofs; long proof_stride; int m, k, B; ge_p3 *pts; long pts_stride; int *status;
   HD void operator()(long tid) const {
     int np = 11 + m + 2 * k;

@@ -60,6 +60,10 @@ typedef struct bp_circuit bp_circuit; /* a compiled constraint system for batche
 int32_t bp_version(void);
 /* number of CUDA kernels this library has launched in this process (bench.py reports it) */
 int64_t bp_launch_count(void);
+/* per-kernel device timing: while enabled every kernel launch is bracketed by CUDA events on its stream.
+ * bp_profile_report (after the caller synchronised) writes lines "kernel launches total_ms threads" and clears the records. */
+void bp_profile_enable(int32_t on);
+int32_t bp_profile_report(char *buf, size_t cap);
 
 /* ---- generators --------------------------------------------------------------------------------
  * PedersenGens::default() (reference src/gadget_mimc.rs:99) and BulletproofGens::new(capacity, 1)
