@@ -136,13 +136,20 @@ static int32_t compile_cs(const bp_cs *cs, bool with_tape, BpCircuit **out) {
   for (size_t t = 0; t < nnz; t++) { kind[t] = (uint8_t)cs->terms[t].var.kind; idx[t] = cs->terms[t].var.index; co[t] = cs->terms[t].coeff; }
   if (!with_tape || cs->pending >= 0)
     return circuit_create(cs->num_mult, (uint32_t)cs->V.size(), (uint32_t)cs->pub.size(), (uint32_t)cs->num_constraints(), cs->cons_ptr.data(), kind.data(), idx.data(),
-                          co.data(), nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, out);
+                          co.data(), nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, out);
   size_t wn = cs->wlc_terms.size();
   std::vector<uint8_t> wkind(wn ? wn : 1); std::vector<uint32_t> widx(wn ? wn : 1); std::vector<scm> wco(wn ? wn : 1);
   for (size_t t = 0; t < wn; t++) { wkind[t] = (uint8_t)cs->wlc_terms[t].var.kind; widx[t] = cs->wlc_terms[t].var.index; wco[t] = cs->wlc_terms[t].coeff; }
+  HostPoseidonTape pt{}; std::vector<scm> mds;
+  if (!cs->pblocks.empty()) {
+    const bp_poseidon_params *pp = cs->pparams;
+    for (auto &row : pp->mds) mds.insert(mds.end(), row.begin(), row.end());
+    pt = HostPoseidonTape{cs->pblocks.data(), (uint32_t)cs->pblocks.size(), pp->round_keys.data(), (uint32_t)pp->round_keys.size(), mds.data(),
+                          pp->full_rounds_beginning, pp->partial_rounds, pp->full_rounds_end};
+  }
   return circuit_create(cs->num_mult, (uint32_t)cs->V.size(), (uint32_t)cs->pub.size(), (uint32_t)cs->num_constraints(), cs->cons_ptr.data(), kind.data(), idx.data(),
                         co.data(), cs->tape.data(), cs->naux, (uint32_t)cs->wlc_ptr.size() - 1, cs->wlc_ptr.data(), wkind.data(), widx.data(),
-                        wco.data(), out);
+                        wco.data(), cs->pblocks.empty() ? nullptr : &pt, out);
 }
 
 struct DevBuf {
@@ -316,7 +323,7 @@ int32_t bp_circuit_from_arrays(uint32_t n, uint32_t m, uint32_t q, const uint32_
   std::vector<scm> co(nnz ? nnz : 1);
   for (uint32_t t = 0; t < nnz; t++) co[t] = load_scalar(coeff + 32 * (size_t)t);
   BpCircuit *c = nullptr;
-  int rc = circuit_create(n, m, 0, q, cons_ptr, kind, idx, co.data(), nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, &c);
+  int rc = circuit_create(n, m, 0, q, cons_ptr, kind, idx, co.data(), nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, &c);
   if (rc) return rc;
   *out = new bp_circuit{c};
   return BP_OK;

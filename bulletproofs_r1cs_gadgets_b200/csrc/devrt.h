@@ -39,6 +39,18 @@ inline int dev_h2d(void *d, const void *h, size_t n, dev_stream s) { return n ? 
 inline int dev_d2h(void *h, const void *d, size_t n, dev_stream s) { return n ? cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s) != cudaSuccess : 0; }
 inline int dev_d2d(void *d, const void *s_, size_t n, dev_stream s) { return n ? cudaMemcpyAsync(d, s_, n, cudaMemcpyDeviceToDevice, s) != cudaSuccess : 0; }
 inline int dev_memset(void *d, int v, size_t n, dev_stream s) { return n ? cudaMemsetAsync(d, v, n, s) != cudaSuccess : 0; }
+// fork/join helpers for the second internal stream (witness generation runs beside the transcript RNG)
+struct dev_side { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+inline int dev_side_init(dev_side &d) {
+  if (d.s) return 0;
+  if (cudaStreamCreateWithFlags(&d.s, cudaStreamNonBlocking) != cudaSuccess) return 1;
+  if (cudaEventCreateWithFlags(&d.fork, cudaEventDisableTiming) != cudaSuccess) return 1;
+  if (cudaEventCreateWithFlags(&d.join, cudaEventDisableTiming) != cudaSuccess) return 1;
+  return 0;
+}
+inline void dev_side_free(dev_side &d) { if (d.s) { cudaStreamDestroy(d.s); cudaEventDestroy(d.fork); cudaEventDestroy(d.join); d = dev_side(); } }
+inline dev_stream dev_side_fork(dev_side &d, dev_stream main) { cudaEventRecord(d.fork, main); cudaStreamWaitEvent(d.s, d.fork, 0); return d.s; }
+inline void dev_side_join(dev_side &d, dev_stream main) { cudaEventRecord(d.join, d.s); cudaStreamWaitEvent(main, d.join, 0); }
 inline int dev_sync(dev_stream s) {
   cudaError_t e = cudaStreamSynchronize(s);
   if (e != cudaSuccess) { fprintf(stderr, "bp_b200: stream sync failed: %s\n", cudaGetErrorString(e)); return 1; }
@@ -59,5 +71,10 @@ inline int dev_h2d(void *d, const void *h, size_t n, dev_stream) { if (n) memcpy
 inline int dev_d2h(void *h, const void *d, size_t n, dev_stream) { if (n) memcpy(h, d, n); return 0; }
 inline int dev_d2d(void *d, const void *s_, size_t n, dev_stream) { if (n) memcpy(d, s_, n); return 0; }
 inline int dev_memset(void *d, int v, size_t n, dev_stream) { if (n) memset(d, v, n); return 0; }
+struct dev_side { int s = 0; };
+inline int dev_side_init(dev_side &) { return 0; }
+inline void dev_side_free(dev_side &) {}
+inline dev_stream dev_side_fork(dev_side &, dev_stream main) { return main; }
+inline void dev_side_join(dev_side &, dev_stream) {}
 inline int dev_sync(dev_stream) { return 0; }
 #endif

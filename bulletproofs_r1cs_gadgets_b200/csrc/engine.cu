@@ -73,7 +73,9 @@ struct Workspace {
   ge_p3 *buckets = 0; size_t bucket_slots = 0;
   ge_p3 *wsum = 0, *Q = 0, *Gt = 0, *Ht = 0, *pts = 0;
   int8_t *naf = 0; int *naf_top = 0;
+  dev_side side;
   void release() {
+    dev_side_free(side);
     void *ps[] = {pub, uj, v, vbl, aux, wit, rand1, w_all, zpow, ypow, yinvpow, a, b, chal, t, tb, clr, part, ts, rng, dig, buckets, wsum, Q, Gt, Ht, pts, naf, naf_top};
     for (void *p : ps) dev_free(p);
     *this = Workspace();
@@ -139,7 +141,7 @@ size_t circuit_proof_len(const BpCircuit *c) { return 32 * (size_t)(14 + 2 * c->
 
 int circuit_create(uint32_t n, uint32_t m, uint32_t npub, uint32_t q, const uint32_t *cons_ptr, const uint8_t *kind, const uint32_t *idx,
                    const scm *coeff, const TapeOp *tape, uint32_t naux, uint32_t nwlc, const uint32_t *wlc_ptr,
-                   const uint8_t *wkind, const uint32_t *widx, const scm *wcoeff, BpCircuit **out) {
+                   const uint8_t *wkind, const uint32_t *widx, const scm *wcoeff, const HostPoseidonTape *ptape, BpCircuit **out) {
   int rc = bp_device_init();
   if (rc) return rc;
   BpCircuit *c = new BpCircuit();
@@ -186,6 +188,8 @@ int circuit_create(uint32_t n, uint32_t m, uint32_t npub, uint32_t q, const uint
     }
     for (uint32_t i = 0; i < n; i++) {
       const TapeOp &op = tape[i];
+      if (op.opL == W_SKIP) continue;
+      if (op.opL == W_POSEIDON) { if (!ptape || op.argL >= ptape->nblocks) { circuit_free(c); return BP_ERR_INVALID_ARGUMENT; } continue; }
       bool okL = (op.opL == W_LC && op.argL < nwlc) || (op.opL == W_AUX && op.argL < naux);
       bool okR = (op.opR == W_LC && op.argR < nwlc) || (op.opR == W_AUX && op.argR < naux) || op.opR == W_INV_L;
       if (!okL || !okR) { circuit_free(c); return BP_ERR_INVALID_ARGUMENT; }
@@ -197,6 +201,22 @@ int circuit_create(uint32_t n, uint32_t m, uint32_t npub, uint32_t q, const uint
     CK(dev_h2d(c->d_wkind, wkind, wn, s));
     CK(dev_h2d(c->d_widx, widx, wn * sizeof(uint32_t), s));
     CK(dev_h2d(c->d_wcoeff, wcoeff, wn * sizeof(scm), s));
+    if (ptape && ptape->nblocks) {
+      const uint32_t total = ptape->full_b + ptape->partial + ptape->full_e;
+      if (ptape->nkeys < total * POSEIDON_WIDTH) { circuit_free(c); return BP_ERR_INVALID_ARGUMENT; }
+      for (uint32_t b = 0; b < ptape->nblocks; b++) {
+        const PoseidonBlock &pb = ptape->blocks[b];
+        uint32_t per = pb.sbox == 1 ? 3 : 2, cnt = per * (POSEIDON_WIDTH * (ptape->full_b + ptape->full_e) + ptape->partial);
+        bool ok = pb.sbox <= 1 && (uint64_t)pb.first_mult + cnt <= n;
+        for (int i = 0; i < POSEIDON_WIDTH; i++) ok = ok && pb.in_lc[i] < nwlc;
+        if (!ok) { circuit_free(c); return BP_ERR_INVALID_ARGUMENT; }
+      }
+      if (dalloc(&c->d_pblocks, ptape->nblocks) || dalloc(&c->d_pos_rk, ptape->nkeys) || dalloc(&c->d_pos_mds, POSEIDON_WIDTH * POSEIDON_WIDTH)) { circuit_free(c); return BP_ERR_OOM; }
+      CK(dev_h2d(c->d_pblocks, ptape->blocks, ptape->nblocks * sizeof(PoseidonBlock), s));
+      CK(dev_h2d(c->d_pos_rk, ptape->round_keys, ptape->nkeys * sizeof(scm), s));
+      CK(dev_h2d(c->d_pos_mds, ptape->mds, POSEIDON_WIDTH * POSEIDON_WIDTH * sizeof(scm), s));
+      c->pos = PoseidonDev{c->d_pos_rk, c->d_pos_mds, ptape->full_b, ptape->partial, ptape->full_e};
+    }
   }
   CK(dev_sync(s));
   c->ws = new Workspace();
@@ -206,7 +226,7 @@ int circuit_create(uint32_t n, uint32_t m, uint32_t npub, uint32_t q, const uint
 void circuit_free(BpCircuit *c) {
   if (!c) return;
   dev_free(c->d_slot_ptr); dev_free(c->d_tq); dev_free(c->d_tcoeff); dev_free(c->d_tape); dev_free(c->d_wptr); dev_free(c->d_wkind);
-  dev_free(c->d_widx); dev_free(c->d_wcoeff);
+  dev_free(c->d_widx); dev_free(c->d_wcoeff); dev_free(c->d_pblocks); dev_free(c->d_pos_rk); dev_free(c->d_pos_mds);
   if (c->ws) { c->ws->release(); delete c->ws; }
   delete c;
 }
@@ -290,8 +310,22 @@ int engine_prove(const BpGens *g, BpCircuit *c, const ProveArgs &A, dev_stream s
   // 1. inputs -> Montgomery, commitments V_j = v_j*B + r_j*B_blinding
   CK(launch(m * B, s, KLoadScalars{A.v, w->v, (int)m, B}));
   CK(launch(m * B, s, KLoadScalars{A.vbl, w->vbl, (int)m, B}));
+  // 2+3. witness generation on a side stream, beside the transcript start + transcript RNG draws (A.3 steps 1-3):
+  // both are one-thread-per-proof sequential chains (latency-bound), so they overlap almost perfectly.
+  CK(dev_side_init(w->side));
+  {
+    dev_stream s2 = dev_side_fork(w->side, s);
+    if (A.aL) {
+      CK(launch(n * B, s2, KLoadScalars{A.aL, aL, (int)n, B}));
+      CK(launch(n * B, s2, KLoadScalars{A.aR, aR, (int)n, B}));
+      CK(launch(n * B, s2, KLoadScalars{A.aO, aO, (int)n, B}));
+    } else {
+      if (c->naux) CK(launch((long)c->naux * B, s2, KLoadScalars{A.aux, w->aux, (int)c->naux, B}));
+      if (c->npub && A.pub) CK(launch((long)c->npub * B, s2, KLoadScalars{A.pub, w->pub, (int)c->npub, B}));
+      CK(launch(B, s2, KWitnessTape{c->d_tape, WitnessLcs{c->d_wptr, c->d_wkind, c->d_widx, c->d_wcoeff}, c->d_pblocks, c->pos, (int)n, B, w->v, w->aux, w->pub, aL, aR, aO}));
+    }
+  }
   CK(launch(m * B, s, KCommit{w->v, w->vbl, (int)m, B, g->pc_table, A.V_out, m * 32, 32, nullptr}));
-  // 2. transcript start + transcript RNG, blinding draws (A.3 steps 1-3)
   strobe128 base; base_transcript(base, A.label, A.label_len);
   CK(launch(B, s, KTsStart{base, A.V_out, (int)m, B, w->vbl, A.entropy, w->ts, w->rng, 1}));
   std::vector<uint8_t> dbg_states;
@@ -302,16 +336,7 @@ int engine_prove(const BpGens *g, BpCircuit *c, const ProveArgs &A, dev_stream s
     CK(dev_sync(s));
   }
   CK(launch(B, s, KRngDraw{w->rng, w->rand1, (int)(3 + 2 * n), B}));
-  // 3. witness
-  if (A.aL) {
-    CK(launch(n * B, s, KLoadScalars{A.aL, aL, (int)n, B}));
-    CK(launch(n * B, s, KLoadScalars{A.aR, aR, (int)n, B}));
-    CK(launch(n * B, s, KLoadScalars{A.aO, aO, (int)n, B}));
-  } else {
-    if (c->naux) CK(launch((long)c->naux * B, s, KLoadScalars{A.aux, w->aux, (int)c->naux, B}));
-    if (c->npub && A.pub) CK(launch((long)c->npub * B, s, KLoadScalars{A.pub, w->pub, (int)c->npub, B}));
-    CK(launch(B, s, KWitnessTape{c->d_tape, WitnessLcs{c->d_wptr, c->d_wkind, c->d_widx, c->d_wcoeff}, (int)n, B, w->v, w->aux, w->pub, aL, aR, aO}));
-  }
+  dev_side_join(w->side, s);
   // 4. A_I1, A_O1, S1 (A.3 step 4)
   {
     const long rowsI = 2 * n + 1, rowsO = n + 1;

@@ -19,6 +19,8 @@ struct BpGens {
   struct Workspace *msm_ws; uint32_t msm_ws_n;  // scratch of the MSM microbenchmark entry
 };
 
+// Poseidon block ops of a witness tape (host side): blocks + the parameters they share
+struct HostPoseidonTape { const PoseidonBlock *blocks; uint32_t nblocks; const scm *round_keys; uint32_t nkeys; const scm *mds; uint32_t full_b, partial, full_e; };
 struct HostTerm { uint8_t kind; uint32_t idx; uint8_t coeff[32]; };  // kind: 0 committed,1 left,2 right,3 output,4 one
 
 struct Workspace;
@@ -27,6 +29,7 @@ struct BpCircuit {
   uint32_t *d_slot_ptr, *d_tq; scm *d_tcoeff;
   int has_tape;
   TapeOp *d_tape; uint32_t *d_wptr; uint8_t *d_wkind; uint32_t *d_widx; scm *d_wcoeff;
+  PoseidonBlock *d_pblocks; scm *d_pos_rk, *d_pos_mds; PoseidonDev pos;
   Workspace *ws;
 };
 
@@ -38,7 +41,7 @@ int gens_export(const BpGens *g, int which, uint32_t count, uint8_t *out);  // w
 // cons_ptr[q+1], terms in constraint order, coefficients in Montgomery form (host).  tape (optional, n entries) + witness LCs.
 int circuit_create(uint32_t n, uint32_t m, uint32_t npub, uint32_t q, const uint32_t *cons_ptr, const uint8_t *kind, const uint32_t *idx,
                    const scm *coeff, const TapeOp *tape, uint32_t naux, uint32_t nwlc, const uint32_t *wlc_ptr,
-                   const uint8_t *wkind, const uint32_t *widx, const scm *wcoeff, BpCircuit **out);
+                   const uint8_t *wkind, const uint32_t *widx, const scm *wcoeff, const struct HostPoseidonTape *ptape, BpCircuit **out);
 void circuit_free(BpCircuit *c);
 size_t circuit_proof_len(const BpCircuit *c);
 

@@ -149,6 +149,14 @@ static int synthesize_sbox(bp_cs &cs, const LC &input, const scm &round_key, int
 int poseidon_permutation_constraints(bp_cs &cs, const bp_poseidon_params &p, std::vector<LC> &st, int sbox) {  // gadget_poseidon.rs:282-399
   const uint32_t w = p.width, total = p.full_rounds_beginning + p.partial_rounds + p.full_rounds_end;
   if (st.size() != w) return BP_ERR_GADGET;
+  // witness program: the whole permutation becomes one block op when it has the standard shape
+  const bool block = w == POSEIDON_WIDTH && cs.pending < 0 && (cs.pparams == nullptr || cs.pparams == &p);
+  PoseidonBlock blk{};
+  if (block) {
+    cs.pparams = &p;
+    for (uint32_t i = 0; i < w; i++) blk.in_lc[i] = cs.add_wlc(st[i]);
+    blk.sbox = (uint32_t)sbox; blk.first_mult = cs.num_mult;
+  }
   size_t off = 0;
   for (uint32_t rnd = 0; rnd < total; rnd++) {
     bool full = rnd < p.full_rounds_beginning || rnd >= p.full_rounds_beginning + p.partial_rounds;
@@ -162,6 +170,11 @@ int poseidon_permutation_constraints(bp_cs &cs, const bp_poseidon_params &p, std
     for (uint32_t j = 0; j < w; j++)
       for (uint32_t i = 0; i < w; i++) nx[i] += outs[j] * p.mds[i][j];
     for (uint32_t i = 0; i < w; i++) st[i] = full ? nx[i] : nx[i].simplified();
+  }
+  if (block && cs.num_mult > blk.first_mult) {
+    for (uint32_t i = blk.first_mult; i < cs.num_mult; i++) { cs.tape[i] = TapeOp{}; cs.tape[i].opL = W_SKIP; }
+    cs.tape[blk.first_mult].opL = W_POSEIDON; cs.tape[blk.first_mult].argL = (uint32_t)cs.pblocks.size();
+    cs.pblocks.push_back(blk);
   }
   return BP_OK;
 }

@@ -91,6 +91,12 @@ HD void strobe_absorb(strobe128 &s, const uint8_t *d, int n) {
 HD void strobe_overwrite(strobe128 &s, const uint8_t *d, int n) {
   for (int i = 0; i < n; i++) { st_set(s.st, s.pos, d[i]); if (++s.pos == STROBE_R) strobe_run_f(s); }
 }
+// squeeze whole 64-bit words (pos and n multiples of 8, no rate crossing): the transcript-RNG fast path
+HD void strobe_squeeze_words(strobe128 &s, uint64_t *d, int nwords) {
+  int w0 = s.pos >> 3;
+  for (int i = 0; i < nwords; i++) { d[i] = s.st[w0 + i]; s.st[w0 + i] = 0; }
+  s.pos = (uint8_t)(s.pos + 8 * nwords);
+}
 HD void strobe_squeeze(strobe128 &s, uint8_t *d, int n) {
   for (int i = 0; i < n; i++) { d[i] = st_get(s.st, s.pos); st_set(s.st, s.pos, 0); if (++s.pos == STROBE_R) strobe_run_f(s); }
 }
@@ -164,6 +170,17 @@ HD void trng_rekey(strobe128 &r, const char (&label)[LN], const uint8_t *w, int 
 HD void trng_finalize(strobe128 &r, const uint8_t entropy[32]) {
   const uint8_t lb[3] = {'r', 'n', 'g'};
   strobe_meta_ad(r, lb, 3, 0); strobe_key(r, entropy, 32);
+}
+// 64 uniform bytes as eight little-endian words (what Scalar::random reduces): same stream as trng_fill(r, out, 64)
+HD void trng_fill64_words(strobe128 &r, uint64_t w[8]) {
+  uint8_t l4[4]; u32le(l4, 64);
+  strobe_meta_ad(r, l4, 4, 0);
+  strobe_begin_op(r, SF_I | SF_A | SF_C, 0);
+  if ((r.pos & 7) == 0 && r.pos + 64 < STROBE_R) strobe_squeeze_words(r, w, 8);
+  else {
+    uint8_t b[64]; strobe_squeeze(r, b, 64);
+    for (int i = 0; i < 8; i++) { uint64_t x = 0; for (int j = 7; j >= 0; j--) x = (x << 8) | b[8 * i + j]; w[i] = x; }
+  }
 }
 HD void trng_fill(strobe128 &r, uint8_t *out, int n) {
   uint8_t l4[4]; u32le(l4, (uint32_t)n);

@@ -216,7 +216,7 @@ struct KRngDraw {
   strobe128 *rng; scm *dst; int count, B;
   HD void operator()(long p) const {
     strobe128 r; strobe_load(r, &rng[p]);
-    for (int i = 0; i < count; i++) { uint8_t b[64]; trng_fill(r, b, 64); dst[(long)i * B + p] = sc_from_bytes_wide(b); }
+    for (int i = 0; i < count; i++) { uint64_t w[8]; trng_fill64_words(r, w); dst[(long)i * B + p] = sc_from_words_wide(w); }
     strobe_store(&rng[p], r);
   }
 };
@@ -623,13 +623,21 @@ struct KEncodePoints {
 // W_AUX reads per-proof auxiliary input #arg (allocate_multiplier with caller-computed values,
 // reference src/r1cs_utils.rs:29-32).
 // ------------------------------------------------------------------------------------------------
-enum { W_LC = 0, W_INV_L = 1, W_AUX = 2 };
+enum { W_LC = 0, W_INV_L = 1, W_AUX = 2, W_POSEIDON = 3, W_SKIP = 4 };
 struct TapeOp { uint8_t opL, opR, pad[2]; uint32_t argL, argR; };
 struct WitnessLcs { const uint32_t *ptr; const uint8_t *kind; const uint32_t *idx; const scm *coeff; };
+// Block op: one whole Poseidon permutation (reference src/gadget_poseidon.rs:282-399) evaluated natively on the
+// 6-lane state instead of through its ~12k-term linear combinations; fills the multipliers of all its S-boxes in
+// circuit order (inverse S-box: (x, 1/x, x/x), (x, 0, 0), (x, 1/x, x/x); cube: (x, x, x^2), (x^2, x, x^3)).
+struct PoseidonBlock { uint32_t in_lc[6]; uint32_t sbox; uint32_t first_mult; };
+struct PoseidonDev { const scm *round_keys; const scm *mds; uint32_t full_b, partial, full_e; };
+#define POSEIDON_WIDTH 6
+
 struct KWitnessTape {
   static constexpr int kBlock = 32, kMinBlocks = 1;
   static constexpr const char *kName = "KWitnessTape";
-  const TapeOp *tape; WitnessLcs lcs; int n, B; const scm *v; const scm *aux; const scm *pub; scm *aL, *aR, *aO;
+  const TapeOp *tape; WitnessLcs lcs; const PoseidonBlock *pblocks; PoseidonDev pos; int n, B;
+  const scm *v; const scm *aux; const scm *pub; scm *aL, *aR, *aO;
   HD scm eval(uint32_t lc, int p) const {
     scm acc = sc_zero();
     for (uint32_t t = lcs.ptr[lc]; t < lcs.ptr[lc + 1]; t++) {
@@ -645,15 +653,65 @@ struct KWitnessTape {
     }
     return acc;
   }
+  HD void put(long i, int p, const scm &l, const scm &r, const scm &o) const { long at = i * B + p; aL[at] = l; aR[at] = r; aO[at] = o; }
+  HD long sbox_out(long at, int p, scm &x, int sbox) const {  // writes the S-box multipliers, replaces x by the S-box output
+    if (sbox == 0) {
+      scm sq = sc_sqr(x), cu = sc_mul(sq, x);
+      put(at, p, x, x, sq); put(at + 1, p, sq, x, cu);
+      x = cu; return at + 2;
+    }
+    scm inv = sc_invert(x), o = sc_mul(x, inv);
+    put(at, p, x, inv, o); put(at + 1, p, x, sc_zero(), sc_zero()); put(at + 2, p, x, inv, o);
+    x = inv; return at + 3;
+  }
+  HD void poseidon(const PoseidonBlock &blk, int p) const {
+    scm st[POSEIDON_WIDTH];
+    for (int i = 0; i < POSEIDON_WIDTH; i++) st[i] = eval(blk.in_lc[i], p);
+    long at = blk.first_mult; uint32_t off = 0;
+    const uint32_t total = pos.full_b + pos.partial + pos.full_e;
+    for (uint32_t rnd = 0; rnd < total; rnd++) {
+      const bool full = rnd < pos.full_b || rnd >= pos.full_b + pos.partial;
+      for (int i = 0; i < POSEIDON_WIDTH; i++) st[i] = sc_add(st[i], pos.round_keys[off + i]);
+      off += POSEIDON_WIDTH;
+      if (full && blk.sbox == 1) {
+        // six inversions with one field inversion (Montgomery's trick); zero inputs map to zero as Scalar::invert does
+        scm x[POSEIDON_WIDTH], pre[POSEIDON_WIDTH], acc = sc_one();
+        for (int i = 0; i < POSEIDON_WIDTH; i++) { x[i] = sc_is_zero(st[i]) ? sc_one() : st[i]; pre[i] = acc; acc = sc_mul(acc, x[i]); }
+        scm inv = sc_invert(acc);
+        for (int i = POSEIDON_WIDTH - 1; i >= 0; i--) {
+          scm xi = sc_mul(inv, pre[i]); inv = sc_mul(inv, x[i]);
+          if (sc_is_zero(st[i])) xi = sc_zero();
+          x[i] = xi;
+        }
+        for (int i = 0; i < POSEIDON_WIDTH; i++) {
+          scm o = sc_is_zero(st[i]) ? sc_zero() : sc_one();
+          put(at, p, st[i], x[i], o); put(at + 1, p, st[i], sc_zero(), sc_zero()); put(at + 2, p, st[i], x[i], o);
+          at += 3; st[i] = x[i];
+        }
+      } else if (full) {
+        for (int i = 0; i < POSEIDON_WIDTH; i++) at = sbox_out(at, p, st[i], blk.sbox);
+      } else {
+        at = sbox_out(at, p, st[POSEIDON_WIDTH - 1], blk.sbox);
+      }
+      scm nx[POSEIDON_WIDTH];
+      for (int i = 0; i < POSEIDON_WIDTH; i++) {
+        scm acc = sc_zero();
+        for (int j = 0; j < POSEIDON_WIDTH; j++) acc = sc_add(acc, sc_mul(st[j], pos.mds[i * POSEIDON_WIDTH + j]));
+        nx[i] = acc;
+      }
+      for (int i = 0; i < POSEIDON_WIDTH; i++) st[i] = nx[i];
+    }
+  }
   HD void operator()(long p_) const {
     int p = (int)p_;
     for (int i = 0; i < n; i++) {
       TapeOp op = tape[i];
+      if (op.opL == W_SKIP) continue;
+      if (op.opL == W_POSEIDON) { poseidon(pblocks[op.argL], p); continue; }
       scm l, r;
       if (op.opL == W_LC) l = eval(op.argL, p); else l = aux[(long)op.argL * B + p];
       if (op.opR == W_LC) r = eval(op.argR, p); else if (op.opR == W_INV_L) r = sc_invert(l); else r = aux[(long)op.argR * B + p];
-      long at = (long)i * B + p;
-      aL[at] = l; aR[at] = r; aO[at] = sc_mul(l, r);
+      put(i, p, l, r, sc_mul(l, r));
     }
   }
 };

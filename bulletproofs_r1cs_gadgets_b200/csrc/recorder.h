@@ -52,6 +52,8 @@ struct bp_cs {
   std::vector<scm> aux;                          // prover only: values of the auxiliary inputs
   uint32_t naux = 0;
   std::vector<scm> pub;                          // public inputs (values for this cs; zero when recording only)
+  std::vector<PoseidonBlock> pblocks;            // block ops of the witness program
+  const struct bp_poseidon_params *pparams = nullptr;  // parameters shared by every block op
 
 
   uint32_t add_wlc(const LC &lc) {

@@ -54,7 +54,44 @@ HD scm sc_neg(const scm &a) { return sc_sub(sc_zero(), a); }
 HD int sc_is_zero(const scm &a) { return (a.v[0] | a.v[1] | a.v[2] | a.v[3]) == 0; }
 HD int sc_equal(const scm &a, const scm &b) { return ((a.v[0] ^ b.v[0]) | (a.v[1] ^ b.v[1]) | (a.v[2] ^ b.v[2]) | (a.v[3] ^ b.v[3])) == 0; }
 
-// Montgomery product a*b/2^256 mod l (CIOS); a may be any 256-bit value, b < l  ->  result < l
+// Montgomery product a*b/2^256 mod l (CIOS); a may be any 256-bit value, b < l  ->  result < l.
+// Two forms: 4 x 64-bit words with 128-bit products for host code, and 8 x 32-bit words for the device,
+// where one 32x32+64 multiply-add is a single IMAD.WIDE (the emulation build uses the device form too,
+// so the CPU-side kernel-body tests cover it).
+#if defined(__CUDA_ARCH__) || defined(BP_HOST_EMUL)
+HD scm sc_montmul(const scm &a, const scm &b) {
+  const uint64_t l64[4] = SC_L_LIMBS;
+  uint32_t l[8], aw[8], bw[8];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    l[2 * i] = (uint32_t)l64[i]; l[2 * i + 1] = (uint32_t)(l64[i] >> 32);
+    aw[2 * i] = (uint32_t)a.v[i]; aw[2 * i + 1] = (uint32_t)(a.v[i] >> 32);
+    bw[2 * i] = (uint32_t)b.v[i]; bw[2 * i + 1] = (uint32_t)(b.v[i] >> 32);
+  }
+  const uint32_t ninv = (uint32_t)SC_NINV;
+  uint32_t t[10];
+#pragma unroll
+  for (int i = 0; i < 10; i++) t[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    uint64_t acc, carry = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { acc = (uint64_t)aw[j] * bw[i] + t[j] + carry; t[j] = (uint32_t)acc; carry = acc >> 32; }
+    acc = (uint64_t)t[8] + carry; t[8] = (uint32_t)acc; t[9] = (uint32_t)(acc >> 32);
+    uint32_t m = t[0] * ninv;
+    acc = (uint64_t)m * l[0] + t[0]; carry = acc >> 32;
+#pragma unroll
+    for (int j = 1; j < 8; j++) { acc = (uint64_t)m * l[j] + t[j] + carry; t[j - 1] = (uint32_t)acc; carry = acc >> 32; }
+    acc = (uint64_t)t[8] + carry; t[7] = (uint32_t)acc; t[8] = t[9] + (uint32_t)(acc >> 32);
+  }
+  scm r;
+#pragma unroll
+  for (int i = 0; i < 4; i++) r.v[i] = (uint64_t)t[2 * i] | ((uint64_t)t[2 * i + 1] << 32);
+  sc_cond_sub_l(r.v, t[8]);
+  sc_cond_sub_l(r.v, 0);
+  return r;
+}
+#else
 HD scm sc_montmul(const scm &a, const scm &b) {
   uint64_t l[4]; sc_const_l(l);
   uint64_t t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0;
@@ -82,6 +119,7 @@ HD scm sc_montmul(const scm &a, const scm &b) {
   sc_cond_sub_l(r.v, 0);
   return r;
 }
+#endif
 HD scm sc_mul(const scm &a, const scm &b) { return sc_montmul(a, b); }  // both Montgomery -> Montgomery
 HD scm sc_sqr(const scm &a) { return sc_montmul(a, a); }
 HD scm sc_muladd(const scm &a, const scm &b, const scm &c) { return sc_add(sc_montmul(a, b), c); }
@@ -100,6 +138,11 @@ HD scm sc_from_bytes_mod_order(const uint8_t *s) { scm x; load_le64x4(x.v, s); r
 // 64 bytes, wide reduction -> Montgomery:  lo*R + hi*2^256*R = montmul(lo,R^2) + montmul(hi,R^3)
 HD scm sc_from_bytes_wide(const uint8_t *s) {
   scm lo, hi; load_le64x4(lo.v, s); load_le64x4(hi.v, s + 32);
+  return sc_add(sc_montmul(lo, sc_r2()), sc_montmul(hi, sc_r3()));
+}
+HD scm sc_from_words_wide(const uint64_t w[8]) {
+  scm lo, hi;
+  lo.v[0] = w[0]; lo.v[1] = w[1]; lo.v[2] = w[2]; lo.v[3] = w[3]; hi.v[0] = w[4]; hi.v[1] = w[5]; hi.v[2] = w[6]; hi.v[3] = w[7];
   return sc_add(sc_montmul(lo, sc_r2()), sc_montmul(hi, sc_r3()));
 }
 // Montgomery -> canonical integer limbs
