@@ -1,0 +1,62 @@
+"""The shipped C-ABI library: loads, exports every entry point include/bp_b200.h declares, and fails loudly without a GPU."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "bp_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(bp_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_the_boundary():
+    names = declared_functions()
+    for must in ("bp_gens_new", "bp_prover_new", "bp_prover_commit", "bp_verifier_commit", "bp_cs_multiply", "bp_cs_allocate_multiplier",
+                 "bp_cs_allocate_single", "bp_cs_evaluate_lc", "bp_cs_constrain", "bp_cs_num_constraints", "bp_cs_num_multipliers",
+                 "bp_prover_prove", "bp_verifier_verify", "bp_circuit_compile", "bp_prove_batch", "bp_verify_batch", "bp_prove_batch_device",
+                 "bp_msm_gens_device"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol(product_so):
+    lib = C.CDLL(product_so)
+    missing = [n for n in declared_functions() if not hasattr(lib, n)]
+    assert not missing, missing
+    assert lib.bp_version() >= 1
+
+
+def test_emulation_build_is_not_the_product(product_so):
+    """the product library is a CUDA binary for sm_100a (no host-emulation launcher inside)"""
+    out = os.popen("cuobjdump -lelf %s 2>/dev/null" % product_so).read()
+    assert "sm_100a" in out
+    api_src = open(os.path.join(ROOT, "bulletproofs_r1cs_gadgets_b200", "api.py")).read()
+    assert "emul" not in api_src.replace("emulation build", "")  # the Python layer never reaches for the emulation library
+
+
+def test_fails_loudly_without_gpu(product_so):
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    lib = C.CDLL(product_so)
+    h = C.c_void_p()
+    assert lib.bp_gens_new(C.c_uint32(16), C.byref(h)) == 7  # BP_ERR_NO_DEVICE: no CPU fallback
+    out = (C.c_uint8 * 32)()
+    assert lib.bp_selftest_device(1, (C.c_uint8 * 32)(), C.c_size_t(32), out, C.c_size_t(32)) == 7
+
+
+def test_python_layer_requires_the_library(tmp_path, monkeypatch):
+    from bulletproofs_r1cs_gadgets_b200 import api
+    saved = api._lib
+    api._lib = None
+    monkeypatch.setattr(api, "DEFAULT_SO", str(tmp_path / "missing.so"))
+    with pytest.raises(RuntimeError):
+        api.load()
+    api._lib = saved

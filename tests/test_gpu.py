@@ -1,0 +1,195 @@
+"""Parity tests proper: the CUDA library on a real B200, through the C-ABI, against the oracle.
+Run with  python -m pytest tests -m gpu.  The small-case bodies are shared with tests/test_host_emul.py."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+import test_host_emul as E
+from helpers import R, G, CO, L
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api(product_so):
+    from bulletproofs_r1cs_gadgets_b200 import api as a
+    a._lib = None
+    a.load(product_so)
+    return a
+
+
+@pytest.fixture(scope="module")
+def gens(api):
+    return api.Gens(256)
+
+
+@pytest.fixture(scope="module")
+def gens_big(api):
+    return api.Gens(32768)
+
+
+def test_primitives(api): E.test_primitives(api)
+def test_generators(api, gens, oracle_lib): E.test_generators(api, gens, oracle_lib)
+def test_msm_entry(api, gens): E.test_msm_entry(api, gens)
+def test_golden_proofs_tier1(api, gens): E.test_golden_proofs_tier1(api, gens)
+def test_python_gadget_code_drives_product_cs(api, gens): E.test_python_gadget_code_drives_product_cs(api, gens)
+def test_verifier_rejects_tampering(api, gens): E.test_verifier_rejects_tampering(api, gens)
+def test_batch_witness_program_and_public_inputs(api, gens): E.test_batch_witness_program_and_public_inputs(api, gens)
+def test_batch_aux_inputs_bound_check(api, gens): E.test_batch_aux_inputs_bound_check(api, gens)
+def test_explicit_witness_equals_witness_program(api, gens, oracle_lib): E.test_explicit_witness_equals_witness_program(api, gens, oracle_lib)
+def test_chunking_is_invisible(api, gens, monkeypatch): E.test_chunking_is_invisible(api, gens, monkeypatch)
+def test_error_codes(api, gens): E.test_error_codes(api, gens)
+def test_single_multiplier_and_allocate_single(api, gens): E.test_single_multiplier_and_allocate_single(api, gens)
+
+
+def test_msm_entry_larger_sizes(api, gens_big, oracle_lib):
+    """MSM microbenchmark entry (BASELINE config 3) against the C oracle's Pippenger, device buffers"""
+    import torch
+    og = np.zeros((4096, 32), np.uint8)
+    oracle_lib.lib().bpo_gens_compressed(0, 4096, og.ctypes.data_as(CO.u8p))
+    for n, seed in ((1, 1), (33, 2), (1024, 3), (4096, 4)):
+        sc = H.rand_scalars(seed, n)
+        if n == 1024:
+            sc = [s if i % 2 else 0 for i, s in enumerate(sc)]  # 50 % zeros (inverse-S-box a_R shape)
+        arr = api.scalars_to_array(sc)
+        d_in = torch.from_numpy(arr).cuda()
+        d_out = torch.zeros(32, dtype=torch.uint8, device="cuda")
+        assert api.load().bp_msm_gens_device(gens_big._h, n, C.c_void_p(d_in.data_ptr()), C.c_void_p(d_out.data_ptr()), None) == 0
+        torch.cuda.synchronize()
+        out = np.zeros(32, np.uint8)
+        assert oracle_lib.lib().bpo_msm(n, arr.ctypes.data_as(CO.u8p), og.ctypes.data_as(CO.u8p), out.ctypes.data_as(CO.u8p)) == 0
+        assert d_out.cpu().numpy().tobytes() == out.tobytes(), n
+
+
+def _oracle_circuit(build, m, label):
+    v = R.Verifier(R.Transcript(label)); vs = [v.commit(bytes(32)) for _ in range(m)]; build(v, vs)
+    return CO.Circuit.from_cs(v, m)
+
+
+def _check_batch_against_c_oracle(api, gens, wl, ocirc, witness_fn, B, cap, first=0):
+    inp = wl.inputs(first, B)
+    V, P, st = wl.circuit.prove_batch(gens, wl.label, inp["v"], inp["v_blinding"], inp["entropy"], aux=inp.get("aux"), pub=inp.get("pub"))
+    assert not st.any()
+    assert (ocirc.n, ocirc.q, ocirc.m) == (wl.circuit.n, wl.circuit.q, wl.circuit.m)
+    for i in range(B):
+        aL, aR, aO = witness_fn(inp, i)
+        rc, oV, oP = CO.prove(ocirc, aL, aR, aO, inp["v"][i], inp["v_blinding"][i], wl.label, inp["entropy"][i].tobytes(), cap)
+        assert rc == 0 and oV.tobytes() == V[i].tobytes(), "commitments differ from the oracle (proof %d)" % i
+        assert oP == P[i].tobytes(), "proof bytes differ from the oracle (proof %d)" % i
+    ok = wl.circuit.verify_batch(gens, wl.label, V, P, inp["entropy"], pub=inp.get("pub"))
+    assert not ok.any()
+    return inp, V, P
+
+
+@pytest.mark.parametrize("sbox", [0, 1])
+def test_poseidon_2to1_reference_parameters(api, gens_big, oracle_lib, sbox):
+    """BASELINE config 2 shape: width 6, 4+140+4 rounds, both S-boxes (reference src/gadget_poseidon.rs:691-785, :889-894)"""
+    from bulletproofs_r1cs_gadgets_b200 import workloads
+    oracle_lib.poseidon_set_params(H.POSEIDON_BLOB)
+    wl = workloads.PoseidonHash2(gens_big, sbox)
+    assert (wl.circuit.n, wl.circuit.q) == ((376, 753), (564, 1317))[sbox]
+    pp = G.PoseidonParams()
+    # the constant in the last constraint does not enter the proof: record the oracle circuit with hash = 0
+    oc = _oracle_circuit(lambda cs, v: G.poseidon_hash_2_gadget(cs, v[0], v[1], v[2:], pp, sbox, 0), 6, wl.label)
+
+    def wit(inp, i):
+        aL, aR, aO, h = oracle_lib.poseidon_hash2_witness(inp["v"][i][0].tobytes(), inp["v"][i][1].tobytes(), sbox, oc.n)
+        assert h == inp["pub"][i][0].tobytes()
+        return aL, aR, aO
+    _check_batch_against_c_oracle(api, gens_big, wl, oc, wit, 4, 1024)
+
+
+def test_mimc_322(api, gens_big, oracle_lib):
+    """BASELINE config 4 shape (reference src/gadget_mimc.rs:92-175)"""
+    from bulletproofs_r1cs_gadgets_b200 import workloads
+    wl = workloads.Mimc(gens_big)
+    assert (wl.circuit.n, wl.circuit.q, wl.circuit.m) == (644, 1289, 2)
+    oc = _oracle_circuit(lambda cs, v: G.mimc_gadget(cs, v[0], v[1], 322, wl.constants, 0), 2, wl.label)
+    cb = CO.scalars_to_array(wl.constants, L).tobytes()
+
+    def wit(inp, i):
+        aL, aR, aO, img = oracle_lib.mimc_witness(inp["v"][i][0].tobytes(), inp["v"][i][1].tobytes(), cb, oc.n)
+        assert img == inp["pub"][i][0].tobytes()
+        return aL, aR, aO
+    _check_batch_against_c_oracle(api, gens_big, wl, oc, wit, 3, 1024)
+
+
+def test_bound_check_64bit(api, gens, oracle_lib):
+    """BASELINE config 1 (reference src/gadget_bound_check.rs:49-116): n = 128 = N, no padding"""
+    from bulletproofs_r1cs_gadgets_b200 import workloads
+    wl = workloads.BoundCheck(gens)
+    assert (wl.circuit.n, wl.circuit.q, wl.circuit.m) == (128, 261, 3)
+    oc = _oracle_circuit(lambda cs, v: G.bound_check_gadget(cs, (v[0], None), (v[1], None), (v[2], None), 2 ** 64 - 1, 0, 64), 3, wl.label)
+
+    def wit(inp, i):
+        vals = [int.from_bytes(inp["v"][i][j].tobytes(), "little") for j in range(3)]
+        p = R.Prover(R.PedersenGens(), R.Transcript(b"x")); vs = [p.commit(v, 0)[1] for v in vals]
+        G.bound_check_gadget(p, (vs[0], vals[0]), (vs[1], vals[1]), (vs[2], vals[2]), 2 ** 64 - 1, 0, 64)
+        return tuple(CO.scalars_to_array(a, L) for a in (p.aL, p.aR, p.aO))
+    _check_batch_against_c_oracle(api, gens, wl, oc, wit, 3, 128)
+
+
+@pytest.mark.parametrize("depth,B", [(3, 3), (32, 2)])
+def test_vsmt2_membership(api, gens_big, oracle_lib, depth, B):
+    """BASELINE config 5 (headline): Poseidon VSMT-2 membership, inverse S-box; depth 32 is the full-size case"""
+    from bulletproofs_r1cs_gadgets_b200 import workloads
+    oracle_lib.poseidon_set_params(H.POSEIDON_BLOB)
+    wl = workloads.Vsmt2(gens_big, depth=depth)
+    assert (wl.circuit.n, wl.circuit.q, wl.circuit.m) == (568 * depth, 1324 * depth + 1, 2 * depth + 5)
+    pp = G.PoseidonParams()
+    oc = _oracle_circuit(lambda cs, v: G.vanilla_merkle_tree_verif_gadget(cs, depth, 0, v[0], v[1:1 + depth], v[1 + depth:1 + 2 * depth], v[1 + 2 * depth:], pp),
+                         2 * depth + 5, wl.label)
+
+    def wit(inp, i):
+        leaf, bits, sibs = wl.witness_values(i)
+        aL, aR, aO, root = oracle_lib.vsmt2_witness(depth, api.scalar_bytes(leaf), bits, api.scalars_to_array(sibs), oc.n)
+        assert root == inp["pub"][i][0].tobytes()
+        return aL, aR, aO
+    N = 1
+    while N < oc.n:
+        N *= 2
+    inp, V, P = _check_batch_against_c_oracle(api, gens_big, wl, oc, wit, B, N)
+    # wrong root, wrong sibling commitment, tampered proof bytes are rejected, proof by proof
+    bad = inp["pub"].copy(); bad[0, 0, 5] ^= 4
+    assert wl.circuit.verify_batch(gens_big, wl.label, V, P, inp["entropy"], pub=bad).tolist() == [3] + [0] * (B - 1)
+    V2 = V.copy(); V2[B - 1, 1 + depth] = V2[B - 1, 2 + depth]
+    assert wl.circuit.verify_batch(gens_big, wl.label, V2, P, inp["entropy"], pub=inp["pub"]).tolist() == [0] * (B - 1) + [3]
+    P2 = P.copy(); P2[0, 500] ^= 1
+    assert wl.circuit.verify_batch(gens_big, wl.label, V, P2, inp["entropy"], pub=inp["pub"])[0] == 3
+
+
+def test_vsmt2_depth32_batch_properties(api, gens_big):
+    """full-size batch: prove -> verify round trip, determinism, host-buffer and device-buffer entry points agree,
+    results independent of how the batch is chunked"""
+    import torch
+    from bulletproofs_r1cs_gadgets_b200 import workloads
+    wl = workloads.Vsmt2(gens_big, depth=32)
+    B = 24
+    inp = wl.inputs(1000, B, with_root=False)
+    roots = wl.inputs(1000, 3)["pub"]  # native roots for the first three proofs only (host Poseidon is slow)
+    V, P, st = wl.circuit.prove_batch(gens_big, wl.label, inp["v"], inp["v_blinding"], inp["entropy"])
+    assert not st.any()
+    V_again, P_again, _ = wl.circuit.prove_batch(gens_big, wl.label, inp["v"], inp["v_blinding"], inp["entropy"])
+    assert P.tobytes() == P_again.tobytes() and V.tobytes() == V_again.tobytes()
+    os.environ["BP_B200_CHUNK"] = "7"
+    try:
+        V_c, P_c, _ = wl.circuit.prove_batch(gens_big, wl.label, inp["v"], inp["v_blinding"], inp["entropy"])
+    finally:
+        del os.environ["BP_B200_CHUNK"]
+    assert P.tobytes() == P_c.tobytes() and V.tobytes() == V_c.tobytes()
+    d = {k: torch.from_numpy(inp[k]).cuda() for k in ("v", "v_blinding", "entropy")}
+    dV = torch.empty((B, wl.circuit.m, 32), dtype=torch.uint8, device="cuda")
+    dP = torch.empty((B, wl.circuit.proof_len), dtype=torch.uint8, device="cuda")
+    dS = torch.empty((B,), dtype=torch.int32, device="cuda")
+    p = lambda t: C.c_void_p(t.data_ptr())
+    rc = api.load().bp_prove_batch_device(gens_big._h, wl.circuit._h, C.c_uint32(B), api._buf(wl.label), C.c_size_t(len(wl.label)), p(d["v"]), p(d["v_blinding"]),
+                                          p(d["entropy"]), None, None, None, None, None, p(dV), p(dP), p(dS), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert rc == 0 and dP.cpu().numpy().tobytes() == P.tobytes() and not dS.cpu().numpy().any()
+    ok = wl.circuit.verify_batch(gens_big, wl.label, V[:3], P[:3], inp["entropy"][:3], pub=roots)
+    assert not ok.any()
+    assert len({P[i].tobytes() for i in range(B)}) == B  # distinct statements, distinct proofs
+    assert P.shape[1] == 1472 and all(P[i, 96:192].tobytes() == bytes(96) for i in range(B))  # single-phase: A_I2, A_O2, S2 are the identity

@@ -1,0 +1,224 @@
+"""Kernel-body tests on the CPU: the CUDA sources compiled with g++ -DBP_HOST_EMUL (tests/emul).  Every kernel functor,
+the engine orchestration, the recorder and the C-ABI run here exactly as on the device, one "thread" at a time, and
+are compared with the oracle.  This is test infrastructure -- the product library has no CPU path."""
+import numpy as np
+import pytest
+
+import helpers as H
+from helpers import R, G, CO, L
+
+
+@pytest.fixture(scope="module")
+def api(emul_so):
+    from bulletproofs_r1cs_gadgets_b200 import api as a
+    a._lib = None
+    a.load(emul_so)
+    yield a
+    a._lib = None
+
+
+@pytest.fixture(scope="module")
+def gens(api):
+    return api.Gens(256)
+
+
+def test_primitives(api):
+    H.run_primitive_selftests(api)
+
+
+def test_generators(api, gens, oracle_lib):
+    B, Bb = gens.pedersen()
+    assert B == R.BASEPOINT_COMPRESSED and Bb == R.ristretto_encode(R.PedersenGens().B_blinding)
+    og = np.zeros((256, 32), np.uint8); oracle_lib.lib().bpo_gens_compressed(0, 256, og.ctypes.data_as(CO.u8p))
+    oh = np.zeros((256, 32), np.uint8); oracle_lib.lib().bpo_gens_compressed(1, 256, oh.ctypes.data_as(CO.u8p))
+    assert gens.export(0, 256).tobytes() == og.tobytes() and gens.export(1, 256).tobytes() == oh.tobytes()
+    for v, r in [(0, 0), (1, 0), (0, 1), (L - 1, L - 1)] + [tuple(H.rand_scalars(4, 2))]:
+        assert gens.commit(v, r) == R.ristretto_encode(R.PedersenGens().commit(v, r))
+
+
+def test_msm_entry(api, gens):
+    import ctypes as C
+    rnd_sets = {"one": [1], "rand3": H.rand_scalars(1, 3), "rand200": H.rand_scalars(2, 200), "bits": [x & 1 for x in H.rand_scalars(3, 200)],
+                "edge": [L - 1, L - 2, 127, 128, 129, 255, 256, 2 ** 252, 0], "zeros": [0, 0, 0]}
+    for name, sc in rnd_sets.items():
+        arr = api.scalars_to_array(sc)
+        out = np.zeros(32, np.uint8)
+        rc = api.load().bp_msm_gens_device(gens._h, len(sc), arr.ctypes.data_as(api.u8p), out.ctypes.data_as(api.u8p), None)
+        assert rc == 0
+        assert out.tobytes() == R.ristretto_encode(R.msm(sc, R.BulletproofGens(256).G(len(sc)))), name
+
+
+def test_golden_proofs_tier1(api, gens):
+    H.check_golden_tier1(api, gens)
+
+
+def test_python_gadget_code_drives_product_cs(api, gens):
+    """the oracle's generic gadget functions run unchanged against the product's ConstraintSystem mirror (tier-1 C-ABI):
+    same recorded circuit, same proof bytes"""
+    case = next(c for c in H.golden_cases() if c["name"] == "poseidon_2_3_2_inverse")
+    build = H.golden_builder(case)
+
+    class Adapter:  # maps the oracle's (kind, index) variables / LC objects onto the product API
+        def __init__(self, cs): self.cs = cs
+        def _lc(self, lc): return api.LinearCombination([(api.Variable(k, i), c) for (k, i), c in R.LC.of(lc).terms])
+        def _v(self, v): return (v.kind, v.index)
+        def multiply(self, l, r): return tuple(self._v(x) for x in self.cs.multiply(self._lc(l), self._lc(r)))
+        def constrain(self, lc): self.cs.constrain(self._lc(lc))
+        def evaluate_lc(self, lc): return self.cs.evaluate_lc(self._lc(lc))
+        def allocate_single(self, a):
+            v, o = self.cs.allocate_single(a)
+            return self._v(v), (self._v(o) if o is not None else None)
+        def allocate_multiplier(self, a): return tuple(self._v(x) for x in self.cs.allocate_multiplier(a))
+    p = api.Prover(gens, case["label"].encode())
+    vs = []
+    for v, b in zip(case["values"], case["blindings"]):
+        V, var = p.commit(int(v, 16), int(b, 16)); vs.append((var.kind, var.index))
+    build(Adapter(p), vs, True)
+    assert (p.num_multipliers(), p.num_constraints()) == (case["n"], case["q"])
+    assert p.prove(bytes.fromhex(case["entropy"])).hex() == case["proof"]
+
+
+def test_verifier_rejects_tampering(api, gens):
+    case = next(c for c in H.golden_cases() if c["name"] == "vsmt2_depth2_2_3_2")
+    Vs, proof, _ = H.product_tier1_prove(api, gens, case)
+    assert H.product_tier1_verify(api, gens, case, Vs, proof) == 0
+    assert H.product_tier1_verify(api, gens, case, Vs, proof, entropy=bytes(range(32))) == 0  # verifier entropy is free
+    for what, bad in H.tamper_cases(proof):
+        rc = H.product_tier1_verify(api, gens, case, Vs, bad)
+        assert rc in (2, 3), (what, rc)
+    Vbad = list(Vs); Vbad[0], Vbad[1] = Vbad[1], Vbad[0]
+    assert H.product_tier1_verify(api, gens, case, Vbad, proof) == 3
+    case2 = dict(case, label="VSMT-other")
+    assert H.product_tier1_verify(api, gens, case2, Vs, proof) == 3
+
+
+def test_batch_witness_program_and_public_inputs(api, gens):
+    """tier 2: circuit compiled once, witness program on the device, per-proof public inputs; bytes equal the oracle's"""
+    pp = api.PoseidonParams(6, 2, 2, 3)
+    opp = G.PoseidonParams(6, 2, 2, 3)
+    for sbox in (api.SBOX_CUBE, api.SBOX_INVERSE):
+        rec = api.Verifier(gens, b"P"); xs = [rec.commit(bytes(32)) for _ in range(2)]; st = [rec.commit(bytes(32)) for _ in range(4)]
+        hv = rec.public_input()
+        rec.poseidon_hash_2_gadget(pp, xs[0], xs[1], st, sbox, hv)
+        circ = rec.compile()
+        assert circ.has_witness_program and circ.num_public == 1 and circ.num_aux == 0
+        Bn = 3
+        sc = H.rand_scalars(10 + sbox, 4 * Bn)
+        ins = [(sc[4 * i], sc[4 * i + 1]) for i in range(Bn)]
+        ins[1] = ((-opp.round_keys[1]) % L, ins[1][1])  # proof 1 hits Scalar::invert(0) in round 0 (invalid statement for the inverse S-box)
+        hs = [G.poseidon_hash_2(a, b, opp, sbox) for a, b in ins]
+        vals = api.scalars_to_array(sum(([a, b, 0, 101, 0, 0] for a, b in ins), [])).reshape(Bn, 6, 32)
+        bls = api.scalars_to_array(sum(([sc[4 * i + 2], sc[4 * i + 3], 0, 0, 0, 0] for i in range(Bn)), [])).reshape(Bn, 6, 32)
+        ents = np.arange(32 * Bn, dtype=np.uint8).reshape(Bn, 32)
+        pub = api.scalars_to_array(hs).reshape(Bn, 1, 32)
+        V, proofs, status = circ.prove_batch(gens, b"P", vals, bls, ents, pub=pub)
+        assert not status.any()
+        for i in range(Bn):
+            op = R.Prover(R.PedersenGens(), R.Transcript(b"P"))
+            ops = [op.commit(int.from_bytes(vals[i][j].tobytes(), "little"), int.from_bytes(bls[i][j].tobytes(), "little")) for j in range(6)]
+            G.poseidon_hash_2_gadget(op, ops[0][1], ops[1][1], [o[1] for o in ops[2:]], opp, sbox, hs[i])
+            assert b"".join(o[0] for o in ops) == V[i].tobytes()
+            assert R.proof_to_bytes(op.prove(R.BulletproofGens(256), ents[i].tobytes())) == proofs[i].tobytes()
+        ok = circ.verify_batch(gens, b"P", V, proofs, ents, pub=pub)
+        assert ok.tolist() == ([0, 3, 0] if sbox == api.SBOX_INVERSE else [0, 0, 0])
+        bad = pub.copy(); bad[2, 0, 0] ^= 1
+        assert circ.verify_batch(gens, b"P", V, proofs, ents, pub=bad)[2] == 3
+
+
+def test_batch_aux_inputs_bound_check(api, gens):
+    """allocate_multiplier assignments (range-proof bits) travel as auxiliary inputs of the witness program"""
+    from bulletproofs_r1cs_gadgets_b200 import workloads
+    wl = workloads.BoundCheck(gens, vmin=10, vmax=200, bit_size=8)
+    assert (wl.circuit.n, wl.circuit.q, wl.circuit.m, wl.circuit.num_aux) == (16, 37, 3, 32)
+    inp = wl.inputs(0, 3)
+    V, proofs, status = wl.circuit.prove_batch(gens, wl.label, inp["v"], inp["v_blinding"], inp["entropy"], aux=inp["aux"])
+    assert not status.any()
+    for i in range(3):
+        v = int.from_bytes(inp["v"][i][0].tobytes(), "little")
+        op = R.Prover(R.PedersenGens(), R.Transcript(b"BoundsTest"))
+        ops = [op.commit(int.from_bytes(inp["v"][i][j].tobytes(), "little"), int.from_bytes(inp["v_blinding"][i][j].tobytes(), "little")) for j in range(3)]
+        G.bound_check_gadget(op, (ops[0][1], v), (ops[1][1], v - 10), (ops[2][1], 200 - v), 200, 10, 8)
+        assert R.proof_to_bytes(op.prove(R.BulletproofGens(16), inp["entropy"][i].tobytes())) == proofs[i].tobytes()
+    assert not wl.circuit.verify_batch(gens, wl.label, V, proofs, inp["entropy"]).any()
+    # a value outside the range cannot be proven: a = v - min wraps, its bits no longer recompose
+    bad = {k: a.copy() for k, a in inp.items()}
+    bad["v"][0, 0, 0] ^= 0x80
+    V2, proofs2, st2 = wl.circuit.prove_batch(gens, wl.label, bad["v"], bad["v_blinding"], bad["entropy"], aux=bad["aux"])
+    assert wl.circuit.verify_batch(gens, wl.label, V2, proofs2, bad["entropy"]).tolist()[0] == 3
+
+
+def test_explicit_witness_equals_witness_program(api, gens, oracle_lib):
+    from bulletproofs_r1cs_gadgets_b200 import workloads
+    wl = workloads.Mimc(gens, rounds=6)
+    inp = wl.inputs(5, 2)
+    V1, P1, s1 = wl.circuit.prove_batch(gens, wl.label, inp["v"], inp["v_blinding"], inp["entropy"], pub=inp["pub"])
+    cb = CO.scalars_to_array(wl.constants, L).tobytes()
+    wit = [oracle_lib.mimc_witness(inp["v"][i][0].tobytes(), inp["v"][i][1].tobytes(), cb, wl.circuit.n) for i in range(2)]
+    aL, aR, aO = (np.stack([w[j] for w in wit]) for j in range(3))
+    V2, P2, s2 = wl.circuit.prove_batch(gens, wl.label, inp["v"], inp["v_blinding"], inp["entropy"], witness=(aL, aR, aO))
+    assert P1.tobytes() == P2.tobytes() and V1.tobytes() == V2.tobytes() and not s1.any() and not s2.any()
+    assert not wl.circuit.verify_batch(gens, wl.label, V1, P1, inp["entropy"], pub=inp["pub"]).any()
+
+
+def test_chunking_is_invisible(api, gens, monkeypatch):
+    from bulletproofs_r1cs_gadgets_b200 import workloads
+    wl = workloads.Mimc(gens, rounds=3)
+    inp = wl.inputs(0, 5)
+    V1, P1, _ = wl.circuit.prove_batch(gens, wl.label, inp["v"], inp["v_blinding"], inp["entropy"], pub=inp["pub"])
+    monkeypatch.setenv("BP_B200_CHUNK", "2")  # ragged: 2 + 2 + 1
+    V2, P2, _ = wl.circuit.prove_batch(gens, wl.label, inp["v"], inp["v_blinding"], inp["entropy"], pub=inp["pub"])
+    assert P1.tobytes() == P2.tobytes() and V1.tobytes() == V2.tobytes()
+    st = wl.circuit.verify_batch(gens, wl.label, V2, P2, inp["entropy"], pub=inp["pub"])
+    assert not st.any()
+
+
+def test_error_codes(api, gens):
+    small = api.Gens(8)
+    case = H.golden_cases()[0]  # mimc5: n = 10 -> N = 16 > 8
+    build = H.product_builder(api, case)
+    p = api.Prover(small, b"MiMC")
+    vs = [p.commit(int(v, 16), int(b, 16))[1] for v, b in zip(case["values"], case["blindings"])]
+    build(p, vs, True)
+    with pytest.raises(api.R1CSError) as e:
+        p.prove(bytes(32))
+    assert e.value.code == 1  # InvalidGeneratorsLength
+    p2 = api.Prover(gens, b"x")
+    with pytest.raises(api.R1CSError) as e:
+        p2.allocate_multiplier(None)
+    assert e.value.code == 4  # MissingAssignment
+    v = api.Verifier(gens, b"x")
+    assert v.evaluate_lc(api.LinearCombination.of(5)) is None  # Option::None on the verifier
+    assert v.allocate_multiplier(None)[2].kind == api.VAR_MULT_OUT
+    with pytest.raises(api.R1CSError) as e:
+        v.constrain(api.LinearCombination([(api.Variable(api.VAR_MULT_LEFT, 99), 1)]))
+    assert e.value.code == 6
+    # empty batch is a no-op; circuits without multipliers prove and verify (N = 1, no inner-product rounds)
+    pr = api.Prover(gens, b"lin"); V, a = pr.commit(7, 3); pr.constrain(a - 7)
+    proof = pr.prove(bytes(32))
+    assert len(proof) == 32 * 16
+    vf = api.Verifier(gens, b"lin"); b = vf.commit(V); vf.constrain(b - 7)
+    assert vf.verify(proof, bytes(32))
+    vf = api.Verifier(gens, b"lin"); b = vf.commit(V); vf.constrain(b - 8)
+    with pytest.raises(api.R1CSError):
+        vf.verify(proof, bytes(32))
+
+
+def test_single_multiplier_and_allocate_single(api, gens):
+    """factors-style circuit p*q = r (reference src/factors.rs:12-21) and the fork's allocate_single pairing"""
+    pq = (17, 19)
+    pr = api.Prover(gens, b"Factors")
+    cp = pr.commit(pq[0], 11); cq = pr.commit(pq[1], 12); cr = pr.commit(pq[0] * pq[1], 13)
+    _, _, o = pr.multiply(cp[1] + 0, cq[1] + 0)
+    pr.constrain(o - cr[1])
+    l, none = pr.allocate_single(5)
+    r, out = pr.allocate_single(9)
+    assert none is None and out.kind == api.VAR_MULT_OUT and pr.evaluate_lc(api.LinearCombination.of(out)) == 45
+    pr.constrain(out - 45)
+    proof = pr.prove(bytes(32))
+    op = R.Prover(R.PedersenGens(), R.Transcript(b"Factors"))
+    a = op.commit(17, 11)[1]; b = op.commit(19, 12)[1]; c = op.commit(17 * 19, 13)[1]
+    _, _, oo = op.multiply(R.LC.of(a) + 0, R.LC.of(b) + 0)
+    op.constrain(R.LC.of(oo) - R.LC.of(c))
+    op.allocate_single(5); _, o2 = op.allocate_single(9)
+    op.constrain(R.LC.of(o2) - 45)
+    assert R.proof_to_bytes(op.prove(R.BulletproofGens(256), bytes(32))) == proof

@@ -1,0 +1,184 @@
+"""The oracles against everything that pins them: RFC 9496 vectors, the Merlin vector, the reference's constants
+file and gadget shapes, the committed golden proofs, and each other."""
+import hashlib
+import os
+import random
+
+import numpy as np
+import pytest
+
+from helpers import R, G, CO, L, POSEIDON_BLOB, golden_cases, oracle_prove_case, c_oracle_prove_case, golden_builder
+
+REF = "/root/reference/src/poseidon_constants.rs"
+
+
+def test_rfc9496_vectors_python():
+    assert R.ristretto_encode(R.BASEPOINT) == R.BASEPOINT_COMPRESSED
+    assert R.ristretto_encode(R.pt_mul(2, R.BASEPOINT)).hex() == "6a493210f7499cd17fecb510ae0cea23a110e8d5b901f8acadd3095c73a3b919"
+    assert R.ristretto_encode(R.pt_mul(0, R.BASEPOINT)) == bytes(32)
+    h = hashlib.sha512(b"Ristretto is traditionally a short shot of espresso coffee").digest()
+    assert R.ristretto_encode(R.from_uniform_bytes(h)).hex() == "3066f82a1a747d45120d1740f14358531a8f04bbffe6a819f86dfe50f44a0a46"
+    # invalid encodings: non-canonical field element, negative, not a square
+    for bad in (bytes([0xed] + [0xff] * 30 + [0x7f]), bytes([1] + [0] * 31), bytes([0xff] * 32)):
+        assert R.ristretto_decode(bad) is None
+    # l * B is the identity
+    assert R.pt_eq(R.pt_mul(L - 1, R.BASEPOINT), R.pt_neg(R.BASEPOINT))
+
+
+def test_rfc9496_vectors_c(oracle_lib):
+    rc, two = oracle_lib.call_bytes("bpo_scalarmult", 32, (2).to_bytes(32, "little"), R.BASEPOINT_COMPRESSED)
+    assert rc == 0 and two.hex() == "6a493210f7499cd17fecb510ae0cea23a110e8d5b901f8acadd3095c73a3b919"
+    h = hashlib.sha512(b"Ristretto is traditionally a short shot of espresso coffee").digest()
+    rc, ow = oracle_lib.call_bytes("bpo_from_uniform", 32, h)
+    assert ow.hex() == "3066f82a1a747d45120d1740f14358531a8f04bbffe6a819f86dfe50f44a0a46"
+    for bad in (bytes([0xed] + [0xff] * 30 + [0x7f]), bytes([1] + [0] * 31), bytes([0xff] * 32)):
+        rc, _ = oracle_lib.call_bytes("bpo_ristretto_roundtrip", 32, bad)
+        assert rc != 0
+    rnd = random.Random(1)
+    for _ in range(8):  # random points / scalars: C vs big-int
+        k, s = rnd.randrange(L), rnd.randrange(L)
+        P = R.ristretto_encode(R.pt_mul(k, R.BASEPOINT))
+        rc, got = oracle_lib.call_bytes("bpo_scalarmult", 32, s.to_bytes(32, "little"), P)
+        assert rc == 0 and got == R.ristretto_encode(R.pt_mul(s * k % L, R.BASEPOINT))
+
+
+def test_merlin_vector_both():
+    t = R.Transcript(b"test protocol")
+    t.append_message(b"some label", b"some data")
+    want = "d5a21972d0d5fe320c0d263fac7fffb8145aa640af6e9bca177c03c7efcf0615"  # merlin's own "equivalence_simple" test
+    assert t.challenge_bytes(b"challenge", 32).hex() == want
+    out = np.zeros(32, np.uint8)
+    args = []
+    for x in (b"test protocol", b"some label", b"some data", b"challenge"):
+        a = np.frombuffer(x, np.uint8)
+        args += [a.ctypes.data_as(CO.u8p), len(x)]
+    CO.lib().bpo_merlin_kat(*args, out.ctypes.data_as(CO.u8p), 32)
+    assert out.tobytes().hex() == want
+
+
+def test_generators_and_pedersen(oracle_lib):
+    B, Bb = np.zeros(32, np.uint8), np.zeros(32, np.uint8)
+    oracle_lib.lib().bpo_pedersen(B.ctypes.data_as(CO.u8p), Bb.ctypes.data_as(CO.u8p))
+    assert B.tobytes() == R.BASEPOINT_COMPRESSED
+    assert Bb.tobytes().hex() == "8c9240b456a9e6dc65c377a1048d745f94a08cdb7f44cbcd7b46f34048871134"  # dalek's RISTRETTO B_blinding
+    assert R.ristretto_encode(R.PedersenGens().B_blinding) == Bb.tobytes()
+    g = np.zeros((4, 32), np.uint8); h = np.zeros((4, 32), np.uint8)
+    oracle_lib.lib().bpo_gens_compressed(0, 4, g.ctypes.data_as(CO.u8p)); oracle_lib.lib().bpo_gens_compressed(1, 4, h.ctypes.data_as(CO.u8p))
+    bp = R.BulletproofGens(4)
+    assert [R.ristretto_encode(p) for p in bp.G(4)] == [bytes(x) for x in g]
+    assert [R.ristretto_encode(p) for p in bp.H(4)] == [bytes(x) for x in h]
+    assert bytes(g[0]).hex() == "fc3b25801422672a6a8d3adb5d8457d4301fe92324b4fc56ae934c8713ddfe2d"
+
+
+def test_poseidon_constants_blob_matches_reference_file():
+    """the committed constants blob = the reference's hex strings with the LITTLE-endian semantics of scalar_utils.rs:232-237"""
+    assert hashlib.sha256(POSEIDON_BLOB).hexdigest() == "01d3e4d958b951b62934605b2baf0214c53738f6a87b03f73b6aa44fffd211f1"
+    assert len(POSEIDON_BLOB) == 32 * (36 + 960)
+    assert POSEIDON_BLOB[:32].hex() == "b8e1b01068d9af3cccd1a09a818c7e9965b9d03987ce5807f40f5295f822300b"       # MDS[0][0], SURVEY App. B
+    assert POSEIDON_BLOB[36 * 32:37 * 32].hex() == "b26a3fe94173d232fea854644d346d7fdc25fa2473e1ab9aba302e0f2f27770a"  # RK[0]
+    if not os.path.exists(REF):
+        pytest.skip("reference tree not present on this box")
+    src = open(REF, "rb").read()
+    assert hashlib.sha256(src).hexdigest() == "c9d320eb8b41e39f4e35badd0f03debfddbc44b5ffa368fc04e501295a01af5e"
+    import re
+    hexes = re.findall(rb'"0x([0-9a-fA-F]{64})"', src)
+    assert len(hexes) == 36 + 960
+    blob = b"".join((int.from_bytes(bytes.fromhex(h.decode()), "little") % L).to_bytes(32, "little") for h in hexes)
+    assert blob == POSEIDON_BLOB
+
+
+def test_poseidon_known_answers(oracle_lib):
+    pp = G.PoseidonParams()
+    kat = {(0, 0, G.INVERSE): "9545e53710401d3a82fdaff157057f56dc4d687f09ee7e045f72b516e96eec00",
+           (0, 0, G.CUBE): "d4a08102b197caad58cd08e94730556be317236d9ee0961332568238359c0307",
+           (1, 2, G.INVERSE): "c69cbbcf39be8e422439786fb0511ae49fc30561e76ff888d9cf005196526704"}
+    oracle_lib.poseidon_set_params(POSEIDON_BLOB)
+    for (a, b, sb), want in kat.items():
+        assert G.poseidon_hash_2(a, b, pp, sb).to_bytes(32, "little").hex() == want
+    # C oracle agrees on random inputs (hash2 takes the sbox flag as an int argument)
+    import ctypes as C
+    rnd = random.Random(2)
+    for sb in (G.CUBE, G.INVERSE):
+        a, b = rnd.randrange(L), rnd.randrange(L)
+        out = np.zeros(32, np.uint8)
+        ka, kb = np.frombuffer(a.to_bytes(32, "little"), np.uint8), np.frombuffer(b.to_bytes(32, "little"), np.uint8)
+        oracle_lib.lib().bpo_poseidon_hash2(ka.ctypes.data_as(CO.u8p), kb.ctypes.data_as(CO.u8p), C.c_int(sb), out.ctypes.data_as(CO.u8p))
+        assert int.from_bytes(out.tobytes(), "little") == G.poseidon_hash_2(a, b, pp, sb)
+    # empty-subtree hash at height 32 (reference src/gadget_vsmt_2.rs:41-50 recurrence), SURVEY App. B
+    cur = 0
+    for _ in range(32):
+        cur = G.poseidon_hash_2(cur, cur, pp, G.INVERSE)
+    assert cur.to_bytes(32, "little").hex() == "714b757099d394ad749e674d34705c5832394d9b26ba897386fa8a98509d930c"
+
+
+def test_circuit_shapes():
+    """multiplier / constraint counts of SURVEY.md section 8 (derived from the reference's gadget code)"""
+    def shape(build, m):
+        v = R.Verifier(R.Transcript(b"x")); vs = [v.commit(bytes(32)) for _ in range(m)]; build(v, vs)
+        return v.num_multipliers(), v.num_constraints()
+    pp = G.PoseidonParams()
+    assert shape(lambda cs, v: G.bound_check_gadget(cs, (v[0], None), (v[1], None), (v[2], None), 2 ** 64 - 1, 0, 64), 3) == (128, 261)
+    assert shape(lambda cs, v: G.poseidon_hash_2_gadget(cs, v[0], v[1], v[2:], pp, G.CUBE, 0), 6) == (376, 753)
+    assert shape(lambda cs, v: G.poseidon_hash_2_gadget(cs, v[0], v[1], v[2:], pp, G.INVERSE, 0), 6) == (564, 1317)
+    assert shape(lambda cs, v: G.mimc_gadget(cs, v[0], v[1], 322, [1] * 322, 0), 2) == (644, 1289)
+    d = 2
+    n, q = shape(lambda cs, v: G.vanilla_merkle_tree_verif_gadget(cs, d, 0, v[0], v[1:1 + d], v[1 + d:1 + 2 * d], v[1 + 2 * d:], pp), 1 + 2 * d + 4)
+    assert (n, q) == (d * 568, d * 1324 + 1)  # depth 32 -> (18176, 42369)
+    assert (32 * 568, 32 * 1324 + 1) == (18176, 42369)
+
+
+@pytest.mark.parametrize("case", golden_cases(), ids=lambda c: c["name"])
+def test_golden_python_oracle(case):
+    Vs, p = oracle_prove_case(case)
+    assert [V.hex() for V in Vs] == case["commitments"]
+    assert (p.num_multipliers(), p.num_constraints()) == (case["n"], case["q"])
+    proof = R.proof_to_bytes(p.prove(R.BulletproofGens(case["gens_capacity"]), bytes.fromhex(case["entropy"])))
+    assert proof.hex() == case["proof"]
+
+
+@pytest.mark.parametrize("case", golden_cases(), ids=lambda c: c["name"])
+def test_golden_c_oracle(case, oracle_lib):
+    rc, V, proof, circ = c_oracle_prove_case(case)
+    assert rc == 0
+    assert V.tobytes().hex() == "".join(case["commitments"])
+    assert proof.hex() == case["proof"]
+    ok = CO.verify(circ, V, proof, case["label"].encode(), bytes(32), case["gens_capacity"])
+    assert (ok == 0) == case["verifies"]
+    bad = bytearray(proof); bad[360] ^= 1
+    assert CO.verify(circ, V, bytes(bad), case["label"].encode(), bytes(32), case["gens_capacity"]) != 0
+
+
+def test_c_oracle_native_witness_matches_recorded_circuit(oracle_lib):
+    """the native witness helpers (used by the CPU baseline) produce exactly the assignment the gadget code derives"""
+    pp = G.PoseidonParams()
+    oracle_lib.poseidon_set_params(POSEIDON_BLOB)
+    rnd = random.Random(9)
+    depth = 1
+    leaf, bits, sibs = rnd.randrange(L), [1], [rnd.randrange(L)]
+    root = G.vsmt_root_from_path(leaf, bits, sibs, pp)
+    p = R.Prover(R.PedersenGens(), R.Transcript(b"VSMT"))
+    vs = [p.commit(v, 0)[1] for v in [leaf] + bits + sibs + [0, 101, 0, 0]]
+    G.vanilla_merkle_tree_verif_gadget(p, depth, root, vs[0], vs[1:2], vs[2:3], vs[3:], pp)
+    aL, aR, aO, croot = oracle_lib.vsmt2_witness(depth, leaf.to_bytes(32, "little"), bits, CO.scalars_to_array(sibs, L), p.num_multipliers())
+    assert croot == root.to_bytes(32, "little")
+    assert aL.tobytes() == CO.scalars_to_array(p.aL, L).tobytes()
+    assert aR.tobytes() == CO.scalars_to_array(p.aR, L).tobytes()
+    assert aO.tobytes() == CO.scalars_to_array(p.aO, L).tobytes()
+    # MiMC
+    consts = [rnd.randrange(L) for _ in range(7)]
+    xl, xr = rnd.randrange(L), rnd.randrange(L)
+    p = R.Prover(R.PedersenGens(), R.Transcript(b"MiMC")); a = p.commit(xl, 0)[1]; b = p.commit(xr, 0)[1]
+    G.mimc_gadget(p, a, b, 7, consts, G.mimc(xl, xr, consts))
+    aL, aR, aO, img = oracle_lib.mimc_witness(xl.to_bytes(32, "little"), xr.to_bytes(32, "little"), CO.scalars_to_array(consts, L).tobytes(), 14)
+    assert img == G.mimc(xl, xr, consts).to_bytes(32, "little") and aL.tobytes() == CO.scalars_to_array(p.aL, L).tobytes()
+
+
+def test_oracle_verifier_rejects(oracle_lib):
+    case = golden_cases()[0]
+    rc, V, proof, circ = c_oracle_prove_case(case)
+    lab = case["label"].encode()
+    assert CO.verify(circ, V, proof, lab, bytes(32), 16) == 0
+    assert CO.verify(circ, V, proof, b"other", bytes(32), 16) != 0        # different transcript label
+    assert CO.verify(circ, V[::-1].copy(), proof, lab, bytes(32), 16) != 0  # commitments swapped
+    assert CO.verify(circ, V, proof, lab, bytes(32), 8) == 1              # InvalidGeneratorsLength
+    assert CO.verify(circ, V, proof[:-32], lab, bytes(32), 16) != 0
