@@ -33,7 +33,16 @@ def gens_big(api):
 
 def test_primitives(api): E.test_primitives(api)
 def test_generators(api, gens, oracle_lib): E.test_generators(api, gens, oracle_lib)
-def test_msm_entry(api, gens): E.test_msm_entry(api, gens)
+def _msm_device_pointers(api, gens, arr):
+    import torch
+    d_in = torch.from_numpy(arr).cuda()
+    d_out = torch.zeros(32, dtype=torch.uint8, device="cuda")
+    rc = api.load().bp_msm_gens_device(gens._h, arr.shape[0], C.c_void_p(d_in.data_ptr()), C.c_void_p(d_out.data_ptr()), None)
+    torch.cuda.synchronize()
+    return rc, d_out.cpu().numpy().tobytes()
+
+
+def test_msm_entry(api, gens): E.test_msm_entry(api, gens, call=_msm_device_pointers)
 def test_golden_proofs_tier1(api, gens): E.test_golden_proofs_tier1(api, gens)
 def test_python_gadget_code_drives_product_cs(api, gens): E.test_python_gadget_code_drives_product_cs(api, gens)
 def test_verifier_rejects_tampering(api, gens): E.test_verifier_rejects_tampering(api, gens)
