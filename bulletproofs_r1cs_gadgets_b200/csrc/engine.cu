@@ -73,10 +73,11 @@ struct Workspace {
   ge_p3 *buckets = 0; size_t bucket_slots = 0;
   ge_p3 *wsum = 0, *Q = 0, *Gt = 0, *Ht = 0, *pts = 0;
   int8_t *naf = 0; int *naf_top = 0;
+  scm *utab = 0; uint32_t *rg_as = 0; long rg_cap = -1;
   dev_side side;
   void release() {
     dev_side_free(side);
-    void *ps[] = {pub, uj, v, vbl, aux, wit, rand1, w_all, zpow, ypow, yinvpow, a, b, chal, t, tb, clr, part, ts, rng, dig, buckets, wsum, Q, Gt, Ht, pts, naf, naf_top};
+    void *ps[] = {utab, rg_as, pub, uj, v, vbl, aux, wit, rand1, w_all, zpow, ypow, yinvpow, a, b, chal, t, tb, clr, part, ts, rng, dig, buckets, wsum, Q, Gt, Ht, pts, naf, naf_top};
     for (void *p : ps) dev_free(p);
     *this = Workspace();
   }
@@ -115,13 +116,20 @@ int gens_create(uint32_t capacity, BpGens **out) {
   CK(dev_sync(s));
   dev_free(d_uni); dev_free(d_small); dev_free(d_ok);
   if (!ok) { gens_free(g); return BP_ERR_CUDA; }
+  // fixed-base tables (512 KiB per generator); BP_B200_NO_TABLE=1 keeps the bucket-method-only pipeline
+  if (!getenv("BP_B200_NO_TABLE")) {
+    const size_t ngen = 2 * (size_t)capacity + 2;
+    if (dalloc(&g->table, ngen * TBL_W * TBL_E)) { gens_free(g); return BP_ERR_OOM; }
+    CK(launch((long)ngen * TBL_W, s, KTableBuild{g->G_p3, g->H_p3, g->pc, (long)capacity, g->table}));
+    CK(dev_sync(s));
+  }
   *out = g;
   return BP_OK;
 }
 void gens_free(BpGens *g) {
   if (!g) return;
   if (g->msm_ws) { g->msm_ws->release(); delete g->msm_ws; }
-  dev_free(g->G_p3); dev_free(g->H_p3); dev_free(g->G_n); dev_free(g->H_n); dev_free(g->pc); dev_free(g->pc_niels); dev_free(g->pc_table);
+  dev_free(g->G_p3); dev_free(g->H_p3); dev_free(g->G_n); dev_free(g->H_n); dev_free(g->pc); dev_free(g->pc_niels); dev_free(g->pc_table); dev_free(g->table);
   delete g;
 }
 int gens_export(const BpGens *g, int which, uint32_t count, uint8_t *out) {
@@ -231,6 +239,7 @@ void circuit_free(BpCircuit *c) {
   delete c;
 }
 
+static const int UNFOLD_ROUNDS = 3;  // inner-product rounds computed over the original generators (fixed-base tables)
 static const int CH_DOT = 256;  // multipliers per partial-sum thread
 static const int CH_POW = 64;   // exponents per powers thread
 static long msm_target_warps() { return 148L * 8 * 4; }
@@ -258,6 +267,7 @@ static int ensure_workspace(BpCircuit *c, int B) {
   bad |= dalloc(&w->Q, Bz); bad |= dalloc(&w->Gt, (N / 2 + 1) * Bz); bad |= dalloc(&w->Ht, (N / 2 + 1) * Bz);
   bad |= dalloc(&w->pts, (m + 11 + 2 * k + 1) * Bz);
   bad |= dalloc(&w->naf, 4 * 256 * Bz); bad |= dalloc(&w->naf_top, 4 * Bz);
+  bad |= dalloc(&w->utab, 4 * (size_t)(1 << UNFOLD_ROUNDS) * Bz + 4 * Bz); bad |= dalloc(&w->rg_as, 2 * n + 2);
   if (bad) { w->release(); return BP_ERR_OOM; }
   w->B = B;
   return BP_OK;
@@ -279,6 +289,19 @@ static int run_msm(Workspace *w, const MsmSeg *segs, int nseg, long ninst, const
   k.nseg = nseg; k.S = (int)S; k.dig = dig; k.dig_inst_stride = dig_inst_stride; k.buckets = w->buckets; k.wsum = w->wsum;
   CK(launch(ninst * S * MSM_WINDOWS, s, k));
   CK(launch(ninst, s, KMsmFinish{w->wsum, (int)S, out, out_stride, mode, status, BP_ERR_VERIFICATION}));
+  return BP_OK;
+}
+
+// table-driven MSM over shared generators: ninst instances, rows digit rows each
+static int run_msm_table(const BpGens *g, Workspace *w, const RowMap &rmap, long rows, long ninst, const int8_t *dig, long dig_inst_stride,
+                         uint8_t *out, long out_stride, dev_stream s) {
+  long S = 262144 / (ninst > 0 ? ninst : 1);
+  if (S > rows / 16) S = rows / 16;
+  if (S > 1024) S = 1024;
+  if (S < 1) S = 1;
+  while ((size_t)(ninst * S) > w->bucket_slots && S > 1) S--;
+  CK(launch(ninst * S, s, KMsmTable{g->table, rmap, dig, dig_inst_stride, rows, (int)S, w->buckets}));
+  CK(launch(ninst, s, KMsmTableFinish{w->buckets, (int)S, out, out_stride}));
   return BP_OK;
 }
 
@@ -349,10 +372,24 @@ int engine_prove(const BpGens *g, BpCircuit *c, const ProveArgs &A, dev_stream s
     CK(launch(B, s, KRecode{i_b + 2L * B, nullptr, 1, B, dS, rowsI * 32, 0}));
     CK(launch(n * B, s, KRecode{sL, nullptr, (int)n, B, dS, rowsI * 32, 1}));
     CK(launch(n * B, s, KRecode{sR, nullptr, (int)n, B, dS, rowsI * 32, (int)(1 + n)}));
-    MsmSeg segs[3] = {{g->pc_niels + 1, 0, 0, 1}, {g->G_n, 0, 0, (int)n}, {g->H_n, 0, 0, (int)n}};
-    rc = run_msm(w, segs, 3, B, dI, rowsI * 32, A.proofs + 0, plen, 0, nullptr, s); if (rc) return rc;
-    rc = run_msm(w, segs, 2, B, dO, rowsO * 32, A.proofs + 32, plen, 0, nullptr, s); if (rc) return rc;
-    rc = run_msm(w, segs, 3, B, dS, rowsI * 32, A.proofs + 64, plen, 0, nullptr, s); if (rc) return rc;
+    if (g->table) {
+      if (w->rg_cap != (long)g->capacity) {
+        std::vector<uint32_t> rg(2 * n + 1);
+        rg[0] = 2 * g->capacity + 1;
+        for (long i = 0; i < n; i++) { rg[1 + i] = (uint32_t)i; rg[1 + n + i] = g->capacity + (uint32_t)i; }
+        CK(dev_h2d(w->rg_as, rg.data(), rg.size() * sizeof(uint32_t), s)); CK(dev_sync(s));
+        w->rg_cap = g->capacity;
+      }
+      RowMap rm{0, w->rg_as, (long)g->capacity, 0, 0, 0};
+      rc = run_msm_table(g, w, rm, rowsI, B, dI, rowsI * 32, A.proofs + 0, plen, s); if (rc) return rc;
+      rc = run_msm_table(g, w, rm, rowsO, B, dO, rowsO * 32, A.proofs + 32, plen, s); if (rc) return rc;
+      rc = run_msm_table(g, w, rm, rowsI, B, dS, rowsI * 32, A.proofs + 64, plen, s); if (rc) return rc;
+    } else {
+      MsmSeg segs[3] = {{g->pc_niels + 1, 0, 0, 1}, {g->G_n, 0, 0, (int)n}, {g->H_n, 0, 0, (int)n}};
+      rc = run_msm(w, segs, 3, B, dI, rowsI * 32, A.proofs + 0, plen, 0, nullptr, s); if (rc) return rc;
+      rc = run_msm(w, segs, 2, B, dO, rowsO * 32, A.proofs + 32, plen, 0, nullptr, s); if (rc) return rc;
+      rc = run_msm(w, segs, 3, B, dS, rowsI * 32, A.proofs + 64, plen, 0, nullptr, s); if (rc) return rc;
+    }
   }
   // 5. y, z; powers; flattened weights (A.3 steps 5-7)
   CK(launch(B, s, KTsPhase2{w->ts, A.proofs, plen, ch_y, ch_z, ch_yinv, A.status, 0}));
@@ -381,23 +418,50 @@ int engine_prove(const BpGens *g, BpCircuit *c, const ProveArgs &A, dev_stream s
   CK(launch(B, s, KProverScalars{w->t, w->tb, i_b, wV, w->vbl, (int)m, B, ch_x, A.proofs, plen}));
   CK(launch(B, s, KTsPhase4{w->ts, A.proofs, plen, ch_w, (unsigned)N}));
   CK(launch(B, s, KCommit{ch_w, nullptr, 1, B, g->pc_table, nullptr, 0, 0, w->Q}));
-  // 8. inner-product argument (A.4)
+  // 8. inner-product argument (A.4).  With fixed-base tables the first UNFOLD_ROUNDS rounds never fold generators: L_j, R_j are
+  // multiscalar multiplications over the ORIGINAL generators with scalars a_i * prod u_t^(+-1); the folded generators are then
+  // materialised once (KFoldTable) and the remaining, short rounds run on per-proof points (bucket method + NAF fold).
   CK(launch(2L * B, s, KFillScalar{alpha, sc_one()}));  // alpha, beta are adjacent
+  const int J = g->table ? (int)std::min<long>(UNFOLD_ROUNDS, k) : 0;
+  scm *UG[2] = {w->utab, w->utab + ((size_t)1 << UNFOLD_ROUNDS) * B}, *UH[2] = {w->utab + 2 * ((size_t)1 << UNFOLD_ROUNDS) * B, w->utab + 3 * ((size_t)1 << UNFOLD_ROUNDS) * B};
+  if (J > 0) { CK(launch(B, s, KFillScalar{UG[0], sc_one()})); CK(launch(B, s, KFillScalar{UH[0], sc_one()})); }
+  int yfree = 0;
   long len = N;
+  const long gs = N / 2 + 1;
   for (int round = 0; round < k; round++) {
     const long h = len / 2;
     long nch = (h + CH_DOT - 1) / CH_DOT;
     CK(launch(nch * B, s, KIpaDots{w->a, w->b, (int)h, B, CH_DOT, w->part}));
     CK(launch(2L * B, s, KSumPartials{w->part, (int)nch, 2, B, w->clr}));
+    if (round < J) {
+      const long rows = N + 1;
+      int8_t *dL = w->dig, *dR = w->dig + rows * 32 * B;
+      const int cur = round & 1;
+      CK(launch((N / 2) * B, s, KRecodeUnfolded{w->a, w->b, UG[cur], UH[cur], w->yinvpow, ch_u, w->clr, ch_w, N, len, h, n, B, dL, dR, rows * 32}));
+      RowMap rl{1, nullptr, (long)g->capacity, N, len, h}, rr{2, nullptr, (long)g->capacity, N, len, h};
+      rc = run_msm_table(g, w, rl, rows, B, dL, rows * 32, A.proofs + 448 + 64 * round, plen, s); if (rc) return rc;
+      rc = run_msm_table(g, w, rr, rows, B, dR, rows * 32, A.proofs + 448 + 64 * round + 32, plen, s); if (rc) return rc;
+      CK(launch(B, s, KTsIpaRound{w->ts, A.proofs, plen, round, B, (int)h, w->yinvpow, ch_u, ipa_u, ipa_uinv, alpha, beta, w->naf, w->naf_top,
+                                 A.status, 1, 0}));  // transcript + u, u^-1 only (verifier mode skips the fold scalars)
+      CK(launch(h * B, s, KFoldAB{w->a, w->b, ipa_u, ipa_uinv, (int)h, B}));
+      CK(launch((2L << round) * B, s, KIpaUTable{ipa_u, ipa_uinv, UG[cur], UH[cur], UG[cur ^ 1], UH[cur ^ 1], B}));
+      if (round == J - 1 && h > 1) {
+        // true folded generators of level J straight from the tables; alpha = beta = 1 and the y^-i factors are inside
+        CK(launch(N * B, s, KRecodeFoldTable{UG[cur ^ 1], UH[cur ^ 1], w->yinvpow, ch_u, N, h, n, B, w->dig, 2 * N * 32}));
+        CK(launch(2 * h * B, s, KFoldTable{g->table, (long)g->capacity, N, h, w->dig, 2 * N * 32, w->Gt, w->Ht, gs}));
+        yfree = 1;
+      }
+      len = h;
+      continue;
+    }
     const long rows = 2 * h + 1;
     int8_t *dL = w->dig, *dR = w->dig + rows * 32 * B;
-    CK(launch(h * B, s, KRecodeIpa{w->a, w->b, alpha, beta, w->yinvpow, ch_u, w->clr, (int)h, B, (int)n, round, dL, dR, rows * 32}));
+    CK(launch(h * B, s, KRecodeIpa{w->a, w->b, alpha, beta, w->yinvpow, ch_u, w->clr, (int)h, B, (int)n, round, dL, dR, rows * 32, yfree}));
     MsmSeg sL_[3], sR_[3];
     if (round == 0) {
       sL_[0] = {g->G_n + h, 0, 0, (int)h}; sL_[1] = {g->H_n, 0, 0, (int)h};
       sR_[0] = {g->G_n, 0, 0, (int)h};     sR_[1] = {g->H_n + h, 0, 0, (int)h};
     } else {
-      const long gs = N / 2 + 1;
       sL_[0] = {w->Gt + h, gs, 1, (int)h}; sL_[1] = {w->Ht, gs, 1, (int)h};
       sR_[0] = {w->Gt, gs, 1, (int)h};     sR_[1] = {w->Ht + h, gs, 1, (int)h};
     }
@@ -405,10 +469,9 @@ int engine_prove(const BpGens *g, BpCircuit *c, const ProveArgs &A, dev_stream s
     rc = run_msm(w, sL_, 3, B, dL, rows * 32, A.proofs + 448 + 64 * round, plen, 0, nullptr, s); if (rc) return rc;
     rc = run_msm(w, sR_, 3, B, dR, rows * 32, A.proofs + 448 + 64 * round + 32, plen, 0, nullptr, s); if (rc) return rc;
     CK(launch(B, s, KTsIpaRound{w->ts, A.proofs, plen, round, B, (int)h, w->yinvpow, ch_u, ipa_u, ipa_uinv, alpha, beta, w->naf, w->naf_top,
-                               A.status, 0}));
+                               A.status, 0, yfree}));
     CK(launch(h * B, s, KFoldAB{w->a, w->b, ipa_u, ipa_uinv, (int)h, B}));
     if (h > 1) {
-      const long gs = N / 2 + 1;
       if (round == 0) CK(launch(2 * h * B, s, KFoldGens{g->G_p3, g->H_p3, 0, w->Gt, w->Ht, gs, w->naf, w->naf_top, (int)h, (int)n, round}));
       else CK(launch(2 * h * B, s, KFoldGens{w->Gt, w->Ht, gs, w->Gt, w->Ht, gs, w->naf, w->naf_top, (int)h, (int)n, round}));
     }

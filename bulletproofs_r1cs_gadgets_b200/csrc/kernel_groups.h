@@ -6,11 +6,12 @@
 #include "devrt.h"
 
 #define KGROUP_MSM(X) X(KMsmAccumulate) X(KMsmFinish)
-#define KGROUP_FOLD(X) X(KFoldGens)
+#define KGROUP_FOLD(X) X(KFoldGens) X(KFoldTable)
+#define KGROUP_TABLE(X) X(KTableBuild) X(KMsmTable) X(KMsmTableFinish)
 #define KGROUP_POINTS(X) X(KCommit) X(KGensFromUniform) X(KPcBases) X(KPcTable) X(KEncodePoints) X(KVerifyDecompress)
 #define KGROUP_TRANSCRIPT(X) X(KTsStart) X(KRngDraw) X(KTsPhase2) X(KTsPhase3) X(KTsPhase4) X(KTsIpaRound) X(KSelfTest) X(KTsVerify)
 #define KGROUP_SCALAR(X) X(KLoadScalars) X(KRecode) X(KPowers) X(KFillScalar) X(KFlatten) X(KPolyT) X(KSumPartials) X(KPolyEval) \
-  X(KProverScalars) X(KIpaDots) X(KRecodeIpa) X(KFoldAB) X(KStoreAB) X(KWitnessTape) X(KVerifyS) X(KVerifyDelta) X(KVerifyGH) X(KVerifyScalars)
+  X(KProverScalars) X(KIpaDots) X(KRecodeIpa) X(KFoldAB) X(KStoreAB) X(KWitnessTape) X(KVerifyS) X(KVerifyDelta) X(KVerifyGH) X(KVerifyScalars) X(KIpaUTable) X(KRecodeUnfolded) X(KRecodeFoldTable)
 
 #define KDECL_EXTERN(K) extern template int launch<K>(long, dev_stream, const K &);
 #define KDEFINE(K) template int launch<K>(long, dev_stream, const K &);
@@ -18,6 +19,7 @@
 #ifndef KGROUP_DEFINING
 KGROUP_MSM(KDECL_EXTERN)
 KGROUP_FOLD(KDECL_EXTERN)
+KGROUP_TABLE(KDECL_EXTERN)
 KGROUP_POINTS(KDECL_EXTERN)
 KGROUP_TRANSCRIPT(KDECL_EXTERN)
 KGROUP_SCALAR(KDECL_EXTERN)

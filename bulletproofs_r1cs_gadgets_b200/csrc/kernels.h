@@ -305,7 +305,7 @@ struct KTsIpaRound {
   static constexpr const char *kName = "KTsIpaRound";
   strobe128 *ts; const uint8_t *proofs; long proof_stride; int round; int B; int h;
   const scm *yinvpow; const scm *ufac;  // y^-i table [N][B]; the r1cs challenge u (class factor, round 0 only)
-  scm *u, *uinv, *alpha, *beta; int8_t *naf; int *naf_top; int *status; int verifier;
+  scm *u, *uinv, *alpha, *beta; int8_t *naf; int *naf_top; int *status; int verifier; int yfree;  // yfree: generators already carry y^-i
   HD void operator()(long p) const {
     strobe128 t; strobe_load(t, &ts[p]);
     const uint8_t *pf = proofs + p * proof_stride + 448 + 64 * round;
@@ -318,7 +318,8 @@ struct KTsIpaRound {
     scm ui = sc_invert(uu);
     u[p] = uu; uinv[p] = ui;
     if (verifier) return;
-    scm eG = sc_sqr(uu), eH = sc_mul(sc_sqr(ui), yinvpow[(long)h * B + p]);
+    scm eG = sc_sqr(uu), eH = sc_sqr(ui);
+    if (!yfree) eH = sc_mul(eH, yinvpow[(long)h * B + p]);
     int8_t nf[256];
     int8_t *dst = naf + p * 4 * 256;
     int top;
@@ -484,7 +485,7 @@ struct KRecodeIpa {
   static constexpr int kBlock = 128, kMinBlocks = 1;
   static constexpr const char *kName = "KRecodeIpa";
   const scm *a, *b, *alpha, *beta, *yinvpow, *ufac, *clr; int h, B, n, round;
-  int8_t *digL, *digR; long inst_stride;
+  int8_t *digL, *digR; long inst_stride; int yfree;
   HD void operator()(long tid) const {
     int p = (int)(tid % B); int i = (int)(tid / B);
     long lo = (long)i * B + p, hi = (long)(h + i) * B + p;
@@ -494,9 +495,10 @@ struct KRecodeIpa {
     int8_t d[32];
     int8_t *L = digL + (long)p * inst_stride, *R = digR + (long)p * inst_stride;
     sc_recode_bytes(d, sc_mul(sc_mul(al, a[lo]), gf_hi)); store_digits(L + (long)i * 32, d);
-    sc_recode_bytes(d, sc_mul(sc_mul(sc_mul(be, yinvpow[lo]), b[hi]), gf_lo)); store_digits(L + (long)(h + i) * 32, d);
+    scm ylo = yfree ? sc_one() : yinvpow[lo], yhi = yfree ? sc_one() : yinvpow[hi];
+    sc_recode_bytes(d, sc_mul(sc_mul(sc_mul(be, ylo), b[hi]), gf_lo)); store_digits(L + (long)(h + i) * 32, d);
     sc_recode_bytes(d, sc_mul(sc_mul(al, a[hi]), gf_lo)); store_digits(R + (long)i * 32, d);
-    sc_recode_bytes(d, sc_mul(sc_mul(sc_mul(be, yinvpow[hi]), b[lo]), gf_hi)); store_digits(R + (long)(h + i) * 32, d);
+    sc_recode_bytes(d, sc_mul(sc_mul(sc_mul(be, yhi), b[lo]), gf_hi)); store_digits(R + (long)(h + i) * 32, d);
     if (i == 0) {
       sc_recode_bytes(d, clr[p]); store_digits(L + (long)2 * h * 32, d);
       sc_recode_bytes(d, clr[B + p]); store_digits(R + (long)2 * h * 32, d);
@@ -922,5 +924,189 @@ struct KVerifyDecompress {
     ge_p3 pt;
     if (!ristretto_decode(pt, src)) { status[p] = BP_ERR_VERIFICATION_; ge_identity(pt); }
     store_struct(&pts[p * pts_stride + j], pt);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Fixed-base tables.  All generators (G_0.., H_0.., B, B_blinding) are shared by every proof and never change, so for
+// each generator P, window w and digit magnitude e+1 the point (e+1)*2^(8w)*P is precomputed in affine Niels form:
+//   table[(gen*32 + w)*128 + e]            (128 B each; 512 KiB per generator)
+// A scalar*generator term then costs <= 32 mixed additions into a REGISTER accumulator: no buckets, no bucket traffic,
+// no reduction pass, and any subset of (row, window) pairs can be summed by any thread.
+// Generator index space: [0,cap) = G, [cap,2cap) = H, 2cap = B, 2cap+1 = B_blinding.
+// ------------------------------------------------------------------------------------------------
+#define TBL_W 32
+#define TBL_E 128
+struct KTableBuild {
+  static constexpr int kBlock = 64, kMinBlocks = 1;
+  static constexpr const char *kName = "KTableBuild";
+  const ge_p3 *G, *H, *pc; long cap; ge_niels *table;
+  HD void operator()(long tid) const {
+    long gen = tid / TBL_W; int w = (int)(tid % TBL_W);
+    ge_p3 P;
+    if (gen < cap) load_struct(P, &G[gen]); else if (gen < 2 * cap) load_struct(P, &H[gen - cap]); else load_struct(P, &pc[gen - 2 * cap]);
+    for (int i = 0; i < 8 * w; i++) ge_dbl(P, P);
+    ge_niels *slot = table + tid * TBL_E;
+    // pass 1: multiples in projective form parked in the slots, prefix products of Z kept locally
+    fe pre[TBL_E];
+    ge_p3 acc = P;
+    fe run; fe_1(run);
+    for (int e = 0; e < TBL_E; e++) {
+      ge_niels tmp; tmp.ypx = acc.X; tmp.ymx = acc.Y; tmp.xy2d = acc.Z; tmp.pad[0] = tmp.pad[1] = 0;
+      store_struct(&slot[e], tmp);
+      pre[e] = run;
+      fe_mul(run, run, acc.Z);
+      ge_add(acc, acc, P);
+    }
+    // pass 2: one inversion for all 128 Z (Montgomery's trick), then normalise to affine Niels
+    fe inv, d2; fe_invert(inv, run); FE_2D(d2);
+    for (int e = TBL_E - 1; e >= 0; e--) {
+      ge_niels t; load_struct(t, &slot[e]);
+      fe zi, x, y;
+      fe_mul(zi, inv, pre[e]); fe_mul(inv, inv, t.xy2d);
+      fe_mul(x, t.ypx, zi); fe_mul(y, t.ymx, zi);
+      ge_niels nl;
+      fe_add(nl.ypx, y, x); fe_carry(nl.ypx); fe_sub(nl.ymx, y, x); fe_carry(nl.ymx);
+      fe_mul(nl.xy2d, x, y); fe_mul(nl.xy2d, nl.xy2d, d2);
+      nl.pad[0] = nl.pad[1] = 0;
+      store_struct(&slot[e], nl);
+    }
+  }
+};
+
+// row -> generator index.  mode 0: explicit map; 1/2: the L / R multiscalar multiplication of an UNFOLDED inner-product
+// round over the original generators (nj = current vector length, h = nj/2, N rows of G then H, last row = B).
+struct RowMap { int mode; const uint32_t *map; long cap, N, nj, h; };
+HD long row_gen(const RowMap &m, long r) {
+  if (m.mode == 0) return m.map[r];
+  if (r == m.N) return 2 * m.cap;  // B
+  const long half = m.N / 2;
+  const bool isH = r >= half;
+  const long rr = isH ? r - half : r, blk = rr / m.h, i = rr % m.h;
+  // L takes G_hi and H_lo, R takes G_lo and H_hi
+  const bool hi = (m.mode == 1) != isH;
+  return (isH ? m.cap : 0) + blk * m.nj + (hi ? m.h : 0) + i;
+}
+// table-driven multiscalar multiplication: one thread per (instance, split); partial[tid] = sum over its rows
+struct KMsmTable {
+  static constexpr int kBlock = 128, kMinBlocks = 1;
+  static constexpr const char *kName = "KMsmTable";
+  const ge_niels *table; RowMap rmap; const int8_t *dig; long dig_inst_stride; long rows; int S; ge_p3 *partial;
+  HD void operator()(long tid) const {
+    long inst = tid / S; int sp = (int)(tid % S);
+    const long r0 = rows * sp / S, r1 = rows * (sp + 1) / S;
+    const int8_t *drow = dig + inst * dig_inst_stride;
+    ge_p3 acc; ge_identity(acc);
+    for (long r = r0; r < r1; r++) {
+      int8_t d[32];
+#if defined(__CUDA_ARCH__)
+      { const uint4 *src = reinterpret_cast<const uint4 *>(drow + r * 32); uint4 a = src[0], b = src[1]; memcpy(d, &a, 16); memcpy(d + 16, &b, 16); }
+#else
+      memcpy(d, drow + r * 32, 32);
+#endif
+      const ge_niels *tg = table + row_gen(rmap, r) * (long)(TBL_W * TBL_E);
+#pragma unroll 4
+      for (int w = 0; w < TBL_W; w++) {
+        int dv = d[w];
+        if (dv != 0) {
+          int neg = dv < 0; int e = (neg ? -dv : dv) - 1;
+          ge_niels q; load_struct(q, &tg[w * TBL_E + e]);
+          ge_madd(acc, acc, q, neg);
+        }
+      }
+    }
+    store_struct(&partial[tid], acc);
+  }
+};
+struct KMsmTableFinish {
+  static constexpr int kBlock = 64, kMinBlocks = 1;
+  static constexpr const char *kName = "KMsmTableFinish";
+  const ge_p3 *partial; int S; uint8_t *out; long out_stride;
+  HD void operator()(long inst) const {
+    ge_p3 acc; load_struct(acc, &partial[inst * S]);
+    for (int s = 1; s < S; s++) { ge_p3 t; load_struct(t, &partial[inst * S + s]); ge_add(acc, acc, t); }
+    ristretto_encode(out + inst * out_stride, acc);
+  }
+};
+
+// per-round coefficient tables of the unfolded rounds: UG[b] = prod_t u_t^(+1 if bit t of b else -1), UH[b] = its inverse pattern,
+// b in [0, 2^(j+1)) after round j (round t <-> bit (j-t) of b, i.e. round 0 is the most significant bit).
+struct KIpaUTable {
+  static constexpr int kBlock = 128, kMinBlocks = 1;
+  static constexpr const char *kName = "KIpaUTable";
+  const scm *u, *uinv; const scm *UGin, *UHin; scm *UGout, *UHout; int B;  // in: [2^j][B], out: [2^(j+1)][B]
+  HD void operator()(long tid) const {
+    int p = (int)(tid % B); long b = tid / B;
+    scm uu = u[p], ui = uinv[p];
+    scm g = UGin[(b >> 1) * B + p], h = UHin[(b >> 1) * B + p];
+    UGout[b * B + p] = sc_mul(g, (b & 1) ? uu : ui);
+    UHout[b * B + p] = sc_mul(h, (b & 1) ? ui : uu);
+  }
+};
+// digit rows of L and R for an unfolded round (layout of RowMap modes 1 / 2); thread = (row pair index, proof)
+//   G rows: UG[b]*gf(idx)*a[partner],  H rows: UH[b]*y^-idx*gf(idx)*b[partner],  last row: c*w on B
+struct KRecodeUnfolded {
+  static constexpr int kBlock = 128, kMinBlocks = 1;
+  static constexpr const char *kName = "KRecodeUnfolded";
+  const scm *a, *b, *UG, *UH, *yinvpow, *ufac, *clr, *w; long N, nj, h, n; int B; int8_t *digL, *digR; long inst_stride;
+  HD void operator()(long tid) const {
+    int p = (int)(tid % B); long rr = tid / B;  // rr in [0, N/2): block blk, offset i
+    const long blk = rr / h, i = rr % h;
+    const long lo = blk * nj + i, hi = lo + h;            // original generator indices of the low / high half entries
+    scm ug = UG[blk * B + p], uh = UH[blk * B + p];
+    scm gf_lo = lo >= n ? ufac[p] : sc_one(), gf_hi = hi >= n ? ufac[p] : sc_one();
+    scm a_lo = a[i * B + p], a_hi = a[(h + i) * B + p], b_lo = b[i * B + p], b_hi = b[(h + i) * B + p];
+    int8_t d[32];
+    int8_t *L = digL + (long)p * inst_stride, *R = digR + (long)p * inst_stride;
+    const long half = N / 2;
+    // L: G_hi with a_lo ; H_lo with b_hi.   R: G_lo with a_hi ; H_hi with b_lo.
+    sc_recode_bytes(d, sc_mul(sc_mul(ug, gf_hi), a_lo)); store_digits(L + rr * 32, d);
+    sc_recode_bytes(d, sc_mul(sc_mul(sc_mul(uh, yinvpow[lo * B + p]), gf_lo), b_hi)); store_digits(L + (half + rr) * 32, d);
+    sc_recode_bytes(d, sc_mul(sc_mul(ug, gf_lo), a_hi)); store_digits(R + rr * 32, d);
+    sc_recode_bytes(d, sc_mul(sc_mul(sc_mul(uh, yinvpow[hi * B + p]), gf_hi), b_lo)); store_digits(R + (half + rr) * 32, d);
+    if (rr == 0) {
+      sc_recode_bytes(d, sc_mul(clr[p], w[p])); store_digits(L + N * 32, d);
+      sc_recode_bytes(d, sc_mul(clr[B + p], w[p])); store_digits(R + N * 32, d);
+    }
+  }
+};
+// digit rows for materialising the TRUE folded generators at level J: row idx (G) = UG[b]*gf(idx), row N+idx (H) = UH[b]*y^-idx*gf(idx)
+struct KRecodeFoldTable {
+  static constexpr int kBlock = 128, kMinBlocks = 1;
+  static constexpr const char *kName = "KRecodeFoldTable";
+  const scm *UG, *UH, *yinvpow, *ufac; long N, nJ, n; int B; int8_t *dig; long inst_stride;
+  HD void operator()(long tid) const {
+    int p = (int)(tid % B); long idx = tid / B;
+    const long blk = idx / nJ;
+    scm gf = idx >= n ? ufac[p] : sc_one();
+    int8_t d[32];
+    int8_t *row = dig + (long)p * inst_stride;
+    sc_recode_bytes(d, sc_mul(UG[blk * B + p], gf)); store_digits(row + idx * 32, d);
+    sc_recode_bytes(d, sc_mul(sc_mul(UH[blk * B + p], yinvpow[idx * B + p]), gf)); store_digits(row + (N + idx) * 32, d);
+  }
+};
+// G_J[i] = sum_b (row b*nJ+i) * G_{b*nJ+i}, H_J[i] likewise: the folded generators after J rounds, straight from the tables
+struct KFoldTable {
+  static constexpr int kBlock = 128, kMinBlocks = 1;
+  static constexpr const char *kName = "KFoldTable";
+  const ge_niels *table; long cap, N, nJ; const int8_t *dig; long dig_inst_stride; ge_p3 *dstG, *dstH; long dst_stride;
+  HD void operator()(long tid) const {
+    long p = tid / (2 * nJ); long r = tid % (2 * nJ); int which = (int)(r / nJ); long i = r % nJ;
+    const int8_t *drow = dig + p * dig_inst_stride + (which ? N * 32 : 0);
+    ge_p3 acc; ge_identity(acc);
+    for (long blk = 0; blk < N / nJ; blk++) {
+      long idx = blk * nJ + i;
+      const int8_t *d = drow + idx * 32;
+      const ge_niels *tg = table + ((which ? cap : 0) + idx) * (long)(TBL_W * TBL_E);
+      for (int w = 0; w < TBL_W; w++) {
+        int dv = d[w];
+        if (dv != 0) {
+          int neg = dv < 0; int e = (neg ? -dv : dv) - 1;
+          ge_niels q; load_struct(q, &tg[w * TBL_E + e]);
+          ge_madd(acc, acc, q, neg);
+        }
+      }
+    }
+    store_struct(&(which ? dstH : dstG)[p * dst_stride + i], acc);
   }
 };
