@@ -25,7 +25,7 @@ SBOX_CUBE, SBOX_INVERSE = 0, 1
 VAR_COMMITTED, VAR_MULT_LEFT, VAR_MULT_RIGHT, VAR_MULT_OUT, VAR_ONE, VAR_PUBLIC = 0, 1, 2, 3, 4, 5
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-DEFAULT_SO = os.path.join(_PKG, "libbp_b200.so")
+DEFAULT_SO = os.environ.get("BP_B200_LIB") or os.path.join(_PKG, "libbp_b200.so")  # BP_B200_LIB: developer override for kernel-variant builds
 
 
 class R1CSError(Exception):

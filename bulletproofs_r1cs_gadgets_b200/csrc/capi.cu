@@ -184,7 +184,7 @@ int32_t bp_prover_prove(bp_cs *cs, const uint8_t entropy[32], uint8_t *proof, si
   ProveArgs a{}; a.B = 1; a.label = cs->label.data(); a.label_len = (int)cs->label.size();
   a.v = dv.p; a.vbl = dvb.p; a.entropy = de.p; a.aL = daL.p; a.aR = daR.p; a.aO = daO.p; a.aux = nullptr;
   a.V_out = dV.p; a.proofs = dP.p; a.status = (int *)dS.p;
-  rc = engine_prove(g, c, a, s);
+  rc = engine_prove(g, c, a, 1, s);
   int st = 0;
   if (!rc) { dev_d2h(proof, dP.p, plen, s); dev_d2h(&st, dS.p, sizeof st, s); if (dev_sync(s)) rc = BP_ERR_CUDA; }
   circuit_free(c);
@@ -340,11 +340,13 @@ size_t bp_circuit_proof_len(const bp_circuit *c) { return c ? circuit_proof_len(
 // proofs per device chunk: bounded by a workspace budget (bytes) and BP_B200_CHUNK
 static uint32_t chunk_size(const BpCircuit *c, uint32_t B) {
   double per = 32.0 * (12.0 * c->n + 8.0 * c->N + c->q) + 160.0 * c->N + 64.0 * (5.0 * c->n + 2.0 * c->N) + 4096;
-  double budget = 48e9;
+  double budget = 40e9;
   uint32_t ch = (uint32_t)std::max(1.0, std::min((double)B, budget / per));
+  if (ch > 32768) ch = 32768;
+  uint32_t nchunks = (B + ch - 1) / ch;
+  ch = (B + nchunks - 1) / nchunks;  // equal-sized chunks
   const char *e = getenv("BP_B200_CHUNK");
   if (e && atoi(e) > 0) ch = std::min<uint32_t>(B, (uint32_t)atoi(e));
-  if (ch > 32768) ch = 32768;
   return ch;
 }
 
@@ -361,20 +363,10 @@ int32_t bp_prove_batch_device(const bp_gens *g, bp_circuit *c, uint32_t B, const
 #else
   dev_stream s = 0; (void)stream;
 #endif
-  const size_t m = cc->m, n = cc->n, plen = circuit_proof_len(cc);
-  uint32_t ch = chunk_size(cc, B);
-  for (uint32_t p0 = 0; p0 < B; p0 += ch) {
-    uint32_t bc = std::min(ch, B - p0);
-    ProveArgs a{}; a.B = (int)bc; a.label = label; a.label_len = (int)label_len;
-    a.v = d_v + (size_t)p0 * m * 32; a.vbl = d_vb + (size_t)p0 * m * 32; a.entropy = d_entropy + (size_t)p0 * 32;
-    a.aux = d_aux ? d_aux + (size_t)p0 * cc->naux * 32 : nullptr;
-    a.pub = d_pub ? d_pub + (size_t)p0 * cc->npub * 32 : nullptr;
-    if (d_aL) { a.aL = d_aL + (size_t)p0 * n * 32; a.aR = d_aR + (size_t)p0 * n * 32; a.aO = d_aO + (size_t)p0 * n * 32; }
-    a.V_out = d_V + (size_t)p0 * m * 32; a.proofs = d_proofs + (size_t)p0 * plen; a.status = d_status + p0;
-    int rc = engine_prove(g->g, cc, a, s);
-    if (rc) return rc;
-  }
-  return BP_OK;
+  ProveArgs a{}; a.B = (int)B; a.label = label; a.label_len = (int)label_len;
+  a.v = d_v; a.vbl = d_vb; a.entropy = d_entropy; a.aux = d_aux; a.pub = d_pub; a.aL = d_aL; a.aR = d_aR; a.aO = d_aO;
+  a.V_out = d_V; a.proofs = d_proofs; a.status = d_status;
+  return engine_prove(g->g, cc, a, (int)chunk_size(cc, B), s);
 }
 
 int32_t bp_prove_batch(const bp_gens *g, bp_circuit *c, uint32_t B, const uint8_t *label, size_t label_len, const uint8_t *v, const uint8_t *vb,

@@ -64,20 +64,35 @@ int bp_device_init() {
 template <class T>
 static int dalloc(T **p, size_t count) { return dev_malloc((void **)p, count * sizeof(T)); }
 
+// Outputs of the latency-bound first phase of a chunk (inputs in Montgomery form, witness, blinding draws, transcript
+// and RNG states).  One Front per chunk of a batch so that phase A of EVERY chunk runs concurrently (each on its own
+// pair of streams) before the throughput-bound phase B walks the chunks one after the other.
+struct Front {
+  int B = 0;
+  scm *v = 0, *vbl = 0, *aux = 0, *pub = 0, *wit = 0, *rand1 = 0;
+  strobe128 *ts = 0, *rng = 0;
+  dev_side sideR, sideW;
+  void release() {
+    void *ps[] = {v, vbl, aux, pub, wit, rand1, ts, rng};
+    for (void *p : ps) dev_free(p);
+    dev_side_free(sideR); dev_side_free(sideW);
+    *this = Front();
+  }
+};
 struct Workspace {
   int B = 0;
-  scm *v = 0, *vbl = 0, *aux = 0, *pub = 0, *uj = 0, *wit = 0, *rand1 = 0, *w_all = 0, *zpow = 0, *ypow = 0, *yinvpow = 0, *a = 0, *b = 0, *chal = 0, *t = 0, *tb = 0,
+  std::vector<Front> fronts;
+  scm *vpub = 0, *uj = 0, *w_all = 0, *zpow = 0, *ypow = 0, *yinvpow = 0, *a = 0, *b = 0, *chal = 0, *t = 0, *tb = 0,
       *clr = 0, *part = 0;
-  strobe128 *ts = 0, *rng = 0;
   int8_t *dig = 0; size_t dig_bytes = 0;
   ge_p3 *buckets = 0; size_t bucket_slots = 0;
   ge_p3 *wsum = 0, *Q = 0, *Gt = 0, *Ht = 0, *pts = 0;
   int8_t *naf = 0; int *naf_top = 0;
   scm *utab = 0; uint32_t *rg_as = 0; long rg_cap = -1;
-  dev_side side;
   void release() {
-    dev_side_free(side);
-    void *ps[] = {utab, rg_as, pub, uj, v, vbl, aux, wit, rand1, w_all, zpow, ypow, yinvpow, a, b, chal, t, tb, clr, part, ts, rng, dig, buckets, wsum, Q, Gt, Ht, pts, naf, naf_top};
+    for (Front &f : fronts) f.release();
+    fronts.clear();
+    void *ps[] = {utab, rg_as, vpub, uj, w_all, zpow, ypow, yinvpow, a, b, chal, t, tb, clr, part, dig, buckets, wsum, Q, Gt, Ht, pts, naf, naf_top};
     for (void *p : ps) dev_free(p);
     *this = Workspace();
   }
@@ -257,12 +272,11 @@ static int ensure_workspace(BpCircuit *c, int B) {
   size_t max_warps = (size_t)std::max<long>(msm_target_warps(), 2L * B) + B;
   w->bucket_slots = max_warps * MSM_WINDOWS * MSM_BUCKETS;
   int bad = 0;
-  bad |= dalloc(&w->v, (m + 1) * Bz); bad |= dalloc(&w->vbl, (m + 1) * Bz); bad |= dalloc(&w->aux, (size_t)(c->naux + 1) * Bz); bad |= dalloc(&w->pub, (size_t)(c->npub + 1) * Bz); bad |= dalloc(&w->uj, (2 * k + 2) * Bz);
-  bad |= dalloc(&w->wit, 3 * (n + 1) * Bz); bad |= dalloc(&w->rand1, (3 + 2 * n) * Bz); bad |= dalloc(&w->w_all, (size_t)c->nslots * Bz);
+  bad |= dalloc(&w->vpub, (size_t)(c->npub + 1) * Bz); bad |= dalloc(&w->uj, (2 * k + 2) * Bz);
+  bad |= dalloc(&w->w_all, (size_t)c->nslots * Bz);
   bad |= dalloc(&w->zpow, (q + 1) * Bz); bad |= dalloc(&w->ypow, N * Bz); bad |= dalloc(&w->yinvpow, N * Bz);
   bad |= dalloc(&w->a, N * Bz); bad |= dalloc(&w->b, N * Bz); bad |= dalloc(&w->chal, 16 * Bz);
   bad |= dalloc(&w->t, 6 * Bz); bad |= dalloc(&w->tb, 5 * Bz); bad |= dalloc(&w->clr, 2 * Bz); bad |= dalloc(&w->part, nchunks * 6 * Bz);
-  bad |= dalloc(&w->ts, Bz); bad |= dalloc(&w->rng, Bz);
   bad |= dalloc(&w->dig, w->dig_bytes); bad |= dalloc(&w->buckets, w->bucket_slots); bad |= dalloc(&w->wsum, max_warps * MSM_WINDOWS);
   bad |= dalloc(&w->Q, Bz); bad |= dalloc(&w->Gt, (N / 2 + 1) * Bz); bad |= dalloc(&w->Ht, (N / 2 + 1) * Bz);
   bad |= dalloc(&w->pts, (m + 11 + 2 * k + 1) * Bz);
@@ -270,6 +284,23 @@ static int ensure_workspace(BpCircuit *c, int B) {
   bad |= dalloc(&w->utab, 4 * (size_t)(1 << UNFOLD_ROUNDS) * Bz + 4 * Bz); bad |= dalloc(&w->rg_as, 2 * n + 2);
   if (bad) { w->release(); return BP_ERR_OOM; }
   w->B = B;
+  return BP_OK;
+}
+
+static int ensure_front(BpCircuit *c, size_t idx, int B) {
+  Workspace *w = c->ws;
+  if (w->fronts.size() <= idx) w->fronts.resize(idx + 1);
+  Front &f = w->fronts[idx];
+  if (f.B >= B) return BP_OK;
+  f.release();
+  const size_t n = c->n, m = c->m, Bz = (size_t)B;
+  int bad = 0;
+  bad |= dalloc(&f.v, (m + 1) * Bz); bad |= dalloc(&f.vbl, (m + 1) * Bz); bad |= dalloc(&f.aux, (size_t)(c->naux + 1) * Bz);
+  bad |= dalloc(&f.pub, (size_t)(c->npub + 1) * Bz); bad |= dalloc(&f.wit, 3 * (n + 1) * Bz); bad |= dalloc(&f.rand1, (3 + 2 * n) * Bz);
+  bad |= dalloc(&f.ts, Bz); bad |= dalloc(&f.rng, Bz);
+  bad |= dev_side_init(f.sideR); bad |= dev_side_init(f.sideW);
+  if (bad) { f.release(); return BP_ERR_OOM; }
+  f.B = B;
   return BP_OK;
 }
 
@@ -312,54 +343,81 @@ static void base_transcript(strobe128 &t, const uint8_t *label, int label_len) {
 }
 
 // ------------------------------------------------------------------------------------------------ prover
-int engine_prove(const BpGens *g, BpCircuit *c, const ProveArgs &A, dev_stream s) {
+// Phase A of one chunk (SURVEY A.3 steps 1-3 + witness): everything here is a one-thread-per-proof sequential chain
+// (Keccak permutations, field inversions), i.e. latency-bound and nearly free in throughput terms.  It runs on the chunk's
+// own two streams -- transcript/RNG on one, witness on the other -- forked from the caller's stream.
+static int prove_phase_a(const BpGens *g, BpCircuit *c, Front &f, const ProveArgs &A, dev_stream s) {
+  const int B = A.B;
+  const long n = c->n, m = c->m;
+  scm *aL = f.wit, *aR = f.wit + n * B, *aO = f.wit + 2 * n * B;
+  dev_stream sR = dev_side_fork(f.sideR, s);
+  CK(launch(m * B, sR, KLoadScalars{A.v, f.v, (int)m, B}));
+  CK(launch(m * B, sR, KLoadScalars{A.vbl, f.vbl, (int)m, B}));
+  dev_stream sW = dev_side_fork(f.sideW, sR);
+  if (A.aL) {
+    CK(launch(n * B, sW, KLoadScalars{A.aL, aL, (int)n, B}));
+    CK(launch(n * B, sW, KLoadScalars{A.aR, aR, (int)n, B}));
+    CK(launch(n * B, sW, KLoadScalars{A.aO, aO, (int)n, B}));
+  } else {
+    if (c->naux) CK(launch((long)c->naux * B, sW, KLoadScalars{A.aux, f.aux, (int)c->naux, B}));
+    if (c->npub && A.pub) CK(launch((long)c->npub * B, sW, KLoadScalars{A.pub, f.pub, (int)c->npub, B}));
+    CK(launch(B, sW, KWitnessTape{c->d_tape, WitnessLcs{c->d_wptr, c->d_wkind, c->d_widx, c->d_wcoeff}, c->d_pblocks, c->pos, (int)n, B, f.v, f.aux, f.pub, aL, aR, aO}));
+  }
+  CK(launch(m * B, sR, KCommit{f.v, f.vbl, (int)m, B, g->pc_table, A.V_out, m * 32, 32, nullptr}));
+  strobe128 base; base_transcript(base, A.label, A.label_len);
+  CK(launch(B, sR, KTsStart{base, A.V_out, (int)m, B, f.vbl, A.entropy, f.ts, f.rng, 1}));
+  CK(launch(B, sR, KRngDraw{f.rng, f.rand1, (int)(3 + 2 * n), B}));
+  return BP_OK;
+}
+
+static int prove_phase_b(const BpGens *g, BpCircuit *c, Front &f, const ProveArgs &A, dev_stream s);
+
+// Whole batch: phase A of every chunk first (all chunks concurrently), then phase B chunk by chunk on the caller's stream.
+int engine_prove(const BpGens *g, BpCircuit *c, const ProveArgs &A, int chunk, dev_stream s) {
   const int B = A.B;
   if (B <= 0) return BP_OK;
   if (g->capacity < c->n || g->capacity < c->N) return BP_ERR_INVALID_GENERATORS_LENGTH;
   if (!A.aL && !c->has_tape) return BP_ERR_MISSING_ASSIGNMENT;
-  int rc = ensure_workspace(c, B);
+  if (chunk <= 0 || chunk > B) chunk = B;
+  int rc = ensure_workspace(c, chunk);
   if (rc) return rc;
+  const size_t m = c->m, n = c->n, plen = circuit_proof_len(c);
+  const int nchunks = (B + chunk - 1) / chunk;
+  auto slice = [&](int ci) {
+    ProveArgs a = A;
+    const size_t p0 = (size_t)ci * chunk;
+    a.B = (int)std::min<size_t>(chunk, B - p0);
+    a.v = A.v + p0 * m * 32; a.vbl = A.vbl + p0 * m * 32; a.entropy = A.entropy + p0 * 32;
+    a.aux = A.aux ? A.aux + p0 * c->naux * 32 : nullptr; a.pub = A.pub ? A.pub + p0 * c->npub * 32 : nullptr;
+    if (A.aL) { a.aL = A.aL + p0 * n * 32; a.aR = A.aR + p0 * n * 32; a.aO = A.aO + p0 * n * 32; }
+    a.V_out = A.V_out + p0 * m * 32; a.proofs = A.proofs + p0 * plen; a.status = A.status + p0;
+    return a;
+  };
+  CK(dev_memset(A.status, 0, sizeof(int) * B, s));
+  CK(dev_memset(A.proofs, 0, plen * B, s));
+  for (int ci = 0; ci < nchunks; ci++) {
+    rc = ensure_front(c, ci, chunk); if (rc) return rc;
+    rc = prove_phase_a(g, c, c->ws->fronts[ci], slice(ci), s); if (rc) return rc;
+  }
+  for (int ci = 0; ci < nchunks; ci++) {
+    Front &f = c->ws->fronts[ci];
+    dev_side_join(f.sideR, s); dev_side_join(f.sideW, s);
+    rc = prove_phase_b(g, c, f, slice(ci), s); if (rc) return rc;
+  }
+  return BP_OK;
+}
+
+static int prove_phase_b(const BpGens *g, BpCircuit *c, Front &f, const ProveArgs &A, dev_stream s) {
+  const int B = A.B;
+  int rc;
   Workspace *w = c->ws;
   const long n = c->n, N = c->N, m = c->m, q = c->q, k = c->k;
   const long plen = (long)circuit_proof_len(c);
-  scm *aL = w->wit, *aR = w->wit + n * B, *aO = w->wit + 2 * n * B;
-  scm *i_b = w->rand1, *sL = w->rand1 + 3L * B, *sR = w->rand1 + (3 + n) * B;
+  scm *aL = f.wit, *aR = f.wit + n * B, *aO = f.wit + 2 * n * B;
+  scm *i_b = f.rand1, *sL = f.rand1 + 3L * B, *sR = f.rand1 + (3 + n) * B;
   scm *wL = w->w_all, *wR = w->w_all + n * B, *wO = w->w_all + 2 * n * B, *wV = w->w_all + 3 * n * B;
   scm *ch_y = w->chal, *ch_z = w->chal + B, *ch_yinv = w->chal + 2L * B, *ch_u = w->chal + 3L * B, *ch_x = w->chal + 4L * B,
       *ch_w = w->chal + 5L * B, *ipa_u = w->chal + 6L * B, *ipa_uinv = w->chal + 7L * B, *alpha = w->chal + 8L * B, *beta = w->chal + 9L * B;
-
-  CK(dev_memset(A.status, 0, sizeof(int) * B, s));
-  CK(dev_memset(A.proofs, 0, (size_t)plen * B, s));
-  // 1. inputs -> Montgomery, commitments V_j = v_j*B + r_j*B_blinding
-  CK(launch(m * B, s, KLoadScalars{A.v, w->v, (int)m, B}));
-  CK(launch(m * B, s, KLoadScalars{A.vbl, w->vbl, (int)m, B}));
-  // 2+3. witness generation on a side stream, beside the transcript start + transcript RNG draws (A.3 steps 1-3):
-  // both are one-thread-per-proof sequential chains (latency-bound), so they overlap almost perfectly.
-  CK(dev_side_init(w->side));
-  {
-    dev_stream s2 = dev_side_fork(w->side, s);
-    if (A.aL) {
-      CK(launch(n * B, s2, KLoadScalars{A.aL, aL, (int)n, B}));
-      CK(launch(n * B, s2, KLoadScalars{A.aR, aR, (int)n, B}));
-      CK(launch(n * B, s2, KLoadScalars{A.aO, aO, (int)n, B}));
-    } else {
-      if (c->naux) CK(launch((long)c->naux * B, s2, KLoadScalars{A.aux, w->aux, (int)c->naux, B}));
-      if (c->npub && A.pub) CK(launch((long)c->npub * B, s2, KLoadScalars{A.pub, w->pub, (int)c->npub, B}));
-      CK(launch(B, s2, KWitnessTape{c->d_tape, WitnessLcs{c->d_wptr, c->d_wkind, c->d_widx, c->d_wcoeff}, c->d_pblocks, c->pos, (int)n, B, w->v, w->aux, w->pub, aL, aR, aO}));
-    }
-  }
-  CK(launch(m * B, s, KCommit{w->v, w->vbl, (int)m, B, g->pc_table, A.V_out, m * 32, 32, nullptr}));
-  strobe128 base; base_transcript(base, A.label, A.label_len);
-  CK(launch(B, s, KTsStart{base, A.V_out, (int)m, B, w->vbl, A.entropy, w->ts, w->rng, 1}));
-  std::vector<uint8_t> dbg_states;
-  if (getenv("BP_B200_DEBUG_DUMP")) {
-    dbg_states.resize(2 * sizeof(strobe128) + 32 * m);
-    CK(dev_d2h(dbg_states.data(), w->ts, sizeof(strobe128), s)); CK(dev_d2h(dbg_states.data() + sizeof(strobe128), w->rng, sizeof(strobe128), s));
-    CK(dev_d2h(dbg_states.data() + 2 * sizeof(strobe128), A.V_out, 32 * m, s));
-    CK(dev_sync(s));
-  }
-  CK(launch(B, s, KRngDraw{w->rng, w->rand1, (int)(3 + 2 * n), B}));
-  dev_side_join(w->side, s);
   // 4. A_I1, A_O1, S1 (A.3 step 4)
   {
     const long rowsI = 2 * n + 1, rowsO = n + 1;
@@ -392,7 +450,7 @@ int engine_prove(const BpGens *g, BpCircuit *c, const ProveArgs &A, dev_stream s
     }
   }
   // 5. y, z; powers; flattened weights (A.3 steps 5-7)
-  CK(launch(B, s, KTsPhase2{w->ts, A.proofs, plen, ch_y, ch_z, ch_yinv, A.status, 0}));
+  CK(launch(B, s, KTsPhase2{f.ts, A.proofs, plen, ch_y, ch_z, ch_yinv, A.status, 0}));
   CK(launch(((q + CH_POW - 1) / CH_POW) * B, s, KPowers{ch_z, w->zpow, (int)q, B, 1, CH_POW}));
   CK(launch(((N + CH_POW - 1) / CH_POW) * B, s, KPowers{ch_y, w->ypow, (int)N, B, 0, CH_POW}));
   CK(launch(((N + CH_POW - 1) / CH_POW) * B, s, KPowers{ch_yinv, w->yinvpow, (int)N, B, 0, CH_POW}));
@@ -405,18 +463,18 @@ int engine_prove(const BpGens *g, BpCircuit *c, const ProveArgs &A, dev_stream s
     CK(launch(nch * B, s, KPolyT{pin, (int)n, B, CH_DOT, w->part}));
     CK(launch(6L * B, s, KSumPartials{w->part, (int)nch, 6, B, w->t}));
   }
-  CK(launch(B, s, KRngDraw{w->rng, w->tb, 5, B}));
+  CK(launch(B, s, KRngDraw{f.rng, w->tb, 5, B}));
   {
     // T_1,T_3,T_4,T_5,T_6 use t[0],t[2],t[3],t[4],t[5]: commit rows individually
     const int tj[5] = {0, 2, 3, 4, 5};
     for (int j = 0; j < 5; j++)
       CK(launch(B, s, KCommit{w->t + (long)tj[j] * B, w->tb + (long)j * B, 1, B, g->pc_table, A.proofs + 192 + 32 * j, plen, 0, nullptr}));
   }
-  CK(launch(B, s, KTsPhase3{w->ts, A.proofs, plen, ch_u, ch_x, A.status, 0}));
+  CK(launch(B, s, KTsPhase3{f.ts, A.proofs, plen, ch_u, ch_x, A.status, 0}));
   // 7. evaluate l, r at x; scalars of the proof (A.3 steps 11-13); w and Q (step 14)
   CK(launch(N * B, s, KPolyEval{pin, (int)n, B, ch_x, w->a, w->b}));
-  CK(launch(B, s, KProverScalars{w->t, w->tb, i_b, wV, w->vbl, (int)m, B, ch_x, A.proofs, plen}));
-  CK(launch(B, s, KTsPhase4{w->ts, A.proofs, plen, ch_w, (unsigned)N}));
+  CK(launch(B, s, KProverScalars{w->t, w->tb, i_b, wV, f.vbl, (int)m, B, ch_x, A.proofs, plen}));
+  CK(launch(B, s, KTsPhase4{f.ts, A.proofs, plen, ch_w, (unsigned)N}));
   CK(launch(B, s, KCommit{ch_w, nullptr, 1, B, g->pc_table, nullptr, 0, 0, w->Q}));
   // 8. inner-product argument (A.4).  With fixed-base tables the first UNFOLD_ROUNDS rounds never fold generators: L_j, R_j are
   // multiscalar multiplications over the ORIGINAL generators with scalars a_i * prod u_t^(+-1); the folded generators are then
@@ -441,7 +499,7 @@ int engine_prove(const BpGens *g, BpCircuit *c, const ProveArgs &A, dev_stream s
       RowMap rl{1, nullptr, (long)g->capacity, N, len, h}, rr{2, nullptr, (long)g->capacity, N, len, h};
       rc = run_msm_table(g, w, rl, rows, B, dL, rows * 32, A.proofs + 448 + 64 * round, plen, s); if (rc) return rc;
       rc = run_msm_table(g, w, rr, rows, B, dR, rows * 32, A.proofs + 448 + 64 * round + 32, plen, s); if (rc) return rc;
-      CK(launch(B, s, KTsIpaRound{w->ts, A.proofs, plen, round, B, (int)h, w->yinvpow, ch_u, ipa_u, ipa_uinv, alpha, beta, w->naf, w->naf_top,
+      CK(launch(B, s, KTsIpaRound{f.ts, A.proofs, plen, round, B, (int)h, w->yinvpow, ch_u, ipa_u, ipa_uinv, alpha, beta, w->naf, w->naf_top,
                                  A.status, 1, 0}));  // transcript + u, u^-1 only (verifier mode skips the fold scalars)
       CK(launch(h * B, s, KFoldAB{w->a, w->b, ipa_u, ipa_uinv, (int)h, B}));
       CK(launch((2L << round) * B, s, KIpaUTable{ipa_u, ipa_uinv, UG[cur], UH[cur], UG[cur ^ 1], UH[cur ^ 1], B}));
@@ -468,7 +526,7 @@ int engine_prove(const BpGens *g, BpCircuit *c, const ProveArgs &A, dev_stream s
     sL_[2] = {w->Q, 1, 1, 1}; sR_[2] = sL_[2];
     rc = run_msm(w, sL_, 3, B, dL, rows * 32, A.proofs + 448 + 64 * round, plen, 0, nullptr, s); if (rc) return rc;
     rc = run_msm(w, sR_, 3, B, dR, rows * 32, A.proofs + 448 + 64 * round + 32, plen, 0, nullptr, s); if (rc) return rc;
-    CK(launch(B, s, KTsIpaRound{w->ts, A.proofs, plen, round, B, (int)h, w->yinvpow, ch_u, ipa_u, ipa_uinv, alpha, beta, w->naf, w->naf_top,
+    CK(launch(B, s, KTsIpaRound{f.ts, A.proofs, plen, round, B, (int)h, w->yinvpow, ch_u, ipa_u, ipa_uinv, alpha, beta, w->naf, w->naf_top,
                                A.status, 0, yfree}));
     CK(launch(h * B, s, KFoldAB{w->a, w->b, ipa_u, ipa_uinv, (int)h, B}));
     if (h > 1) {
@@ -478,20 +536,18 @@ int engine_prove(const BpGens *g, BpCircuit *c, const ProveArgs &A, dev_stream s
     len = h;
   }
   CK(launch(B, s, KStoreAB{w->a, w->b, A.proofs, plen, 448 + 64 * k}));
-  if (const char *dump = getenv("BP_B200_DEBUG_DUMP")) {  // developer aid: raw Montgomery scalars of proof 0..B-1
+  if (const char *dump = getenv("BP_B200_DEBUG_DUMP")) {  // developer aid: scalars of the chunk as canonical bytes
     CK(dev_sync(s));
-    FILE *f = fopen(dump, "wb");
-    if (f) {
+    FILE *fp = fopen(dump, "wb");
+    if (fp) {
       auto put = [&](const char *name, const scm *d, long count) {
         std::vector<scm> h(count); dev_d2h(h.data(), d, count * sizeof(scm), s); dev_sync(s);
-        std::vector<uint8_t> b(count * 32); for (long i = 0; i < count; i++) sc_tobytes(b.data() + 32 * i, h[i]);
-        char hdr[32] = {0}; snprintf(hdr, sizeof hdr, "%s", name); fwrite(hdr, 1, 24, f); uint64_t c = count; fwrite(&c, 8, 1, f); fwrite(b.data(), 1, b.size(), f);
+        std::vector<uint8_t> bts(count * 32); for (long i = 0; i < count; i++) sc_tobytes(bts.data() + 32 * i, h[i]);
+        char hdr[32] = {0}; snprintf(hdr, sizeof hdr, "%s", name); fwrite(hdr, 1, 24, fp); uint64_t cnt = count; fwrite(&cnt, 8, 1, fp); fwrite(bts.data(), 1, bts.size(), fp);
       };
-      put("rand1", w->rand1, (3 + 2 * n) * B); put("chal", w->chal, 10L * B); put("t", w->t, 6L * B); put("tb", w->tb, 5L * B);
-      put("wit", w->wit, 3 * n * B); put("w_all", w->w_all, (long)c->nslots * B); put("v", w->v, m * B); put("vbl", w->vbl, m * B);
-      { char hdr[32] = {0}; snprintf(hdr, sizeof hdr, "raw_states"); fwrite(hdr, 1, 24, f); uint64_t cnt = 0; fwrite(&cnt, 8, 1, f); }
-      fwrite(dbg_states.data(), 1, dbg_states.size(), f);
-      fclose(f);
+      put("rand1", f.rand1, (3 + 2 * n) * B); put("chal", w->chal, 10L * B); put("t", w->t, 6L * B); put("tb", w->tb, 5L * B);
+      put("wit", f.wit, 3 * n * B); put("w_all", w->w_all, (long)c->nslots * B); put("v", f.v, m * B); put("vbl", f.vbl, m * B);
+      fclose(fp);
     }
   }
   return BP_OK;
@@ -553,7 +609,7 @@ int engine_verify(const BpGens *g, BpCircuit *c, const VerifyArgs &A, dev_stream
   CK(launch(((q + CH_POW - 1) / CH_POW) * B, s, KPowers{ch_z, w->zpow, (int)q, B, 1, CH_POW}));
   CK(launch(((N + CH_POW - 1) / CH_POW) * B, s, KPowers{ch_yinv, w->yinvpow, (int)N, B, 0, CH_POW}));
   CK(launch((long)c->nslots * B, s, KFlatten{c->d_slot_ptr, c->d_tq, c->d_tcoeff, w->zpow, w->w_all, B}));
-  if (c->npub) CK(launch((long)c->npub * B, s, KLoadScalars{A.pub, w->pub, (int)c->npub, B}));
+  if (c->npub) CK(launch((long)c->npub * B, s, KLoadScalars{A.pub, w->vpub, (int)c->npub, B}));
   CK(launch(N * B, s, KVerifyS{uj, ujinv, (int)k, B, w->a}));
   {
     long nch = (n + CH_DOT - 1) / CH_DOT; if (nch == 0) nch = 1;
@@ -562,7 +618,7 @@ int engine_verify(const BpGens *g, BpCircuit *c, const VerifyArgs &A, dev_stream
   }
   const long npts = 11 + m + 2 * k, rows = 2 + 2 * N + npts;
   CK(launch(N * B, s, KVerifyGH{wL, wR, wO, w->yinvpow, w->a, w->chal, A.proofs, plen, (int)n, (int)N, (int)k, B, w->dig, rows * 32}));
-  CK(launch(B, s, KVerifyScalars{w->chal, uj, ujinv, wV, wc, wP, w->pub, w->clr, A.proofs, plen, (int)m, (int)c->npub, (int)N, (int)k, B, w->dig, rows * 32}));
+  CK(launch(B, s, KVerifyScalars{w->chal, uj, ujinv, wV, wc, wP, w->vpub, w->clr, A.proofs, plen, (int)m, (int)c->npub, (int)N, (int)k, B, w->dig, rows * 32}));
   CK(launch(npts * B, s, KVerifyDecompress{A.V, A.proofs, plen, (int)m, (int)k, B, w->pts, npts, A.status}));
   MsmSeg segs[4] = {{g->pc_niels, 0, 0, 2}, {g->G_n, 0, 0, (int)N}, {g->H_n, 0, 0, (int)N}, {w->pts, npts, 1, (int)npts}};
   return run_msm(w, segs, 4, B, w->dig, rows * 32, nullptr, 0, 1, A.status, s);

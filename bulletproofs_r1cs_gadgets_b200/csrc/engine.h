@@ -58,7 +58,8 @@ struct ProveArgs {
   uint8_t *proofs;               // [B][proof_len]
   int *status;                   // [B]
 };
-int engine_prove(const BpGens *g, BpCircuit *c, const ProveArgs &a, dev_stream s);
+// proves a.B statements; `chunk` = proofs per device chunk (<= 0: one chunk)
+int engine_prove(const BpGens *g, BpCircuit *c, const ProveArgs &a, int chunk, dev_stream s);
 
 struct VerifyArgs {
   int B;

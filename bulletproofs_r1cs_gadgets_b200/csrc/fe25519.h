@@ -66,7 +66,7 @@ HD void fe_carry_wide(fe &out, int64_t h[10]) {
   for (int i = 0; i < 10; i++) out.v[i] = (int32_t)h[i];
 }
 
-HD void fe_mul(fe &out, const fe &f, const fe &g) {
+HD void fe_mul_inl(fe &out, const fe &f, const fe &g) {
   int32_t g19[10], f2[10];
 #pragma unroll
   for (int i = 0; i < 10; i++) { g19[i] = 19 * g.v[i]; f2[i] = 2 * f.v[i]; }
@@ -105,18 +105,50 @@ HD void fe_sq_wide(int64_t h[10], const fe &f) {
     }
   }
 }
-HD void fe_sq(fe &out, const fe &f) {
+HD void fe_sq_inl(fe &out, const fe &f) {
   int64_t h[10];
   fe_sq_wide(h, f);
   fe_carry_wide(out, h);
 }
 // out = 2 f^2
-HD void fe_sq2(fe &out, const fe &f) {
+HD void fe_sq2_inl(fe &out, const fe &f) {
   int64_t h[10];
   fe_sq_wide(h, f);
 #pragma unroll
   for (int k = 0; k < 10; k++) h[k] += h[k];
   fe_carry_wide(out, h);
+}
+// On the device the three multiplication primitives are real functions (operands and result travel in registers):
+// a point addition is then ~10 calls instead of ~2000 inlined instructions per multiplication site, which keeps the
+// hot loops inside the instruction cache (ncu showed 20 % "no_instructions" stalls with everything inlined).
+#ifndef BP_FE_CALL
+#define BP_FE_CALL 1
+#endif
+#if defined(__CUDACC__) && BP_FE_CALL
+static __device__ __noinline__ fe fe_mul_fn(fe f, fe g) { fe h; fe_mul_inl(h, f, g); return h; }
+static __device__ __noinline__ fe fe_sq_fn(fe f) { fe h; fe_sq_inl(h, f); return h; }
+static __device__ __noinline__ fe fe_sq2_fn(fe f) { fe h; fe_sq2_inl(h, f); return h; }
+#endif
+HD void fe_mul(fe &out, const fe &f, const fe &g) {
+#if defined(__CUDA_ARCH__) && BP_FE_CALL
+  out = fe_mul_fn(f, g);
+#else
+  fe_mul_inl(out, f, g);
+#endif
+}
+HD void fe_sq(fe &out, const fe &f) {
+#if defined(__CUDA_ARCH__) && BP_FE_CALL
+  out = fe_sq_fn(f);
+#else
+  fe_sq_inl(out, f);
+#endif
+}
+HD void fe_sq2(fe &out, const fe &f) {
+#if defined(__CUDA_ARCH__) && BP_FE_CALL
+  out = fe_sq2_fn(f);
+#else
+  fe_sq2_inl(out, f);
+#endif
 }
 HD void fe_sqn(fe &out, const fe &f, int n) {
   fe_sq(out, f);

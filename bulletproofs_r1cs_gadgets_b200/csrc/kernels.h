@@ -16,6 +16,16 @@
 #include "ge25519.h"
 #include "sc25519.h"
 #include "keccak.h"
+// occupancy knobs of the point-arithmetic kernels (blocks of 128 threads per SM the compiler must allow for)
+#ifndef BP_OCC_TABLE
+#define BP_OCC_TABLE 1
+#endif
+#ifndef BP_OCC_FOLD
+#define BP_OCC_FOLD 1
+#endif
+#ifndef BP_OCC_BUCKET
+#define BP_OCC_BUCKET 1
+#endif
 #define BP_ERR_FORMAT_ 2
 #define BP_ERR_VERIFICATION_ 3
 
@@ -105,7 +115,7 @@ struct MsmSeg { const void *bases; long inst_stride; int fmt; int count; };  // 
 #define MSM_BUCKETS 128
 
 struct KMsmAccumulate {
-  static constexpr int kBlock = 128, kMinBlocks = 1;
+  static constexpr int kBlock = 128, kMinBlocks = BP_OCC_BUCKET;
   static constexpr const char *kName = "KMsmAccumulate";
   MsmSeg seg[4]; int nseg; int S;  // S = row-range splits per instance (each split owns its own buckets)
   const int8_t *dig; long dig_inst_stride; ge_p3 *buckets; ge_p3 *wsum;
@@ -530,7 +540,7 @@ struct KStoreAB {
 // thread order is proof-major so a warp walks one NAF (uniform branches).
 // ------------------------------------------------------------------------------------------------
 struct KFoldGens {
-  static constexpr int kBlock = 128, kMinBlocks = 1;
+  static constexpr int kBlock = 128, kMinBlocks = BP_OCC_FOLD;
   static constexpr const char *kName = "KFoldGens";
   const ge_p3 *srcG, *srcH; long src_stride;  // round 0: shared generators (stride 0); later: per-proof
   ge_p3 *dstG, *dstH; long dst_stride;
@@ -989,7 +999,7 @@ HD long row_gen(const RowMap &m, long r) {
 }
 // table-driven multiscalar multiplication: one thread per (instance, split); partial[tid] = sum over its rows
 struct KMsmTable {
-  static constexpr int kBlock = 128, kMinBlocks = 1;
+  static constexpr int kBlock = 128, kMinBlocks = BP_OCC_TABLE;
   static constexpr const char *kName = "KMsmTable";
   const ge_niels *table; RowMap rmap; const int8_t *dig; long dig_inst_stride; long rows; int S; ge_p3 *partial;
   HD void operator()(long tid) const {
@@ -1087,7 +1097,7 @@ struct KRecodeFoldTable {
 };
 // G_J[i] = sum_b (row b*nJ+i) * G_{b*nJ+i}, H_J[i] likewise: the folded generators after J rounds, straight from the tables
 struct KFoldTable {
-  static constexpr int kBlock = 128, kMinBlocks = 1;
+  static constexpr int kBlock = 128, kMinBlocks = BP_OCC_TABLE;
   static constexpr const char *kName = "KFoldTable";
   const ge_niels *table; long cap, N, nJ; const int8_t *dig; long dig_inst_stride; ge_p3 *dstG, *dstH; long dst_stride;
   HD void operator()(long tid) const {
