@@ -89,10 +89,11 @@ struct Workspace {
   ge_p3 *wsum = 0, *Q = 0, *Gt = 0, *Ht = 0, *pts = 0;
   int8_t *naf = 0; int *naf_top = 0;
   scm *utab = 0; uint32_t *rg_as = 0; long rg_cap = -1;
+  uint32_t *rg_ver = 0; long rg_ver_cap = -1, rg_ver_N = -1;
   void release() {
     for (Front &f : fronts) f.release();
     fronts.clear();
-    void *ps[] = {utab, rg_as, vpub, uj, w_all, zpow, ypow, yinvpow, a, b, chal, t, tb, clr, part, dig, buckets, wsum, Q, Gt, Ht, pts, naf, naf_top};
+    void *ps[] = {rg_ver, utab, rg_as, vpub, uj, w_all, zpow, ypow, yinvpow, a, b, chal, t, tb, clr, part, dig, buckets, wsum, Q, Gt, Ht, pts, naf, naf_top};
     for (void *p : ps) dev_free(p);
     *this = Workspace();
   }
@@ -132,7 +133,8 @@ int gens_create(uint32_t capacity, BpGens **out) {
   dev_free(d_uni); dev_free(d_small); dev_free(d_ok);
   if (!ok) { gens_free(g); return BP_ERR_CUDA; }
   // fixed-base tables (512 KiB per generator); BP_B200_NO_TABLE=1 keeps the bucket-method-only pipeline
-  if (!getenv("BP_B200_NO_TABLE")) {
+  const size_t table_bytes = (2 * (size_t)capacity + 2) * TBL_W * TBL_E * sizeof(ge_niels);
+  if (!getenv("BP_B200_NO_TABLE") && table_bytes <= ((size_t)48 << 30)) {  // capacities above ~49k generators fall back to the bucket method
     const size_t ngen = 2 * (size_t)capacity + 2;
     if (dalloc(&g->table, ngen * TBL_W * TBL_E)) { gens_free(g); return BP_ERR_OOM; }
     CK(launch((long)ngen * TBL_W, s, KTableBuild{g->G_p3, g->H_p3, g->pc, (long)capacity, g->table}));
@@ -277,7 +279,7 @@ static int ensure_workspace(BpCircuit *c, int B) {
   bad |= dalloc(&w->zpow, (q + 1) * Bz); bad |= dalloc(&w->ypow, N * Bz); bad |= dalloc(&w->yinvpow, N * Bz);
   bad |= dalloc(&w->a, N * Bz); bad |= dalloc(&w->b, N * Bz); bad |= dalloc(&w->chal, 16 * Bz);
   bad |= dalloc(&w->t, 6 * Bz); bad |= dalloc(&w->tb, 5 * Bz); bad |= dalloc(&w->clr, 2 * Bz); bad |= dalloc(&w->part, nchunks * 6 * Bz);
-  bad |= dalloc(&w->dig, w->dig_bytes); bad |= dalloc(&w->buckets, w->bucket_slots); bad |= dalloc(&w->wsum, max_warps * MSM_WINDOWS);
+  bad |= dalloc(&w->dig, w->dig_bytes); bad |= dalloc(&w->buckets, w->bucket_slots); bad |= dalloc(&w->wsum, (max_warps + (size_t)B + 64) * MSM_WINDOWS);
   bad |= dalloc(&w->Q, Bz); bad |= dalloc(&w->Gt, (N / 2 + 1) * Bz); bad |= dalloc(&w->Ht, (N / 2 + 1) * Bz);
   bad |= dalloc(&w->pts, (m + 11 + 2 * k + 1) * Bz);
   bad |= dalloc(&w->naf, 4 * 256 * Bz); bad |= dalloc(&w->naf_top, 4 * Bz);
@@ -310,7 +312,7 @@ static int run_msm(Workspace *w, const MsmSeg *segs, int nseg, long ninst, const
   long rows = 0;
   for (int i = 0; i < nseg; i++) rows += segs[i].count;
   long S = (msm_target_warps() + ninst - 1) / ninst;
-  long maxS = rows / 256; if (maxS < 1) maxS = 1;
+  long maxS = rows / 1024; if (maxS < 1) maxS = 1;  // keep the 256-addition bucket reduction of a split below ~25 % of its accumulation
   if (S > maxS) S = maxS;
   if (S < 1) S = 1;
   while ((size_t)(ninst * S) * MSM_WINDOWS * MSM_BUCKETS > w->bucket_slots && S > 1) S--;
@@ -319,7 +321,13 @@ static int run_msm(Workspace *w, const MsmSeg *segs, int nseg, long ninst, const
   for (int i = 0; i < nseg; i++) k.seg[i] = segs[i];
   k.nseg = nseg; k.S = (int)S; k.dig = dig; k.dig_inst_stride = dig_inst_stride; k.buckets = w->buckets; k.wsum = w->wsum;
   CK(launch(ninst * S * MSM_WINDOWS, s, k));
-  CK(launch(ninst, s, KMsmFinish{w->wsum, (int)S, out, out_stride, mode, status, BP_ERR_VERIFICATION}));
+  if (S > 4) {  // many splits (few, large instances): add them up in parallel per window first
+    ge_p3 *sums = w->wsum + (size_t)ninst * S * MSM_WINDOWS;
+    CK(launch(ninst * MSM_WINDOWS, s, KMsmWindowSum{w->wsum, (int)S, sums}));
+    CK(launch(ninst, s, KMsmFinish{sums, 1, out, out_stride, mode, status, BP_ERR_VERIFICATION}));
+  } else {
+    CK(launch(ninst, s, KMsmFinish{w->wsum, (int)S, out, out_stride, mode, status, BP_ERR_VERIFICATION}));
+  }
   return BP_OK;
 }
 
@@ -332,7 +340,15 @@ static int run_msm_table(const BpGens *g, Workspace *w, const RowMap &rmap, long
   if (S < 1) S = 1;
   while ((size_t)(ninst * S) > w->bucket_slots && S > 1) S--;
   CK(launch(ninst * S, s, KMsmTable{g->table, rmap, dig, dig_inst_stride, rows, (int)S, w->buckets}));
-  CK(launch(ninst, s, KMsmTableFinish{w->buckets, (int)S, out, out_stride}));
+  if (S > 64 && ninst < 4096) {  // two-stage reduction of the per-thread partial sums
+    const int R = 32;
+    ge_p3 *stage = w->buckets + (size_t)ninst * S;
+    if ((size_t)ninst * (S + R) > w->bucket_slots) return BP_ERR_OOM;
+    CK(launch(ninst * R, s, KMsmTableReduce{w->buckets, (int)S, R, stage}));
+    CK(launch(ninst, s, KMsmTableFinish{stage, R, out, out_stride}));
+  } else {
+    CK(launch(ninst, s, KMsmTableFinish{w->buckets, (int)S, out, out_stride}));
+  }
   return BP_OK;
 }
 
@@ -576,7 +592,7 @@ int engine_msm_gens(BpGens *g, uint32_t n, const uint8_t *d_scalars, uint8_t *d_
     Workspace *w = g->msm_ws = new Workspace();
     size_t max_warps = (size_t)msm_target_warps() + 1;
     w->bucket_slots = max_warps * MSM_WINDOWS * MSM_BUCKETS;
-    if (dalloc(&w->a, n) || dalloc(&w->dig, (size_t)n * 32) || dalloc(&w->buckets, w->bucket_slots) || dalloc(&w->wsum, max_warps * MSM_WINDOWS)) {
+    if (dalloc(&w->a, n) || dalloc(&w->dig, (size_t)n * 32) || dalloc(&w->buckets, w->bucket_slots) || dalloc(&w->wsum, (max_warps + 64) * MSM_WINDOWS)) {
       w->release(); return BP_ERR_OOM;
     }
     g->msm_ws_n = n;
@@ -584,6 +600,17 @@ int engine_msm_gens(BpGens *g, uint32_t n, const uint8_t *d_scalars, uint8_t *d_
   Workspace *w = g->msm_ws;
   CK(launch(n, s, KLoadScalars{d_scalars, w->a, (int)n, 1}));
   CK(launch(n, s, KRecode{w->a, nullptr, (int)n, 1, w->dig, (long)n * 32, 0}));
+  if (g->table && !getenv("BP_B200_MSM_BUCKET")) {  // fixed-base tables cover these generators
+    if (!w->rg_as || w->rg_cap < (long)n) {
+      dev_free(w->rg_as); w->rg_as = nullptr;
+      std::vector<uint32_t> id(n); for (uint32_t i = 0; i < n; i++) id[i] = i;
+      if (dalloc(&w->rg_as, n)) return BP_ERR_OOM;
+      CK(dev_h2d(w->rg_as, id.data(), n * sizeof(uint32_t), s)); CK(dev_sync(s));
+      w->rg_cap = n;
+    }
+    RowMap rm{0, w->rg_as, (long)g->capacity, 0, 0, 0};
+    return run_msm_table(g, w, rm, n, 1, w->dig, (long)n * 32, d_out, 32, s);
+  }
   MsmSeg seg[1] = {{g->G_n, 0, 0, (int)n}};
   return run_msm(w, seg, 1, 1, w->dig, (long)n * 32, d_out, 32, 0, nullptr, s);
 }
@@ -620,6 +647,33 @@ int engine_verify(const BpGens *g, BpCircuit *c, const VerifyArgs &A, dev_stream
   CK(launch(N * B, s, KVerifyGH{wL, wR, wO, w->yinvpow, w->a, w->chal, A.proofs, plen, (int)n, (int)N, (int)k, B, w->dig, rows * 32}));
   CK(launch(B, s, KVerifyScalars{w->chal, uj, ujinv, wV, wc, wP, w->vpub, w->clr, A.proofs, plen, (int)m, (int)c->npub, (int)N, (int)k, B, w->dig, rows * 32}));
   CK(launch(npts * B, s, KVerifyDecompress{A.V, A.proofs, plen, (int)m, (int)k, B, w->pts, npts, A.status}));
+  if (g->table) {
+    // generator rows (B, B_blinding, G, H) from the fixed-base tables; the ~110 per-proof points by the bucket method; the two
+    // partial results are added in KVerifyCheck
+    if (w->rg_ver_cap != (long)g->capacity || w->rg_ver_N != N) {
+      std::vector<uint32_t> rg(2 + 2 * N);
+      rg[0] = 2 * g->capacity; rg[1] = 2 * g->capacity + 1;
+      for (long i = 0; i < N; i++) { rg[2 + i] = (uint32_t)i; rg[2 + N + i] = g->capacity + (uint32_t)i; }
+      dev_free(w->rg_ver); w->rg_ver = nullptr;
+      if (dalloc(&w->rg_ver, rg.size())) return BP_ERR_OOM;
+      CK(dev_h2d(w->rg_ver, rg.data(), rg.size() * sizeof(uint32_t), s)); CK(dev_sync(s));
+      w->rg_ver_cap = g->capacity; w->rg_ver_N = N;
+    }
+    const long trows = 2 + 2 * N;
+    long S = 262144 / B; if (S > trows / 16) S = trows / 16; if (S > 1024) S = 1024; if (S < 1) S = 1;
+    // partial sums of the table part live behind the bucket area used by the per-proof-point MSM
+    const size_t bucket_need = (size_t)B * MSM_WINDOWS * MSM_BUCKETS;
+    if (bucket_need + (size_t)B * S > w->bucket_slots) return BP_ERR_OOM;
+    ge_p3 *tpart = w->buckets + bucket_need;
+    RowMap rm{0, w->rg_ver, (long)g->capacity, 0, 0, 0};
+    CK(launch(B * S, s, KMsmTable{g->table, rm, w->dig, rows * 32, trows, (int)S, tpart}));
+    MsmSeg seg[1] = {{w->pts, npts, 1, (int)npts}};
+    KMsmAccumulate k{};
+    k.seg[0] = seg[0]; k.nseg = 1; k.S = 1; k.dig = w->dig + trows * 32; k.dig_inst_stride = rows * 32; k.buckets = w->buckets; k.wsum = w->wsum;
+    CK(launch((long)B * MSM_WINDOWS, s, k));
+    CK(launch(B, s, KVerifyCheck{w->wsum, tpart, (int)S, A.status}));
+    return BP_OK;
+  }
   MsmSeg segs[4] = {{g->pc_niels, 0, 0, 2}, {g->G_n, 0, 0, (int)N}, {g->H_n, 0, 0, (int)N}, {w->pts, npts, 1, (int)npts}};
   return run_msm(w, segs, 4, B, w->dig, rows * 32, nullptr, 0, 1, A.status, s);
 }

@@ -5,9 +5,9 @@
 #include "kernels.h"
 #include "devrt.h"
 
-#define KGROUP_MSM(X) X(KMsmAccumulate) X(KMsmFinish)
+#define KGROUP_MSM(X) X(KMsmAccumulate) X(KMsmFinish) X(KMsmWindowSum)
 #define KGROUP_FOLD(X) X(KFoldGens) X(KFoldTable)
-#define KGROUP_TABLE(X) X(KTableBuild) X(KMsmTable) X(KMsmTableFinish)
+#define KGROUP_TABLE(X) X(KTableBuild) X(KMsmTable) X(KMsmTableFinish) X(KVerifyCheck) X(KMsmTableReduce)
 #define KGROUP_POINTS(X) X(KCommit) X(KGensFromUniform) X(KPcBases) X(KPcTable) X(KEncodePoints) X(KVerifyDecompress)
 #define KGROUP_TRANSCRIPT(X) X(KTsStart) X(KRngDraw) X(KTsPhase2) X(KTsPhase3) X(KTsPhase4) X(KTsIpaRound) X(KSelfTest) X(KTsVerify)
 #define KGROUP_SCALAR(X) X(KLoadScalars) X(KRecode) X(KPowers) X(KFillScalar) X(KFlatten) X(KPolyT) X(KSumPartials) X(KPolyEval) \

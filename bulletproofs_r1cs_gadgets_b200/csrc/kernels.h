@@ -174,6 +174,19 @@ struct KMsmAccumulate {
   }
 };
 
+// sum the S splits of every (instance, window) in parallel; output compacted to [inst][32] at the front of the same buffer is
+// not possible in place, so the sums go to a second array
+struct KMsmWindowSum {
+  static constexpr int kBlock = 64, kMinBlocks = 1;
+  static constexpr const char *kName = "KMsmWindowSum";
+  const ge_p3 *wsum; int S; ge_p3 *out;
+  HD void operator()(long tid) const {
+    long inst = tid / MSM_WINDOWS; int w = (int)(tid % MSM_WINDOWS);
+    ge_p3 r; load_struct(r, &wsum[(inst * S) * MSM_WINDOWS + w]);
+    for (int s = 1; s < S; s++) { ge_p3 t; load_struct(t, &wsum[(inst * S + s) * MSM_WINDOWS + w]); ge_add(r, r, t); }
+    store_struct(&out[tid], r);
+  }
+};
 // sum the splits, Horner over the 32 window sums, then ristretto-encode (mode 0) or test for the identity (mode 1)
 struct KMsmFinish {
   static constexpr int kBlock = 64, kMinBlocks = 1;
@@ -1028,6 +1041,18 @@ struct KMsmTable {
     store_struct(&partial[tid], acc);
   }
 };
+// first reduction stage for many splits: thread (inst, j) adds partials j, j+R, j+2R, ... into out[inst*R + j]
+struct KMsmTableReduce {
+  static constexpr int kBlock = 64, kMinBlocks = 1;
+  static constexpr const char *kName = "KMsmTableReduce";
+  const ge_p3 *partial; int S, R; ge_p3 *out;
+  HD void operator()(long tid) const {
+    long inst = tid / R; int j = (int)(tid % R);
+    ge_p3 acc; load_struct(acc, &partial[inst * S + j]);
+    for (int s = j + R; s < S; s += R) { ge_p3 t; load_struct(t, &partial[inst * S + s]); ge_add(acc, acc, t); }
+    store_struct(&out[tid], acc);
+  }
+};
 struct KMsmTableFinish {
   static constexpr int kBlock = 64, kMinBlocks = 1;
   static constexpr const char *kName = "KMsmTableFinish";
@@ -1036,6 +1061,24 @@ struct KMsmTableFinish {
     ge_p3 acc; load_struct(acc, &partial[inst * S]);
     for (int s = 1; s < S; s++) { ge_p3 t; load_struct(t, &partial[inst * S + s]); ge_add(acc, acc, t); }
     ristretto_encode(out + inst * out_stride, acc);
+  }
+};
+
+// verifier: (bucket-method window sums of the per-proof points) + (table partial sums of the generator rows) must be the identity
+struct KVerifyCheck {
+  static constexpr int kBlock = 64, kMinBlocks = 1;
+  static constexpr const char *kName = "KVerifyCheck";
+  const ge_p3 *wsum; const ge_p3 *tpart; int S; int *status;
+  HD void operator()(long inst) const {
+    ge_p3 acc; load_struct(acc, &wsum[inst * MSM_WINDOWS + MSM_WINDOWS - 1]);
+    for (int w = MSM_WINDOWS - 2; w >= 0; w--) {
+      for (int i = 0; i < 7; i++) ge_dbl_p2(acc, acc);
+      ge_dbl(acc, acc);
+      ge_p3 sp; load_struct(sp, &wsum[inst * MSM_WINDOWS + w]);
+      ge_add(acc, acc, sp);
+    }
+    for (int s = 0; s < S; s++) { ge_p3 t; load_struct(t, &tpart[inst * S + s]); ge_add(acc, acc, t); }
+    if (!ge_is_identity_ristretto(acc) && status[inst] == 0) status[inst] = BP_ERR_VERIFICATION_;
   }
 };
 

@@ -54,12 +54,16 @@ def test_error_codes(api, gens): E.test_error_codes(api, gens)
 def test_single_multiplier_and_allocate_single(api, gens): E.test_single_multiplier_and_allocate_single(api, gens)
 
 
-def test_msm_entry_larger_sizes(api, gens_big, oracle_lib):
-    """MSM microbenchmark entry (BASELINE config 3) against the C oracle's Pippenger, device buffers"""
+@pytest.mark.parametrize("path", ["tables", "buckets"])
+def test_msm_entry_larger_sizes(api, gens_big, oracle_lib, path, monkeypatch):
+    """MSM microbenchmark entry (BASELINE config 3) against the C oracle's Pippenger, device buffers; both the fixed-base
+    table path and the bucket method (the path capacities above ~49k generators use), including their split reductions"""
     import torch
-    og = np.zeros((4096, 32), np.uint8)
-    oracle_lib.lib().bpo_gens_compressed(0, 4096, og.ctypes.data_as(CO.u8p))
-    for n, seed in ((1, 1), (33, 2), (1024, 3), (4096, 4)):
+    if path == "buckets":
+        monkeypatch.setenv("BP_B200_MSM_BUCKET", "1")
+    og = np.zeros((8192, 32), np.uint8)
+    oracle_lib.lib().bpo_gens_compressed(0, 8192, og.ctypes.data_as(CO.u8p))
+    for n, seed in ((1, 1), (33, 2), (1024, 3), (4096, 4), (8192, 5)):
         sc = H.rand_scalars(seed, n)
         if n == 1024:
             sc = [s if i % 2 else 0 for i, s in enumerate(sc)]  # 50 % zeros (inverse-S-box a_R shape)
