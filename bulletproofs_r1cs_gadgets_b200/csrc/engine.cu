@@ -90,10 +90,11 @@ struct Workspace {
   int8_t *naf = 0; int *naf_top = 0;
   scm *utab = 0; uint32_t *rg_as = 0; long rg_cap = -1;
   uint32_t *rg_ver = 0; long rg_ver_cap = -1, rg_ver_N = -1;
+  uint32_t *items = 0, *boff = 0, *soff = 0; size_t items_cap = 0, slices_cap = 0; ge_p3 *seg = 0;
   void release() {
     for (Front &f : fronts) f.release();
     fronts.clear();
-    void *ps[] = {rg_ver, utab, rg_as, vpub, uj, w_all, zpow, ypow, yinvpow, a, b, chal, t, tb, clr, part, dig, buckets, wsum, Q, Gt, Ht, pts, naf, naf_top};
+    void *ps[] = {items, boff, soff, seg, rg_ver, utab, rg_as, vpub, uj, w_all, zpow, ypow, yinvpow, a, b, chal, t, tb, clr, part, dig, buckets, wsum, Q, Gt, Ht, pts, naf, naf_top};
     for (void *p : ps) dev_free(p);
     *this = Workspace();
   }
@@ -140,13 +141,19 @@ int gens_create(uint32_t capacity, BpGens **out) {
     CK(launch((long)ngen * TBL_W, s, KTableBuild{g->G_p3, g->H_p3, g->pc, (long)capacity, g->table}));
     CK(dev_sync(s));
   }
+  if (g->table && !getenv("BP_B200_NO_SORTED")) {
+    const size_t ngen = 2 * (size_t)capacity + 2;
+    if (dalloc(&g->sg, ngen * SB_WINDOWS)) { gens_free(g); return BP_ERR_OOM; }
+    CK(launch((long)ngen, s, KShiftTableBuild{g->G_p3, g->H_p3, g->pc, (long)capacity, g->sg}));
+    CK(dev_sync(s));
+  }
   *out = g;
   return BP_OK;
 }
 void gens_free(BpGens *g) {
   if (!g) return;
   if (g->msm_ws) { g->msm_ws->release(); delete g->msm_ws; }
-  dev_free(g->G_p3); dev_free(g->H_p3); dev_free(g->G_n); dev_free(g->H_n); dev_free(g->pc); dev_free(g->pc_niels); dev_free(g->pc_table); dev_free(g->table);
+  dev_free(g->G_p3); dev_free(g->H_p3); dev_free(g->G_n); dev_free(g->H_n); dev_free(g->pc); dev_free(g->pc_niels); dev_free(g->pc_table); dev_free(g->table); dev_free(g->sg);
   delete g;
 }
 int gens_export(const BpGens *g, int which, uint32_t count, uint8_t *out) {
@@ -269,7 +276,7 @@ static int ensure_workspace(BpCircuit *c, int B) {
   const size_t k = c->k;
   size_t nchunks = (std::max(n, N) + CH_DOT - 1) / CH_DOT + 1;
   size_t rows_as = (2 * n + 1) + (n + 1) + (2 * n + 1), rows_ipa = 2 * (N + 1), rows_ver = 2 * N + m + 13 + 2 * k + 2;
-  w->dig_bytes = std::max(std::max(rows_as, rows_ipa), rows_ver) * 32 * Bz;
+  w->dig_bytes = std::max(std::max(rows_as, rows_ipa), rows_ver) * SB_ROW_BYTES * Bz;  // sized for the wider 13-bit rows
   // bucket slots: enough for one MSM launch at the largest split the launcher will pick
   size_t max_warps = (size_t)std::max<long>(msm_target_warps(), 2L * B) + B;
   w->bucket_slots = max_warps * MSM_WINDOWS * MSM_BUCKETS;
@@ -283,6 +290,10 @@ static int ensure_workspace(BpCircuit *c, int B) {
   bad |= dalloc(&w->Q, Bz); bad |= dalloc(&w->Gt, (N / 2 + 1) * Bz); bad |= dalloc(&w->Ht, (N / 2 + 1) * Bz);
   bad |= dalloc(&w->pts, (m + 11 + 2 * k + 1) * Bz);
   bad |= dalloc(&w->naf, 4 * 256 * Bz); bad |= dalloc(&w->naf_top, 4 * Bz);
+  w->items_cap = (size_t)std::max(2 * n + 1, N + 1) * SB_WINDOWS;  // items of one instance
+  bad |= dalloc(&w->items, w->items_cap * Bz); bad |= dalloc(&w->boff, (size_t)(SB_BUCKETS + 1) * Bz); bad |= dalloc(&w->soff, (size_t)(SB_BUCKETS + 1) * Bz);
+  w->slices_cap = SB_BUCKETS + w->items_cap / SB_SLICE + 1;
+  bad |= dalloc(&w->seg, (size_t)SB_SEGS * 2 * Bz);
   bad |= dalloc(&w->utab, 4 * (size_t)(1 << UNFOLD_ROUNDS) * Bz + 4 * Bz); bad |= dalloc(&w->rg_as, 2 * n + 2);
   if (bad) { w->release(); return BP_ERR_OOM; }
   w->B = B;
@@ -349,6 +360,18 @@ static int run_msm_table(const BpGens *g, Workspace *w, const RowMap &rmap, long
   } else {
     CK(launch(ninst, s, KMsmTableFinish{w->buckets, (int)S, out, out_stride}));
   }
+  return BP_OK;
+}
+
+// sorted-bucket MSM over shared generators (13-bit digit rows): counting sort -> bucket sums -> segment reduce -> finish
+static int run_msm_sorted(const BpGens *g, Workspace *w, const RowMap &rmap, long rows, long ninst, const int8_t *dig, long dig_inst_stride,
+                          uint8_t *out, long out_stride, dev_stream s) {
+  if ((size_t)rows * SB_WINDOWS > w->items_cap || (size_t)ninst * w->slices_cap > w->bucket_slots) return BP_ERR_OOM;
+  CK(launch_sort_buckets(rmap, dig, dig_inst_stride, rows, ninst, w->items, (long)w->items_cap, w->boff, w->soff, s));
+  SortedView sv{w->items, w->boff, w->soff, (long)w->items_cap, (long)w->slices_cap};
+  CK(launch(ninst * (long)w->slices_cap, s, KBucketAccumulate{g->sg, sv, w->buckets}));
+  CK(launch(ninst * SB_SEGS, s, KBucketReduce{w->buckets, sv, w->seg}));
+  CK(launch(ninst, s, KBucketFinish{w->seg, out, out_stride}));
   return BP_OK;
 }
 
@@ -437,15 +460,28 @@ static int prove_phase_b(const BpGens *g, BpCircuit *c, Front &f, const ProveArg
   // 4. A_I1, A_O1, S1 (A.3 step 4)
   {
     const long rowsI = 2 * n + 1, rowsO = n + 1;
-    int8_t *dI = w->dig, *dO = dI + rowsI * 32 * B, *dS = dO + rowsO * 32 * B;
-    CK(launch(B, s, KRecode{i_b, nullptr, 1, B, dI, rowsI * 32, 0}));
-    CK(launch(n * B, s, KRecode{aL, nullptr, (int)n, B, dI, rowsI * 32, 1}));
-    CK(launch(n * B, s, KRecode{aR, nullptr, (int)n, B, dI, rowsI * 32, (int)(1 + n)}));
-    CK(launch(B, s, KRecode{i_b + B, nullptr, 1, B, dO, rowsO * 32, 0}));
-    CK(launch(n * B, s, KRecode{aO, nullptr, (int)n, B, dO, rowsO * 32, 1}));
-    CK(launch(B, s, KRecode{i_b + 2L * B, nullptr, 1, B, dS, rowsI * 32, 0}));
-    CK(launch(n * B, s, KRecode{sL, nullptr, (int)n, B, dS, rowsI * 32, 1}));
-    CK(launch(n * B, s, KRecode{sR, nullptr, (int)n, B, dS, rowsI * 32, (int)(1 + n)}));
+    const bool sorted = g->sg != nullptr;
+    const long rb = sorted ? SB_ROW_BYTES : 32;
+    int8_t *dI = w->dig, *dO = dI + rowsI * rb * B, *dS = dO + rowsO * rb * B;
+    if (sorted) {
+      CK(launch(B, s, KRecode13{i_b, nullptr, 1, B, dI, rowsI * rb, 0}));
+      CK(launch(n * B, s, KRecode13{aL, nullptr, (int)n, B, dI, rowsI * rb, 1}));
+      CK(launch(n * B, s, KRecode13{aR, nullptr, (int)n, B, dI, rowsI * rb, (int)(1 + n)}));
+      CK(launch(B, s, KRecode{i_b + B, nullptr, 1, B, dO, rowsO * 32, 0}));   // A_O stays on the direct tables: its scalars are 0/1
+      CK(launch(n * B, s, KRecode{aO, nullptr, (int)n, B, dO, rowsO * 32, 1}));
+      CK(launch(B, s, KRecode13{i_b + 2L * B, nullptr, 1, B, dS, rowsI * rb, 0}));
+      CK(launch(n * B, s, KRecode13{sL, nullptr, (int)n, B, dS, rowsI * rb, 1}));
+      CK(launch(n * B, s, KRecode13{sR, nullptr, (int)n, B, dS, rowsI * rb, (int)(1 + n)}));
+    } else {
+      CK(launch(B, s, KRecode{i_b, nullptr, 1, B, dI, rowsI * rb, 0}));
+      CK(launch(n * B, s, KRecode{aL, nullptr, (int)n, B, dI, rowsI * rb, 1}));
+      CK(launch(n * B, s, KRecode{aR, nullptr, (int)n, B, dI, rowsI * rb, (int)(1 + n)}));
+      CK(launch(B, s, KRecode{i_b + B, nullptr, 1, B, dO, rowsO * rb, 0}));
+      CK(launch(n * B, s, KRecode{aO, nullptr, (int)n, B, dO, rowsO * rb, 1}));
+      CK(launch(B, s, KRecode{i_b + 2L * B, nullptr, 1, B, dS, rowsI * rb, 0}));
+      CK(launch(n * B, s, KRecode{sL, nullptr, (int)n, B, dS, rowsI * rb, 1}));
+      CK(launch(n * B, s, KRecode{sR, nullptr, (int)n, B, dS, rowsI * rb, (int)(1 + n)}));
+    }
     if (g->table) {
       if (w->rg_cap != (long)g->capacity) {
         std::vector<uint32_t> rg(2 * n + 1);
@@ -455,9 +491,15 @@ static int prove_phase_b(const BpGens *g, BpCircuit *c, Front &f, const ProveArg
         w->rg_cap = g->capacity;
       }
       RowMap rm{0, w->rg_as, (long)g->capacity, 0, 0, 0};
-      rc = run_msm_table(g, w, rm, rowsI, B, dI, rowsI * 32, A.proofs + 0, plen, s); if (rc) return rc;
-      rc = run_msm_table(g, w, rm, rowsO, B, dO, rowsO * 32, A.proofs + 32, plen, s); if (rc) return rc;
-      rc = run_msm_table(g, w, rm, rowsI, B, dS, rowsI * 32, A.proofs + 64, plen, s); if (rc) return rc;
+      if (sorted) {
+        rc = run_msm_sorted(g, w, rm, rowsI, B, dI, rowsI * rb, A.proofs + 0, plen, s); if (rc) return rc;
+        rc = run_msm_table(g, w, rm, rowsO, B, dO, rowsO * 32, A.proofs + 32, plen, s); if (rc) return rc;
+        rc = run_msm_sorted(g, w, rm, rowsI, B, dS, rowsI * rb, A.proofs + 64, plen, s); if (rc) return rc;
+      } else {
+        rc = run_msm_table(g, w, rm, rowsI, B, dI, rowsI * rb, A.proofs + 0, plen, s); if (rc) return rc;
+        rc = run_msm_table(g, w, rm, rowsO, B, dO, rowsO * rb, A.proofs + 32, plen, s); if (rc) return rc;
+        rc = run_msm_table(g, w, rm, rowsI, B, dS, rowsI * rb, A.proofs + 64, plen, s); if (rc) return rc;
+      }
     } else {
       MsmSeg segs[3] = {{g->pc_niels + 1, 0, 0, 1}, {g->G_n, 0, 0, (int)n}, {g->H_n, 0, 0, (int)n}};
       rc = run_msm(w, segs, 3, B, dI, rowsI * 32, A.proofs + 0, plen, 0, nullptr, s); if (rc) return rc;
@@ -509,12 +551,20 @@ static int prove_phase_b(const BpGens *g, BpCircuit *c, Front &f, const ProveArg
     CK(launch(2L * B, s, KSumPartials{w->part, (int)nch, 2, B, w->clr}));
     if (round < J) {
       const long rows = N + 1;
-      int8_t *dL = w->dig, *dR = w->dig + rows * 32 * B;
+      const bool sorted = g->sg != nullptr;
+      const long rb = sorted ? SB_ROW_BYTES : 32;
+      int8_t *dL = w->dig, *dR = w->dig + rows * rb * B;
       const int cur = round & 1;
-      CK(launch((N / 2) * B, s, KRecodeUnfolded{w->a, w->b, UG[cur], UH[cur], w->yinvpow, ch_u, w->clr, ch_w, N, len, h, n, B, dL, dR, rows * 32}));
       RowMap rl{1, nullptr, (long)g->capacity, N, len, h}, rr{2, nullptr, (long)g->capacity, N, len, h};
-      rc = run_msm_table(g, w, rl, rows, B, dL, rows * 32, A.proofs + 448 + 64 * round, plen, s); if (rc) return rc;
-      rc = run_msm_table(g, w, rr, rows, B, dR, rows * 32, A.proofs + 448 + 64 * round + 32, plen, s); if (rc) return rc;
+      if (sorted) {
+        CK(launch((N / 2) * B, s, KRecodeUnfolded13{w->a, w->b, UG[cur], UH[cur], w->yinvpow, ch_u, w->clr, ch_w, N, len, h, n, B, dL, dR, rows * rb}));
+        rc = run_msm_sorted(g, w, rl, rows, B, dL, rows * rb, A.proofs + 448 + 64 * round, plen, s); if (rc) return rc;
+        rc = run_msm_sorted(g, w, rr, rows, B, dR, rows * rb, A.proofs + 448 + 64 * round + 32, plen, s); if (rc) return rc;
+      } else {
+        CK(launch((N / 2) * B, s, KRecodeUnfolded{w->a, w->b, UG[cur], UH[cur], w->yinvpow, ch_u, w->clr, ch_w, N, len, h, n, B, dL, dR, rows * rb}));
+        rc = run_msm_table(g, w, rl, rows, B, dL, rows * rb, A.proofs + 448 + 64 * round, plen, s); if (rc) return rc;
+        rc = run_msm_table(g, w, rr, rows, B, dR, rows * rb, A.proofs + 448 + 64 * round + 32, plen, s); if (rc) return rc;
+      }
       CK(launch(B, s, KTsIpaRound{f.ts, A.proofs, plen, round, B, (int)h, w->yinvpow, ch_u, ipa_u, ipa_uinv, alpha, beta, w->naf, w->naf_top,
                                  A.status, 1, 0}));  // transcript + u, u^-1 only (verifier mode skips the fold scalars)
       CK(launch(h * B, s, KFoldAB{w->a, w->b, ipa_u, ipa_uinv, (int)h, B}));

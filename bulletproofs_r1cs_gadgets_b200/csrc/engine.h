@@ -15,6 +15,7 @@ struct BpGens {
   ge_p3 *pc;            // B, B_blinding
   ge_niels *pc_niels;
   ge_niels *pc_table;   // [2][64][16]
+  ge_niels *sg;         // shift table [(2cap+2)][20]: 2^(13w) * P (sorted-bucket MSM); NULL when disabled
   ge_niels *table;      // fixed-base tables [(2cap+2)][32][128] (see KTableBuild); NULL when disabled
   uint8_t pc_c[64];     // compressed B, B_blinding (host copy)
   struct Workspace *msm_ws; uint32_t msm_ws_n;  // scratch of the MSM microbenchmark entry

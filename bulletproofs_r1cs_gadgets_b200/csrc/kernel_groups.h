@@ -13,6 +13,8 @@
 #define KGROUP_SCALAR(X) X(KLoadScalars) X(KRecode) X(KPowers) X(KFillScalar) X(KFlatten) X(KPolyT) X(KSumPartials) X(KPolyEval) \
   X(KProverScalars) X(KIpaDots) X(KRecodeIpa) X(KFoldAB) X(KStoreAB) X(KWitnessTape) X(KVerifyS) X(KVerifyDelta) X(KVerifyGH) X(KVerifyScalars) X(KIpaUTable) X(KRecodeUnfolded) X(KRecodeFoldTable)
 
+#define KGROUP_SORTED(X) X(KShiftTableBuild) X(KRecode13) X(KRecodeUnfolded13) X(KSortBucketsSerial) X(KBucketAccumulate) X(KBucketReduce) X(KBucketFinish)
+
 #define KDECL_EXTERN(K) extern template int launch<K>(long, dev_stream, const K &);
 #define KDEFINE(K) template int launch<K>(long, dev_stream, const K &);
 
@@ -20,7 +22,12 @@
 KGROUP_MSM(KDECL_EXTERN)
 KGROUP_FOLD(KDECL_EXTERN)
 KGROUP_TABLE(KDECL_EXTERN)
+KGROUP_SORTED(KDECL_EXTERN)
 KGROUP_POINTS(KDECL_EXTERN)
 KGROUP_TRANSCRIPT(KDECL_EXTERN)
 KGROUP_SCALAR(KDECL_EXTERN)
 #endif
+
+// block-cooperative counting sort of digit items by bucket (k_sorted.cu)
+int launch_sort_buckets(const RowMap &rmap, const int8_t *dig, long dig_inst_stride, long rows, long ninst, uint32_t *items, long items_stride,
+                        uint32_t *boff, uint32_t *soff, dev_stream s);

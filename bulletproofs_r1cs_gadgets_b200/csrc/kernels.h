@@ -1163,3 +1163,199 @@ struct KFoldTable {
     store_struct(&(which ? dstH : dstG)[p * dst_stride + i], acc);
   }
 };
+
+// ------------------------------------------------------------------------------------------------
+// Sorted-bucket multiscalar multiplication over the shared generators (13-bit signed windows).
+// For every generator P and window w the point 2^(13w)*P is tabulated (shift table, 20 x 128 B per generator), so all 20
+// windows of an instance feed ONE set of 4096 buckets: ~20 additions per term instead of 32 with the 8-bit direct tables,
+// and one running-sum reduction per instance instead of one per window.  Per launch:
+//   sort_buckets (block per instance, counting sort in shared memory)  ->  item list grouped by bucket
+//   KBucketAccumulate (thread per bucket: register accumulator over its items; ~160 items per bucket at N = 32768)
+//   KBucketReduce (32 segments of 128 buckets: plain and weighted sums)  ->  KBucketFinish (combine, encode)
+// ------------------------------------------------------------------------------------------------
+#define SB_WINDOWS 20
+#define SB_BITS 13
+#define SB_BUCKETS 4096
+#define SB_ROW_BYTES 48   // 20 int16 digits, padded to 3 x 16 B
+#define SB_SEGS 32
+#define SB_SEG_LEN (SB_BUCKETS / SB_SEGS)
+
+HD void sc_recode13(int16_t dig[SB_WINDOWS], const scm &s) {
+  uint64_t w[4]; sc_to_canonical(w, s);
+  int carry = 0;
+#pragma unroll
+  for (int i = 0; i < SB_WINDOWS; i++) {
+    const int bit = SB_BITS * i, word = bit >> 6, off = bit & 63;
+    uint64_t v = word < 4 ? (w[word] >> off) : 0;
+    if (off > 64 - SB_BITS && word + 1 < 4) v |= w[word + 1] << (64 - off);
+    int d = (int)(v & ((1 << SB_BITS) - 1)) + carry;
+    carry = d >= (1 << (SB_BITS - 1));
+    d -= carry << SB_BITS;
+    dig[i] = (int16_t)d;
+  }
+}
+HD void store_digits13(int8_t *dst, const int16_t dig[SB_WINDOWS]) {
+  int16_t tmp[24];
+#pragma unroll
+  for (int i = 0; i < 24; i++) tmp[i] = i < SB_WINDOWS ? dig[i] : 0;
+#if defined(__CUDA_ARCH__)
+  uint4 a, b, c;
+  memcpy(&a, tmp, 16); memcpy(&b, tmp + 8, 16); memcpy(&c, tmp + 16, 16);
+  uint4 *d = reinterpret_cast<uint4 *>(dst); d[0] = a; d[1] = b; d[2] = c;
+#else
+  memcpy(dst, tmp, SB_ROW_BYTES);
+#endif
+}
+HD void load_digits13(int16_t dig[24], const int8_t *src) {
+#if defined(__CUDA_ARCH__)
+  const uint4 *s = reinterpret_cast<const uint4 *>(src);
+  uint4 a = s[0], b = s[1], c = s[2];
+  memcpy(dig, &a, 16); memcpy(dig + 8, &b, 16); memcpy(dig + 16, &c, 16);
+#else
+  memcpy(dig, src, SB_ROW_BYTES);
+#endif
+}
+// shift table: sg[gen*20 + w] = 2^(13w) * P_gen in affine Niels form
+struct KShiftTableBuild {
+  static constexpr int kBlock = 64, kMinBlocks = 1;
+  static constexpr const char *kName = "KShiftTableBuild";
+  const ge_p3 *G, *H, *pc; long cap; ge_niels *sg;
+  HD void operator()(long gen) const {
+    ge_p3 P;
+    if (gen < cap) load_struct(P, &G[gen]); else if (gen < 2 * cap) load_struct(P, &H[gen - cap]); else load_struct(P, &pc[gen - 2 * cap]);
+    for (int w = 0; w < SB_WINDOWS; w++) {
+      ge_niels nl; ge_to_niels(nl, P); store_struct(&sg[gen * SB_WINDOWS + w], nl);
+      for (int i = 0; i < SB_BITS; i++) ge_dbl(P, P);
+    }
+  }
+};
+// src [cnt][B] (optionally times mul[p]) -> 13-bit digit rows row0.. of each instance
+struct KRecode13 {
+  static constexpr int kBlock = 128, kMinBlocks = 1;
+  static constexpr const char *kName = "KRecode13";
+  const scm *src; const scm *mul; int cnt, B; int8_t *dig; long inst_stride; int row0;
+  HD void operator()(long tid) const {
+    int p = (int)(tid % B); long i = tid / B;
+    scm s = src[i * B + p];
+    if (mul) s = sc_mul(s, mul[p]);
+    int16_t d[SB_WINDOWS]; sc_recode13(d, s);
+    store_digits13(dig + (long)p * inst_stride + (row0 + i) * SB_ROW_BYTES, d);
+  }
+};
+// same scalars as KRecodeUnfolded, 13-bit rows
+struct KRecodeUnfolded13 {
+  static constexpr int kBlock = 128, kMinBlocks = 1;
+  static constexpr const char *kName = "KRecodeUnfolded13";
+  const scm *a, *b, *UG, *UH, *yinvpow, *ufac, *clr, *w; long N, nj, h, n; int B; int8_t *digL, *digR; long inst_stride;
+  HD void put(int8_t *base, long row, const scm &v) const { int16_t d[SB_WINDOWS]; sc_recode13(d, v); store_digits13(base + row * SB_ROW_BYTES, d); }
+  HD void operator()(long tid) const {
+    int p = (int)(tid % B); long rr = tid / B;
+    const long blk = rr / h, i = rr % h;
+    const long lo = blk * nj + i, hi = lo + h;
+    scm ug = UG[blk * B + p], uh = UH[blk * B + p];
+    scm gf_lo = lo >= n ? ufac[p] : sc_one(), gf_hi = hi >= n ? ufac[p] : sc_one();
+    scm a_lo = a[i * B + p], a_hi = a[(h + i) * B + p], b_lo = b[i * B + p], b_hi = b[(h + i) * B + p];
+    int8_t *L = digL + (long)p * inst_stride, *R = digR + (long)p * inst_stride;
+    const long half = N / 2;
+    put(L, rr, sc_mul(sc_mul(ug, gf_hi), a_lo));
+    put(L, half + rr, sc_mul(sc_mul(sc_mul(uh, yinvpow[lo * B + p]), gf_lo), b_hi));
+    put(R, rr, sc_mul(sc_mul(ug, gf_lo), a_hi));
+    put(R, half + rr, sc_mul(sc_mul(sc_mul(uh, yinvpow[hi * B + p]), gf_hi), b_lo));
+    if (rr == 0) { put(L, N, sc_mul(clr[p], w[p])); put(R, N, sc_mul(clr[B + p], w[p])); }
+  }
+};
+// item = (generator*20 + window) | sign << 31
+// boff: [inst][SB_BUCKETS + 1] item offsets; soff: [inst][SB_BUCKETS + 1] slice offsets (a bucket with c items is cut into
+// ceil(c / SB_SLICE) slices so that no thread adds more than SB_SLICE points: padded circuits put thousands of identical
+// scalars -- hence identical digits -- into a handful of buckets)
+#define SB_SLICE 256
+struct SortedView { const uint32_t *items; const uint32_t *boff; const uint32_t *soff; long items_stride; long slices_cap; };
+// reference (one thread per instance) counting sort: used by the emulation build and as the fallback for tiny launches
+struct KSortBucketsSerial {
+  static constexpr int kBlock = 32, kMinBlocks = 1;
+  static constexpr const char *kName = "KSortBucketsSerial";
+  RowMap rmap; const int8_t *dig; long dig_inst_stride; long rows; uint32_t *items; long items_stride; uint32_t *boff; uint32_t *soff;
+  HD void operator()(long inst) const {
+    uint32_t *off = boff + inst * (SB_BUCKETS + 1);
+    for (int b = 0; b <= SB_BUCKETS; b++) off[b] = 0;
+    const int8_t *drow = dig + inst * dig_inst_stride;
+    for (long r = 0; r < rows; r++) {
+      int16_t d[24]; load_digits13(d, drow + r * SB_ROW_BYTES);
+      for (int w = 0; w < SB_WINDOWS; w++) if (d[w]) off[(d[w] < 0 ? -d[w] : d[w])]++;   // count into slot b+1
+    }
+    for (int b = 0; b < SB_BUCKETS; b++) off[b + 1] += off[b];
+    // scatter, walking a cursor per bucket (cursor = off[b] advanced, restored afterwards)
+    uint32_t *it = items + inst * items_stride;
+    for (long r = 0; r < rows; r++) {
+      int16_t d[24]; load_digits13(d, drow + r * SB_ROW_BYTES);
+      const uint32_t g = (uint32_t)row_gen(rmap, r) * SB_WINDOWS;
+      for (int w = 0; w < SB_WINDOWS; w++) if (d[w]) {
+        int neg = d[w] < 0; int b = (neg ? -d[w] : d[w]) - 1;
+        it[off[b]++] = (g + w) | ((uint32_t)neg << 31);
+      }
+    }
+    for (int b = SB_BUCKETS; b > 0; b--) off[b] = off[b - 1];
+    off[0] = 0;
+    uint32_t *so = soff + inst * (SB_BUCKETS + 1);
+    so[0] = 0;
+    for (int b = 0; b < SB_BUCKETS; b++) so[b + 1] = so[b] + (off[b + 1] - off[b] + SB_SLICE - 1) / SB_SLICE;
+  }
+};
+// one thread per slice of a bucket (slice j of the instance; its bucket is found by binary search in the slice offsets)
+struct KBucketAccumulate {
+  static constexpr int kBlock = 128, kMinBlocks = 1;
+  static constexpr const char *kName = "KBucketAccumulate";
+  const ge_niels *sg; SortedView sv; ge_p3 *psum;  // psum[inst*slices_cap + slice]
+  HD void operator()(long tid) const {
+    long inst = tid / sv.slices_cap; uint32_t j = (uint32_t)(tid % sv.slices_cap);
+    const uint32_t *so = sv.soff + inst * (SB_BUCKETS + 1);
+    if (j >= so[SB_BUCKETS]) return;
+    int lo = 0, hi = SB_BUCKETS;  // largest b with so[b] <= j
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (so[mid] <= j) lo = mid; else hi = mid; }
+    const int b = lo;
+    const uint32_t *off = sv.boff + inst * (SB_BUCKETS + 1);
+    const uint32_t k0 = off[b] + (j - so[b]) * SB_SLICE;
+    const uint32_t k1 = k0 + SB_SLICE < off[b + 1] ? k0 + SB_SLICE : off[b + 1];
+    const uint32_t *it = sv.items + inst * sv.items_stride;
+    ge_p3 acc; ge_identity(acc);
+    for (uint32_t k = k0; k < k1; k++) {
+      uint32_t item = it[k];
+      ge_niels q; load_struct(q, &sg[item & 0x7fffffffu]);
+      ge_madd(acc, acc, q, (int)(item >> 31));
+    }
+    store_struct(&psum[tid], acc);
+  }
+};
+// per segment of 128 buckets: S = sum b_i, W = sum (local index + 1) * b_i   (running-sum trick); b_i = sum of its slices
+struct KBucketReduce {
+  static constexpr int kBlock = 64, kMinBlocks = 1;
+  static constexpr const char *kName = "KBucketReduce";
+  const ge_p3 *psum; SortedView sv; ge_p3 *seg;  // seg[(inst*32 + s)*2 + {0: S, 1: W}]
+  HD void operator()(long tid) const {
+    long inst = tid / SB_SEGS; int sgm = (int)(tid % SB_SEGS);
+    const uint32_t *so = sv.soff + inst * (SB_BUCKETS + 1);
+    const ge_p3 *ps = psum + inst * sv.slices_cap;
+    ge_p3 run, tot; ge_identity(run); ge_identity(tot);
+    for (int i = SB_SEG_LEN - 1; i >= 0; i--) {
+      const int b = sgm * SB_SEG_LEN + i;
+      for (uint32_t j = so[b]; j < so[b + 1]; j++) { ge_p3 t; load_struct(t, &ps[j]); ge_add(run, run, t); }
+      ge_add(tot, tot, run);
+    }
+    store_struct(&seg[tid * 2], run); store_struct(&seg[tid * 2 + 1], tot);
+  }
+};
+// result = sum_s W_s + 128 * sum_s s * S_s
+struct KBucketFinish {
+  static constexpr int kBlock = 64, kMinBlocks = 1;
+  static constexpr const char *kName = "KBucketFinish";
+  const ge_p3 *seg; uint8_t *out; long out_stride;
+  HD void operator()(long inst) const {
+    const ge_p3 *sgp = seg + inst * SB_SEGS * 2;
+    ge_p3 run, T, Wsum; ge_identity(run); ge_identity(T); ge_identity(Wsum);
+    for (int s = SB_SEGS - 1; s >= 1; s--) { ge_p3 t; load_struct(t, &sgp[s * 2]); ge_add(run, run, t); ge_add(T, T, run); }
+    for (int i = 0; i < 7; i++) ge_dbl(T, T);  // * SB_SEG_LEN (128)
+    for (int s = 0; s < SB_SEGS; s++) { ge_p3 t; load_struct(t, &sgp[s * 2 + 1]); ge_add(Wsum, Wsum, t); }
+    ge_add(T, T, Wsum);
+    ristretto_encode(out + inst * out_stride, T);
+  }
+};
