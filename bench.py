@@ -286,7 +286,7 @@ def main():
                "sample": "first %d proofs of the step, one thread per proof (oracle/bp_oracle.c)" % sample, "bit_exact_vs_gpu": bool(same)}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 (F_l Montgomery 4x64, GF(2^255-19) 10x25.5-bit)",
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 (F_l Montgomery 4x64, GF(2^255-19) 8x32-bit saturated)",
             "data": "synthetic",
             "config": {"workload": "gadget_vsmt_2 depth-%d membership proofs, inverse S-box (n=%d, N=%d, m=%d, q=%d)" % (args.depth, circ.n, N, circ.m, circ.q),
                        "proofs_per_gpu_per_step": B, "global_proofs_per_step": world * B,

@@ -1,133 +1,205 @@
-// GF(2^255-19) arithmetic, 10 signed limbs in radix 2^25.5 (limb i holds ceil(25.5*i) bits),
-// 64-bit column accumulators.  On sm_100a every limb product is one IMAD.WIDE on the fma pipe;
-// carries run on the alu pipe.  Replaces curve25519-dalek's FieldElement (reference
-// Cargo.toml:8, an un-vendored dependency); representation and schedule are our own.
+// GF(2^255-19) arithmetic, 8 saturated 32-bit limbs: an element is ANY 256-bit integer congruent to the
+// value mod p (2^256 = 38 mod p), so there are no limb bounds to track -- every function accepts and
+// returns arbitrary 256-bit representatives, and only fe_tobytes reduces fully.
 //
-// Bounds (standard for this radix): fe_mul/fe_sq accept limbs up to ~1.65*2^26 (even) /
-// 1.65*2^25 (odd) in magnitude, i.e. a sum or difference of up to three carried elements,
-// and return carried limbs (|h_even| <= 1.01*2^25, |h_odd| <= 1.01*2^24).
+// On sm_100a a limb product is one IMAD.WIDE.U32 with carry-in/carry-out predicates: ptxas fuses each
+// mad.lo.cc / madc.hi.cc pair below into IMAD.WIDE.U32[.X], so the 8x8 schoolbook product is 64 of them
+// plus 8 for the 2^256 = 38 fold (72 fma-pipe instructions, ~125 in total; the radix-2^25.5 form this
+// replaces needed 100 IMAD.WIDE with a 64-bit addend plus ~100 carry/shift instructions).  Products of
+// equal column parity go to one of two accumulators (even-/odd-aligned 64-bit lanes) so that a row of four
+// products is one carry chain with no overlap between neighbouring lanes.
+//
+// Replaces curve25519-dalek's FieldElement (reference Cargo.toml:8, an un-vendored dependency);
+// representation and schedule are our own.  The host (emulation-test) build uses plain 64-bit C.
 #pragma once
 #include "hd.h"
 #include "constants.h"
 
-struct fe { int32_t v[10]; };
+struct fe { uint32_t v[8]; };
 
 HD void fe_0(fe &h) {
 #pragma unroll
-  for (int i = 0; i < 10; i++) h.v[i] = 0;
+  for (int i = 0; i < 8; i++) h.v[i] = 0;
 }
 HD void fe_1(fe &h) { fe_0(h); h.v[0] = 1; }
+
+// h = f + g
 HD void fe_add(fe &h, const fe &f, const fe &g) {
-#pragma unroll
-  for (int i = 0; i < 10; i++) h.v[i] = f.v[i] + g.v[i];
+#if defined(__CUDA_ARCH__)
+  uint32_t r0, r1, r2, r3, r4, r5, r6, r7, c;
+  asm("add.cc.u32 %0, %9, %17;\n\taddc.cc.u32 %1, %10, %18;\n\taddc.cc.u32 %2, %11, %19;\n\taddc.cc.u32 %3, %12, %20;\n\t"
+      "addc.cc.u32 %4, %13, %21;\n\taddc.cc.u32 %5, %14, %22;\n\taddc.cc.u32 %6, %15, %23;\n\taddc.cc.u32 %7, %16, %24;\n\t"
+      "addc.u32 %8, 0, 0;"
+      : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7), "=r"(c)
+      : "r"(f.v[0]), "r"(f.v[1]), "r"(f.v[2]), "r"(f.v[3]), "r"(f.v[4]), "r"(f.v[5]), "r"(f.v[6]), "r"(f.v[7]),
+        "r"(g.v[0]), "r"(g.v[1]), "r"(g.v[2]), "r"(g.v[3]), "r"(g.v[4]), "r"(g.v[5]), "r"(g.v[6]), "r"(g.v[7]));
+  uint32_t t = c * 38u;
+  asm("add.cc.u32 %0, %0, %9;\n\taddc.cc.u32 %1, %1, 0;\n\taddc.cc.u32 %2, %2, 0;\n\taddc.cc.u32 %3, %3, 0;\n\t"
+      "addc.cc.u32 %4, %4, 0;\n\taddc.cc.u32 %5, %5, 0;\n\taddc.cc.u32 %6, %6, 0;\n\taddc.cc.u32 %7, %7, 0;\n\t"
+      "addc.u32 %8, 0, 0;"
+      : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "+r"(r4), "+r"(r5), "+r"(r6), "+r"(r7), "=r"(c)
+      : "r"(t));
+  h.v[0] = r0 + c * 38u;  // a second wrap leaves a value below 38: no further carry
+  h.v[1] = r1; h.v[2] = r2; h.v[3] = r3; h.v[4] = r4; h.v[5] = r5; h.v[6] = r6; h.v[7] = r7;
+#else
+  uint32_t r[8]; uint64_t c = 0;
+  for (int i = 0; i < 8; i++) { c += (uint64_t)f.v[i] + g.v[i]; r[i] = (uint32_t)c; c >>= 32; }
+  c *= 38;
+  for (int i = 0; i < 8; i++) { c += r[i]; r[i] = (uint32_t)c; c >>= 32; }
+  r[0] += (uint32_t)c * 38u;
+  for (int i = 0; i < 8; i++) h.v[i] = r[i];
+#endif
 }
+// h = f - g
 HD void fe_sub(fe &h, const fe &f, const fe &g) {
-#pragma unroll
-  for (int i = 0; i < 10; i++) h.v[i] = f.v[i] - g.v[i];
+#if defined(__CUDA_ARCH__)
+  uint32_t r0, r1, r2, r3, r4, r5, r6, r7, b;
+  asm("sub.cc.u32 %0, %9, %17;\n\tsubc.cc.u32 %1, %10, %18;\n\tsubc.cc.u32 %2, %11, %19;\n\tsubc.cc.u32 %3, %12, %20;\n\t"
+      "subc.cc.u32 %4, %13, %21;\n\tsubc.cc.u32 %5, %14, %22;\n\tsubc.cc.u32 %6, %15, %23;\n\tsubc.cc.u32 %7, %16, %24;\n\t"
+      "subc.u32 %8, 0, 0;"
+      : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7), "=r"(b)
+      : "r"(f.v[0]), "r"(f.v[1]), "r"(f.v[2]), "r"(f.v[3]), "r"(f.v[4]), "r"(f.v[5]), "r"(f.v[6]), "r"(f.v[7]),
+        "r"(g.v[0]), "r"(g.v[1]), "r"(g.v[2]), "r"(g.v[3]), "r"(g.v[4]), "r"(g.v[5]), "r"(g.v[6]), "r"(g.v[7]));
+  uint32_t t = b & 38u;  // b = 0xffffffff on borrow: the wrapped value is 2^256 too large, i.e. 38 too large mod p
+  asm("sub.cc.u32 %0, %0, %9;\n\tsubc.cc.u32 %1, %1, 0;\n\tsubc.cc.u32 %2, %2, 0;\n\tsubc.cc.u32 %3, %3, 0;\n\t"
+      "subc.cc.u32 %4, %4, 0;\n\tsubc.cc.u32 %5, %5, 0;\n\tsubc.cc.u32 %6, %6, 0;\n\tsubc.cc.u32 %7, %7, 0;\n\t"
+      "subc.u32 %8, 0, 0;"
+      : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "+r"(r4), "+r"(r5), "+r"(r6), "+r"(r7), "=r"(b)
+      : "r"(t));
+  h.v[0] = r0 - (b & 38u);  // a second wrap leaves a value within 38 of 2^256: no further borrow
+  h.v[1] = r1; h.v[2] = r2; h.v[3] = r3; h.v[4] = r4; h.v[5] = r5; h.v[6] = r6; h.v[7] = r7;
+#else
+  uint32_t r[8]; int64_t c = 0;
+  for (int i = 0; i < 8; i++) { c += (int64_t)f.v[i] - (int64_t)g.v[i]; r[i] = (uint32_t)c; c >>= 32; }
+  int64_t t = c ? 38 : 0; c = 0;
+  for (int i = 0; i < 8; i++) { c += (int64_t)r[i] - (i == 0 ? t : 0); r[i] = (uint32_t)c; c >>= 32; }
+  if (c) r[0] -= 38u;
+  for (int i = 0; i < 8; i++) h.v[i] = r[i];
+#endif
 }
-HD void fe_neg(fe &h, const fe &f) {
-#pragma unroll
-  for (int i = 0; i < 10; i++) h.v[i] = -f.v[i];
-}
+HD void fe_neg(fe &h, const fe &f) { fe z; fe_0(z); fe_sub(h, z, f); }
 // h = b ? g : f   (branch-free)
 HD void fe_select(fe &h, const fe &f, const fe &g, int b) {
-  int32_t m = -(int32_t)(b != 0);
+  uint32_t m = (uint32_t)(-(int32_t)(b != 0));
 #pragma unroll
-  for (int i = 0; i < 10; i++) h.v[i] = f.v[i] ^ (m & (f.v[i] ^ g.v[i]));
+  for (int i = 0; i < 8; i++) h.v[i] = f.v[i] ^ (m & (f.v[i] ^ g.v[i]));
 }
 HD void fe_cswap(fe &f, fe &g, int b) {
-  int32_t m = -(int32_t)(b != 0);
+  uint32_t m = (uint32_t)(-(int32_t)(b != 0));
 #pragma unroll
-  for (int i = 0; i < 10; i++) { int32_t x = m & (f.v[i] ^ g.v[i]); f.v[i] ^= x; g.v[i] ^= x; }
+  for (int i = 0; i < 8; i++) { uint32_t x = m & (f.v[i] ^ g.v[i]); f.v[i] ^= x; g.v[i] ^= x; }
 }
 // h = b ? -f : f
-HD void fe_cneg(fe &h, const fe &f, int b) {
-  int32_t m = -(int32_t)(b != 0);
-#pragma unroll
-  for (int i = 0; i < 10; i++) h.v[i] = (f.v[i] ^ m) - m;
-}
+HD void fe_cneg(fe &h, const fe &f, int b) { fe n; fe_neg(n, f); fe_select(h, f, n, b); }
 
-// carry 10 wide columns into limbs
-HD void fe_carry_wide(fe &out, int64_t h[10]) {
-  int64_t c;
-  c = (h[0] + (1LL << 25)) >> 26; h[1] += c; h[0] -= c << 26;
-  c = (h[4] + (1LL << 25)) >> 26; h[5] += c; h[4] -= c << 26;
-  c = (h[1] + (1LL << 24)) >> 25; h[2] += c; h[1] -= c << 25;
-  c = (h[5] + (1LL << 24)) >> 25; h[6] += c; h[5] -= c << 25;
-  c = (h[2] + (1LL << 25)) >> 26; h[3] += c; h[2] -= c << 26;
-  c = (h[6] + (1LL << 25)) >> 26; h[7] += c; h[6] -= c << 26;
-  c = (h[3] + (1LL << 24)) >> 25; h[4] += c; h[3] -= c << 25;
-  c = (h[7] + (1LL << 24)) >> 25; h[8] += c; h[7] -= c << 25;
-  c = (h[4] + (1LL << 25)) >> 26; h[5] += c; h[4] -= c << 26;
-  c = (h[8] + (1LL << 25)) >> 26; h[9] += c; h[8] -= c << 26;
-  c = (h[9] + (1LL << 24)) >> 25; h[0] += c * 19; h[9] -= c << 25;
-  c = (h[0] + (1LL << 25)) >> 26; h[1] += c; h[0] -= c << 26;
+#if defined(__CUDA_ARCH__)
+// one carry chain of four 32x32 products into four neighbouring 64-bit lanes, carry-out into the word above
+#define FE_ROW4(A, s, x0, x1, x2, x3, y)                                                                                     \
+  asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\tmadc.hi.cc.u32 %1, %9, %13, %1;\n\t"                                                \
+      "madc.lo.cc.u32 %2, %10, %13, %2;\n\tmadc.hi.cc.u32 %3, %10, %13, %3;\n\t"                                             \
+      "madc.lo.cc.u32 %4, %11, %13, %4;\n\tmadc.hi.cc.u32 %5, %11, %13, %5;\n\t"                                             \
+      "madc.lo.cc.u32 %6, %12, %13, %6;\n\tmadc.hi.cc.u32 %7, %12, %13, %7;\n\t"                                             \
+      "addc.u32 %8, %8, 0;"                                                                                                  \
+      : "+r"(A[s]), "+r"(A[s + 1]), "+r"(A[s + 2]), "+r"(A[s + 3]), "+r"(A[s + 4]), "+r"(A[s + 5]), "+r"(A[s + 6]),          \
+        "+r"(A[s + 7]), "+r"(A[s + 8])                                                                                       \
+      : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(y))
+
+// 2^256 = 38: R (8 words) = W[0..7] + 38 * W[8..15], fully folded back into 256 bits
+HD void fe_fold512(fe &out, const uint32_t W[16]) {
+  uint32_t R[9];
 #pragma unroll
-  for (int i = 0; i < 10; i++) out.v[i] = (int32_t)h[i];
+  for (int i = 0; i < 8; i++) R[i] = W[i];
+  R[8] = 0;
+  const uint32_t c38 = 38;
+  FE_ROW4(R, 0, W[8], W[10], W[12], W[14], c38);
+  asm("mad.lo.cc.u32 %0, %8, %12, %0;\n\tmadc.hi.cc.u32 %1, %8, %12, %1;\n\t"
+      "madc.lo.cc.u32 %2, %9, %12, %2;\n\tmadc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+      "madc.lo.cc.u32 %4, %10, %12, %4;\n\tmadc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+      "madc.lo.cc.u32 %6, %11, %12, %6;\n\tmadc.hi.u32 %7, %11, %12, %7;"
+      : "+r"(R[1]), "+r"(R[2]), "+r"(R[3]), "+r"(R[4]), "+r"(R[5]), "+r"(R[6]), "+r"(R[7]), "+r"(R[8])
+      : "r"(W[9]), "r"(W[11]), "r"(W[13]), "r"(W[15]), "r"(c38));
+  uint32_t t = R[8] * 38u, c;  // R[8] <= 39
+  asm("add.cc.u32 %0, %0, %9;\n\taddc.cc.u32 %1, %1, 0;\n\taddc.cc.u32 %2, %2, 0;\n\taddc.cc.u32 %3, %3, 0;\n\t"
+      "addc.cc.u32 %4, %4, 0;\n\taddc.cc.u32 %5, %5, 0;\n\taddc.cc.u32 %6, %6, 0;\n\taddc.cc.u32 %7, %7, 0;\n\t"
+      "addc.u32 %8, 0, 0;"
+      : "+r"(R[0]), "+r"(R[1]), "+r"(R[2]), "+r"(R[3]), "+r"(R[4]), "+r"(R[5]), "+r"(R[6]), "+r"(R[7]), "=r"(c)
+      : "r"(t));
+  R[0] += c * 38u;
+#pragma unroll
+  for (int i = 0; i < 8; i++) out.v[i] = R[i];
 }
+#endif
 
 HD void fe_mul_inl(fe &out, const fe &f, const fe &g) {
-  int32_t g19[10], f2[10];
+#if defined(__CUDA_ARCH__)
+  uint32_t E[17], O[17];  // word w of the even-/odd-aligned accumulator
 #pragma unroll
-  for (int i = 0; i < 10; i++) { g19[i] = 19 * g.v[i]; f2[i] = 2 * f.v[i]; }
-  int64_t h[10];
+  for (int i = 0; i < 17; i++) { E[i] = 0; O[i] = 0; }
 #pragma unroll
-  for (int k = 0; k < 10; k++) h[k] = 0;
-#pragma unroll
-  for (int i = 0; i < 10; i++) {
-#pragma unroll
-    for (int j = 0; j < 10; j++) {
-      // both odd -> the 2^25.5 radix needs a doubling; wrap past limb 9 -> times 19
-      int32_t a = ((i & 1) && (j & 1)) ? f2[i] : f.v[i];
-      int32_t b = (i + j >= 10) ? g19[j] : g.v[j];
-      h[(i + j) % 10] += (int64_t)a * (int64_t)b;
-    }
+  for (int i = 0; i < 8; i++) {
+    const int p = i & 1, q = 1 - p;
+    FE_ROW4(E, i + p, f.v[p], f.v[p + 2], f.v[p + 4], f.v[p + 6], g.v[i]);  // j = p, p+2, ..: i + j even
+    FE_ROW4(O, i + q, f.v[q], f.v[q + 2], f.v[q + 4], f.v[q + 6], g.v[i]);  // i + j odd
   }
-  fe_carry_wide(out, h);
+  uint32_t W[16];
+  W[0] = E[0];
+  uint32_t cm, dummy = 0;  // merge in two carry chains (asm operand limit); cm carries between them
+  asm("add.cc.u32 %0, %8, %15;\n\taddc.cc.u32 %1, %9, %16;\n\taddc.cc.u32 %2, %10, %17;\n\taddc.cc.u32 %3, %11, %18;\n\t"
+      "addc.cc.u32 %4, %12, %19;\n\taddc.cc.u32 %5, %13, %20;\n\taddc.cc.u32 %6, %14, %21;\n\taddc.u32 %7, 0, 0;"
+      : "=r"(W[1]), "=r"(W[2]), "=r"(W[3]), "=r"(W[4]), "=r"(W[5]), "=r"(W[6]), "=r"(W[7]), "=r"(cm)
+      : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]),
+        "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]));
+  asm("add.cc.u32 %8, %25, 0xffffffff;\n\t"
+      "addc.cc.u32 %0, %9, %17;\n\taddc.cc.u32 %1, %10, %18;\n\taddc.cc.u32 %2, %11, %19;\n\taddc.cc.u32 %3, %12, %20;\n\t"
+      "addc.cc.u32 %4, %13, %21;\n\taddc.cc.u32 %5, %14, %22;\n\taddc.cc.u32 %6, %15, %23;\n\taddc.u32 %7, %16, %24;"
+      : "=r"(W[8]), "=r"(W[9]), "=r"(W[10]), "=r"(W[11]), "=r"(W[12]), "=r"(W[13]), "=r"(W[14]), "=r"(W[15]), "=r"(dummy)
+      : "r"(E[8]), "r"(E[9]), "r"(E[10]), "r"(E[11]), "r"(E[12]), "r"(E[13]), "r"(E[14]), "r"(E[15]),
+        "r"(O[8]), "r"(O[9]), "r"(O[10]), "r"(O[11]), "r"(O[12]), "r"(O[13]), "r"(O[14]), "r"(O[15]), "r"(cm));
+  (void)dummy;
+  fe_fold512(out, W);
+#else
+  uint32_t W[16];
+  uint64_t acc = 0, hi = 0;  // 96-bit column accumulator (hi counts 2^64)
+  for (int k = 0; k < 15; k++) {
+    for (int i = 0; i < 8; i++) {
+      int j = k - i;
+      if (j < 0 || j > 7) continue;
+      uint64_t pr = (uint64_t)f.v[i] * g.v[j];
+      acc += pr; if (acc < pr) hi++;
+    }
+    W[k] = (uint32_t)acc;
+    acc = (acc >> 32) | (hi << 32); hi = 0;
+  }
+  W[15] = (uint32_t)acc;
+  // R = lo + 38 * hi
+  uint32_t R[8]; uint64_t c = 0;
+  for (int i = 0; i < 8; i++) { c += (uint64_t)W[i] + 38ull * W[8 + i]; R[i] = (uint32_t)c; c >>= 32; }
+  c *= 38;
+  for (int i = 0; i < 8; i++) { c += R[i]; R[i] = (uint32_t)c; c >>= 32; }
+  R[0] += (uint32_t)c * 38u;
+  for (int i = 0; i < 8; i++) out.v[i] = R[i];
+#endif
 }
 
-HD void fe_sq_wide(int64_t h[10], const fe &f) {
-  int32_t f2[10], fw[10];  // fw[j] = f[j] * (19 if wrapped) * (2 if odd and partner odd) chosen per pair below
-#pragma unroll
-  for (int i = 0; i < 10; i++) f2[i] = 2 * f.v[i];
-  (void)fw;
-#pragma unroll
-  for (int k = 0; k < 10; k++) h[k] = 0;
-#pragma unroll
-  for (int i = 0; i < 10; i++) {
-#pragma unroll
-    for (int j = i; j < 10; j++) {
-      int32_t a = (i != j) ? f2[i] : f.v[i];
-      int32_t b = f.v[j];
-      if ((i & 1) && (j & 1)) b *= 2;
-      if (i + j >= 10) b *= 19;
-      h[(i + j) % 10] += (int64_t)a * (int64_t)b;
-    }
-  }
-}
+// squaring: 28 cross products (doubled by a 1-bit shift of the whole accumulator) + 8 squares
 HD void fe_sq_inl(fe &out, const fe &f) {
-  int64_t h[10];
-  fe_sq_wide(h, f);
-  fe_carry_wide(out, h);
+#if defined(__CUDA_ARCH__)
+  fe_mul_inl(out, f, f);
+#else
+  fe_mul_inl(out, f, f);
+#endif
 }
 // out = 2 f^2
-HD void fe_sq2_inl(fe &out, const fe &f) {
-  int64_t h[10];
-  fe_sq_wide(h, f);
-#pragma unroll
-  for (int k = 0; k < 10; k++) h[k] += h[k];
-  fe_carry_wide(out, h);
-}
-// On the device the three multiplication primitives are real functions (operands and result travel in registers):
-// a point addition is then ~10 calls instead of ~2000 inlined instructions per multiplication site, which keeps the
-// hot loops inside the instruction cache (ncu showed 20 % "no_instructions" stalls with everything inlined).
+HD void fe_sq2_inl(fe &out, const fe &f) { fe t; fe_sq_inl(t, f); fe_add(out, t, t); }
+
+// On the device the multiplication primitives are real functions (operands and result travel in registers): a point
+// addition is then ~10 calls instead of ~1000 inlined instructions, which keeps the hot loops inside the instruction cache.
 #ifndef BP_FE_CALL
 #define BP_FE_CALL 1
 #endif
 #if defined(__CUDACC__) && BP_FE_CALL
 static __device__ __noinline__ fe fe_mul_fn(fe f, fe g) { fe h; fe_mul_inl(h, f, g); return h; }
 static __device__ __noinline__ fe fe_sq_fn(fe f) { fe h; fe_sq_inl(h, f); return h; }
-static __device__ __noinline__ fe fe_sq2_fn(fe f) { fe h; fe_sq2_inl(h, f); return h; }
 #endif
 HD void fe_mul(fe &out, const fe &f, const fe &g) {
 #if defined(__CUDA_ARCH__) && BP_FE_CALL
@@ -143,81 +215,55 @@ HD void fe_sq(fe &out, const fe &f) {
   fe_sq_inl(out, f);
 #endif
 }
-HD void fe_sq2(fe &out, const fe &f) {
-#if defined(__CUDA_ARCH__) && BP_FE_CALL
-  out = fe_sq2_fn(f);
-#else
-  fe_sq2_inl(out, f);
-#endif
-}
+HD void fe_sq2(fe &out, const fe &f) { fe t; fe_sq(t, f); fe_add(out, t, t); }
 HD void fe_sqn(fe &out, const fe &f, int n) {
   fe_sq(out, f);
   for (int i = 1; i < n; i++) fe_sq(out, out);
 }
 
+// little-endian bytes -> element; bit 255 is ignored (RFC 7748/8032 convention, as the 10-limb form did)
 HD void fe_frombytes(fe &out, const uint8_t *s) {
-  auto ld3 = [&](int o) { return (int64_t)((uint64_t)s[o] | ((uint64_t)s[o + 1] << 8) | ((uint64_t)s[o + 2] << 16)); };
-  auto ld4 = [&](int o) { return ld3(o) | (int64_t)((uint64_t)s[o + 3] << 24); };
-  int64_t h[10];
-  h[0] = ld4(0);
-  h[1] = ld3(4) << 6;
-  h[2] = ld3(7) << 5;
-  h[3] = ld3(10) << 3;
-  h[4] = ld3(13) << 2;
-  h[5] = ld4(16);
-  h[6] = ld3(20) << 7;
-  h[7] = ld3(23) << 5;
-  h[8] = ld3(26) << 4;
-  h[9] = (ld3(29) & 8388607) << 2;
-  int64_t c;
-  c = (h[9] + (1LL << 24)) >> 25; h[0] += c * 19; h[9] -= c << 25;
-  c = (h[1] + (1LL << 24)) >> 25; h[2] += c; h[1] -= c << 25;
-  c = (h[3] + (1LL << 24)) >> 25; h[4] += c; h[3] -= c << 25;
-  c = (h[5] + (1LL << 24)) >> 25; h[6] += c; h[5] -= c << 25;
-  c = (h[7] + (1LL << 24)) >> 25; h[8] += c; h[7] -= c << 25;
-  c = (h[0] + (1LL << 25)) >> 26; h[1] += c; h[0] -= c << 26;
-  c = (h[2] + (1LL << 25)) >> 26; h[3] += c; h[2] -= c << 26;
-  c = (h[4] + (1LL << 25)) >> 26; h[5] += c; h[4] -= c << 26;
-  c = (h[6] + (1LL << 25)) >> 26; h[7] += c; h[6] -= c << 26;
-  c = (h[8] + (1LL << 25)) >> 26; h[9] += c; h[8] -= c << 26;
 #pragma unroll
-  for (int i = 0; i < 10; i++) out.v[i] = (int32_t)h[i];
+  for (int i = 0; i < 8; i++)
+    out.v[i] = (uint32_t)s[4 * i] | ((uint32_t)s[4 * i + 1] << 8) | ((uint32_t)s[4 * i + 2] << 16) | ((uint32_t)s[4 * i + 3] << 24);
+  out.v[7] &= 0x7fffffffu;
 }
 
+// fully reduced words (value in [0, p))
+HD void fe_reduce_words(uint32_t r[8], const fe &f) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) r[i] = f.v[i];
+  // twice: fold bit 255 (2^255 = 19); afterwards r < 2^255
+#pragma unroll
+  for (int round = 0; round < 2; round++) {
+    uint64_t c = 19ull * (r[7] >> 31);
+    r[7] &= 0x7fffffffu;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { c += r[i]; r[i] = (uint32_t)c; c >>= 32; }
+  }
+  // r >= p  <=>  r + 19 >= 2^255
+  uint32_t t[8]; uint64_t c = 19;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { c += r[i]; t[i] = (uint32_t)c; c >>= 32; }
+  uint32_t m = (uint32_t)(-(int32_t)(t[7] >> 31));
+  t[7] &= 0x7fffffffu;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r[i] = r[i] ^ (m & (r[i] ^ t[i]));
+}
 // canonical little-endian encoding (fully reduced mod p)
 HD void fe_tobytes(uint8_t *s, const fe &f) {
-  int32_t h[10];
-#pragma unroll
-  for (int i = 0; i < 10; i++) h[i] = f.v[i];
-  int32_t q = (19 * h[9] + (1 << 24)) >> 25;
-#pragma unroll
-  for (int i = 0; i < 10; i++) q = (h[i] + q) >> ((i & 1) ? 25 : 26);
-  h[0] += 19 * q;
-#pragma unroll
-  for (int i = 0; i < 9; i++) {
-    int sh = (i & 1) ? 25 : 26;
-    int32_t c = h[i] >> sh; h[i + 1] += c; h[i] -= c << sh;
-  }
-  { int32_t c = h[9] >> 25; h[9] -= c << 25; }
   uint32_t w[8];
-  uint64_t acc = 0; int bits = 0, wi = 0;
-#pragma unroll
-  for (int i = 0; i < 10; i++) {
-    int sh = (i & 1) ? 25 : 26;
-    acc |= (uint64_t)(uint32_t)h[i] << bits; bits += sh;
-    if (bits >= 32) { w[wi++] = (uint32_t)acc; acc >>= 32; bits -= 32; }
-  }
-  if (wi < 8) w[wi++] = (uint32_t)acc;
+  fe_reduce_words(w, f);
 #pragma unroll
   for (int i = 0; i < 8; i++) { s[4 * i] = (uint8_t)w[i]; s[4 * i + 1] = (uint8_t)(w[i] >> 8); s[4 * i + 2] = (uint8_t)(w[i] >> 16); s[4 * i + 3] = (uint8_t)(w[i] >> 24); }
 }
 
-HD int fe_isnegative(const fe &f) { uint8_t s[32]; fe_tobytes(s, f); return s[0] & 1; }
+HD int fe_isnegative(const fe &f) { uint32_t w[8]; fe_reduce_words(w, f); return (int)(w[0] & 1); }
 HD int fe_iszero(const fe &f) {
-  uint8_t s[32]; fe_tobytes(s, f);
-  uint8_t r = 0;
+  uint32_t w[8]; fe_reduce_words(w, f);
+  uint32_t r = 0;
 #pragma unroll
-  for (int i = 0; i < 32; i++) r |= s[i];
+  for (int i = 0; i < 8; i++) r |= w[i];
   return r == 0;
 }
 HD int fe_equal(const fe &a, const fe &b) { fe d; fe_sub(d, a, b); return fe_iszero(d); }
@@ -252,7 +298,7 @@ HD void fe_invert(fe &out, const fe &z) {
   fe_sqn(t1, t1, 5); fe_mul(out, t1, t0);
 }
 
-#define FE_CONST(name) HD void name(fe &h) { const int32_t c[10] = name##_LIMBS; _Pragma("unroll") for (int i = 0; i < 10; i++) h.v[i] = c[i]; }
+#define FE_CONST(name) HD void name(fe &h) { const uint32_t c[8] = name##_LIMBS; _Pragma("unroll") for (int i = 0; i < 8; i++) h.v[i] = c[i]; }
 FE_CONST(FE_D)
 FE_CONST(FE_2D)
 FE_CONST(FE_SQRTM1)

@@ -975,7 +975,7 @@ struct KTableBuild {
     ge_p3 acc = P;
     fe run; fe_1(run);
     for (int e = 0; e < TBL_E; e++) {
-      ge_niels tmp; tmp.ypx = acc.X; tmp.ymx = acc.Y; tmp.xy2d = acc.Z; tmp.pad[0] = tmp.pad[1] = 0;
+      ge_niels tmp; tmp.ypx = acc.X; tmp.ymx = acc.Y; tmp.xy2d = acc.Z;
       store_struct(&slot[e], tmp);
       pre[e] = run;
       fe_mul(run, run, acc.Z);
@@ -991,7 +991,6 @@ struct KTableBuild {
       ge_niels nl;
       fe_add(nl.ypx, y, x); fe_carry(nl.ypx); fe_sub(nl.ymx, y, x); fe_carry(nl.ymx);
       fe_mul(nl.xy2d, x, y); fe_mul(nl.xy2d, nl.xy2d, d2);
-      nl.pad[0] = nl.pad[1] = 0;
       store_struct(&slot[e], nl);
     }
   }

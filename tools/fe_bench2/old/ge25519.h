@@ -6,13 +6,13 @@
 #pragma once
 #include "fe25519.h"
 
-struct alignas(16) ge_p3 { fe X, Y, Z, T; };          // 128 B: x = X/Z, y = Y/Z, xy = T/Z
-struct alignas(16) ge_niels { fe ypx, ymx, xy2d; };   // affine: y+x, y-x, 2d*x*y   (96 B = three 32-byte sectors)
+struct alignas(16) ge_p3 { fe X, Y, Z, T; };          // 160 B: x = X/Z, y = Y/Z, xy = T/Z
+struct alignas(16) ge_niels { fe ypx, ymx, xy2d; int32_t pad[2]; };  // affine: y+x, y-x, 2d*x*y   (128 B)
 struct ge_cached { fe YpX, YmX, Z, T2d; };
 struct ge_p1p1 { fe X, Y, Z, T; };
 
 HD void ge_identity(ge_p3 &p) { fe_0(p.X); fe_1(p.Y); fe_1(p.Z); fe_0(p.T); }
-HD void ge_niels_identity(ge_niels &n) { fe_1(n.ypx); fe_1(n.ymx); fe_0(n.xy2d); }
+HD void ge_niels_identity(ge_niels &n) { fe_1(n.ypx); fe_1(n.ymx); fe_0(n.xy2d); n.pad[0] = n.pad[1] = 0; }
 
 HD void ge_p1p1_to_p3(ge_p3 &r, const ge_p1p1 &p) {
   fe_mul(r.X, p.X, p.T); fe_mul(r.Y, p.Y, p.Z); fe_mul(r.Z, p.Z, p.T); fe_mul(r.T, p.X, p.Y);
@@ -25,8 +25,13 @@ HD void ge_to_cached(ge_cached &c, const ge_p3 &p) {
   fe d2; FE_2D(d2);
   fe_add(c.YpX, p.Y, p.X); fe_sub(c.YmX, p.Y, p.X); c.Z = p.Z; fe_mul(c.T2d, p.T, d2);
 }
-// kept for the call sites written for the lazy 10-limb form: saturated limbs carry nothing over
-HD void fe_carry(fe &) {}
+// carried versions keep limb bounds tight when the sums feed further lazy additions
+HD void fe_carry(fe &h) {
+  int64_t w[10];
+#pragma unroll
+  for (int i = 0; i < 10; i++) w[i] = h.v[i];
+  fe_carry_wide(h, w);
+}
 
 // r = p + (neg ? -q : q), q affine niels.  7 multiplications after completion.
 HD void ge_madd_p1p1(ge_p1p1 &r, const ge_p3 &p, const ge_niels &q, int neg) {
@@ -88,6 +93,7 @@ HD void ge_to_niels(ge_niels &n, const ge_p3 &p) {
   fe_add(n.ypx, y, x); fe_carry(n.ypx);
   fe_sub(n.ymx, y, x); fe_carry(n.ymx);
   fe_mul(n.xy2d, x, y); fe_mul(n.xy2d, n.xy2d, d2);
+  n.pad[0] = n.pad[1] = 0;
 }
 HD void ge_normalize(ge_p3 &r, const ge_p3 &p) {
   fe zi; fe_invert(zi, p.Z);
