@@ -292,7 +292,7 @@ static int ensure_workspace(BpCircuit *c, int B) {
   bad |= dalloc(&w->naf, 4 * 256 * Bz); bad |= dalloc(&w->naf_top, 4 * Bz);
   w->items_cap = (size_t)std::max(2 * n + 1, N + 1) * SB_WINDOWS;  // items of one instance
   bad |= dalloc(&w->items, w->items_cap * Bz); bad |= dalloc(&w->boff, (size_t)(SB_BUCKETS + 1) * Bz); bad |= dalloc(&w->soff, (size_t)(SB_BUCKETS + 1) * Bz);
-  w->slices_cap = SB_BUCKETS + w->items_cap / SB_SLICE + 1;
+  w->slices_cap = SB_BUCKETS + w->items_cap / SB_SEG + 2;  // partial sums: one per (bucket, segment) crossing
   bad |= dalloc(&w->seg, (size_t)SB_SEGS * 2 * Bz);
   bad |= dalloc(&w->utab, 4 * (size_t)(1 << UNFOLD_ROUNDS) * Bz + 4 * Bz); bad |= dalloc(&w->rg_as, 2 * n + 2);
   if (bad) { w->release(); return BP_ERR_OOM; }
@@ -369,7 +369,8 @@ static int run_msm_sorted(const BpGens *g, Workspace *w, const RowMap &rmap, lon
   if ((size_t)rows * SB_WINDOWS > w->items_cap || (size_t)ninst * w->slices_cap > w->bucket_slots) return BP_ERR_OOM;
   CK(launch_sort_buckets(rmap, dig, dig_inst_stride, rows, ninst, w->items, (long)w->items_cap, w->boff, w->soff, s));
   SortedView sv{w->items, w->boff, w->soff, (long)w->items_cap, (long)w->slices_cap};
-  CK(launch(ninst * (long)w->slices_cap, s, KBucketAccumulate{g->sg, sv, w->buckets}));
+  const long segs = (rows * SB_WINDOWS + SB_SEG - 1) / SB_SEG;  // segments of this launch's longest possible item list
+  CK(launch(ninst * segs, s, KBucketAccumulate{g->sg, sv, w->buckets, segs}));
   CK(launch(ninst * SB_SEGS, s, KBucketReduce{w->buckets, sv, w->seg}));
   CK(launch(ninst, s, KBucketFinish{w->seg, out, out_stride}));
   return BP_OK;

@@ -130,8 +130,106 @@ HD void fe_fold512(fe &out, const uint32_t W[16]) {
 }
 #endif
 
+#if defined(__CUDA_ARCH__)
+// shorter carry chains (1-3 lanes) for the triangular cross products of a squaring
+#define FE_ROW3(A, s, x0, x1, x2, y)                                                                                         \
+  asm("mad.lo.cc.u32 %0, %7, %10, %0;\n\tmadc.hi.cc.u32 %1, %7, %10, %1;\n\t"                                                \
+      "madc.lo.cc.u32 %2, %8, %10, %2;\n\tmadc.hi.cc.u32 %3, %8, %10, %3;\n\t"                                               \
+      "madc.lo.cc.u32 %4, %9, %10, %4;\n\tmadc.hi.cc.u32 %5, %9, %10, %5;\n\t"                                               \
+      "addc.u32 %6, %6, 0;"                                                                                                  \
+      : "+r"(A[s]), "+r"(A[s + 1]), "+r"(A[s + 2]), "+r"(A[s + 3]), "+r"(A[s + 4]), "+r"(A[s + 5]), "+r"(A[s + 6])           \
+      : "r"(x0), "r"(x1), "r"(x2), "r"(y))
+#define FE_ROW2(A, s, x0, x1, y)                                                                                             \
+  asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\tmadc.hi.cc.u32 %1, %5, %7, %1;\n\t"                                                  \
+      "madc.lo.cc.u32 %2, %6, %7, %2;\n\tmadc.hi.cc.u32 %3, %6, %7, %3;\n\t"                                                 \
+      "addc.u32 %4, %4, 0;"                                                                                                  \
+      : "+r"(A[s]), "+r"(A[s + 1]), "+r"(A[s + 2]), "+r"(A[s + 3]), "+r"(A[s + 4])                                           \
+      : "r"(x0), "r"(x1), "r"(y))
+#define FE_ROW1(A, s, x0, y)                                                                                                 \
+  asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;"                                \
+      : "+r"(A[s]), "+r"(A[s + 1]), "+r"(A[s + 2])                                                                           \
+      : "r"(x0), "r"(y))
+#endif
+
+#ifndef BP_FE_KARATSUBA
+#define BP_FE_KARATSUBA 0
+#endif
+#if defined(__CUDA_ARCH__)
+// 4x4 words -> 8 words, same even/odd lane scheme as the 8x8 product (16 wide multiplies)
+HD void fe_mul4(uint32_t r[8], const uint32_t a[4], const uint32_t b[4]) {
+  uint32_t E[9], O[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) { E[i] = 0; O[i] = 0; }
+  FE_ROW2(E, 0, a[0], a[2], b[0]); FE_ROW2(O, 1, a[1], a[3], b[0]);
+  FE_ROW2(E, 2, a[1], a[3], b[1]); FE_ROW2(O, 1, a[0], a[2], b[1]);
+  FE_ROW2(E, 2, a[0], a[2], b[2]); FE_ROW2(O, 3, a[1], a[3], b[2]);
+  FE_ROW2(E, 4, a[1], a[3], b[3]); FE_ROW2(O, 3, a[0], a[2], b[3]);
+  r[0] = E[0];
+  asm("add.cc.u32 %0, %7, %14;\n\taddc.cc.u32 %1, %8, %15;\n\taddc.cc.u32 %2, %9, %16;\n\taddc.cc.u32 %3, %10, %17;\n\t"
+      "addc.cc.u32 %4, %11, %18;\n\taddc.cc.u32 %5, %12, %19;\n\taddc.u32 %6, %13, %20;"
+      : "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]),
+        "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]));
+}
+// d = |x - y| (4 words), m = all-ones when x < y
+HD void fe_absdiff4(uint32_t d[4], uint32_t &m, const uint32_t x[4], const uint32_t y[4]) {
+  uint32_t t0, t1, t2, t3;
+  asm("sub.cc.u32 %0, %5, %9;\n\tsubc.cc.u32 %1, %6, %10;\n\tsubc.cc.u32 %2, %7, %11;\n\tsubc.cc.u32 %3, %8, %12;\n\tsubc.u32 %4, 0, 0;"
+      : "=r"(t0), "=r"(t1), "=r"(t2), "=r"(t3), "=r"(m)
+      : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(y[0]), "r"(y[1]), "r"(y[2]), "r"(y[3]));
+  t0 ^= m; t1 ^= m; t2 ^= m; t3 ^= m;
+  const uint32_t one = m & 1u;
+  asm("add.cc.u32 %0, %4, %8;\n\taddc.cc.u32 %1, %5, 0;\n\taddc.cc.u32 %2, %6, 0;\n\taddc.u32 %3, %7, 0;"
+      : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]) : "r"(t0), "r"(t1), "r"(t2), "r"(t3), "r"(one));
+}
+// one level of (subtractive) Karatsuba: 3 x 16 wide multiplies instead of 64.  With z0 = f_lo g_lo, z2 = f_hi g_hi and
+// zm = |f_lo - f_hi| |g_lo - g_hi|, the middle term f_lo g_hi + f_hi g_lo is z0 + z2 -/+ zm (sign from the two differences).
+HD void fe_mul_kara(fe &out, const fe &f, const fe &g) {
+  uint32_t z0[8], z2[8], zm[8], da[4], db[4], sa, sb;
+  fe_mul4(z0, f.v, g.v);
+  fe_mul4(z2, f.v + 4, g.v + 4);
+  fe_absdiff4(da, sa, f.v, f.v + 4);
+  fe_absdiff4(db, sb, g.v, g.v + 4);
+  fe_mul4(zm, da, db);
+  uint32_t t[9];
+  asm("add.cc.u32 %0, %9, %17;\n\taddc.cc.u32 %1, %10, %18;\n\taddc.cc.u32 %2, %11, %19;\n\taddc.cc.u32 %3, %12, %20;\n\t"
+      "addc.cc.u32 %4, %13, %21;\n\taddc.cc.u32 %5, %14, %22;\n\taddc.cc.u32 %6, %15, %23;\n\taddc.cc.u32 %7, %16, %24;\n\t"
+      "addc.u32 %8, 0, 0;"
+      : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(t[8])
+      : "r"(z0[0]), "r"(z0[1]), "r"(z0[2]), "r"(z0[3]), "r"(z0[4]), "r"(z0[5]), "r"(z0[6]), "r"(z0[7]),
+        "r"(z2[0]), "r"(z2[1]), "r"(z2[2]), "r"(z2[3]), "r"(z2[4]), "r"(z2[5]), "r"(z2[6]), "r"(z2[7]));
+  // mid = t - zm when the differences have equal signs (M = ~0: add the complement plus one), t + zm otherwise (M = 0)
+  const uint32_t M = ~(sa ^ sb);
+  uint32_t x[8], mid[9], dummy = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) x[i] = zm[i] ^ M;
+  asm("add.cc.u32 %9, %27, 1;\n\t"
+      "addc.cc.u32 %0, %10, %19;\n\taddc.cc.u32 %1, %11, %20;\n\taddc.cc.u32 %2, %12, %21;\n\taddc.cc.u32 %3, %13, %22;\n\t"
+      "addc.cc.u32 %4, %14, %23;\n\taddc.cc.u32 %5, %15, %24;\n\taddc.cc.u32 %6, %16, %25;\n\taddc.cc.u32 %7, %17, %26;\n\t"
+      "addc.u32 %8, %18, %27;"
+      : "=r"(mid[0]), "=r"(mid[1]), "=r"(mid[2]), "=r"(mid[3]), "=r"(mid[4]), "=r"(mid[5]), "=r"(mid[6]), "=r"(mid[7]), "=r"(mid[8]), "=r"(dummy)
+      : "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t[7]), "r"(t[8]),
+        "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]), "r"(M));
+  (void)dummy;
+  uint32_t W[16];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { W[i] = z0[i]; W[8 + i] = z2[i]; }
+  asm("add.cc.u32 %0, %0, %12;\n\taddc.cc.u32 %1, %1, %13;\n\taddc.cc.u32 %2, %2, %14;\n\taddc.cc.u32 %3, %3, %15;\n\t"
+      "addc.cc.u32 %4, %4, %16;\n\taddc.cc.u32 %5, %5, %17;\n\taddc.cc.u32 %6, %6, %18;\n\taddc.cc.u32 %7, %7, %19;\n\t"
+      "addc.cc.u32 %8, %8, %20;\n\taddc.cc.u32 %9, %9, 0;\n\taddc.cc.u32 %10, %10, 0;\n\taddc.u32 %11, %11, 0;"
+      : "+r"(W[4]), "+r"(W[5]), "+r"(W[6]), "+r"(W[7]), "+r"(W[8]), "+r"(W[9]), "+r"(W[10]), "+r"(W[11]), "+r"(W[12]), "+r"(W[13]),
+        "+r"(W[14]), "+r"(W[15])
+      : "r"(mid[0]), "r"(mid[1]), "r"(mid[2]), "r"(mid[3]), "r"(mid[4]), "r"(mid[5]), "r"(mid[6]), "r"(mid[7]), "r"(mid[8]));
+  fe_fold512(out, W);
+}
+#endif
+
 HD void fe_mul_inl(fe &out, const fe &f, const fe &g) {
 #if defined(__CUDA_ARCH__)
+#if BP_FE_KARATSUBA
+  fe_mul_kara(out, f, g);
+  return;
+#endif
   uint32_t E[17], O[17];  // word w of the even-/odd-aligned accumulator
 #pragma unroll
   for (int i = 0; i < 17; i++) { E[i] = 0; O[i] = 0; }
@@ -181,10 +279,54 @@ HD void fe_mul_inl(fe &out, const fe &f, const fe &g) {
 #endif
 }
 
-// squaring: 28 cross products (doubled by a 1-bit shift of the whole accumulator) + 8 squares
+
+// squaring: 28 cross products (doubled by a 1-bit shift of the merged accumulators) + 8 squares = 36 wide multiplies
+// instead of 64; rows are processed in increasing i so that a chain's carry-out always lands above every lane used so far
 HD void fe_sq_inl(fe &out, const fe &f) {
 #if defined(__CUDA_ARCH__)
-  fe_mul_inl(out, f, f);
+  uint32_t E[17], O[17];
+#pragma unroll
+  for (int i = 0; i < 17; i++) { E[i] = 0; O[i] = 0; }
+  const uint32_t *a = f.v;
+  FE_ROW4(O, 1, a[1], a[3], a[5], a[7], a[0]);  FE_ROW3(E, 2, a[2], a[4], a[6], a[0]);
+  FE_ROW3(O, 3, a[2], a[4], a[6], a[1]);        FE_ROW3(E, 4, a[3], a[5], a[7], a[1]);
+  FE_ROW3(O, 5, a[3], a[5], a[7], a[2]);        FE_ROW2(E, 6, a[4], a[6], a[2]);
+  FE_ROW2(O, 7, a[4], a[6], a[3]);              FE_ROW2(E, 8, a[5], a[7], a[3]);
+  FE_ROW2(O, 9, a[5], a[7], a[4]);              FE_ROW1(E, 10, a[6], a[4]);
+  FE_ROW1(O, 11, a[6], a[5]);                   FE_ROW1(E, 12, a[7], a[5]);
+  FE_ROW1(O, 13, a[7], a[6]);
+  // C = E + O (words 1..15; word 0 of the cross sum is empty), then W = 2C + sum a_i^2 2^(64 i)
+  uint32_t C[16];
+  C[0] = 0;
+  uint32_t cm, dummy = 0;
+  asm("add.cc.u32 %0, %8, %15;\n\taddc.cc.u32 %1, %9, %16;\n\taddc.cc.u32 %2, %10, %17;\n\taddc.cc.u32 %3, %11, %18;\n\t"
+      "addc.cc.u32 %4, %12, %19;\n\taddc.cc.u32 %5, %13, %20;\n\taddc.cc.u32 %6, %14, %21;\n\taddc.u32 %7, 0, 0;"
+      : "=r"(C[1]), "=r"(C[2]), "=r"(C[3]), "=r"(C[4]), "=r"(C[5]), "=r"(C[6]), "=r"(C[7]), "=r"(cm)
+      : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]),
+        "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]));
+  asm("add.cc.u32 %8, %25, 0xffffffff;\n\t"
+      "addc.cc.u32 %0, %9, %17;\n\taddc.cc.u32 %1, %10, %18;\n\taddc.cc.u32 %2, %11, %19;\n\taddc.cc.u32 %3, %12, %20;\n\t"
+      "addc.cc.u32 %4, %13, %21;\n\taddc.cc.u32 %5, %14, %22;\n\taddc.cc.u32 %6, %15, %23;\n\taddc.u32 %7, %16, %24;"
+      : "=r"(C[8]), "=r"(C[9]), "=r"(C[10]), "=r"(C[11]), "=r"(C[12]), "=r"(C[13]), "=r"(C[14]), "=r"(C[15]), "=r"(dummy)
+      : "r"(E[8]), "r"(E[9]), "r"(E[10]), "r"(E[11]), "r"(E[12]), "r"(E[13]), "r"(E[14]), "r"(E[15]),
+        "r"(O[8]), "r"(O[9]), "r"(O[10]), "r"(O[11]), "r"(O[12]), "r"(O[13]), "r"(O[14]), "r"(O[15]), "r"(cm));
+  (void)dummy;
+  uint32_t W[16];
+#pragma unroll
+  for (int i = 15; i >= 1; i--) W[i] = __funnelshift_l(C[i - 1], C[i], 1);
+  W[0] = 0;
+  asm("mad.lo.cc.u32 %0, %16, %16, %0;\n\tmadc.hi.cc.u32 %1, %16, %16, %1;\n\t"
+      "madc.lo.cc.u32 %2, %17, %17, %2;\n\tmadc.hi.cc.u32 %3, %17, %17, %3;\n\t"
+      "madc.lo.cc.u32 %4, %18, %18, %4;\n\tmadc.hi.cc.u32 %5, %18, %18, %5;\n\t"
+      "madc.lo.cc.u32 %6, %19, %19, %6;\n\tmadc.hi.cc.u32 %7, %19, %19, %7;\n\t"
+      "madc.lo.cc.u32 %8, %20, %20, %8;\n\tmadc.hi.cc.u32 %9, %20, %20, %9;\n\t"
+      "madc.lo.cc.u32 %10, %21, %21, %10;\n\tmadc.hi.cc.u32 %11, %21, %21, %11;\n\t"
+      "madc.lo.cc.u32 %12, %22, %22, %12;\n\tmadc.hi.cc.u32 %13, %22, %22, %13;\n\t"
+      "madc.lo.cc.u32 %14, %23, %23, %14;\n\tmadc.hi.u32 %15, %23, %23, %15;"
+      : "+r"(W[0]), "+r"(W[1]), "+r"(W[2]), "+r"(W[3]), "+r"(W[4]), "+r"(W[5]), "+r"(W[6]), "+r"(W[7]), "+r"(W[8]), "+r"(W[9]),
+        "+r"(W[10]), "+r"(W[11]), "+r"(W[12]), "+r"(W[13]), "+r"(W[14]), "+r"(W[15])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]));
+  fe_fold512(out, W);
 #else
   fe_mul_inl(out, f, f);
 #endif

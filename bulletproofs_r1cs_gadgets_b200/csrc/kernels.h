@@ -1300,44 +1300,61 @@ struct KSortBucketsSerial {
     for (int b = 0; b < SB_BUCKETS; b++) so[b + 1] = so[b] + (off[b + 1] - off[b] + SB_SLICE - 1) / SB_SLICE;
   }
 };
-// one thread per slice of a bucket (slice j of the instance; its bucket is found by binary search in the slice offsets)
+// One thread per SEGMENT of SB_SEG consecutive items of the sorted list (not per bucket): every thread performs the same number
+// of additions, whatever the bucket sizes (one-thread-per-bucket lost ~20 % of the lanes to the Poisson spread of bucket
+// sizes, and needed a slice table for buckets holding thousands of identical digits).  A segment that crosses a bucket
+// boundary stores its partial sum and starts a new one: partial (bucket b, segment s) lives at psum[b + s], which is
+// unique because buckets and segments are both ordered along the list.
+#define SB_SEG 128
 struct KBucketAccumulate {
   static constexpr int kBlock = 128, kMinBlocks = 1;
   static constexpr const char *kName = "KBucketAccumulate";
-  const ge_niels *sg; SortedView sv; ge_p3 *psum;  // psum[inst*slices_cap + slice]
+  const ge_niels *sg; SortedView sv; ge_p3 *psum; long segs_cap;  // psum[inst*slices_cap + b + s]
   HD void operator()(long tid) const {
-    long inst = tid / sv.slices_cap; uint32_t j = (uint32_t)(tid % sv.slices_cap);
-    const uint32_t *so = sv.soff + inst * (SB_BUCKETS + 1);
-    if (j >= so[SB_BUCKETS]) return;
-    int lo = 0, hi = SB_BUCKETS;  // largest b with so[b] <= j
-    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (so[mid] <= j) lo = mid; else hi = mid; }
-    const int b = lo;
+    const long inst = tid / segs_cap; const uint32_t s = (uint32_t)(tid % segs_cap);
     const uint32_t *off = sv.boff + inst * (SB_BUCKETS + 1);
-    const uint32_t k0 = off[b] + (j - so[b]) * SB_SLICE;
-    const uint32_t k1 = k0 + SB_SLICE < off[b + 1] ? k0 + SB_SLICE : off[b + 1];
+    const uint32_t total = off[SB_BUCKETS];
+    const uint32_t k0 = s * SB_SEG;
+    if (k0 >= total) return;
+    const uint32_t k1 = k0 + SB_SEG < total ? k0 + SB_SEG : total;
+    int lo = 0, hi = SB_BUCKETS;  // largest b with off[b] <= k0 (then off[b + 1] > k0)
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (off[mid] <= k0) lo = mid; else hi = mid; }
+    uint32_t b = (uint32_t)lo, next = off[b + 1];
     const uint32_t *it = sv.items + inst * sv.items_stride;
+    ge_p3 *ps = psum + inst * sv.slices_cap + s;
     ge_p3 acc; ge_identity(acc);
+    // software pipeline: the (random, mostly L2-missing) table entry of item k+1 is in flight during addition k
+    uint32_t item = it[k0];
+    ge_niels q; load_struct(q, &sg[item & 0x7fffffffu]);
     for (uint32_t k = k0; k < k1; k++) {
-      uint32_t item = it[k];
-      ge_niels q; load_struct(q, &sg[item & 0x7fffffffu]);
-      ge_madd(acc, acc, q, (int)(item >> 31));
+      if (k == next) {
+        store_struct(&ps[b], acc); ge_identity(acc);
+        do { b++; next = off[b + 1]; } while (next == k);
+      }
+      const uint32_t cur = item; const ge_niels qc = q;
+      if (k + 1 < k1) { item = it[k + 1]; load_struct(q, &sg[item & 0x7fffffffu]); }
+      ge_madd(acc, acc, qc, (int)(cur >> 31));
     }
-    store_struct(&psum[tid], acc);
+    store_struct(&ps[b], acc);
   }
 };
-// per segment of 128 buckets: S = sum b_i, W = sum (local index + 1) * b_i   (running-sum trick); b_i = sum of its slices
+// per group of 128 buckets: S = sum b_i, W = sum (local index + 1) * b_i   (running-sum trick); b_i = sum of its partials
 struct KBucketReduce {
   static constexpr int kBlock = 64, kMinBlocks = 1;
   static constexpr const char *kName = "KBucketReduce";
   const ge_p3 *psum; SortedView sv; ge_p3 *seg;  // seg[(inst*32 + s)*2 + {0: S, 1: W}]
   HD void operator()(long tid) const {
     long inst = tid / SB_SEGS; int sgm = (int)(tid % SB_SEGS);
-    const uint32_t *so = sv.soff + inst * (SB_BUCKETS + 1);
+    const uint32_t *off = sv.boff + inst * (SB_BUCKETS + 1);
     const ge_p3 *ps = psum + inst * sv.slices_cap;
     ge_p3 run, tot; ge_identity(run); ge_identity(tot);
     for (int i = SB_SEG_LEN - 1; i >= 0; i--) {
       const int b = sgm * SB_SEG_LEN + i;
-      for (uint32_t j = so[b]; j < so[b + 1]; j++) { ge_p3 t; load_struct(t, &ps[j]); ge_add(run, run, t); }
+      const uint32_t o0 = off[b], o1 = off[b + 1];
+      if (o1 > o0) {
+        const uint32_t s0 = o0 / SB_SEG, s1 = (o1 - 1) / SB_SEG;
+        for (uint32_t sj = s0; sj <= s1; sj++) { ge_p3 t; load_struct(t, &ps[b + sj]); ge_add(run, run, t); }
+      }
       ge_add(tot, tot, run);
     }
     store_struct(&seg[tid * 2], run); store_struct(&seg[tid * 2 + 1], tot);
