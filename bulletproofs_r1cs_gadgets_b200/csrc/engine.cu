@@ -263,7 +263,14 @@ void circuit_free(BpCircuit *c) {
   delete c;
 }
 
-static const int UNFOLD_ROUNDS = 3;  // inner-product rounds computed over the original generators (fixed-base tables)
+static const int UNFOLD_MAX = 6;
+// inner-product rounds computed over the original generators (sorted-bucket MSM on the shift table) before the folded
+// generators are materialised; 4 is the measured optimum at N = 32768 (BP_B200_UNFOLD overrides, for experiments)
+static int unfold_rounds() {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("BP_B200_UNFOLD"); v = e ? atoi(e) : 4; if (v < 0) v = 0; if (v > UNFOLD_MAX) v = UNFOLD_MAX; }
+  return v;
+}
 static const int CH_DOT = 256;  // multipliers per partial-sum thread
 static const int CH_POW = 64;   // exponents per powers thread
 static long msm_target_warps() { return 148L * 8 * 4; }
@@ -294,7 +301,7 @@ static int ensure_workspace(BpCircuit *c, int B) {
   bad |= dalloc(&w->items, w->items_cap * Bz); bad |= dalloc(&w->boff, (size_t)(SB_BUCKETS + 1) * Bz); bad |= dalloc(&w->soff, (size_t)(SB_BUCKETS + 1) * Bz);
   w->slices_cap = SB_BUCKETS + w->items_cap / SB_SEG + 2;  // partial sums: one per (bucket, segment) crossing
   bad |= dalloc(&w->seg, (size_t)SB_SEGS * 2 * Bz);
-  bad |= dalloc(&w->utab, 4 * (size_t)(1 << UNFOLD_ROUNDS) * Bz + 4 * Bz); bad |= dalloc(&w->rg_as, 2 * n + 2);
+  bad |= dalloc(&w->utab, 4 * (size_t)(1 << UNFOLD_MAX) * Bz + 4 * Bz); bad |= dalloc(&w->rg_as, 2 * n + 2);
   if (bad) { w->release(); return BP_ERR_OOM; }
   w->B = B;
   return BP_OK;
@@ -535,12 +542,12 @@ static int prove_phase_b(const BpGens *g, BpCircuit *c, Front &f, const ProveArg
   CK(launch(B, s, KProverScalars{w->t, w->tb, i_b, wV, f.vbl, (int)m, B, ch_x, A.proofs, plen}));
   CK(launch(B, s, KTsPhase4{f.ts, A.proofs, plen, ch_w, (unsigned)N}));
   CK(launch(B, s, KCommit{ch_w, nullptr, 1, B, g->pc_table, nullptr, 0, 0, w->Q}));
-  // 8. inner-product argument (A.4).  With fixed-base tables the first UNFOLD_ROUNDS rounds never fold generators: L_j, R_j are
+  // 8. inner-product argument (A.4).  With fixed-base tables the first unfold_rounds() rounds never fold generators: L_j, R_j are
   // multiscalar multiplications over the ORIGINAL generators with scalars a_i * prod u_t^(+-1); the folded generators are then
   // materialised once (KFoldTable) and the remaining, short rounds run on per-proof points (bucket method + NAF fold).
   CK(launch(2L * B, s, KFillScalar{alpha, sc_one()}));  // alpha, beta are adjacent
-  const int J = g->table ? (int)std::min<long>(UNFOLD_ROUNDS, k) : 0;
-  scm *UG[2] = {w->utab, w->utab + ((size_t)1 << UNFOLD_ROUNDS) * B}, *UH[2] = {w->utab + 2 * ((size_t)1 << UNFOLD_ROUNDS) * B, w->utab + 3 * ((size_t)1 << UNFOLD_ROUNDS) * B};
+  const int J = g->table ? (int)std::min<long>(unfold_rounds(), k) : 0;
+  scm *UG[2] = {w->utab, w->utab + ((size_t)1 << UNFOLD_MAX) * B}, *UH[2] = {w->utab + 2 * ((size_t)1 << UNFOLD_MAX) * B, w->utab + 3 * ((size_t)1 << UNFOLD_MAX) * B};
   if (J > 0) { CK(launch(B, s, KFillScalar{UG[0], sc_one()})); CK(launch(B, s, KFillScalar{UH[0], sc_one()})); }
   int yfree = 0;
   long len = N;

@@ -5,80 +5,108 @@
 KGROUP_SORTED(KDEFINE)
 
 #ifndef BP_HOST_EMUL
-#define SORT_THREADS 512
-__global__ void __launch_bounds__(SORT_THREADS) sort_buckets_kernel(RowMap rmap, const int8_t *dig, long dig_inst_stride, long rows,
-                                                                   uint32_t *items, long items_stride, uint32_t *boff, uint32_t *soff) {
-  __shared__ uint32_t cnt[SB_BUCKETS];
-  __shared__ uint32_t warp_tot[SORT_THREADS / 32];
-  const long inst = blockIdx.x;
-  const int tid = threadIdx.x;
-  for (int b = tid; b < SB_BUCKETS; b += SORT_THREADS) cnt[b] = 0;
-  __syncthreads();
-  const int8_t *drow = dig + inst * dig_inst_stride;
-  // pass 1: histogram
-  for (long r = tid; r < rows; r += SORT_THREADS) {
-    int16_t d[24]; load_digits13(d, drow + r * SB_ROW_BYTES);
-#pragma unroll
-    for (int w = 0; w < SB_WINDOWS; w++) if (d[w]) atomicAdd(&cnt[(d[w] < 0 ? -d[w] : d[w]) - 1], 1u);
-  }
-  __syncthreads();
-  // exclusive scan of the 4096 counters: 8 consecutive counters per thread, warp scan, block scan
+// One block per instance.  Pass 0 counts the items of every bucket (shared-memory atomics) and scans the counts into the
+// bucket offsets.  Pass 1 walks the rows in tiles of SORT_THREADS rows: the tile's items are ranked per bucket in shared
+// memory, staged there in bucket order and copied out one bucket run per warp step, so that global memory sees short
+// CONTIGUOUS runs appended to each bucket's region instead of one random 4-byte store per item (that scatter cost a
+// 32-byte read-modify-write in DRAM per item once the item lists of all resident blocks outgrew the L2: 16x amplification).
+#define SORT_THREADS 1024
+#define SORT_TILE_ITEMS (SORT_THREADS * SB_WINDOWS)
+#define SORT_SMEM_BYTES ((2 * SB_BUCKETS + 32 + SORT_TILE_ITEMS) * 4)
+// in-place exclusive scan of the SB_BUCKETS counters at c[]; returns the total to every thread
+__device__ __forceinline__ uint32_t sort_block_scan(uint32_t *c, uint32_t *warp_tot) {
   constexpr int PER = SB_BUCKETS / SORT_THREADS;
-  uint32_t loc[PER], sum = 0, sloc[PER], ssum = 0;
+  const int tid = threadIdx.x;
+  uint32_t loc[PER], sum = 0;
 #pragma unroll
-  for (int i = 0; i < PER; i++) { uint32_t c = cnt[tid * PER + i]; loc[i] = sum; sum += c; sloc[i] = ssum; ssum += (c + SB_SLICE - 1) / SB_SLICE; }
+  for (int i = 0; i < PER; i++) { loc[i] = sum; sum += c[tid * PER + i]; }
   uint32_t incl = sum;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += v; }
   if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
   __syncthreads();
   if (tid < 32) {
-    uint32_t v = tid < SORT_THREADS / 32 ? warp_tot[tid] : 0, inc = v;
+    uint32_t v = warp_tot[tid], inc = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (tid >= o) inc += t; }
-    if (tid < SORT_THREADS / 32) warp_tot[tid] = inc - v;  // exclusive prefix of the warp totals
+    warp_tot[tid] = inc - v;      // exclusive prefix of the warp totals
+    if (tid == 31) warp_tot[32] = inc;
   }
   __syncthreads();
   const uint32_t base = warp_tot[tid >> 5] + (incl - sum);
-  uint32_t *off = boff + inst * (SB_BUCKETS + 1);
 #pragma unroll
-  for (int i = 0; i < PER; i++) { uint32_t o = base + loc[i]; off[tid * PER + i] = o; }
-  if (tid == SORT_THREADS - 1) off[SB_BUCKETS] = base + sum;
+  for (int i = 0; i < PER; i++) c[tid * PER + i] = base + loc[i];
+  const uint32_t total = warp_tot[32];
   __syncthreads();
-  {  // same block scan for the slice counts
-    uint32_t sincl = ssum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, sincl, o); if ((tid & 31) >= o) sincl += v; }
-    if ((tid & 31) == 31) warp_tot[tid >> 5] = sincl;
-    __syncthreads();
-    if (tid < 32) {
-      uint32_t v = tid < SORT_THREADS / 32 ? warp_tot[tid] : 0, inc = v;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (tid >= o) inc += t; }
-      if (tid < SORT_THREADS / 32) warp_tot[tid] = inc - v;
-    }
-    __syncthreads();
-    const uint32_t sbase = warp_tot[tid >> 5] + (sincl - ssum);
-    uint32_t *so = soff + inst * (SB_BUCKETS + 1);
-#pragma unroll
-    for (int i = 0; i < PER; i++) so[tid * PER + i] = sbase + sloc[i];
-    if (tid == SORT_THREADS - 1) so[SB_BUCKETS] = sbase + ssum;
-    __syncthreads();
-  }
-#pragma unroll
-  for (int i = 0; i < PER; i++) cnt[tid * PER + i] = base + loc[i];  // cursors
-  __syncthreads();
-  // pass 2: scatter
+  return total;
+}
+__global__ void __launch_bounds__(SORT_THREADS, 1) sort_buckets_kernel(RowMap rmap, const int8_t *dig, long dig_inst_stride, long rows,
+                                                                      uint32_t *items, long items_stride, uint32_t *boff) {
+  extern __shared__ uint32_t sort_sm[];
+  uint32_t *cur = sort_sm;                         // [SB_BUCKETS] next free slot of every bucket's global region
+  uint32_t *tcnt = sort_sm + SB_BUCKETS;           // [SB_BUCKETS + 1] counts, then offsets, of the tile in flight
+  uint32_t *stage = sort_sm + 2 * SB_BUCKETS + 32; // [SORT_TILE_ITEMS] the tile's items in bucket order
+  __shared__ uint32_t warp_tot[33];
+  const long inst = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int8_t *drow = dig + inst * dig_inst_stride;
   uint32_t *it = items + inst * items_stride;
+  // pass 0: histogram of the whole instance -> bucket offsets
+  for (int b = tid; b < SB_BUCKETS; b += SORT_THREADS) tcnt[b] = 0;
+  __syncthreads();
   for (long r = tid; r < rows; r += SORT_THREADS) {
     int16_t d[24]; load_digits13(d, drow + r * SB_ROW_BYTES);
-    const uint32_t g = (uint32_t)row_gen(rmap, r) * SB_WINDOWS;
 #pragma unroll
-    for (int w = 0; w < SB_WINDOWS; w++) if (d[w]) {
-      const int neg = d[w] < 0; const int b = (neg ? -d[w] : d[w]) - 1;
-      const uint32_t pos = atomicAdd(&cnt[b], 1u);
-      it[pos] = (g + w) | ((uint32_t)neg << 31);
+    for (int w = 0; w < SB_WINDOWS; w++) if (d[w]) atomicAdd(&tcnt[(d[w] < 0 ? -d[w] : d[w]) - 1], 1u);
+  }
+  __syncthreads();
+  {
+    const uint32_t total = sort_block_scan(tcnt, warp_tot);
+    uint32_t *off = boff + inst * (SB_BUCKETS + 1);
+    for (int b = tid; b < SB_BUCKETS; b += SORT_THREADS) { const uint32_t o = tcnt[b]; off[b] = o; cur[b] = o; }
+    if (tid == 0) off[SB_BUCKETS] = total;
+  }
+  __syncthreads();
+  // pass 1: tiles of SORT_THREADS rows, one row per thread
+  for (long t0 = 0; t0 < rows; t0 += SORT_THREADS) {
+    for (int b = tid; b < SB_BUCKETS; b += SORT_THREADS) tcnt[b] = 0;
+    __syncthreads();
+    const long r = t0 + tid;
+    uint32_t code[SB_WINDOWS];  // sign << 31 | bucket << 16 | rank within (tile, bucket); ~0 = no item
+    if (r < rows) {
+      int16_t d[24]; load_digits13(d, drow + r * SB_ROW_BYTES);
+#pragma unroll
+      for (int w = 0; w < SB_WINDOWS; w++) {
+        code[w] = 0xffffffffu;
+        if (d[w]) {
+          const uint32_t neg = d[w] < 0; const uint32_t b = (uint32_t)(neg ? -d[w] : d[w]) - 1;
+          code[w] = (neg << 31) | (b << 16) | atomicAdd(&tcnt[b], 1u);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int w = 0; w < SB_WINDOWS; w++) code[w] = 0xffffffffu;
     }
+    __syncthreads();
+    const uint32_t ttotal = sort_block_scan(tcnt, warp_tot);
+    if (tid == 0) tcnt[SB_BUCKETS] = ttotal;
+    if (r < rows) {
+      const uint32_t g = (uint32_t)row_gen(rmap, r) * SB_WINDOWS;
+#pragma unroll
+      for (int w = 0; w < SB_WINDOWS; w++) if (code[w] != 0xffffffffu) {
+        const uint32_t b = (code[w] >> 16) & 0xfffu;
+        stage[tcnt[b] + (code[w] & 0xffffu)] = (g + w) | (code[w] & 0x80000000u);
+      }
+    }
+    __syncthreads();
+    // copy-out: warp wid appends the runs of buckets wid, wid + 32, ...
+    for (int b = wid; b < SB_BUCKETS; b += SORT_THREADS / 32) {
+      const uint32_t s0 = tcnt[b], c = tcnt[b + 1] - s0, dst = cur[b];
+      for (uint32_t j = lane; j < c; j += 32) it[dst + j] = stage[s0 + j];
+      __syncwarp();
+      if (lane == 0) cur[b] = dst + c;
+    }
+    __syncthreads();
   }
 }
 #endif
@@ -88,7 +116,9 @@ int launch_sort_buckets(const RowMap &rmap, const int8_t *dig, long dig_inst_str
 #ifndef BP_HOST_EMUL
   if (ninst <= 0) return 0;
   if (g_profile_on) profile_begin("sort_buckets_kernel", ninst * SORT_THREADS, s);
-  sort_buckets_kernel<<<(unsigned)ninst, SORT_THREADS, 0, s>>>(rmap, dig, dig_inst_stride, rows, items, items_stride, boff, soff);
+  static bool smem_set = false;
+  if (!smem_set) { cudaFuncSetAttribute(sort_buckets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM_BYTES); smem_set = true; }
+  sort_buckets_kernel<<<(unsigned)ninst, SORT_THREADS, SORT_SMEM_BYTES, s>>>(rmap, dig, dig_inst_stride, rows, items, items_stride, boff);
   if (g_profile_on) profile_end(s);
   g_launch_count++;
   cudaError_t e = cudaGetLastError();
