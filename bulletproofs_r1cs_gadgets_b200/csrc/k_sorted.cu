@@ -94,17 +94,16 @@ __global__ void __launch_bounds__(SORT_THREADS, 1) sort_buckets_kernel(RowMap rm
       const uint32_t g = (uint32_t)row_gen(rmap, r) * SB_WINDOWS;
 #pragma unroll
       for (int w = 0; w < SB_WINDOWS; w++) if (code[w] != 0xffffffffu) {
-        const uint32_t b = (code[w] >> 16) & 0xfffu;
+        const uint32_t b = (code[w] >> 16) & 0x7fffu;
         stage[tcnt[b] + (code[w] & 0xffffu)] = (g + w) | (code[w] & 0x80000000u);
       }
     }
     __syncthreads();
-    // copy-out: warp wid appends the runs of buckets wid, wid + 32, ...
-    for (int b = wid; b < SB_BUCKETS; b += SORT_THREADS / 32) {
+    // copy-out: every thread appends the runs of its SB_BUCKETS / SORT_THREADS buckets (a few items each) to their global regions
+    for (int b = tid; b < SB_BUCKETS; b += SORT_THREADS) {
       const uint32_t s0 = tcnt[b], c = tcnt[b + 1] - s0, dst = cur[b];
-      for (uint32_t j = lane; j < c; j += 32) it[dst + j] = stage[s0 + j];
-      __syncwarp();
-      if (lane == 0) cur[b] = dst + c;
+      for (uint32_t j = 0; j < c; j++) it[dst + j] = stage[s0 + j];
+      cur[b] = dst + c;
     }
     __syncthreads();
   }

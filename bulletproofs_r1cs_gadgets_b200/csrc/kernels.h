@@ -300,15 +300,24 @@ struct KTsPhase4 {
   }
 };
 
-// non-adjacent form of a canonical scalar; returns index of the top non-zero digit (or -1)
+// width-4 non-adjacent form of a canonical scalar: digits in {+-1, +-3, +-5, +-7}, at most one non-zero digit in any four
+// consecutive positions (about 253/5 = 51 additions per scalar instead of 253/3 = 84 for the plain NAF);
+// returns the index of the top non-zero digit (or -1)
 HD int sc_naf(int8_t naf[256], const scm &s) {
   uint64_t k[4]; sc_to_canonical(k, s);
   int top = -1;
   for (int i = 0; i < 256; i++) {
     int8_t z = 0;
     if (k[0] & 1) {
-      if ((k[0] & 3) == 3) { z = -1; uint64_t c = 1; for (int j = 0; j < 4; j++) { uint64_t t = k[j] + c; c = t < c; k[j] = t; } }
-      else { z = 1; k[0] &= ~(uint64_t)1; }
+      int d = (int)(k[0] & 15);
+      if (d > 8) {  // negative digit d - 16: add its magnitude back
+        d -= 16;
+        uint64_t c = (uint64_t)(-d);
+        for (int j = 0; j < 4; j++) { uint64_t t = k[j] + c; c = t < c; k[j] = t; }
+      } else {
+        k[0] -= (uint64_t)d;
+      }
+      z = (int8_t)d;
       top = i;
     }
     naf[i] = z;
@@ -569,13 +578,22 @@ struct KFoldGens {
     ge_p3 acc;
     if (top < 0) { acc = lo; }
     else {
-      ge_cached c; ge_to_cached(c, hi);
-      if (nf[top] > 0) acc = hi; else ge_neg(acc, hi);
-      for (int bit = top - 1; bit >= 0; bit--) {
+      // odd multiples 1, 3, 5, 7 of the upper point (one doubling, three additions), then double-and-add over the digits
+      ge_cached c[4];
+      {
+        ge_p3 h2, t; ge_cached c2;
+        ge_dbl(h2, hi); ge_to_cached(c2, h2);
+        ge_to_cached(c[0], hi);
+        ge_add_cached(t, hi, c2, 0); ge_to_cached(c[1], t);
+        ge_add_cached(t, t, c2, 0); ge_to_cached(c[2], t);
+        ge_add_cached(t, t, c2, 0); ge_to_cached(c[3], t);
+      }
+      ge_identity(acc);
+      for (int bit = top; bit >= 0; bit--) {
         int d = nf[bit];
         // T is only needed when an addition follows (a digit here, or the final + lo)
-        if (d != 0 || bit == 0) ge_dbl(acc, acc); else ge_dbl_p2(acc, acc);
-        if (d != 0) ge_add_cached(acc, acc, c, d < 0);
+        if (bit != top) { if (d != 0 || bit == 0) ge_dbl(acc, acc); else ge_dbl_p2(acc, acc); }
+        if (d != 0) { const int neg = d < 0; const int idx = ((neg ? -d : d) - 1) >> 1; ge_add_cached(acc, acc, c[idx], neg); }
       }
       ge_cached cl; ge_to_cached(cl, lo);
       ge_add_cached(acc, acc, cl, 0);
@@ -1165,19 +1183,21 @@ struct KFoldTable {
 
 // ------------------------------------------------------------------------------------------------
 // Sorted-bucket multiscalar multiplication over the shared generators (13-bit signed windows).
-// For every generator P and window w the point 2^(13w)*P is tabulated (shift table, 20 x 128 B per generator), so all 20
-// windows of an instance feed ONE set of 4096 buckets: ~20 additions per term instead of 32 with the 8-bit direct tables,
-// and one running-sum reduction per instance instead of one per window.  Per launch:
+// For every generator P and window w the point 2^(SB_BITS w)*P is tabulated (shift table, SB_WINDOWS x 96 B per generator),
+// so all windows of an instance feed ONE set of SB_BUCKETS buckets: 17 additions per term (15-bit windows) instead of 32
+// with the 8-bit direct tables, and one running-sum reduction per instance instead of one per window.  Per launch:
 //   sort_buckets (block per instance, counting sort in shared memory)  ->  item list grouped by bucket
-//   KBucketAccumulate (thread per bucket: register accumulator over its items; ~160 items per bucket at N = 32768)
-//   KBucketReduce (32 segments of 128 buckets: plain and weighted sums)  ->  KBucketFinish (combine, encode)
+//   KBucketAccumulate (thread per 128-item segment of the sorted list: register accumulator, partial sums at bucket borders)
+//   KBucketReduce (groups of 128 buckets: plain and weighted sums)  ->  KBucketFinish (combine, encode)
 // ------------------------------------------------------------------------------------------------
-#define SB_WINDOWS 20
-#define SB_BITS 13
-#define SB_BUCKETS 4096
-#define SB_ROW_BYTES 48   // 20 int16 digits, padded to 3 x 16 B
-#define SB_SEGS 32
-#define SB_SEG_LEN (SB_BUCKETS / SB_SEGS)
+#ifndef SB_BITS
+#define SB_BITS 15        // signed window width: 15 -> 17 windows and 16384 buckets (13 -> 20 windows, 4096 buckets)
+#endif
+#define SB_WINDOWS ((253 + SB_BITS - 1) / SB_BITS)
+#define SB_BUCKETS (1 << (SB_BITS - 1))
+#define SB_ROW_BYTES 48   // up to 24 int16 digits (3 x 16 B)
+#define SB_SEG_LEN 128
+#define SB_SEGS (SB_BUCKETS / SB_SEG_LEN)
 
 HD void sc_recode13(int16_t dig[SB_WINDOWS], const scm &s) {
   uint64_t w[4]; sc_to_canonical(w, s);
