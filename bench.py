@@ -254,25 +254,45 @@ def main():
         pass
     hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
     n, N, k = circ.n, 1 << (circ.n - 1).bit_length(), (circ.n - 1).bit_length()
-    J = min(3, k)  # UNFOLD_ROUNDS in csrc/engine.cu
+    J = min(int(os.environ.get("BP_B200_UNFOLD", "4")), k)  # unfold_rounds() in csrc/engine.cu
+    SB_WINDOWS = 17                                          # 15-bit windows (csrc/kernels.h)
     # algorithmic bytes: 64 B per multiscalar term (32 B scalar + 32 B compressed point), 96 B per folded point
-    terms_table = (2 * n + 1) + (n + 1) + (2 * n + 1) + J * 2 * (N + 1)            # A_I, A_O, S + the unfolded rounds, per proof
-    terms_bucket = sum(2 * (2 * (N >> (j + 1)) + 1) for j in range(J, k))         # L_j, R_j of the folded rounds
+    terms_sorted = 2 * (2 * n + 1) + J * 2 * (N + 1)                              # A_I, S + the unfolded rounds, per proof (sorted-bucket MSM)
+    terms_table = n + 1                                                           # A_O (0/1 scalars, direct tables)
+    terms_bucket = sum(2 * (2 * (N >> (j + 1)) + 1) for j in range(J, k))         # L_j, R_j of the folded rounds (per-proof points)
     fold_outputs = sum(2 * (N >> (j + 1)) for j in range(J, k) if (N >> (j + 1)) > 1)
-    alg_bytes = {"KMsmTable": 64.0 * terms_table * B * args.steps, "KMsmAccumulate": 64.0 * terms_bucket * B * args.steps,
+    alg_bytes = {"KBucketAccumulate": 64.0 * terms_sorted * B * args.steps, "KMsmTable": 64.0 * terms_table * B * args.steps,
+                 "KMsmAccumulate": 64.0 * terms_bucket * B * args.steps,
                  "KFoldTable": 64.0 * 2 * N * B * args.steps, "KFoldGens": 96.0 * fold_outputs * B * args.steps}
     total_kernel_ms = sum(v[1] for v in prof.values()) or 1.0
     shares = {kname: round(v[1] / total_kernel_ms, 4) for kname, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:8]}
+    # DRAM traffic per launch of the same launch geometry from the committed ncu --set full capture (profiles/), if there is one
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(HERE, "profiles", "r01_ncu_traffic.json")))
+    except (OSError, ValueError):
+        pass
 
     def roof(kname):
         if kname not in prof or kname not in alg_bytes:
             return None
         launches_k, ms_k, _ = prof[kname]
         ach = alg_bytes[kname] / (ms_k / 1000.0) / 1e9
-        return {"kernel": kname, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+        tr = traffic.get(kname, {})
+        return {"kernel": kname, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                "traffic": tr.get("dram_bytes_per_launch"), "traffic_note": tr.get("note"),
                 "peak_source": peak_src, "launches": launches_k, "avg_launch_ms": ms_k / launches_k, "share_of_step": shares.get(kname)}
-    dominant = max(prof.items(), key=lambda kv: kv[1][1])[0] if prof else None
-    roofline = roof(dominant) or roof("KMsmTable")
+    dominant = max(((kn, v) for kn, v in prof.items() if kn in alg_bytes), key=lambda kv: kv[1][1])[0] if prof else None
+    roofline = roof(dominant) or roof("KBucketAccumulate")
+    # the roof that actually binds these kernels is the integer pipe: mixed point additions per second against the
+    # measured peak of the same addition in isolation (profiles/r01_field_microbench_3way.jsonl, ge_madd, 32 warps/SM)
+    roofline_int = None
+    if "KBucketAccumulate" in prof:
+        adds = float(terms_sorted) * SB_WINDOWS * B * args.steps  # one addition per non-zero digit (upper bound: zero scalars add nothing)
+        ach = adds / (prof["KBucketAccumulate"][1] / 1000.0) / 1e9
+        roofline_int = {"kernel": "KBucketAccumulate", "bound": "integer pipe (IMAD.WIDE)", "achieved": ach, "peak": 12.57, "unit": "G mixed additions/s",
+                        "frac": ach / 12.57, "peak_source": "measured: ge_madd microbenchmark on this pool (tools/fe_bench2)",
+                        "note": "additions counted as terms x 17 windows; rows with a zero scalar contribute none, so this is an upper bound"}
 
     # ---- cpu_baseline: the oracle port on a bounded sample of the same workload ----
     cpu = None
@@ -292,7 +312,7 @@ def main():
                        "proofs_per_gpu_per_step": B, "global_proofs_per_step": world * B,
                        "note": "BASELINE config 5 is 65536 proofs over 8 GPUs = 8192 per GPU; a step is one GPU's share", "parallelism": "proofs sharded over %d GPU(s), NCCL all-gather of proof bytes" % world,
                        "l2": "per-step working set (GBs of scalars, digits, buckets, folded generators) exceeds the 126 MB L2"},
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_msm": roof("KMsmTable"),
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_msm": roof("KBucketAccumulate"), "roofline_int": roofline_int,
             "kernel_time_shares": shares, "kernel_ms_per_step": {kn: round(v[1] / args.steps, 3) for kn, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:12]},
             "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)

@@ -339,8 +339,10 @@ size_t bp_circuit_proof_len(const bp_circuit *c) { return c ? circuit_proof_len(
 
 // proofs per device chunk: bounded by a workspace budget (bytes) and BP_B200_CHUNK
 static uint32_t chunk_size(const BpCircuit *c, uint32_t B) {
-  double per = 32.0 * (12.0 * c->n + 8.0 * c->N + c->q) + 160.0 * c->N + 48.0 * (5.0 * c->n + 2.0 * c->N) + 80.0 * (2.0 * c->n + c->N) + 4096;
-  double budget = 56e9;
+  double per = engine_workspace_bytes_per_proof(c) * 1.05;
+  // budget for the chunk in flight + the phase-A outputs of every chunk; the generator tables (26 GB at capacity 32768)
+  // and the caller's buffers share the 180 GB with it
+  double budget = 72e9;
   uint32_t ch = (uint32_t)std::max(1.0, std::min((double)B, budget / per));
   if (ch > 32768) ch = 32768;
   uint32_t nchunks = (B + ch - 1) / ch;

@@ -275,6 +275,21 @@ static const int CH_DOT = 256;  // multipliers per partial-sum thread
 static const int CH_POW = 64;   // exponents per powers thread
 static long msm_target_warps() { return 148L * 8 * 4; }
 
+// device bytes ensure_workspace() + ensure_front() allocate per proof of a chunk (the MSM bucket floor of small chunks aside)
+double engine_workspace_bytes_per_proof(const BpCircuit *c) {
+  const double n = c->n, N = c->N, m = c->m, q = c->q, k = c->k;
+  const double rows = std::max(std::max(5 * n + 3, 2 * (N + 1)), 2 * N + m + 13 + 2 * k + 2);
+  const double items = std::max(2 * n + 1, N + 1) * SB_WINDOWS, slices = SB_BUCKETS + items / SB_SEG + 2;
+  const double nch = std::max(n, N) / CH_DOT + 2;
+  double b = 0;
+  b += sizeof(scm) * ((double)c->nslots + (q + 1) + 4 * N + (2 * k + 2) + 40 + nch * 6 + (c->npub + 1));  // w_all, zpow, ypow, yinvpow, a, b, ...
+  b += rows * SB_ROW_BYTES;                                                      // digit rows
+  b += sizeof(ge_p3) * (slices + 2 * (N / 2 + 1) + (m + 12 + 2 * k) + 2 * SB_SEGS + 1 + 2 * MSM_WINDOWS);  // partial sums, folded generators, ...
+  b += 4 * items + 8 * (SB_BUCKETS + 1) + 4 * 256 + 16;                          // sorted items, offsets, NAFs
+  b += sizeof(scm) * (2 * (m + 1) + (c->naux + 1) + (c->npub + 1) + 3 * (n + 1) + (3 + 2 * n)) + 2 * sizeof(strobe128);  // front
+  return b;
+}
+
 static int ensure_workspace(BpCircuit *c, int B) {
   Workspace *w = c->ws;
   if (w->B >= B) return BP_OK;
@@ -286,7 +301,9 @@ static int ensure_workspace(BpCircuit *c, int B) {
   w->dig_bytes = std::max(std::max(rows_as, rows_ipa), rows_ver) * SB_ROW_BYTES * Bz;  // sized for the wider 13-bit rows
   // bucket slots: enough for one MSM launch at the largest split the launcher will pick
   size_t max_warps = (size_t)std::max<long>(msm_target_warps(), 2L * B) + B;
-  w->bucket_slots = max_warps * MSM_WINDOWS * MSM_BUCKETS;
+  w->items_cap = (size_t)std::max(2 * n + 1, N + 1) * SB_WINDOWS;  // items of one instance
+  w->slices_cap = SB_BUCKETS + w->items_cap / SB_SEG + 2;  // partial sums: one per (bucket, segment) crossing
+  w->bucket_slots = std::max(max_warps * MSM_WINDOWS * MSM_BUCKETS, Bz * w->slices_cap);
   int bad = 0;
   bad |= dalloc(&w->vpub, (size_t)(c->npub + 1) * Bz); bad |= dalloc(&w->uj, (2 * k + 2) * Bz);
   bad |= dalloc(&w->w_all, (size_t)c->nslots * Bz);
@@ -297,9 +314,7 @@ static int ensure_workspace(BpCircuit *c, int B) {
   bad |= dalloc(&w->Q, Bz); bad |= dalloc(&w->Gt, (N / 2 + 1) * Bz); bad |= dalloc(&w->Ht, (N / 2 + 1) * Bz);
   bad |= dalloc(&w->pts, (m + 11 + 2 * k + 1) * Bz);
   bad |= dalloc(&w->naf, 4 * 256 * Bz); bad |= dalloc(&w->naf_top, 4 * Bz);
-  w->items_cap = (size_t)std::max(2 * n + 1, N + 1) * SB_WINDOWS;  // items of one instance
   bad |= dalloc(&w->items, w->items_cap * Bz); bad |= dalloc(&w->boff, (size_t)(SB_BUCKETS + 1) * Bz); bad |= dalloc(&w->soff, (size_t)(SB_BUCKETS + 1) * Bz);
-  w->slices_cap = SB_BUCKETS + w->items_cap / SB_SEG + 2;  // partial sums: one per (bucket, segment) crossing
   bad |= dalloc(&w->seg, (size_t)SB_SEGS * 2 * Bz);
   bad |= dalloc(&w->utab, 4 * (size_t)(1 << UNFOLD_MAX) * Bz + 4 * Bz); bad |= dalloc(&w->rg_as, 2 * n + 2);
   if (bad) { w->release(); return BP_ERR_OOM; }

@@ -46,6 +46,7 @@ int circuit_create(uint32_t n, uint32_t m, uint32_t npub, uint32_t q, const uint
                    const uint8_t *wkind, const uint32_t *widx, const scm *wcoeff, const struct HostPoseidonTape *ptape, BpCircuit **out);
 void circuit_free(BpCircuit *c);
 size_t circuit_proof_len(const BpCircuit *c);
+double engine_workspace_bytes_per_proof(const BpCircuit *c);
 
 struct ProveArgs {
   int B;
