@@ -6,8 +6,9 @@
 //   * per-proof scalar vectors are proof-minor: element i of proof p lives at v[i*B + p], so a warp of
 //     consecutive proofs reads/writes 32 consecutive 32-byte scalars (coalesced);
 //   * scalars are in Montgomery form (sc25519.h) while on the device;
-//   * MSM digit rows are signed radix-256: 32 int8 per scalar, row r of instance q at dig[q*stride + r*32 + w];
-//   * points are ge_p3 (160 B) when per-proof, ge_niels (128 B, affine) when shared generators.
+//   * MSM digit rows are signed radix-256 (32 int8 per scalar, row r of instance q at dig[q*stride + r*32 + w]) for the
+//     direct-table and per-proof bucket kernels, and signed radix-2^15 (17 int16 in a 48-byte row) for the sorted-bucket path;
+//   * points are ge_p3 (128 B) when per-proof, ge_niels (96 B, affine) when shared generators.
 //
 // Protocol references: SURVEY.md App. A (Prover::prove A.3, InnerProductProof::create A.4,
 // Verifier::verify A.5) -- the reference takes these from the un-vendored `bulletproofs` fork
