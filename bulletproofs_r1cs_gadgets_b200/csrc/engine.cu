@@ -133,16 +133,16 @@ int gens_create(uint32_t capacity, BpGens **out) {
   CK(dev_sync(s));
   dev_free(d_uni); dev_free(d_small); dev_free(d_ok);
   if (!ok) { gens_free(g); return BP_ERR_CUDA; }
-  // fixed-base tables (512 KiB per generator); BP_B200_NO_TABLE=1 keeps the bucket-method-only pipeline
-  const size_t table_bytes = (2 * (size_t)capacity + 2) * TBL_W * TBL_E * sizeof(ge_niels);
-  if (!getenv("BP_B200_NO_TABLE") && table_bytes <= ((size_t)48 << 30)) {  // capacities above ~49k generators fall back to the bucket method
-    const size_t ngen = 2 * (size_t)capacity + 2;
+  // direct 8-bit tables (384 KiB per generator); BP_B200_NO_TABLE=1 keeps the bucket-method-only pipeline
+  const size_t ngen = 2 * (size_t)capacity + 2;
+  const size_t table_bytes = ngen * TBL_W * TBL_E * sizeof(ge_niels);
+  if (!getenv("BP_B200_NO_TABLE") && table_bytes <= ((size_t)48 << 30)) {  // capacities above ~65k generators do without
     if (dalloc(&g->table, ngen * TBL_W * TBL_E)) { gens_free(g); return BP_ERR_OOM; }
     CK(launch((long)ngen * TBL_W, s, KTableBuild{g->G_p3, g->H_p3, g->pc, (long)capacity, g->table}));
     CK(dev_sync(s));
   }
-  if (g->table && !getenv("BP_B200_NO_SORTED")) {
-    const size_t ngen = 2 * (size_t)capacity + 2;
+  // shift table of the sorted-bucket MSM (SB_WINDOWS x 96 B per generator): kept up to 16 GB, i.e. capacity 2^22
+  if (!getenv("BP_B200_NO_TABLE") && !getenv("BP_B200_NO_SORTED") && ngen * SB_WINDOWS * sizeof(ge_niels) <= ((size_t)16 << 30)) {
     if (dalloc(&g->sg, ngen * SB_WINDOWS)) { gens_free(g); return BP_ERR_OOM; }
     CK(launch((long)ngen, s, KShiftTableBuild{g->G_p3, g->H_p3, g->pc, (long)capacity, g->sg}));
     CK(dev_sync(s));
@@ -263,6 +263,10 @@ void circuit_free(BpCircuit *c) {
   delete c;
 }
 
+// the sorted-bucket path pays ~54k additions per instance for its 16384-bucket reduction: below this many rows per instance the
+// direct 8-bit tables (32 additions per row, no reduction) are cheaper -- the small circuits (bound check, Poseidon 2:1, MiMC)
+static long sorted_min_rows() { const char *e = getenv("BP_B200_SORTED_MIN_ROWS"); return e ? atol(e) : 8192; }  // env: tests force either path
+#define SORTED_MIN_ROWS sorted_min_rows()
 static const int UNFOLD_MAX = 6;
 // inner-product rounds computed over the original generators (sorted-bucket MSM on the shift table) before the folded
 // generators are materialised; 4 is the measured optimum at N = 32768 (BP_B200_UNFOLD overrides, for experiments)
@@ -394,7 +398,7 @@ static int run_msm_sorted(const BpGens *g, Workspace *w, const RowMap &rmap, lon
   const long segs = (rows * SB_WINDOWS + SB_SEG - 1) / SB_SEG;  // segments of this launch's longest possible item list
   CK(launch(ninst * segs, s, KBucketAccumulate{g->sg, sv, w->buckets, segs}));
   CK(launch(ninst * SB_SEGS, s, KBucketReduce{w->buckets, sv, w->seg}));
-  CK(launch(ninst, s, KBucketFinish{w->seg, out, out_stride}));
+  CK(launch(ninst, s, KBucketFinish{w->seg, out, out_stride, nullptr}));
   return BP_OK;
 }
 
@@ -483,7 +487,7 @@ static int prove_phase_b(const BpGens *g, BpCircuit *c, Front &f, const ProveArg
   // 4. A_I1, A_O1, S1 (A.3 step 4)
   {
     const long rowsI = 2 * n + 1, rowsO = n + 1;
-    const bool sorted = g->sg != nullptr;
+    const bool sorted = g->sg != nullptr && rowsI >= SORTED_MIN_ROWS;
     const long rb = sorted ? SB_ROW_BYTES : 32;
     int8_t *dI = w->dig, *dO = dI + rowsI * rb * B, *dS = dO + rowsO * rb * B;
     if (sorted) {
@@ -574,7 +578,7 @@ static int prove_phase_b(const BpGens *g, BpCircuit *c, Front &f, const ProveArg
     CK(launch(2L * B, s, KSumPartials{w->part, (int)nch, 2, B, w->clr}));
     if (round < J) {
       const long rows = N + 1;
-      const bool sorted = g->sg != nullptr;
+      const bool sorted = g->sg != nullptr && rows >= SORTED_MIN_ROWS;
       const long rb = sorted ? SB_ROW_BYTES : 32;
       int8_t *dL = w->dig, *dR = w->dig + rows * rb * B;
       const int cur = round & 1;
@@ -658,9 +662,44 @@ int engine_commit(const BpGens *g, int count, const uint8_t *v, const uint8_t *r
 }
 
 // ------------------------------------------------------------------------------------------------ MSM microbenchmark entry
+// One MSM over the first n generators of chain G.  Large n: split into sub-instances of R consecutive rows that go through the
+// batched sorted-bucket kernels (sort, accumulate, reduce) like the proofs of a batch do; their partial results are summed.
+static int msm_gens_sorted(BpGens *g, uint32_t n, const uint8_t *d_scalars, uint8_t *d_out, dev_stream s) {
+  long R = n / 64; if (R < 8192) R = 8192; if (R > 32768) R = 32768; if (R > (long)n) R = n;
+  const long S = ((long)n + R - 1) / R;
+  if (!g->msm_ws || g->msm_ws_n < n || !g->msm_ws->items) {
+    if (g->msm_ws) { g->msm_ws->release(); delete g->msm_ws; }
+    Workspace *w = g->msm_ws = new Workspace();
+    w->items_cap = (size_t)R * SB_WINDOWS;
+    w->slices_cap = SB_BUCKETS + w->items_cap / SB_SEG + 2;
+    w->bucket_slots = (size_t)S * w->slices_cap + S + 1;
+    w->dig_bytes = (size_t)S * R * SB_ROW_BYTES;
+    if (dalloc(&w->a, (size_t)S * R) || dalloc(&w->dig, w->dig_bytes) || dalloc(&w->buckets, w->bucket_slots) || dalloc(&w->items, w->items_cap * S) ||
+        dalloc(&w->boff, (size_t)(SB_BUCKETS + 1) * S) || dalloc(&w->soff, (size_t)(SB_BUCKETS + 1) * S) || dalloc(&w->seg, (size_t)SB_SEGS * 2 * S)) {
+      w->release(); delete w; g->msm_ws = nullptr; return BP_ERR_OOM;
+    }
+    g->msm_ws_n = n;
+  }
+  Workspace *w = g->msm_ws;
+  if ((size_t)S * R * SB_ROW_BYTES > w->dig_bytes || (size_t)R * SB_WINDOWS > w->items_cap) return BP_ERR_OOM;
+  CK(dev_memset(w->dig, 0, (size_t)S * R * SB_ROW_BYTES, s));  // rows past n stay all-zero digits
+  CK(launch(n, s, KLoadScalars{d_scalars, w->a, (int)n, 1}));
+  CK(launch(n, s, KRecode13{w->a, nullptr, (int)n, 1, w->dig, 0, 0}));  // B = 1: row i at dig + i * SB_ROW_BYTES = sub-instance i / R, row i % R
+  RowMap rm{3, nullptr, (long)g->capacity, 0, 0, 0, R};
+  CK(launch_sort_buckets(rm, w->dig, R * SB_ROW_BYTES, R, S, w->items, (long)w->items_cap, w->boff, w->soff, s));
+  SortedView sv{w->items, w->boff, w->soff, (long)w->items_cap, (long)w->slices_cap};
+  const long segs = (R * SB_WINDOWS + SB_SEG - 1) / SB_SEG;
+  ge_p3 *partial = w->buckets + (size_t)S * w->slices_cap;
+  CK(launch(S * segs, s, KBucketAccumulate{g->sg, sv, w->buckets, segs}));
+  CK(launch(S * SB_SEGS, s, KBucketReduce{w->buckets, sv, w->seg}));
+  CK(launch(S, s, KBucketFinish{w->seg, nullptr, 0, partial}));
+  CK(launch(1, s, KSumPointsEncode{partial, (int)S, d_out}));
+  return BP_OK;
+}
 int engine_msm_gens(BpGens *g, uint32_t n, const uint8_t *d_scalars, uint8_t *d_out, dev_stream s) {
   if (n == 0 || n > g->capacity) return BP_ERR_INVALID_GENERATORS_LENGTH;
-  if (!g->msm_ws || g->msm_ws_n < n) {
+  if (g->sg && n >= 32768 && !getenv("BP_B200_MSM_BUCKET")) return msm_gens_sorted(g, n, d_scalars, d_out, s);
+  if (!g->msm_ws || g->msm_ws_n < n || !g->msm_ws->wsum) {
     if (g->msm_ws) { g->msm_ws->release(); delete g->msm_ws; }
     Workspace *w = g->msm_ws = new Workspace();
     size_t max_warps = (size_t)msm_target_warps() + 1;
@@ -717,9 +756,38 @@ int engine_verify(const BpGens *g, BpCircuit *c, const VerifyArgs &A, dev_stream
     CK(launch(B, s, KSumPartials{w->part, (int)nch, 1, B, w->clr}));
   }
   const long npts = 11 + m + 2 * k, rows = 2 + 2 * N + npts;
-  CK(launch(N * B, s, KVerifyGH{wL, wR, wO, w->yinvpow, w->a, w->chal, A.proofs, plen, (int)n, (int)N, (int)k, B, w->dig, rows * 32}));
-  CK(launch(B, s, KVerifyScalars{w->chal, uj, ujinv, wV, wc, wP, w->vpub, w->clr, A.proofs, plen, (int)m, (int)c->npub, (int)N, (int)k, B, w->dig, rows * 32}));
+  // with the shift table the generator rows (B, G_i | B_blinding, H_i) are two sorted-bucket instances of N + 1 rows per proof;
+  // their 15-bit digit rows live in front of the 8-bit rows of the ~110 per-proof points
+  const bool sorted = g->sg != nullptr && N + 1 >= SORTED_MIN_ROWS && (size_t)(N + 1) * SB_WINDOWS <= w->items_cap &&
+                      (size_t)B * (2 * (N + 1) * SB_ROW_BYTES + npts * 32) <= w->dig_bytes && (size_t)B * w->slices_cap <= w->bucket_slots &&
+                      (size_t)B * MSM_WINDOWS * MSM_BUCKETS <= w->bucket_slots && N / 2 + 1 >= 2;
+  int8_t *wideG = sorted ? w->dig : nullptr, *wideH = sorted ? w->dig + (size_t)B * (N + 1) * SB_ROW_BYTES : nullptr;
+  int8_t *dig8 = sorted ? w->dig + (size_t)B * 2 * (N + 1) * SB_ROW_BYTES : w->dig;
+  const long stride8 = sorted ? npts * 32 : rows * 32;
+  CK(launch(N * B, s, KVerifyGH{wL, wR, wO, w->yinvpow, w->a, w->chal, A.proofs, plen, (int)n, (int)N, (int)k, B, dig8, stride8, wideG, wideH}));
+  CK(launch(B, s, KVerifyScalars{w->chal, uj, ujinv, wV, wc, wP, w->vpub, w->clr, A.proofs, plen, (int)m, (int)c->npub, (int)N, (int)k, B, dig8, stride8, wideG, wideH}));
   CK(launch(npts * B, s, KVerifyDecompress{A.V, A.proofs, plen, (int)m, (int)k, B, w->pts, npts, A.status}));
+  if (sorted) {
+    // the ~110 per-proof points first (bucket method, result in wsum), then the two generator halves through the sorted path;
+    // both use the bucket area in turn, the two half results go to the (otherwise idle) folded-generator buffer
+    MsmSeg seg[1] = {{w->pts, npts, 1, (int)npts}};
+    KMsmAccumulate k{};
+    k.seg[0] = seg[0]; k.nseg = 1; k.S = 1; k.dig = dig8; k.dig_inst_stride = stride8; k.buckets = w->buckets; k.wsum = w->wsum;
+    CK(launch((long)B * MSM_WINDOWS, s, k));
+    ge_p3 *tpart = w->Gt;
+    for (int half = 0; half < 2; half++) {
+      RowMap rm{4, nullptr, (long)g->capacity, 0, half, 0, 0};
+      const int8_t *dg = half ? wideH : wideG;
+      CK(launch_sort_buckets(rm, dg, (N + 1) * SB_ROW_BYTES, N + 1, B, w->items, (long)w->items_cap, w->boff, w->soff, s));
+      SortedView sv{w->items, w->boff, w->soff, (long)w->items_cap, (long)w->slices_cap};
+      const long segs = ((N + 1) * SB_WINDOWS + SB_SEG - 1) / SB_SEG;
+      CK(launch(B * segs, s, KBucketAccumulate{g->sg, sv, w->buckets, segs}));
+      CK(launch((long)B * SB_SEGS, s, KBucketReduce{w->buckets, sv, w->seg}));
+      CK(launch(B, s, KBucketFinish{w->seg, nullptr, 0, tpart + (size_t)half * B}));
+    }
+    CK(launch(B, s, KVerifyCheck{w->wsum, tpart, 2, A.status, (long)B}));
+    return BP_OK;
+  }
   if (g->table) {
     // generator rows (B, B_blinding, G, H) from the fixed-base tables; the ~110 per-proof points by the bucket method; the two
     // partial results are added in KVerifyCheck
@@ -744,7 +812,7 @@ int engine_verify(const BpGens *g, BpCircuit *c, const VerifyArgs &A, dev_stream
     KMsmAccumulate k{};
     k.seg[0] = seg[0]; k.nseg = 1; k.S = 1; k.dig = w->dig + trows * 32; k.dig_inst_stride = rows * 32; k.buckets = w->buckets; k.wsum = w->wsum;
     CK(launch((long)B * MSM_WINDOWS, s, k));
-    CK(launch(B, s, KVerifyCheck{w->wsum, tpart, (int)S, A.status}));
+    CK(launch(B, s, KVerifyCheck{w->wsum, tpart, (int)S, A.status, 0}));
     return BP_OK;
   }
   MsmSeg segs[4] = {{g->pc_niels, 0, 0, 2}, {g->G_n, 0, 0, (int)N}, {g->H_n, 0, 0, (int)N}, {w->pts, npts, 1, (int)npts}};

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 1) sort_buckets_kernel(RowMap rm
     const uint32_t ttotal = sort_block_scan(tcnt, warp_tot);
     if (tid == 0) tcnt[SB_BUCKETS] = ttotal;
     if (r < rows) {
-      const uint32_t g = (uint32_t)row_gen(rmap, r) * SB_WINDOWS;
+      const uint32_t g = (uint32_t)(row_gen(rmap, r) + inst * rmap.inst_off) * SB_WINDOWS;
 #pragma unroll
       for (int w = 0; w < SB_WINDOWS; w++) if (code[w] != 0xffffffffu) {
         const uint32_t b = (code[w] >> 16) & 0x7fffu;
@@ -108,6 +108,44 @@ __global__ void __launch_bounds__(SORT_THREADS, 1) sort_buckets_kernel(RowMap rm
     __syncthreads();
   }
 }
+// Variant without staging: after the histogram pass every item is stored straight at its bucket's cursor (a shared-memory
+// atomic).  With 15-bit windows a tile of 1024 rows holds about one item per bucket, so staging buys no contiguity and its
+// per-tile zero / scan / copy-out over 16384 buckets is pure overhead; one block per SM keeps the open 32-byte sectors of
+// all resident blocks (16384 per block) inside the L2, where the partial writes are merged.
+__global__ void __launch_bounds__(SORT_THREADS, 1) sort_buckets_direct_kernel(RowMap rmap, const int8_t *dig, long dig_inst_stride, long rows,
+                                                                             uint32_t *items, long items_stride, uint32_t *boff) {
+  extern __shared__ uint32_t sort_sm[];
+  uint32_t *cur = sort_sm;  // [SB_BUCKETS] counts, then offsets = cursors
+  __shared__ uint32_t warp_tot[33];
+  const long inst = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int8_t *drow = dig + inst * dig_inst_stride;
+  uint32_t *it = items + inst * items_stride;
+  for (int b = tid; b < SB_BUCKETS; b += SORT_THREADS) cur[b] = 0;
+  __syncthreads();
+  for (long r = tid; r < rows; r += SORT_THREADS) {
+    int16_t d[24]; load_digits13(d, drow + r * SB_ROW_BYTES);
+#pragma unroll
+    for (int w = 0; w < SB_WINDOWS; w++) if (d[w]) atomicAdd(&cur[(d[w] < 0 ? -d[w] : d[w]) - 1], 1u);
+  }
+  __syncthreads();
+  {
+    const uint32_t total = sort_block_scan(cur, warp_tot);
+    uint32_t *off = boff + inst * (SB_BUCKETS + 1);
+    for (int b = tid; b < SB_BUCKETS; b += SORT_THREADS) off[b] = cur[b];
+    if (tid == 0) off[SB_BUCKETS] = total;
+  }
+  __syncthreads();
+  for (long r = tid; r < rows; r += SORT_THREADS) {
+    int16_t d[24]; load_digits13(d, drow + r * SB_ROW_BYTES);
+    const uint32_t g = (uint32_t)(row_gen(rmap, r) + inst * rmap.inst_off) * SB_WINDOWS;
+#pragma unroll
+    for (int w = 0; w < SB_WINDOWS; w++) if (d[w]) {
+      const uint32_t neg = d[w] < 0; const uint32_t b = (uint32_t)(neg ? -d[w] : d[w]) - 1;
+      it[atomicAdd(&cur[b], 1u)] = (g + w) | (neg << 31);
+    }
+  }
+}
 #endif
 
 int launch_sort_buckets(const RowMap &rmap, const int8_t *dig, long dig_inst_stride, long rows, long ninst, uint32_t *items, long items_stride,
@@ -115,9 +153,16 @@ int launch_sort_buckets(const RowMap &rmap, const int8_t *dig, long dig_inst_str
 #ifndef BP_HOST_EMUL
   if (ninst <= 0) return 0;
   if (g_profile_on) profile_begin("sort_buckets_kernel", ninst * SORT_THREADS, s);
-  static bool smem_set = false;
-  if (!smem_set) { cudaFuncSetAttribute(sort_buckets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM_BYTES); smem_set = true; }
-  sort_buckets_kernel<<<(unsigned)ninst, SORT_THREADS, SORT_SMEM_BYTES, s>>>(rmap, dig, dig_inst_stride, rows, items, items_stride, boff);
+  static int mode = -1;  // 0: staged tiles, 1: direct scatter (default for windows of 15 bits and more)
+  if (mode < 0) {
+    const char *e = getenv("BP_B200_SORT");
+    mode = e ? (e[0] == 'd') : (SB_BITS >= 15);
+    cudaFuncSetAttribute(sort_buckets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM_BYTES);
+    cudaFuncSetAttribute(sort_buckets_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM_BYTES);
+  }
+  // the direct variant asks for the same (large) shared-memory carve-out on purpose: one block per SM bounds the open sectors
+  if (mode) sort_buckets_direct_kernel<<<(unsigned)ninst, SORT_THREADS, SORT_SMEM_BYTES, s>>>(rmap, dig, dig_inst_stride, rows, items, items_stride, boff);
+  else sort_buckets_kernel<<<(unsigned)ninst, SORT_THREADS, SORT_SMEM_BYTES, s>>>(rmap, dig, dig_inst_stride, rows, items, items_stride, boff);
   if (g_profile_on) profile_end(s);
   g_launch_count++;
   cudaError_t e = cudaGetLastError();

@@ -30,6 +30,51 @@
 #define BP_ERR_FORMAT_ 2
 #define BP_ERR_VERIFICATION_ 3
 
+// digit geometry and recoding of the sorted-bucket MSM (kernels further down; the verifier kernels write these rows too)
+#ifndef SB_BITS
+#define SB_BITS 15        // signed window width: 15 -> 17 windows and 16384 buckets (13 -> 20 windows, 4096 buckets)
+#endif
+#define SB_WINDOWS ((253 + SB_BITS - 1) / SB_BITS)
+#define SB_BUCKETS (1 << (SB_BITS - 1))
+#define SB_ROW_BYTES 48   // up to 24 int16 digits (3 x 16 B)
+#define SB_SEG_LEN 128
+#define SB_SEGS (SB_BUCKETS / SB_SEG_LEN)
+
+HD void sc_recode13(int16_t dig[SB_WINDOWS], const scm &s) {
+  uint64_t w[4]; sc_to_canonical(w, s);
+  int carry = 0;
+#pragma unroll
+  for (int i = 0; i < SB_WINDOWS; i++) {
+    const int bit = SB_BITS * i, word = bit >> 6, off = bit & 63;
+    uint64_t v = word < 4 ? (w[word] >> off) : 0;
+    if (off > 64 - SB_BITS && word + 1 < 4) v |= w[word + 1] << (64 - off);
+    int d = (int)(v & ((1 << SB_BITS) - 1)) + carry;
+    carry = d >= (1 << (SB_BITS - 1));
+    d -= carry << SB_BITS;
+    dig[i] = (int16_t)d;
+  }
+}
+HD void store_digits13(int8_t *dst, const int16_t dig[SB_WINDOWS]) {
+  int16_t tmp[24];
+#pragma unroll
+  for (int i = 0; i < 24; i++) tmp[i] = i < SB_WINDOWS ? dig[i] : 0;
+#if defined(__CUDA_ARCH__)
+  uint4 a, b, c;
+  memcpy(&a, tmp, 16); memcpy(&b, tmp + 8, 16); memcpy(&c, tmp + 16, 16);
+  uint4 *d = reinterpret_cast<uint4 *>(dst); d[0] = a; d[1] = b; d[2] = c;
+#else
+  memcpy(dst, tmp, SB_ROW_BYTES);
+#endif
+}
+HD void load_digits13(int16_t dig[24], const int8_t *src) {
+#if defined(__CUDA_ARCH__)
+  const uint4 *s = reinterpret_cast<const uint4 *>(src);
+  uint4 a = s[0], b = s[1], c = s[2];
+  memcpy(dig, &a, 16); memcpy(dig + 8, &b, 16); memcpy(dig + 16, &c, 16);
+#else
+  memcpy(dig, src, SB_ROW_BYTES);
+#endif
+}
 // ------------------------------------------------------------------------------------------------
 // scalars in / out
 // ------------------------------------------------------------------------------------------------
@@ -898,6 +943,7 @@ struct KVerifyGH {
   static constexpr int kBlock = 128, kMinBlocks = 1;
   static constexpr const char *kName = "KVerifyGH";
   const scm *wL, *wR, *wO, *yinvpow, *s, *chal; const uint8_t *proofs; long proof_stride; int n, N, k, B; int8_t *dig; long inst_stride;
+  int8_t *wideG, *wideH;  // non-NULL: 15-bit digit rows for the sorted-bucket path, [B][N + 1] rows each (row 0 = B / B_blinding)
   HD void operator()(long tid) const {
     int p = (int)(tid % B); long i = tid / B; long at = i * B + p;
     scm x = chal[4L * B + p], u = chal[3L * B + p];
@@ -912,6 +958,12 @@ struct KVerifyGH {
     }
     hh = sc_sub(sc_mul(yi, hh), sc_one());
     if (i >= n) { g = sc_mul(g, u); hh = sc_mul(hh, u); }
+    if (wideG) {
+      int16_t dw[SB_WINDOWS];
+      sc_recode13(dw, g); store_digits13(wideG + ((long)p * (N + 1) + 1 + i) * SB_ROW_BYTES, dw);
+      sc_recode13(dw, hh); store_digits13(wideH + ((long)p * (N + 1) + 1 + i) * SB_ROW_BYTES, dw);
+      return;
+    }
     int8_t d[32];
     int8_t *row = dig + (long)p * inst_stride;
     sc_recode_bytes(d, g); store_digits(row + (2 + i) * 32, d);
@@ -924,7 +976,9 @@ struct KVerifyScalars {
   static constexpr int kBlock = 64, kMinBlocks = 1;
   static constexpr const char *kName = "KVerifyScalars";
   const scm *chal, *uj, *ujinv, *wV, *wc, *wP, *pub, *delta; const uint8_t *proofs; long proof_stride; int m, npub, N, k, B; int8_t *dig; long inst_stride;
+  int8_t *wideG, *wideH;  // as in KVerifyGH: rows 0 (B, B_blinding) go there when set
   HD void put(int8_t *row, long r, const scm &v) const { int8_t d[32]; sc_recode_bytes(d, v); store_digits(row + r * 32, d); }
+  HD void putw(int8_t *base, long p, const scm &v) const { int16_t dw[SB_WINDOWS]; sc_recode13(dw, v); store_digits13(base + p * (long)(N + 1) * SB_ROW_BYTES, dw); }
   HD void operator()(long p) const {
     const uint8_t *pf = proofs + p * proof_stride;
     scm u = chal[3L * B + p], x = chal[4L * B + p], w = chal[5L * B + p], r = chal[6L * B + p];
@@ -935,9 +989,9 @@ struct KVerifyScalars {
     scm wcv = wc[p];
     for (int i = 0; i < npub; i++) wcv = sc_add(wcv, sc_mul(wP[(long)i * B + p], pub[(long)i * B + p]));
     scm bsc = sc_add(sc_mul(w, sc_sub(t_x, sc_mul(a, b))), sc_mul(r, sc_sub(sc_mul(xx, sc_add(wcv, delta[p])), t_x)));
-    put(row, 0, bsc);
-    put(row, 1, sc_neg(sc_add(e_b, sc_mul(r, t_xb))));
-    long o = 2 + 2L * N;
+    if (wideG) { putw(wideG, p, bsc); putw(wideH, p, sc_neg(sc_add(e_b, sc_mul(r, t_xb)))); }
+    else { put(row, 0, bsc); put(row, 1, sc_neg(sc_add(e_b, sc_mul(r, t_xb)))); }
+    long o = wideG ? 0 : 2 + 2L * N;  // wide mode: the 8-bit rows hold the per-proof points only
     put(row, o + 0, x); put(row, o + 1, xx); put(row, o + 2, xxx);
     put(row, o + 3, sc_mul(u, x)); put(row, o + 4, sc_mul(u, xx)); put(row, o + 5, sc_mul(u, xxx));
     o += 6;
@@ -1017,9 +1071,11 @@ struct KTableBuild {
 
 // row -> generator index.  mode 0: explicit map; 1/2: the L / R multiscalar multiplication of an UNFOLDED inner-product
 // round over the original generators (nj = current vector length, h = nj/2, N rows of G then H, last row = B).
-struct RowMap { int mode; const uint32_t *map; long cap, N, nj, h; };
+struct RowMap { int mode; const uint32_t *map; long cap, N, nj, h; long inst_off; };  // inst_off: generator offset per instance (split MSM)
 HD long row_gen(const RowMap &m, long r) {
   if (m.mode == 0) return m.map[r];
+  if (m.mode == 3) return r;  // row r is generator r (+ inst * inst_off at the call site)
+  if (m.mode == 4) return r == 0 ? 2 * m.cap + m.nj : m.nj * m.cap + (r - 1);  // verifier half nj (0: B, G_i; 1: B_blinding, H_i)
   if (r == m.N) return 2 * m.cap;  // B
   const long half = m.N / 2;
   const bool isH = r >= half;
@@ -1086,7 +1142,7 @@ struct KMsmTableFinish {
 struct KVerifyCheck {
   static constexpr int kBlock = 64, kMinBlocks = 1;
   static constexpr const char *kName = "KVerifyCheck";
-  const ge_p3 *wsum; const ge_p3 *tpart; int S; int *status;
+  const ge_p3 *wsum; const ge_p3 *tpart; int S; int *status; long tpart_s_stride;  // partial s of instance i at tpart[i*S + s], or [s*stride + i] when stride != 0
   HD void operator()(long inst) const {
     ge_p3 acc; load_struct(acc, &wsum[inst * MSM_WINDOWS + MSM_WINDOWS - 1]);
     for (int w = MSM_WINDOWS - 2; w >= 0; w--) {
@@ -1095,7 +1151,7 @@ struct KVerifyCheck {
       ge_p3 sp; load_struct(sp, &wsum[inst * MSM_WINDOWS + w]);
       ge_add(acc, acc, sp);
     }
-    for (int s = 0; s < S; s++) { ge_p3 t; load_struct(t, &tpart[inst * S + s]); ge_add(acc, acc, t); }
+    for (int s = 0; s < S; s++) { ge_p3 t; load_struct(t, tpart_s_stride ? &tpart[s * tpart_s_stride + inst] : &tpart[inst * S + s]); ge_add(acc, acc, t); }
     if (!ge_is_identity_ristretto(acc) && status[inst] == 0) status[inst] = BP_ERR_VERIFICATION_;
   }
 };
@@ -1191,50 +1247,6 @@ struct KFoldTable {
 //   KBucketAccumulate (thread per 128-item segment of the sorted list: register accumulator, partial sums at bucket borders)
 //   KBucketReduce (groups of 128 buckets: plain and weighted sums)  ->  KBucketFinish (combine, encode)
 // ------------------------------------------------------------------------------------------------
-#ifndef SB_BITS
-#define SB_BITS 15        // signed window width: 15 -> 17 windows and 16384 buckets (13 -> 20 windows, 4096 buckets)
-#endif
-#define SB_WINDOWS ((253 + SB_BITS - 1) / SB_BITS)
-#define SB_BUCKETS (1 << (SB_BITS - 1))
-#define SB_ROW_BYTES 48   // up to 24 int16 digits (3 x 16 B)
-#define SB_SEG_LEN 128
-#define SB_SEGS (SB_BUCKETS / SB_SEG_LEN)
-
-HD void sc_recode13(int16_t dig[SB_WINDOWS], const scm &s) {
-  uint64_t w[4]; sc_to_canonical(w, s);
-  int carry = 0;
-#pragma unroll
-  for (int i = 0; i < SB_WINDOWS; i++) {
-    const int bit = SB_BITS * i, word = bit >> 6, off = bit & 63;
-    uint64_t v = word < 4 ? (w[word] >> off) : 0;
-    if (off > 64 - SB_BITS && word + 1 < 4) v |= w[word + 1] << (64 - off);
-    int d = (int)(v & ((1 << SB_BITS) - 1)) + carry;
-    carry = d >= (1 << (SB_BITS - 1));
-    d -= carry << SB_BITS;
-    dig[i] = (int16_t)d;
-  }
-}
-HD void store_digits13(int8_t *dst, const int16_t dig[SB_WINDOWS]) {
-  int16_t tmp[24];
-#pragma unroll
-  for (int i = 0; i < 24; i++) tmp[i] = i < SB_WINDOWS ? dig[i] : 0;
-#if defined(__CUDA_ARCH__)
-  uint4 a, b, c;
-  memcpy(&a, tmp, 16); memcpy(&b, tmp + 8, 16); memcpy(&c, tmp + 16, 16);
-  uint4 *d = reinterpret_cast<uint4 *>(dst); d[0] = a; d[1] = b; d[2] = c;
-#else
-  memcpy(dst, tmp, SB_ROW_BYTES);
-#endif
-}
-HD void load_digits13(int16_t dig[24], const int8_t *src) {
-#if defined(__CUDA_ARCH__)
-  const uint4 *s = reinterpret_cast<const uint4 *>(src);
-  uint4 a = s[0], b = s[1], c = s[2];
-  memcpy(dig, &a, 16); memcpy(dig + 8, &b, 16); memcpy(dig + 16, &c, 16);
-#else
-  memcpy(dig, src, SB_ROW_BYTES);
-#endif
-}
 // shift table: sg[gen*20 + w] = 2^(13w) * P_gen in affine Niels form
 struct KShiftTableBuild {
   static constexpr int kBlock = 64, kMinBlocks = 1;
@@ -1308,7 +1320,7 @@ struct KSortBucketsSerial {
     uint32_t *it = items + inst * items_stride;
     for (long r = 0; r < rows; r++) {
       int16_t d[24]; load_digits13(d, drow + r * SB_ROW_BYTES);
-      const uint32_t g = (uint32_t)row_gen(rmap, r) * SB_WINDOWS;
+      const uint32_t g = (uint32_t)(row_gen(rmap, r) + inst * rmap.inst_off) * SB_WINDOWS;
       for (int w = 0; w < SB_WINDOWS; w++) if (d[w]) {
         int neg = d[w] < 0; int b = (neg ? -d[w] : d[w]) - 1;
         it[off[b]++] = (g + w) | ((uint32_t)neg << 31);
@@ -1385,7 +1397,7 @@ struct KBucketReduce {
 struct KBucketFinish {
   static constexpr int kBlock = 64, kMinBlocks = 1;
   static constexpr const char *kName = "KBucketFinish";
-  const ge_p3 *seg; uint8_t *out; long out_stride;
+  const ge_p3 *seg; uint8_t *out; long out_stride; ge_p3 *out_p3;  // out_p3 != NULL: keep the point (partial result of a split MSM)
   HD void operator()(long inst) const {
     const ge_p3 *sgp = seg + inst * SB_SEGS * 2;
     ge_p3 run, T, Wsum; ge_identity(run); ge_identity(T); ge_identity(Wsum);
@@ -1393,6 +1405,17 @@ struct KBucketFinish {
     for (int i = 0; i < 7; i++) ge_dbl(T, T);  // * SB_SEG_LEN (128)
     for (int s = 0; s < SB_SEGS; s++) { ge_p3 t; load_struct(t, &sgp[s * 2 + 1]); ge_add(Wsum, Wsum, t); }
     ge_add(T, T, Wsum);
-    ristretto_encode(out + inst * out_stride, T);
+    if (out_p3) store_struct(&out_p3[inst], T); else ristretto_encode(out + inst * out_stride, T);
+  }
+};
+// sum of `count` points -> ristretto encoding (last step of a split MSM; one thread)
+struct KSumPointsEncode {
+  static constexpr int kBlock = 32, kMinBlocks = 1;
+  static constexpr const char *kName = "KSumPointsEncode";
+  const ge_p3 *pts; int count; uint8_t *out;
+  HD void operator()(long) const {
+    ge_p3 acc; ge_identity(acc);
+    for (int i = 0; i < count; i++) { ge_p3 t; load_struct(t, &pts[i]); ge_add(acc, acc, t); }
+    ristretto_encode(out, acc);
   }
 };

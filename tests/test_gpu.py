@@ -50,6 +50,7 @@ def test_batch_witness_program_and_public_inputs(api, gens): E.test_batch_witnes
 def test_batch_aux_inputs_bound_check(api, gens): E.test_batch_aux_inputs_bound_check(api, gens)
 def test_explicit_witness_equals_witness_program(api, gens, oracle_lib): E.test_explicit_witness_equals_witness_program(api, gens, oracle_lib)
 def test_chunking_is_invisible(api, gens, monkeypatch): E.test_chunking_is_invisible(api, gens, monkeypatch)
+def test_msm_path_choice_is_invisible(api, gens, monkeypatch): E.test_msm_path_choice_is_invisible(api, gens, monkeypatch)
 def test_error_codes(api, gens): E.test_error_codes(api, gens)
 def test_single_multiplier_and_allocate_single(api, gens): E.test_single_multiplier_and_allocate_single(api, gens)
 
@@ -75,6 +76,36 @@ def test_msm_entry_larger_sizes(api, gens_big, oracle_lib, path, monkeypatch):
         out = np.zeros(32, np.uint8)
         assert oracle_lib.lib().bpo_msm(n, arr.ctypes.data_as(CO.u8p), og.ctypes.data_as(CO.u8p), out.ctypes.data_as(CO.u8p)) == 0
         assert d_out.cpu().numpy().tobytes() == out.tobytes(), n
+
+
+def test_msm_entry_split_sorted_path(api, oracle_lib):
+    """n >= 32768 goes through the split sorted-bucket path (sub-instances of consecutive rows through the batched sort /
+    accumulate / reduce kernels, partial results summed): bit-exact against the C oracle's Pippenger at 32768 and 40000
+    generators (ragged last sub-instance), and linear in the scalars at 2^17 (sum of two MSMs = MSM of the sums)"""
+    import torch
+    g = api.Gens(1 << 17)
+    og = np.zeros((40000, 32), np.uint8)
+    oracle_lib.lib().bpo_ensure_gens(40000)
+    oracle_lib.lib().bpo_gens_compressed(0, 40000, og.ctypes.data_as(CO.u8p))
+
+    def msm(sc):
+        arr = api.scalars_to_array(sc)
+        d_in = torch.from_numpy(arr).cuda()
+        d_out = torch.zeros(32, dtype=torch.uint8, device="cuda")
+        assert api.load().bp_msm_gens_device(g._h, len(sc), C.c_void_p(d_in.data_ptr()), C.c_void_p(d_out.data_ptr()), None) == 0
+        torch.cuda.synchronize()
+        return arr, d_out.cpu().numpy().tobytes()
+    for n, seed in ((32768, 11), (40000, 12)):
+        sc = H.rand_scalars(seed, n)
+        sc[5] = 0; sc[6] = 1; sc[7] = L - 1; sc[n - 1] = 2 ** 252
+        arr, got = msm(sc)
+        out = np.zeros(32, np.uint8)
+        assert oracle_lib.lib().bpo_msm(n, arr.ctypes.data_as(CO.u8p), og.ctypes.data_as(CO.u8p), out.ctypes.data_as(CO.u8p)) == 0
+        assert got == out.tobytes(), n
+    n = 1 << 17
+    a, b = H.rand_scalars(21, n), H.rand_scalars(22, n)
+    _, Pa = msm(a); _, Pb = msm(b); _, Pab = msm([(x + y) % L for x, y in zip(a, b)])
+    assert R.ristretto_encode(R.pt_add(R.ristretto_decode(Pa), R.ristretto_decode(Pb))) == Pab
 
 
 def _oracle_circuit(build, m, label):

@@ -176,6 +176,24 @@ def test_chunking_is_invisible(api, gens, monkeypatch):
     assert not st.any()
 
 
+def test_msm_path_choice_is_invisible(api, gens, monkeypatch):
+    """the direct 8-bit tables (small instances) and the sorted-bucket path on the 15-bit shift table (>= 8192 rows per
+    instance by default) must give the same proof bytes and the same verdicts: force each path on a small circuit"""
+    from bulletproofs_r1cs_gadgets_b200 import workloads
+    wl = workloads.Mimc(gens, rounds=5)
+    inp = wl.inputs(0, 3)
+    outs = []
+    for min_rows in ("1000000000", "0"):
+        monkeypatch.setenv("BP_B200_SORTED_MIN_ROWS", min_rows)
+        V, P, st = wl.circuit.prove_batch(gens, wl.label, inp["v"], inp["v_blinding"], inp["entropy"], pub=inp["pub"])
+        assert not st.any()
+        assert not wl.circuit.verify_batch(gens, wl.label, V, P, inp["entropy"], pub=inp["pub"]).any()
+        bad = inp["pub"].copy(); bad[1, 0, 0] ^= 1
+        assert wl.circuit.verify_batch(gens, wl.label, V, P, inp["entropy"], pub=bad).tolist() == [0, 3, 0]
+        outs.append((V.tobytes(), P.tobytes()))
+    assert outs[0] == outs[1]
+
+
 def test_error_codes(api, gens):
     small = api.Gens(8)
     case = H.golden_cases()[0]  # mimc5: n = 10 -> N = 16 > 8

@@ -44,7 +44,7 @@ for cap_log in ([15, max_log] if max_log > 15 else [max_log]):
             e1.record(); torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / reps
             gbs = 64.0 * n / (ms / 1e3) / 1e9
-            row = {"log2_n": lg, "scalars": kind, "path": "fixed-base tables" if cap_log <= 15 else "bucket method", "ms": round(ms, 4),
+            row = {"log2_n": lg, "scalars": kind, "path": ("sorted buckets on the 15-bit shift table, split into sub-instances" if n >= 32768 else "direct 8-bit tables" if cap_log <= 15 else "bucket method"), "ms": round(ms, 4),
                    "Mterms_per_s": round(n / ms / 1e3, 2), "GB_per_s": round(gbs, 3), "hbm_peak_GB_per_s": peak, "frac_of_hbm": round(gbs / peak, 6),
                    "result": d_out.cpu().numpy().tobytes().hex()[:16]}
             print(json.dumps(row)); out.write(json.dumps(row) + "\n"); out.flush()
