@@ -153,10 +153,10 @@ int launch_sort_buckets(const RowMap &rmap, const int8_t *dig, long dig_inst_str
 #ifndef BP_HOST_EMUL
   if (ninst <= 0) return 0;
   if (g_profile_on) profile_begin("sort_buckets_kernel", ninst * SORT_THREADS, s);
-  static int mode = -1;  // 0: staged tiles, 1: direct scatter (default for windows of 15 bits and more)
+  static int mode = -1;  // 0: staged tiles (default), 1: direct scatter (BP_B200_SORT=direct)
   if (mode < 0) {
     const char *e = getenv("BP_B200_SORT");
-    mode = e ? (e[0] == 'd') : (SB_BITS >= 15);
+    mode = e ? (e[0] == 'd') : 0;  // measured at batch 8192: staged 855 ms, direct 1102 ms per step
     cudaFuncSetAttribute(sort_buckets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM_BYTES);
     cudaFuncSetAttribute(sort_buckets_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM_BYTES);
   }
