@@ -448,6 +448,47 @@ class Circuit:
         return status
 
 
+def _verify_batch_combined(self, gens, label, V, proofs, entropy, pub=None):
+    """cross-proof batched verification: returns (status [B] of the structural checks, combined verdict 0 / 3)"""
+    V, proofs, entropy = _np_u8(V), _np_u8(proofs), _np_u8(entropy)
+    pub = _np_u8(pub) if pub is not None else None
+    B = entropy.shape[0]
+    status = np.zeros(B, dtype=np.int32)
+    combined = C.c_int32(0)
+    f = load().bp_verify_batch_combined
+    f.restype = C.c_int32
+    _check(f(gens._h, self._h, C.c_uint32(B), _buf(label) if label else None, C.c_size_t(len(label)), V.ctypes.data_as(u8p),
+             proofs.ctypes.data_as(u8p), entropy.ctypes.data_as(u8p), pub.ctypes.data_as(u8p) if pub is not None else None,
+             status.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(combined)), "verify_batch_combined")
+    return status, int(combined.value)
+
+
+Circuit.verify_batch_combined = _verify_batch_combined
+
+
+def proof_to_wire(proof):
+    """untagged field tuple -> tagged wire form (App. A.7)"""
+    proof = bytes(proof)
+    out = (C.c_uint8 * (len(proof) + 1))()
+    f = load().bp_proof_to_wire
+    f.restype = C.c_int64
+    n = f(_buf(proof), C.c_size_t(len(proof)), out, C.c_size_t(len(proof) + 1))
+    if n < 0:
+        raise R1CSError(-n, "proof_to_wire")
+    return bytes(out[:n])
+
+
+def proof_from_wire(wire):
+    wire = bytes(wire)
+    out = (C.c_uint8 * (len(wire) + 96))()
+    f = load().bp_proof_from_wire
+    f.restype = C.c_int64
+    n = f(_buf(wire), C.c_size_t(len(wire)), out, C.c_size_t(len(wire) + 96))
+    if n < 0:
+        raise R1CSError(-n, "proof_from_wire")
+    return bytes(out[:n])
+
+
 def launch_count():
     return int(load().bp_launch_count())
 

@@ -421,6 +421,70 @@ int32_t bp_verify_batch_device(const bp_gens *g, bp_circuit *c, uint32_t B, cons
   }
   return BP_OK;
 }
+int32_t bp_verify_batch_combined_device(const bp_gens *g, bp_circuit *c, uint32_t B, const uint8_t *label, size_t label_len, const uint8_t *d_V,
+                                        const uint8_t *d_proofs, const uint8_t *d_entropy, const uint8_t *d_pub, int32_t *d_status, int32_t *d_combined,
+                                        void *stream) {
+  if (!g || !c || !d_V || !d_proofs || !d_entropy || !d_status || !d_combined || (label_len && !label)) return BP_ERR_INVALID_ARGUMENT;
+  BpCircuit *cc = c->c;
+#ifndef BP_HOST_EMUL
+  dev_stream s = (dev_stream)stream;
+#else
+  dev_stream s = 0; (void)stream;
+#endif
+  if (B == 0) return BP_OK;
+  if (chunk_size(cc, B) < B) return BP_ERR_INVALID_ARGUMENT;  // one combination per call: the batch must fit one device chunk
+  VerifyArgs a{}; a.B = (int)B; a.label = label; a.label_len = (int)label_len;
+  a.V = d_V; a.proofs = d_proofs; a.entropy = d_entropy; a.status = d_status; a.pub = d_pub;
+  return engine_verify_combined(g->g, cc, a, d_combined, s);
+}
+int32_t bp_verify_batch_combined(const bp_gens *g, bp_circuit *c, uint32_t B, const uint8_t *label, size_t label_len, const uint8_t *V,
+                                 const uint8_t *proofs, const uint8_t *entropy, const uint8_t *pub, int32_t *status, int32_t *combined) {
+  if (!g || !c || !V || !proofs || !entropy || !status || !combined) return BP_ERR_INVALID_ARGUMENT;
+  *combined = BP_OK;
+  if (B == 0) return BP_OK;
+  BpCircuit *cc = c->c;
+  const size_t m = cc->m, plen = circuit_proof_len(cc);
+  DevBuf dV, dP, de, dS, dpb, dC;
+  const size_t np_ = cc->npub;
+  if (np_ && !pub) return BP_ERR_MISSING_ASSIGNMENT;
+  if (dV.alloc(B * m * 32 + 32) || dP.alloc(B * plen) || de.alloc((size_t)B * 32) || dS.alloc(B * sizeof(int)) || dpb.alloc(B * np_ * 32 + 32) || dC.alloc(sizeof(int))) return BP_ERR_OOM;
+  dev_stream s = 0;
+  if (np_ && dev_h2d(dpb.p, pub, B * np_ * 32, s)) return BP_ERR_CUDA;
+  int bad = dev_h2d(dV.p, V, B * m * 32, s) | dev_h2d(dP.p, proofs, B * plen, s) | dev_h2d(de.p, entropy, (size_t)B * 32, s);
+  if (bad) return BP_ERR_CUDA;
+  int rc = bp_verify_batch_combined_device(g, c, B, label, label_len, dV.p, dP.p, de.p, np_ ? dpb.p : nullptr, (int32_t *)dS.p, (int32_t *)dC.p, nullptr);
+  if (rc) return rc;
+  bad = dev_d2h(status, dS.p, B * sizeof(int), s) | dev_d2h(combined, dC.p, sizeof(int), s) | dev_sync(s);
+  return bad ? BP_ERR_CUDA : BP_OK;
+}
+
+// ---- wire format (App. A.7) ----
+int64_t bp_proof_to_wire(const uint8_t *proof, size_t proof_len, uint8_t *out, size_t out_cap) {
+  if (!proof || !out) return -(int64_t)BP_ERR_INVALID_ARGUMENT;
+  if (proof_len < 16 * 32 || proof_len % 32) return -(int64_t)BP_ERR_FORMAT;
+  bool one_phase = true;
+  for (int i = 96; i < 192; i++) one_phase &= proof[i] == 0;  // A_I2, A_O2, S2 all the identity encoding
+  const size_t need = one_phase ? 1 + proof_len - 96 : 1 + proof_len;
+  if (out_cap < need) return -(int64_t)BP_ERR_INVALID_ARGUMENT;
+  out[0] = one_phase ? 0 : 1;
+  memcpy(out + 1, proof, 96);
+  if (one_phase) memcpy(out + 97, proof + 192, proof_len - 192); else memcpy(out + 97, proof + 96, proof_len - 96);
+  return (int64_t)need;
+}
+int64_t bp_proof_from_wire(const uint8_t *wire, size_t wire_len, uint8_t *proof_out, size_t out_cap) {
+  if (!wire || !proof_out) return -(int64_t)BP_ERR_INVALID_ARGUMENT;
+  if (wire_len < 1 || wire[0] > 1) return -(int64_t)BP_ERR_FORMAT;
+  const bool one_phase = wire[0] == 0;
+  const size_t body = wire_len - 1;
+  if (body % 32 || body < (size_t)(one_phase ? 13 : 16) * 32) return -(int64_t)BP_ERR_FORMAT;
+  const size_t need = one_phase ? body + 96 : body;
+  if ((need / 32 - 14) % 2) return -(int64_t)BP_ERR_FORMAT;  // 14 fixed elements + L/R pairs + a, b
+  if (out_cap < need) return -(int64_t)BP_ERR_INVALID_ARGUMENT;
+  memcpy(proof_out, wire + 1, 96);
+  if (one_phase) { memset(proof_out + 96, 0, 96); memcpy(proof_out + 192, wire + 97, body - 96); } else memcpy(proof_out + 96, wire + 97, body - 96);
+  return (int64_t)need;
+}
+
 int32_t bp_verify_batch(const bp_gens *g, bp_circuit *c, uint32_t B, const uint8_t *label, size_t label_len, const uint8_t *V, const uint8_t *proofs,
                         const uint8_t *entropy, const uint8_t *pub, int32_t *status) {
   if (!g || !c || !V || !proofs || !entropy || !status) return BP_ERR_INVALID_ARGUMENT;

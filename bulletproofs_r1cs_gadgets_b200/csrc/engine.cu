@@ -662,12 +662,16 @@ int engine_commit(const BpGens *g, int count, const uint8_t *v, const uint8_t *r
 }
 
 // ------------------------------------------------------------------------------------------------ MSM microbenchmark entry
-// One MSM over the first n generators of chain G.  Large n: split into sub-instances of R consecutive rows that go through the
+// One MSM over `nrows` rows of shared generators (row -> generator through `mode`: 3 = chain G in order, 5 = the combined
+// verification layout G.., H.., B, B_blinding).  The rows are split into sub-instances of R consecutive rows that go through the
 // batched sorted-bucket kernels (sort, accumulate, reduce) like the proofs of a batch do; their partial results are summed.
-static int msm_gens_sorted(BpGens *g, uint32_t n, const uint8_t *d_scalars, uint8_t *d_out, dev_stream s) {
-  long R = n / 64; if (R < 8192) R = 8192; if (R > 32768) R = 32768; if (R > (long)n) R = n;
-  const long S = ((long)n + R - 1) / R;
-  if (!g->msm_ws || g->msm_ws_n < n || !g->msm_ws->items) {
+// scalars: d_bytes (canonical 32-byte scalars) or d_scm (Montgomery form already on the device); result encoded to d_out or
+// kept as a point in out_p3.  Uses the generator set's own scratch workspace.
+static int sorted_split_msm(BpGens *g, long nrows, const uint8_t *d_bytes, const scm *d_scm, int mode, long mapN, uint8_t *d_out, ge_p3 *out_p3,
+                            dev_stream s) {
+  long R = nrows / 64; if (R < 8192) R = 8192; if (R > 32768) R = 32768; if (R > nrows) R = nrows;
+  const long S = (nrows + R - 1) / R;
+  if (!g->msm_ws || (long)g->msm_ws_n < nrows || !g->msm_ws->items) {
     if (g->msm_ws) { g->msm_ws->release(); delete g->msm_ws; }
     Workspace *w = g->msm_ws = new Workspace();
     w->items_cap = (size_t)R * SB_WINDOWS;
@@ -678,14 +682,17 @@ static int msm_gens_sorted(BpGens *g, uint32_t n, const uint8_t *d_scalars, uint
         dalloc(&w->boff, (size_t)(SB_BUCKETS + 1) * S) || dalloc(&w->soff, (size_t)(SB_BUCKETS + 1) * S) || dalloc(&w->seg, (size_t)SB_SEGS * 2 * S)) {
       w->release(); delete w; g->msm_ws = nullptr; return BP_ERR_OOM;
     }
-    g->msm_ws_n = n;
+    g->msm_ws_n = (uint32_t)nrows;
   }
   Workspace *w = g->msm_ws;
-  if ((size_t)S * R * SB_ROW_BYTES > w->dig_bytes || (size_t)R * SB_WINDOWS > w->items_cap) return BP_ERR_OOM;
-  CK(dev_memset(w->dig, 0, (size_t)S * R * SB_ROW_BYTES, s));  // rows past n stay all-zero digits
-  CK(launch(n, s, KLoadScalars{d_scalars, w->a, (int)n, 1}));
-  CK(launch(n, s, KRecode13{w->a, nullptr, (int)n, 1, w->dig, 0, 0}));  // B = 1: row i at dig + i * SB_ROW_BYTES = sub-instance i / R, row i % R
-  RowMap rm{3, nullptr, (long)g->capacity, 0, 0, 0, R};
+  if ((size_t)S * R * SB_ROW_BYTES > w->dig_bytes || (size_t)R * SB_WINDOWS > w->items_cap || (size_t)S * w->slices_cap + S + 1 > w->bucket_slots) {
+    g->msm_ws_n = 0;  // geometry of an earlier, different size: rebuild
+    return sorted_split_msm(g, nrows, d_bytes, d_scm, mode, mapN, d_out, out_p3, s);
+  }
+  CK(dev_memset(w->dig, 0, (size_t)S * R * SB_ROW_BYTES, s));  // rows past nrows stay all-zero digits
+  if (d_bytes) { CK(launch(nrows, s, KLoadScalars{d_bytes, w->a, (int)nrows, 1})); d_scm = w->a; }
+  CK(launch(nrows, s, KRecode13{d_scm, nullptr, (int)nrows, 1, w->dig, 0, 0}));  // B = 1: row i at dig + i * SB_ROW_BYTES = sub-instance i / R, row i % R
+  RowMap rm{mode, nullptr, (long)g->capacity, mapN, 0, 0, R};
   CK(launch_sort_buckets(rm, w->dig, R * SB_ROW_BYTES, R, S, w->items, (long)w->items_cap, w->boff, w->soff, s));
   SortedView sv{w->items, w->boff, w->soff, (long)w->items_cap, (long)w->slices_cap};
   const long segs = (R * SB_WINDOWS + SB_SEG - 1) / SB_SEG;
@@ -693,8 +700,12 @@ static int msm_gens_sorted(BpGens *g, uint32_t n, const uint8_t *d_scalars, uint
   CK(launch(S * segs, s, KBucketAccumulate{g->sg, sv, w->buckets, segs}));
   CK(launch(S * SB_SEGS, s, KBucketReduce{w->buckets, sv, w->seg}));
   CK(launch(S, s, KBucketFinish{w->seg, nullptr, 0, partial}));
-  CK(launch(1, s, KSumPointsEncode{partial, (int)S, d_out}));
+  if (out_p3) CK(launch(1, s, KSumPointsStrided{partial, S, 1, out_p3}));
+  else CK(launch(1, s, KSumPointsEncode{partial, (int)S, d_out}));
   return BP_OK;
+}
+static int msm_gens_sorted(BpGens *g, uint32_t n, const uint8_t *d_scalars, uint8_t *d_out, dev_stream s) {
+  return sorted_split_msm(g, n, d_scalars, nullptr, 3, 0, d_out, nullptr, s);
 }
 int engine_msm_gens(BpGens *g, uint32_t n, const uint8_t *d_scalars, uint8_t *d_out, dev_stream s) {
   if (n == 0 || n > g->capacity) return BP_ERR_INVALID_GENERATORS_LENGTH;
@@ -727,6 +738,74 @@ int engine_msm_gens(BpGens *g, uint32_t n, const uint8_t *d_scalars, uint8_t *d_
   return run_msm(w, seg, 1, 1, w->dig, (long)n * 32, d_out, 32, 0, nullptr, s);
 }
 
+// ------------------------------------------------------------------------------------------------ combined verification
+// Cross-proof batched verification: the B verification equations  sum_j s_{p,j} P_{p,j} = 0  are combined with
+// random weights rho_p drawn from each proof's verifier RNG (so they depend on the verifier's entropy and on the whole
+// transcript of the proof):  sum_p rho_p * (equation p) = 0.  The generator rows (G_i, H_i, B, B_blinding) are shared by all
+// proofs, so their weighted scalars are SUMMED over the batch and the 2N + 2 rows are paid once per batch instead of once per
+// proof; only the ~110 points that belong to a proof (A_*, S, V_j, T_*, L_j, R_j) remain per-proof work.  A batch of valid
+// proofs always passes; a batch containing an invalid proof passes with probability 2^-252.  Proofs failing a structural check
+// (non-canonical scalar, undecodable or identity point) get their status set and weight zero.  *combined = 0 or BP_ERR_VERIFICATION.
+int engine_verify_combined(BpGens *g, BpCircuit *c, const VerifyArgs &A, int *d_combined, dev_stream s) {
+  const int B = A.B;
+  if (B <= 0) return BP_OK;
+  if (g->capacity < c->N) return BP_ERR_INVALID_GENERATORS_LENGTH;
+  if (c->npub && !A.pub) return BP_ERR_MISSING_ASSIGNMENT;
+  if (!g->sg) return BP_ERR_INVALID_ARGUMENT;  // needs the shift table of the sorted-bucket path
+  int rc = ensure_workspace(c, B);
+  if (rc) return rc;
+  Workspace *w = c->ws;
+  const long n = c->n, N = c->N, m = c->m, q = c->q, k = c->k;
+  const long plen = (long)circuit_proof_len(c);
+  const long npts = 11 + m + 2 * k, chunks = (B + 31) / 32, Bp = chunks * 32;
+  if ((size_t)B * MSM_WINDOWS * MSM_BUCKETS > w->bucket_slots || (size_t)B * npts * 32 > w->dig_bytes) return BP_ERR_OOM;
+  scm *wL = w->w_all, *wR = w->w_all + n * B, *wO = w->w_all + 2 * n * B, *wV = w->w_all + 3 * n * B, *wc = w->w_all + (3 * n + m) * B,
+      *wP = w->w_all + (3 * n + m + 1) * B;
+  scm *ch_z = w->chal + B, *ch_yinv = w->chal + 2L * B, *rho = w->chal + 7L * B, *rowB = w->chal + 8L * B, *rowBb = w->chal + 9L * B;
+  scm *uj = w->uj, *ujinv = w->uj + (k + 1) * B;
+  // the N x chunks partial sums of the G and H scalars reuse the b vector and the y^i table (not needed by a verifier); the
+  // 2N + 2 combined rows sit behind the 8-bit digit rows of the per-proof points
+  const size_t dig8_bytes = (((size_t)B * npts * 32) + 31) & ~(size_t)31;
+  if (dig8_bytes + (size_t)(2 * N + 2) * sizeof(scm) > w->dig_bytes) return BP_ERR_OOM;
+  scm *partG = w->b, *partH = w->ypow, *rows = (scm *)(w->dig + dig8_bytes);
+  CK(dev_memset(A.status, 0, sizeof(int) * B, s));
+  strobe128 base; base_transcript(base, A.label, A.label_len);
+  CK(launch(B, s, KTsVerify{base, A.V, (int)m, B, (int)k, (unsigned)N, A.proofs, plen, A.entropy, w->chal, uj, ujinv, A.status, 1}));
+  CK(launch(npts * B, s, KVerifyDecompress{A.V, A.proofs, plen, (int)m, (int)k, B, w->pts, npts, A.status}));
+  CK(launch(B, s, KVerifyMaskRho{A.status, rho}));
+  CK(launch(((q + CH_POW - 1) / CH_POW) * B, s, KPowers{ch_z, w->zpow, (int)q, B, 1, CH_POW}));
+  CK(launch(((N + CH_POW - 1) / CH_POW) * B, s, KPowers{ch_yinv, w->yinvpow, (int)N, B, 0, CH_POW}));
+  CK(launch((long)c->nslots * B, s, KFlatten{c->d_slot_ptr, c->d_tq, c->d_tcoeff, w->zpow, w->w_all, B}));
+  if (c->npub) CK(launch((long)c->npub * B, s, KLoadScalars{A.pub, w->vpub, (int)c->npub, B}));
+  CK(launch(N * B, s, KVerifyS{uj, ujinv, (int)k, B, w->a}));
+  {
+    long nch = (n + CH_DOT - 1) / CH_DOT; if (nch == 0) nch = 1;
+    CK(launch(nch * B, s, KVerifyDelta{wL, wR, w->yinvpow, (int)n, B, CH_DOT, w->part}));
+    CK(launch(B, s, KSumPartials{w->part, (int)nch, 1, B, w->clr}));
+  }
+#ifdef BP_HOST_EMUL
+  CK(dev_memset(partG, 0, sizeof(scm) * chunks * N, s)); CK(dev_memset(partH, 0, sizeof(scm) * chunks * N, s));
+#endif
+  CK(launch(N * Bp, s, KVerifyGH{wL, wR, wO, w->yinvpow, w->a, w->chal, A.proofs, plen, (int)n, (int)N, (int)k, B, nullptr, 0, nullptr, nullptr, rho, partG, partH}));
+  CK(launch(B, s, KVerifyScalars{w->chal, uj, ujinv, wV, wc, wP, w->vpub, w->clr, A.proofs, plen, (int)m, (int)c->npub, (int)N, (int)k, B, w->dig, npts * 32,
+                                 nullptr, nullptr, rho, rowB, rowBb}));
+  // rows of the single shared-generator MSM (KFlatten is done with the z^q table by now)
+  CK(launch(2 * N + 2, s, KVerifyCombineRows{partG, partH, rowB, rowBb, (int)N, B, rows}));
+  // per-proof points: bucket method per proof, Horner per proof, then a two-level sum
+  MsmSeg seg[1] = {{w->pts, npts, 1, (int)npts}};
+  KMsmAccumulate ka{};
+  ka.seg[0] = seg[0]; ka.nseg = 1; ka.S = 1; ka.dig = w->dig; ka.dig_inst_stride = npts * 32; ka.buckets = w->buckets; ka.wsum = w->wsum;
+  CK(launch((long)B * MSM_WINDOWS, s, ka));
+  ge_p3 *pp = w->buckets + (size_t)B * MSM_WINDOWS * MSM_BUCKETS;  // [B] per-proof parts, then [T + 1] partial sums, behind the buckets in use
+  const long T = B < 64 ? B : 64;
+  if ((size_t)B * MSM_WINDOWS * MSM_BUCKETS + (size_t)B + T + 1 > w->bucket_slots) return BP_ERR_OOM;
+  CK(launch(B, s, KVerifyProofPoint{w->wsum, pp}));
+  CK(launch(T, s, KSumPointsStrided{pp, B, T, pp + B}));
+  rc = sorted_split_msm(g, 2 * N + 2, nullptr, rows, 5, N, nullptr, pp + B + T, s); if (rc) return rc;
+  CK(launch(1, s, KVerifyCombinedCheck{pp + B, (int)(T + 1), d_combined}));
+  return BP_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ verifier (A.5)
 int engine_verify(const BpGens *g, BpCircuit *c, const VerifyArgs &A, dev_stream s) {
   const int B = A.B;
@@ -744,7 +823,7 @@ int engine_verify(const BpGens *g, BpCircuit *c, const VerifyArgs &A, dev_stream
   scm *uj = w->uj, *ujinv = w->uj + (k + 1) * B;
   CK(dev_memset(A.status, 0, sizeof(int) * B, s));
   strobe128 base; base_transcript(base, A.label, A.label_len);
-  CK(launch(B, s, KTsVerify{base, A.V, (int)m, B, (int)k, (unsigned)N, A.proofs, plen, A.entropy, w->chal, uj, ujinv, A.status}));
+  CK(launch(B, s, KTsVerify{base, A.V, (int)m, B, (int)k, (unsigned)N, A.proofs, plen, A.entropy, w->chal, uj, ujinv, A.status, 0}));
   CK(launch(((q + CH_POW - 1) / CH_POW) * B, s, KPowers{ch_z, w->zpow, (int)q, B, 1, CH_POW}));
   CK(launch(((N + CH_POW - 1) / CH_POW) * B, s, KPowers{ch_yinv, w->yinvpow, (int)N, B, 0, CH_POW}));
   CK(launch((long)c->nslots * B, s, KFlatten{c->d_slot_ptr, c->d_tq, c->d_tcoeff, w->zpow, w->w_all, B}));
@@ -764,8 +843,8 @@ int engine_verify(const BpGens *g, BpCircuit *c, const VerifyArgs &A, dev_stream
   int8_t *wideG = sorted ? w->dig : nullptr, *wideH = sorted ? w->dig + (size_t)B * (N + 1) * SB_ROW_BYTES : nullptr;
   int8_t *dig8 = sorted ? w->dig + (size_t)B * 2 * (N + 1) * SB_ROW_BYTES : w->dig;
   const long stride8 = sorted ? npts * 32 : rows * 32;
-  CK(launch(N * B, s, KVerifyGH{wL, wR, wO, w->yinvpow, w->a, w->chal, A.proofs, plen, (int)n, (int)N, (int)k, B, dig8, stride8, wideG, wideH}));
-  CK(launch(B, s, KVerifyScalars{w->chal, uj, ujinv, wV, wc, wP, w->vpub, w->clr, A.proofs, plen, (int)m, (int)c->npub, (int)N, (int)k, B, dig8, stride8, wideG, wideH}));
+  CK(launch(N * B, s, KVerifyGH{wL, wR, wO, w->yinvpow, w->a, w->chal, A.proofs, plen, (int)n, (int)N, (int)k, B, dig8, stride8, wideG, wideH, nullptr, nullptr, nullptr}));
+  CK(launch(B, s, KVerifyScalars{w->chal, uj, ujinv, wV, wc, wP, w->vpub, w->clr, A.proofs, plen, (int)m, (int)c->npub, (int)N, (int)k, B, dig8, stride8, wideG, wideH, nullptr, nullptr, nullptr}));
   CK(launch(npts * B, s, KVerifyDecompress{A.V, A.proofs, plen, (int)m, (int)k, B, w->pts, npts, A.status}));
   if (sorted) {
     // the ~110 per-proof points first (bucket method, result in wsum), then the two generator halves through the sorted path;

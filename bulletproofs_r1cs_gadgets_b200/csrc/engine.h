@@ -73,6 +73,8 @@ struct VerifyArgs {
   int *status;             // [B] device
 };
 int engine_verify(const BpGens *g, BpCircuit *c, const VerifyArgs &a, dev_stream s);
+// cross-proof batched verification: per-proof structural status + one combined verdict (device int)
+int engine_verify_combined(BpGens *g, BpCircuit *c, const VerifyArgs &a, int *d_combined, dev_stream s);
 
 // one-off helper: commitments a*B + b*B_blinding for host scalars
 int engine_commit(const BpGens *g, int count, const uint8_t *v, const uint8_t *r, uint8_t *out);

@@ -872,7 +872,7 @@ struct KTsVerify {
   static constexpr int kBlock = 64, kMinBlocks = 1;
   static constexpr const char *kName = "KTsVerify";
   strobe128 base; const uint8_t *V; int m, B, k; unsigned N; const uint8_t *proofs; long proof_stride; const uint8_t *entropy;
-  scm *chal; scm *uj, *ujinv; int *status;
+  scm *chal; scm *uj, *ujinv; int *status; int combined;  // combined: also draw the batching weight rho_p (chal slot 7)
   HD static int is_zero32(const uint8_t *b) { uint8_t nz = 0; for (int i = 0; i < 32; i++) nz |= b[i]; return nz == 0; }
   HD void operator()(long p) const {
     strobe128 t; strobe_load(t, &base);
@@ -910,6 +910,7 @@ struct KTsVerify {
     trng_finalize(t, entropy + p * 32);
     { uint8_t b[64]; trng_fill(t, b, 64); r = sc_from_bytes_wide(b); }
     chal[p] = y; chal[B + p] = z; chal[2L * B + p] = sc_invert(y); chal[3L * B + p] = u; chal[4L * B + p] = x; chal[5L * B + p] = w; chal[6L * B + p] = r;
+    if (combined) { uint8_t b[64]; trng_fill(t, b, 64); chal[7L * B + p] = sc_from_bytes_wide(b); }
     if (st) status[p] = st;
   }
 };
@@ -944,7 +945,11 @@ struct KVerifyGH {
   static constexpr const char *kName = "KVerifyGH";
   const scm *wL, *wR, *wO, *yinvpow, *s, *chal; const uint8_t *proofs; long proof_stride; int n, N, k, B; int8_t *dig; long inst_stride;
   int8_t *wideG, *wideH;  // non-NULL: 15-bit digit rows for the sorted-bucket path, [B][N + 1] rows each (row 0 = B / B_blinding)
+  // combined (cross-proof) mode: launched over round_up(B, 32) proofs per row; the rho-weighted scalars of 32 consecutive
+  // proofs are summed (warp shuffles) into partG / partH [chunk][N]
+  const scm *rho; scm *partG, *partH;
   HD void operator()(long tid) const {
+    if (rho) { combined(tid); return; }
     int p = (int)(tid % B); long i = tid / B; long at = i * B + p;
     scm x = chal[4L * B + p], u = chal[3L * B + p];
     const uint8_t *pf = proofs + p * proof_stride + 448 + 64 * k;
@@ -969,6 +974,66 @@ struct KVerifyGH {
     sc_recode_bytes(d, g); store_digits(row + (2 + i) * 32, d);
     sc_recode_bytes(d, hh); store_digits(row + (2 + N + i) * 32, d);
   }
+  HD void gh(long i, int p, scm &g, scm &hh) const {
+    long at = i * B + p;
+    scm x = chal[4L * B + p], u = chal[3L * B + p];
+    const uint8_t *pf = proofs + p * proof_stride + 448 + 64 * k;
+    scm a = sc_from_bytes_mod_order(pf), b = sc_from_bytes_mod_order(pf + 32);
+    scm yi = yinvpow[at];
+    g = sc_neg(sc_mul(a, s[at]));
+    hh = sc_neg(sc_mul(b, s[(long)(N - 1 - i) * B + p]));
+    if (i < n) {
+      g = sc_add(g, sc_mul(x, sc_mul(yi, wR[at])));
+      hh = sc_add(hh, sc_add(sc_mul(x, wL[at]), wO[at]));
+    }
+    hh = sc_sub(sc_mul(yi, hh), sc_one());
+    if (i >= n) { g = sc_mul(g, u); hh = sc_mul(hh, u); }
+  }
+  HD void combined(long tid) const {
+    const int Bp = (B + 31) & ~31;
+    int p = (int)(tid % Bp); long i = tid / Bp;
+    scm g = sc_zero(), hh = sc_zero();
+    if (p < B) { gh(i, p, g, hh); scm r = rho[p]; g = sc_mul(g, r); hh = sc_mul(hh, r); }
+    const long slot = (long)(p >> 5) * N + i;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      scm tg, th;
+#pragma unroll
+      for (int j = 0; j < 4; j++) { tg.v[j] = __shfl_down_sync(0xffffffffu, g.v[j], o); th.v[j] = __shfl_down_sync(0xffffffffu, hh.v[j], o); }
+      g = sc_add(g, tg); hh = sc_add(hh, th);
+    }
+    if ((p & 31) == 0) { partG[slot] = g; partH[slot] = hh; }
+#else
+    // host emulation runs the "threads" one after the other: accumulate in place (buffers zeroed by the caller)
+    partG[slot] = sc_add(partG[slot], g); partH[slot] = sc_add(partH[slot], hh);
+#endif
+  }
+};
+// combined mode: rows of the single cross-proof MSM = sums over the proof chunks; rows 2N, 2N+1 (B, B_blinding) = sums over proofs
+struct KVerifyCombineRows {
+  static constexpr int kBlock = 128, kMinBlocks = 1;
+  static constexpr const char *kName = "KVerifyCombineRows";
+  const scm *partG, *partH, *rowB, *rowBb; int N, B; scm *rows;  // rows[2N + 2]
+  HD void operator()(long r) const {
+    const int chunks = (B + 31) >> 5;
+    scm acc = sc_zero();
+    if (r < 2L * N) {
+      const scm *part = r < N ? partG : partH; const long i = r < N ? r : r - N;
+      for (int c = 0; c < chunks; c++) acc = sc_add(acc, part[(long)c * N + i]);
+    } else {
+      const scm *src = r == 2L * N ? rowB : rowBb;
+      for (int p = 0; p < B; p++) acc = sc_add(acc, src[p]);
+    }
+    rows[r] = acc;
+  }
+};
+// combined mode: proofs that failed a structural check (status != 0) take no part in the combination
+struct KVerifyMaskRho {
+  static constexpr int kBlock = 128, kMinBlocks = 1;
+  static constexpr const char *kName = "KVerifyMaskRho";
+  const int *status; scm *rho;
+  HD void operator()(long p) const { if (status[p] != 0) rho[p] = sc_zero(); }
 };
 // remaining scalars: rows 0,1 (B, B_blinding) and the per-proof points after the generators:
 // A_I1 A_O1 S1 A_I2 A_O2 S2 | V_0..V_{m-1} | T_1 T_3 T_4 T_5 T_6 | L_0.. | R_0..
@@ -977,7 +1042,8 @@ struct KVerifyScalars {
   static constexpr const char *kName = "KVerifyScalars";
   const scm *chal, *uj, *ujinv, *wV, *wc, *wP, *pub, *delta; const uint8_t *proofs; long proof_stride; int m, npub, N, k, B; int8_t *dig; long inst_stride;
   int8_t *wideG, *wideH;  // as in KVerifyGH: rows 0 (B, B_blinding) go there when set
-  HD void put(int8_t *row, long r, const scm &v) const { int8_t d[32]; sc_recode_bytes(d, v); store_digits(row + r * 32, d); }
+  const scm *rho; scm *rowB, *rowBb;  // combined mode: every scalar of proof p is weighted by rho[p]; the B / B_blinding scalars go to rowB / rowBb
+  HD void put(long p, int8_t *row, long r, const scm &v) const { int8_t d[32]; sc_recode_bytes(d, rho ? sc_mul(v, rho[p]) : v); store_digits(row + r * 32, d); }
   HD void putw(int8_t *base, long p, const scm &v) const { int16_t dw[SB_WINDOWS]; sc_recode13(dw, v); store_digits13(base + p * (long)(N + 1) * SB_ROW_BYTES, dw); }
   HD void operator()(long p) const {
     const uint8_t *pf = proofs + p * proof_stride;
@@ -989,18 +1055,19 @@ struct KVerifyScalars {
     scm wcv = wc[p];
     for (int i = 0; i < npub; i++) wcv = sc_add(wcv, sc_mul(wP[(long)i * B + p], pub[(long)i * B + p]));
     scm bsc = sc_add(sc_mul(w, sc_sub(t_x, sc_mul(a, b))), sc_mul(r, sc_sub(sc_mul(xx, sc_add(wcv, delta[p])), t_x)));
-    if (wideG) { putw(wideG, p, bsc); putw(wideH, p, sc_neg(sc_add(e_b, sc_mul(r, t_xb)))); }
-    else { put(row, 0, bsc); put(row, 1, sc_neg(sc_add(e_b, sc_mul(r, t_xb)))); }
-    long o = wideG ? 0 : 2 + 2L * N;  // wide mode: the 8-bit rows hold the per-proof points only
-    put(row, o + 0, x); put(row, o + 1, xx); put(row, o + 2, xxx);
-    put(row, o + 3, sc_mul(u, x)); put(row, o + 4, sc_mul(u, xx)); put(row, o + 5, sc_mul(u, xxx));
+    if (rho) { rowB[p] = sc_mul(bsc, rho[p]); rowBb[p] = sc_mul(sc_neg(sc_add(e_b, sc_mul(r, t_xb))), rho[p]); }
+    else if (wideG) { putw(wideG, p, bsc); putw(wideH, p, sc_neg(sc_add(e_b, sc_mul(r, t_xb)))); }
+    else { put(p, row, 0, bsc); put(p, row, 1, sc_neg(sc_add(e_b, sc_mul(r, t_xb)))); }
+    long o = (wideG || rho) ? 0 : 2 + 2L * N;  // wide / combined mode: the 8-bit rows hold the per-proof points only
+    put(p, row, o + 0, x); put(p, row, o + 1, xx); put(p, row, o + 2, xxx);
+    put(p, row, o + 3, sc_mul(u, x)); put(p, row, o + 4, sc_mul(u, xx)); put(p, row, o + 5, sc_mul(u, xxx));
     o += 6;
-    for (int j = 0; j < m; j++) put(row, o + j, sc_mul(wV[(long)j * B + p], rxx));
+    for (int j = 0; j < m; j++) put(p, row, o + j, sc_mul(wV[(long)j * B + p], rxx));
     o += m;
     scm rx = sc_mul(r, x);
-    put(row, o, rx); put(row, o + 1, sc_mul(rxx, x)); put(row, o + 2, sc_mul(rxx, xx)); put(row, o + 3, sc_mul(rxx, xxx)); put(row, o + 4, sc_mul(sc_mul(rxx, xx), xx));
+    put(p, row, o, rx); put(p, row, o + 1, sc_mul(rxx, x)); put(p, row, o + 2, sc_mul(rxx, xx)); put(p, row, o + 3, sc_mul(rxx, xxx)); put(p, row, o + 4, sc_mul(sc_mul(rxx, xx), xx));
     o += 5;
-    for (int j = 0; j < k; j++) { put(row, o + j, sc_sqr(uj[(long)j * B + p])); put(row, o + k + j, sc_sqr(ujinv[(long)j * B + p])); }
+    for (int j = 0; j < k; j++) { put(p, row, o + j, sc_sqr(uj[(long)j * B + p])); put(p, row, o + k + j, sc_sqr(ujinv[(long)j * B + p])); }
   }
 };
 // decompress the per-proof points in the order KVerifyScalars lays their scalars out
@@ -1074,8 +1141,9 @@ struct KTableBuild {
 struct RowMap { int mode; const uint32_t *map; long cap, N, nj, h; long inst_off; };  // inst_off: generator offset per instance (split MSM)
 HD long row_gen(const RowMap &m, long r) {
   if (m.mode == 0) return m.map[r];
-  if (m.mode == 3) return r;  // row r is generator r (+ inst * inst_off at the call site)
+  if (m.mode == 3) return r;  // (global) row r is generator r; sub-instance `inst` of a split MSM covers rows inst * inst_off ..
   if (m.mode == 4) return r == 0 ? 2 * m.cap + m.nj : m.nj * m.cap + (r - 1);  // verifier half nj (0: B, G_i; 1: B_blinding, H_i)
+  if (m.mode == 5) return r < m.N ? r : (r < 2 * m.N ? m.cap + (r - m.N) : 2 * m.cap + (r - 2 * m.N));  // combined check: G_0.., H_0.., B, B_blinding
   if (r == m.N) return 2 * m.cap;  // B
   const long half = m.N / 2;
   const bool isH = r >= half;
@@ -1153,6 +1221,45 @@ struct KVerifyCheck {
     }
     for (int s = 0; s < S; s++) { ge_p3 t; load_struct(t, tpart_s_stride ? &tpart[s * tpart_s_stride + inst] : &tpart[inst * S + s]); ge_add(acc, acc, t); }
     if (!ge_is_identity_ristretto(acc) && status[inst] == 0) status[inst] = BP_ERR_VERIFICATION_;
+  }
+};
+
+// combined (cross-proof) verification: per-proof point part P_p = Horner over the window sums of proof p
+struct KVerifyProofPoint {
+  static constexpr int kBlock = 64, kMinBlocks = 1;
+  static constexpr const char *kName = "KVerifyProofPoint";
+  const ge_p3 *wsum; ge_p3 *out;
+  HD void operator()(long inst) const {
+    ge_p3 acc; load_struct(acc, &wsum[inst * MSM_WINDOWS + MSM_WINDOWS - 1]);
+    for (int w = MSM_WINDOWS - 2; w >= 0; w--) {
+      for (int i = 0; i < 7; i++) ge_dbl_p2(acc, acc);
+      ge_dbl(acc, acc);
+      ge_p3 sp; load_struct(sp, &wsum[inst * MSM_WINDOWS + w]);
+      ge_add(acc, acc, sp);
+    }
+    store_struct(&out[inst], acc);
+  }
+};
+// out[t] = sum of pts[t], pts[t + T], ...   (T threads)
+struct KSumPointsStrided {
+  static constexpr int kBlock = 64, kMinBlocks = 1;
+  static constexpr const char *kName = "KSumPointsStrided";
+  const ge_p3 *pts; long count, T; ge_p3 *out;
+  HD void operator()(long t) const {
+    ge_p3 acc; ge_identity(acc);
+    for (long j = t; j < count; j += T) { ge_p3 q; load_struct(q, &pts[j]); ge_add(acc, acc, q); }
+    store_struct(&out[t], acc);
+  }
+};
+// the one identity test of a combined verification: sum of `count` points (per-proof parts and the shared-generator part)
+struct KVerifyCombinedCheck {
+  static constexpr int kBlock = 32, kMinBlocks = 1;
+  static constexpr const char *kName = "KVerifyCombinedCheck";
+  const ge_p3 *pts; int count; int *combined;
+  HD void operator()(long) const {
+    ge_p3 acc; ge_identity(acc);
+    for (int i = 0; i < count; i++) { ge_p3 t; load_struct(t, &pts[i]); ge_add(acc, acc, t); }
+    *combined = ge_is_identity_ristretto(acc) ? 0 : BP_ERR_VERIFICATION_;
   }
 };
 
@@ -1320,7 +1427,7 @@ struct KSortBucketsSerial {
     uint32_t *it = items + inst * items_stride;
     for (long r = 0; r < rows; r++) {
       int16_t d[24]; load_digits13(d, drow + r * SB_ROW_BYTES);
-      const uint32_t g = (uint32_t)(row_gen(rmap, r) + inst * rmap.inst_off) * SB_WINDOWS;
+      const uint32_t g = (uint32_t)row_gen(rmap, r + inst * rmap.inst_off) * SB_WINDOWS;
       for (int w = 0; w < SB_WINDOWS; w++) if (d[w]) {
         int neg = d[w] < 0; int b = (neg ? -d[w] : d[w]) - 1;
         it[off[b]++] = (g + w) | ((uint32_t)neg << 31);

@@ -182,6 +182,27 @@ int32_t bp_verify_batch_device(const bp_gens *g, bp_circuit *c, uint32_t B, cons
                                const uint8_t *d_V, const uint8_t *d_proofs, const uint8_t *d_entropy, const uint8_t *d_pub, int32_t *d_status,
                                void *stream);
 
+/* Cross-proof batched verification (not part of the reference's dependency, which verifies one
+ * proof at a time -- bulletproofs::r1cs::Verifier::verify, reference call sites src/gadget_vsmt_2.rs:395).  The B verification
+ * equations are combined with random weights drawn from each proof's verifier RNG, so the 2N+2 generator rows shared by all
+ * proofs are paid once per batch.  status[p] reports structural failures only (BP_ERR_FORMAT / BP_ERR_VERIFICATION for a
+ * non-canonical scalar, an undecodable or an identity point); such proofs are left out of the combination.
+ * *combined = BP_OK when the combined equation of the remaining proofs holds, BP_ERR_VERIFICATION otherwise (then at least one
+ * of them is invalid: fall back to bp_verify_batch to find it).  A batch with an invalid proof passes with probability 2^-252.
+ * Needs the generators' shift table (capacity <= 2^22). */
+int32_t bp_verify_batch_combined(const bp_gens *g, bp_circuit *c, uint32_t B, const uint8_t *label, size_t label_len, const uint8_t *V,
+                                 const uint8_t *proofs, const uint8_t *entropy, const uint8_t *pub, int32_t *status, int32_t *combined);
+int32_t bp_verify_batch_combined_device(const bp_gens *g, bp_circuit *c, uint32_t B, const uint8_t *label, size_t label_len,
+                                        const uint8_t *d_V, const uint8_t *d_proofs, const uint8_t *d_entropy, const uint8_t *d_pub,
+                                        int32_t *d_status, int32_t *d_combined, void *stream);
+
+/* ---- wire format (SURVEY.md App. A.7, R1CSProof::to_bytes / from_bytes of the 2.0-era upstream; the reference itself never
+ * serialises a proof).  The library's proof buffers are the untagged field tuple (14 + 2k + 2 elements of 32 bytes).  The
+ * tagged form is 1 byte (0 = one-phase: A_I2, A_O2, S2 are the identity and are dropped; 1 = two-phase: all six kept) followed
+ * by the remaining elements.  Both return the number of bytes written, or a negative BP_ERR_* (FORMAT for a bad tag/length). */
+int64_t bp_proof_to_wire(const uint8_t *proof, size_t proof_len, uint8_t *out, size_t out_cap);
+int64_t bp_proof_from_wire(const uint8_t *wire, size_t wire_len, uint8_t *proof_out, size_t out_cap);
+
 /* ---- MSM microbenchmark entry (BASELINE.json config 3) -------------------------------------------
  * result = sum_i scalars[i] * points[i] over ristretto255; points are the first n generators of chain G.
  * d_scalars: device, [n][32] canonical LE.  out: device, 32 bytes. */

@@ -51,6 +51,8 @@ def test_batch_aux_inputs_bound_check(api, gens): E.test_batch_aux_inputs_bound_
 def test_explicit_witness_equals_witness_program(api, gens, oracle_lib): E.test_explicit_witness_equals_witness_program(api, gens, oracle_lib)
 def test_chunking_is_invisible(api, gens, monkeypatch): E.test_chunking_is_invisible(api, gens, monkeypatch)
 def test_msm_path_choice_is_invisible(api, gens, monkeypatch): E.test_msm_path_choice_is_invisible(api, gens, monkeypatch)
+def test_combined_verification(api, gens): E.test_combined_verification(api, gens)
+def test_wire_format(api, gens): E.test_wire_format(api, gens)
 def test_error_codes(api, gens): E.test_error_codes(api, gens)
 def test_single_multiplier_and_allocate_single(api, gens): E.test_single_multiplier_and_allocate_single(api, gens)
 

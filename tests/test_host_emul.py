@@ -194,6 +194,53 @@ def test_msm_path_choice_is_invisible(api, gens, monkeypatch):
     assert outs[0] == outs[1]
 
 
+def test_combined_verification(api, gens):
+    """cross-proof batched verification: one combined verdict for the batch, per-proof status for structural failures only"""
+    from bulletproofs_r1cs_gadgets_b200 import workloads
+    wl = workloads.Mimc(gens, rounds=5)
+    Bn = 37  # ragged against the 32-proof chunks of the scalar combination
+    inp = wl.inputs(0, Bn)
+    V, P, st = wl.circuit.prove_batch(gens, wl.label, inp["v"], inp["v_blinding"], inp["entropy"], pub=inp["pub"])
+    assert not st.any()
+    st, comb = wl.circuit.verify_batch_combined(gens, wl.label, V, P, inp["entropy"], pub=inp["pub"])
+    assert not st.any() and comb == 0
+    # a wrong public input (image of the hash) in one proof: structurally fine, combined check fails
+    bad = inp["pub"].copy(); bad[33, 0, 0] ^= 1
+    st, comb = wl.circuit.verify_batch_combined(gens, wl.label, V, P, inp["entropy"], pub=bad)
+    assert not st.any() and comb == 3
+    # a tampered scalar of the proof (t_x): same
+    P2 = P.copy(); P2[5, 352] ^= 1
+    st, comb = wl.circuit.verify_batch_combined(gens, wl.label, V, P2, inp["entropy"], pub=inp["pub"])
+    assert comb == 3
+    # structural failures are reported per proof and left out of the combination: the rest still passes
+    P3 = P.copy(); P3[7, 352:384] = 0xff           # non-canonical t_x -> FormatError
+    V3 = V.copy(); V3[9, 0, :] = 0xff              # undecodable commitment -> VerificationError
+    st, comb = wl.circuit.verify_batch_combined(gens, wl.label, V3, P3, inp["entropy"], pub=inp["pub"])
+    assert st[7] == 2 and st[9] == 3 and not np.delete(st, [7, 9]).any() and comb == 0
+    # the combined verdict agrees with per-proof verification
+    assert not wl.circuit.verify_batch(gens, wl.label, V, P, inp["entropy"], pub=inp["pub"]).any()
+    # single proof
+    st, comb = wl.circuit.verify_batch_combined(gens, wl.label, V[:1], P[:1], inp["entropy"][:1], pub=inp["pub"][:1])
+    assert comb == 0 and not st.any()
+
+
+def test_wire_format(api, gens):
+    """tagged wire form: one-phase proofs drop the three identity commitments; round trip; bad tags rejected"""
+    case = H.golden_cases()[0]
+    proof = bytes.fromhex(case["proof"])
+    assert proof[96:192] == bytes(96)
+    wire = api.proof_to_wire(proof)
+    assert len(wire) == 1 + len(proof) - 96 and wire[0] == 0 and wire[1:97] == proof[:96] and wire[97:] == proof[192:]
+    assert api.proof_from_wire(wire) == proof
+    two = bytearray(proof); two[100] = 1            # pretend a second-phase commitment is present
+    w2 = api.proof_to_wire(bytes(two))
+    assert w2[0] == 1 and len(w2) == 1 + len(proof) and api.proof_from_wire(w2) == bytes(two)
+    for bad in (b"", bytes([2]) + wire[1:], wire[:-1], wire + b"\x00" * 32):
+        with pytest.raises(api.R1CSError) as e:
+            api.proof_from_wire(bad)
+        assert e.value.code == 2
+
+
 def test_error_codes(api, gens):
     small = api.Gens(8)
     case = H.golden_cases()[0]  # mimc5: n = 10 -> N = 16 > 8
