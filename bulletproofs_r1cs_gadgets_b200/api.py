@@ -203,6 +203,12 @@ class PoseidonParams:
         _check(load().bp_poseidon_hash_2(self._h, _buf(scalar_bytes(xl)), _buf(scalar_bytes(xr)), sbox, out))
         return int.from_bytes(bytes(out), "little")
 
+    def hash_4(self, xs, sbox):
+        """Poseidon_hash_4 (reference src/gadget_poseidon.rs:488-503)"""
+        out = (C.c_uint8 * 32)()
+        _check(load().bp_poseidon_hash_4(self._h, _buf(b"".join(scalar_bytes(x) for x in xs)), sbox, out))
+        return int.from_bytes(bytes(out), "little")
+
 
 class Gens:
     """PedersenGens::default() + BulletproofGens::new(capacity, 1), resident on the device."""
@@ -326,6 +332,26 @@ class ConstraintSystem:
             return
         _check(load().bp_gadget_vsmt2_verif(self._h, params._h, C.c_uint32(depth), _buf(scalar_bytes(root)), leaf._c(), b, nd, st,
                                             C.c_uint32(len(statics))), "vsmt2_verif_gadget")
+
+    def poseidon_hash_4_gadget(self, params, xs, statics, sbox, expected):
+        st = (bp_var * len(statics))(*[s._c() for s in statics])
+        xv = (bp_var * 4)(*[x._c() for x in xs])
+        if isinstance(expected, Variable):
+            _check(load().bp_gadget_poseidon_hash_4_public(self._h, params._h, xv, st, C.c_uint32(len(statics)), sbox, expected._c()), "poseidon_hash_4_gadget")
+            return
+        _check(load().bp_gadget_poseidon_hash_4(self._h, params._h, xv, st, C.c_uint32(len(statics)), sbox, _buf(scalar_bytes(expected))), "poseidon_hash_4_gadget")
+
+    def vsmt4_verif_gadget(self, params, levels, root, leaf, leaf_index, index_digits, nodes, statics):
+        """vanilla_merkle_merkle_tree_4_verif_gadget (reference src/gadget_vsmt_4.rs:199-312); index_digits: base-4 digits, LSB first, or None"""
+        nd = (bp_var * (3 * levels))(*[x._c() for x in nodes])
+        st = (bp_var * len(statics))(*[s._c() for s in statics])
+        dg = _buf(bytes(index_digits)) if index_digits is not None else None
+        if isinstance(root, Variable):
+            _check(load().bp_gadget_vsmt4_verif_public(self._h, params._h, C.c_uint32(levels), root._c(), leaf._c(), leaf_index._c(), dg, nd, st,
+                                                       C.c_uint32(len(statics))), "vsmt4_verif_gadget")
+            return
+        _check(load().bp_gadget_vsmt4_verif(self._h, params._h, C.c_uint32(levels), _buf(scalar_bytes(root)), leaf._c(), leaf_index._c(), dg, nd, st,
+                                            C.c_uint32(len(statics))), "vsmt4_verif_gadget")
 
     def mimc_gadget(self, left, right, constants, image):
         cb = b"".join(scalar_bytes(c) for c in constants)

@@ -282,6 +282,48 @@ int32_t bp_gadget_vsmt2_verif_public(bp_cs *cs, const bp_poseidon_params *p, uin
   for (uint32_t i = 0; i < ns; i++) if (!var_ok(cs, statics[i])) return BP_ERR_INVALID_ARGUMENT;
   return vsmt2_verif_gadget(*cs, *p, depth, LC(root), leaf, bits, nodes, statics, ns);
 }
+int32_t bp_poseidon_hash_4(const bp_poseidon_params *p, const uint8_t in[4][32], int32_t sbox, uint8_t out[32]) {
+  if (!p || !in || !out || p->width != 6) return BP_ERR_INVALID_ARGUMENT;
+  scm x[4]; for (int i = 0; i < 4; i++) x[i] = load_scalar(in[i]);
+  sc_tobytes(out, poseidon_hash_4(*p, x, sbox));
+  return BP_OK;
+}
+static int hash4_common(bp_cs *cs, const bp_poseidon_params *p, const bp_var in[4], const bp_var *statics, uint32_t ns, int32_t sbox, LC &h) {
+  if (!cs || !p || !in || !statics) return BP_ERR_INVALID_ARGUMENT;
+  std::vector<LC> st; for (uint32_t i = 0; i < ns; i++) { if (!var_ok(cs, statics[i])) return BP_ERR_INVALID_ARGUMENT; st.push_back(LC(statics[i])); }
+  LC x[4]; for (int i = 0; i < 4; i++) { if (!var_ok(cs, in[i])) return BP_ERR_INVALID_ARGUMENT; x[i] = LC(in[i]); }
+  return poseidon_hash_4_constraints(*cs, *p, x, st, sbox, h);
+}
+int32_t bp_gadget_poseidon_hash_4(bp_cs *cs, const bp_poseidon_params *p, const bp_var in[4], const bp_var *statics, uint32_t ns, int32_t sbox,
+                                  const uint8_t expected[32]) {  // gadget_poseidon.rs:532-551
+  if (!expected) return BP_ERR_INVALID_ARGUMENT;
+  LC h; int rc = hash4_common(cs, p, in, statics, ns, sbox, h); if (rc) return rc;
+  cs->constrain(h - LC::constant(load_scalar(expected)));
+  return BP_OK;
+}
+int32_t bp_gadget_poseidon_hash_4_public(bp_cs *cs, const bp_poseidon_params *p, const bp_var in[4], const bp_var *statics, uint32_t ns, int32_t sbox,
+                                         bp_var expected) {
+  if (!cs || !var_ok(cs, expected)) return BP_ERR_INVALID_ARGUMENT;
+  LC h; int rc = hash4_common(cs, p, in, statics, ns, sbox, h); if (rc) return rc;
+  cs->constrain(h - LC(expected));
+  return BP_OK;
+}
+static int vsmt4_args_ok(bp_cs *cs, const bp_poseidon_params *p, uint32_t levels, bp_var leaf, bp_var leaf_index, const bp_var *nodes, const bp_var *statics, uint32_t ns) {
+  if (!cs || !p || !nodes || !statics || !var_ok(cs, leaf) || !var_ok(cs, leaf_index) || levels == 0 || levels > 126) return 0;
+  for (uint32_t i = 0; i < 3 * levels; i++) if (!var_ok(cs, nodes[i])) return 0;
+  for (uint32_t i = 0; i < ns; i++) if (!var_ok(cs, statics[i])) return 0;
+  return 1;
+}
+int32_t bp_gadget_vsmt4_verif(bp_cs *cs, const bp_poseidon_params *p, uint32_t levels, const uint8_t root[32], bp_var leaf, bp_var leaf_index,
+                              const uint8_t *index_digits, const bp_var *nodes, const bp_var *statics, uint32_t ns) {
+  if (!root || !vsmt4_args_ok(cs, p, levels, leaf, leaf_index, nodes, statics, ns)) return BP_ERR_INVALID_ARGUMENT;
+  return vsmt4_verif_gadget(*cs, *p, levels, LC::constant(load_scalar(root)), leaf, leaf_index, index_digits, nodes, statics, ns);
+}
+int32_t bp_gadget_vsmt4_verif_public(bp_cs *cs, const bp_poseidon_params *p, uint32_t levels, bp_var root, bp_var leaf, bp_var leaf_index,
+                                     const uint8_t *index_digits, const bp_var *nodes, const bp_var *statics, uint32_t ns) {
+  if (!vsmt4_args_ok(cs, p, levels, leaf, leaf_index, nodes, statics, ns) || !var_ok(cs, root)) return BP_ERR_INVALID_ARGUMENT;
+  return vsmt4_verif_gadget(*cs, *p, levels, LC(root), leaf, leaf_index, index_digits, nodes, statics, ns);
+}
 int32_t bp_gadget_mimc(bp_cs *cs, bp_var left, bp_var right, uint32_t rounds, const uint8_t *constants, const uint8_t image[32]) {
   if (!cs || !constants || !image || !var_ok(cs, left) || !var_ok(cs, right)) return BP_ERR_INVALID_ARGUMENT;
   std::vector<scm> k(rounds); for (uint32_t i = 0; i < rounds; i++) k[i] = load_scalar(constants + 32 * (size_t)i);

@@ -212,6 +212,76 @@ int vsmt2_verif_gadget(bp_cs &cs, const bp_poseidon_params &p, uint32_t depth, c
   return BP_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ Poseidon 4:1, VSMT-4
+scm poseidon_hash_4(const bp_poseidon_params &p, const scm in[4], int sbox) {  // gadget_poseidon.rs:488-503
+  std::vector<scm> st(p.width, sc_zero());
+  for (int i = 0; i < 4; i++) st[1 + i] = in[i];
+  st[5] = sc_from_u64(101);
+  poseidon_permutation(p, st, sbox);
+  return st[1];
+}
+int poseidon_hash_4_constraints(bp_cs &cs, const bp_poseidon_params &p, const LC in[4], const std::vector<LC> &statics, int sbox, LC &out) {
+  if (statics.size() != p.width - 4) return BP_ERR_GADGET;  // gadget_poseidon.rs:505-530
+  std::vector<LC> inputs;
+  inputs.push_back(statics[0]);
+  for (int i = 0; i < 4; i++) inputs.push_back(in[i]);
+  for (size_t i = 1; i < statics.size(); i++) inputs.push_back(statics[i]);
+  int rc = poseidon_permutation_constraints(cs, p, inputs, sbox);
+  if (rc) return rc;
+  out = inputs[1];
+  return BP_OK;
+}
+// vanilla_merkle_merkle_tree_4_verif_gadget (gadget_vsmt_4.rs:199-312) for `levels` levels (the reference hard-codes
+// 4 * LeafIndexBytes); digits = base-4 digits of the leaf index, least significant first (prover side; NULL otherwise);
+// nodes = 3 * levels siblings, the triple (N1, N2, N3) of the first processed level LAST (the reference pops from the end)
+int vsmt4_verif_gadget(bp_cs &cs, const bp_poseidon_params &p, uint32_t levels, const LC &root, bp_var leaf, bp_var leaf_index,
+                       const uint8_t *digits, const bp_var *nodes, const bp_var *statics, uint32_t num_statics) {
+  std::vector<LC> st;
+  for (uint32_t i = 0; i < num_statics; i++) st.push_back(LC(statics[i]));
+  LC prev(leaf);
+  LC index_lc;  // starts as -leaf_index (gadget_vsmt_4.rs:217)
+  index_lc.terms.push_back(Term{leaf_index, sc_neg(sc_one())});
+  scm exp4 = sc_one();
+  const scm two = sc_from_u64(2), four = sc_from_u64(4);
+  long top = 3L * levels;
+  for (uint32_t lvl = 0; lvl < levels; lvl++) {
+    bp_var b0v[3], b1v[3]; int rc;
+    for (int which = 0; which < 2; which++) {  // the two bits of this base-4 digit, each with its complement (gadget_vsmt_4.rs:227-241)
+      bp_var *o = which ? b1v : b0v;
+      if (cs.is_prover) {
+        if (!digits) return BP_ERR_MISSING_ASSIGNMENT;
+        const uint64_t bit = (digits[lvl] >> which) & 1;
+        scm a = sc_from_u64(bit), b = sc_from_u64(1 - bit);
+        rc = cs.allocate_multiplier(&a, &b, o);
+      } else rc = cs.allocate_multiplier(nullptr, nullptr, o);
+      if (rc) return rc;
+      cs.constrain(LC(o[2]));
+      cs.constrain(LC(o[0]) + (LC(o[1]) - LC::from_u64(1)));
+    }
+    const bp_var b0 = b0v[0], b0_1 = b0v[1], b1 = b1v[0], b1_1 = b1v[1];
+    index_lc.terms.push_back(Term{b1, sc_mul(two, exp4)});
+    index_lc.terms.push_back(Term{b0, exp4});
+    const LC N3(nodes[--top]), N2(nodes[--top]), N1(nodes[--top]);
+    bp_var t[3];
+    cs.multiply(LC(b0_1), LC(b1_1), t); const LC b0_1_b1_1(t[2]);
+    cs.multiply(LC(b0_1), LC(b1), t);   const LC b0_1_b1(t[2]);
+    cs.multiply(LC(b0), LC(b1_1), t);   const LC b0_b1_1(t[2]);
+    cs.multiply(LC(b0), LC(b1), t);     const LC b0_b1(t[2]);
+    auto mul = [&](const LC &a, const LC &b) { bp_var o[3]; cs.multiply(a, b, o); return LC(o[2]); };
+    LC c[4];
+    { LC x = mul(b0_1_b1_1, prev), y = mul(LC(b0), N1), z = mul(b0_1_b1, N1); c[0] = x + y + z; }
+    { LC x = mul(b0_1_b1_1, N1), y = mul(b0_b1_1, prev), z = mul(b0_1_b1, N2), u = mul(b0_b1, N2); c[1] = x + y + z + u; }
+    { LC x = mul(LC(b1_1), N2), y = mul(b0_1_b1, prev), z = mul(b0_b1, N3); c[2] = x + y + z; }
+    { LC x = mul(LC(b1_1), N3), y = mul(b0_1_b1, N3), z = mul(b0_b1, prev); c[3] = x + y + z; }
+    rc = poseidon_hash_4_constraints(cs, p, c, st, BP_SBOX_INVERSE, prev);
+    if (rc) return rc;
+    exp4 = sc_mul(exp4, four);
+  }
+  cs.constrain(index_lc);
+  cs.constrain(prev - root);
+  return BP_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ MiMC
 scm mimc_native(const scm &xl_, const scm &xr_, uint32_t rounds, const scm *constants) {  // gadget_mimc.rs:19-39
   scm xl = xl_, xr = xr_;

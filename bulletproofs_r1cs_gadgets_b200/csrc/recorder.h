@@ -80,6 +80,10 @@ struct bp_poseidon_params {
 void poseidon_permutation(const bp_poseidon_params &p, std::vector<scm> &state, int sbox);
 scm poseidon_hash_2(const bp_poseidon_params &p, const scm &xl, const scm &xr, int sbox);
 int poseidon_permutation_constraints(bp_cs &cs, const bp_poseidon_params &p, std::vector<LC> &state, int sbox);
+scm poseidon_hash_4(const bp_poseidon_params &p, const scm in[4], int sbox);
+int poseidon_hash_4_constraints(bp_cs &cs, const bp_poseidon_params &p, const LC in[4], const std::vector<LC> &statics, int sbox, LC &out);
+int vsmt4_verif_gadget(bp_cs &cs, const bp_poseidon_params &p, uint32_t levels, const LC &root, bp_var leaf, bp_var leaf_index,
+                       const uint8_t *digits, const bp_var *nodes, const bp_var *statics, uint32_t num_statics);
 int poseidon_hash_2_constraints(bp_cs &cs, const bp_poseidon_params &p, const LC &xl, const LC &xr, const std::vector<LC> &statics, int sbox, LC &out);
 int vsmt2_verif_gadget(bp_cs &cs, const bp_poseidon_params &p, uint32_t depth, const LC &root, bp_var leaf, const bp_var *bits,
                        const bp_var *nodes, const bp_var *statics, uint32_t num_statics);

@@ -93,6 +93,70 @@ class Vsmt2(Workload):
         return dict(v=v, v_blinding=vb, entropy=ent, pub=pub)
 
 
+class Vsmt4(Workload):
+    """Membership proof in a 4-ary sparse Merkle tree, Poseidon 4:1, inverse S-box (reference src/gadget_vsmt_4.rs:199-312,
+    test at :362-483).  Commit order of the reference test: leaf value, leaf index, 3 * levels siblings, 2 statics.  The bits of the
+    index digits are allocate_multiplier inputs, i.e. per-proof auxiliary inputs of the batched circuit: b0, 1-b0, b1, 1-b1 per level."""
+
+    def __init__(self, gens_for_recording, levels=16, params=None):
+        self.levels = levels
+        self.params = params or api.PoseidonParams()
+        rec = api.Verifier(gens_for_recording, b"VSMT")
+        zero = bytes(32)
+        leaf = rec.commit(zero)
+        index = rec.commit(zero)
+        nodes = [rec.commit(zero) for _ in range(3 * levels)]
+        statics = [rec.commit(zero) for _ in range(2)]
+        root = rec.public_input()
+        rec.vsmt4_verif_gadget(self.params, levels, root, leaf, index, None, nodes, statics)
+        circ = rec.compile()
+        super().__init__("vsmt4_levels%d" % levels, b"VSMT", circ, _next_pow2(circ.n))
+        self.cfg = b"vsmt4/%d" % levels
+
+    def witness_values(self, p):
+        lv = self.levels
+        leaf = synth_scalar(self.cfg, p, 0)
+        digits = [synth_bytes32(self.cfg, p, 1 + i)[0] & 3 for i in range(lv)]
+        # sibling triples in the order the gadget consumes them: level 0 (leaf level) first
+        sibs = [tuple(synth_scalar(self.cfg, p, 1 + lv + 3 * i + j) for j in range(3)) for i in range(lv)]
+        return leaf, digits, sibs
+
+    def root(self, leaf, digits, sibs):
+        cur = leaf  # arrangements of reference src/gadget_vsmt_4.rs:176-181
+        for d, (n1, n2, n3) in zip(digits, sibs):
+            children = [n1, n2, n3]
+            children.insert(d, cur)
+            cur = self.params.hash_4(children, api.SBOX_INVERSE)
+        return cur
+
+    def inputs(self, first, count, with_root=True):
+        lv, m = self.levels, self.circuit.m
+        v = np.zeros((count, m, 32), dtype=np.uint8)
+        vb = np.zeros((count, m, 32), dtype=np.uint8)
+        ent = np.zeros((count, 32), dtype=np.uint8)
+        pub = np.zeros((count, 1, 32), dtype=np.uint8)
+        aux = np.zeros((count, 4 * lv, 32), dtype=np.uint8)
+        for i in range(count):
+            p = first + i
+            leaf, digits, sibs = self.witness_values(p)
+            index = sum(d << (2 * j) for j, d in enumerate(digits))
+            # the gadget pops (N3, N2, N1) of the level it is processing from the END of the vector
+            nodes = [x for triple in reversed(sibs) for x in triple]
+            vals = [leaf, index] + nodes + [0, 101]
+            bl = [synth_scalar(self.cfg, p, 1000 + j) for j in range(2 + 3 * lv)] + [0, 0]
+            v[i] = api.scalars_to_array(vals)
+            vb[i] = api.scalars_to_array(bl)
+            ent[i] = np.frombuffer(synth_bytes32(self.cfg, p, 2000), dtype=np.uint8)
+            a = []
+            for d in digits:
+                b0, b1 = d & 1, (d >> 1) & 1
+                a += [b0, 1 - b0, b1, 1 - b1]
+            aux[i] = api.scalars_to_array(a)
+            if with_root:
+                pub[i, 0] = np.frombuffer(api.scalar_bytes(self.root(leaf, digits, sibs)), dtype=np.uint8)
+        return dict(v=v, v_blinding=vb, entropy=ent, pub=pub, aux=aux)
+
+
 class PoseidonHash2(Workload):
     """BASELINE config 2: Poseidon 2:1 preimage proofs (reference src/gadget_poseidon.rs:691-785)."""
 

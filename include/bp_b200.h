@@ -136,6 +136,21 @@ int32_t bp_gadget_vsmt2_verif(bp_cs *cs, const bp_poseidon_params *p, uint32_t d
 /* same circuit with the root as a public-input variable (BP_VAR_PUBLIC) instead of a baked-in constant */
 int32_t bp_gadget_vsmt2_verif_public(bp_cs *cs, const bp_poseidon_params *p, uint32_t depth, bp_var root, bp_var leaf,
                                      const bp_var *leaf_index_bits, const bp_var *proof_nodes, const bp_var *statics, uint32_t num_statics);
+/* Poseidon_hash_4 / Poseidon_hash_4_gadget (src/gadget_poseidon.rs:488-551): inputs [0, x0..x3, 101], output lane 1; width 6, two statics */
+int32_t bp_poseidon_hash_4(const bp_poseidon_params *p, const uint8_t in[4][32], int32_t sbox, uint8_t out[32]);
+int32_t bp_gadget_poseidon_hash_4(bp_cs *cs, const bp_poseidon_params *p, const bp_var in[4], const bp_var *statics, uint32_t num_statics,
+                                  int32_t sbox, const uint8_t expected_hash[32]);
+int32_t bp_gadget_poseidon_hash_4_public(bp_cs *cs, const bp_poseidon_params *p, const bp_var in[4], const bp_var *statics, uint32_t num_statics,
+                                         int32_t sbox, bp_var expected_hash);
+/* vanilla_merkle_merkle_tree_4_verif_gadget (src/gadget_vsmt_4.rs:199-312), `levels` levels of the 4-ary tree (the reference
+ * hard-codes 4 * LeafIndexBytes).  leaf_index is a committed variable; index_digits[levels] are its base-4 digits, least
+ * significant first (prover side only; NULL on the verifier -- they become per-proof auxiliary inputs of a batched circuit:
+ * for every level the values b0, 1-b0, b1, 1-b1 in that order).  proof_nodes holds 3 * levels siblings, the triple of the
+ * first processed (leaf) level LAST, as the reference pops them from the end of its vector. */
+int32_t bp_gadget_vsmt4_verif(bp_cs *cs, const bp_poseidon_params *p, uint32_t levels, const uint8_t root[32], bp_var leaf, bp_var leaf_index,
+                              const uint8_t *index_digits, const bp_var *proof_nodes, const bp_var *statics, uint32_t num_statics);
+int32_t bp_gadget_vsmt4_verif_public(bp_cs *cs, const bp_poseidon_params *p, uint32_t levels, bp_var root, bp_var leaf, bp_var leaf_index,
+                                     const uint8_t *index_digits, const bp_var *proof_nodes, const bp_var *statics, uint32_t num_statics);
 /* mimc_gadget (src/gadget_mimc.rs:41-79) */
 int32_t bp_gadget_mimc(bp_cs *cs, bp_var left, bp_var right, uint32_t rounds, const uint8_t *constants, const uint8_t image[32]);
 int32_t bp_gadget_mimc_public(bp_cs *cs, bp_var left, bp_var right, uint32_t rounds, const uint8_t *constants, bp_var image);

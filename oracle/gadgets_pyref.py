@@ -174,6 +174,61 @@ def vanilla_merkle_tree_verif_gadget(cs, depth, root, leaf_var, bit_vars, proof_
     constrain_lc_with_scalar(cs, prev, root)
 
 
+def poseidon_hash_4_constraints(cs, inputs4, statics, params, sbox):  # gadget_poseidon.rs:505-530
+    inputs = [statics[0]] + list(inputs4) + list(statics[1:])
+    return poseidon_permutation_constraints(cs, inputs, params, sbox)[1]
+
+
+def vanilla_merkle_tree_4_verif_gadget(cs, levels, root, leaf_var, leaf_index_var, index_digits, proof_vars, static_vars, params):
+    """gadget_vsmt_4.rs:199-312 for `levels` levels (the reference hard-codes 4 * LeafIndexBytes); index_digits = base-4 digits of
+    the leaf index, least significant first (None on the verifier); proof_vars = 3 * levels siblings, popped from the END."""
+    statics = [LC.of(s) for s in static_vars]
+    prev = LC.of(leaf_var)
+    nodes = list(proof_vars)
+    index_terms = [(leaf_index_var, L - 1)]
+    exp_4 = 1
+    for lvl in range(levels):
+        bits = []
+        for which in range(2):
+            if index_digits is None:
+                b, b_1, o = cs.allocate_multiplier(None)
+            else:
+                bit = (index_digits[lvl] >> which) & 1
+                b, b_1, o = cs.allocate_multiplier((bit, 1 - bit))
+            cs.constrain(LC.of(o))
+            cs.constrain(LC.of(b) + (LC.of(b_1) - LC.of(1)))
+            bits.append((b, b_1))
+        (b0, b0_1), (b1, b1_1) = bits
+        index_terms.append((b1, 2 * exp_4 % L))
+        index_terms.append((b0, exp_4))
+        N3 = LC.of(nodes.pop()); N2 = LC.of(nodes.pop()); N1 = LC.of(nodes.pop())
+        mul = lambda a, b: LC.of(cs.multiply(LC.of(a), LC.of(b))[2])
+        b0_1_b1_1 = mul(b0_1, b1_1); b0_1_b1 = mul(b0_1, b1); b0_b1_1 = mul(b0, b1_1); b0_b1 = mul(b0, b1)
+        c0_1 = mul(b0_1_b1_1, prev); c0_2 = mul(b0, N1); c0_3 = mul(b0_1_b1, N1)
+        c0 = c0_1 + c0_2 + c0_3
+        c1_1 = mul(b0_1_b1_1, N1); c1_2 = mul(b0_b1_1, prev); c1_3 = mul(b0_1_b1, N2); c1_4 = mul(b0_b1, N2)
+        c1 = c1_1 + c1_2 + c1_3 + c1_4
+        c2_1 = mul(b1_1, N2); c2_2 = mul(b0_1_b1, prev); c2_3 = mul(b0_b1, N3)
+        c2 = c2_1 + c2_2 + c2_3
+        c3_1 = mul(b1_1, N3); c3_2 = mul(b0_1_b1, N3); c3_3 = mul(b0_b1, prev)
+        c3 = c3_1 + c3_2 + c3_3
+        prev = poseidon_hash_4_constraints(cs, [c0, c1, c2, c3], statics, params, INVERSE)
+        exp_4 = exp_4 * 4 % L
+    cs.constrain(LC(index_terms))
+    constrain_lc_with_scalar(cs, prev, root)
+
+
+def vsmt4_root_from_path(leaf, digits, siblings3, params):
+    """native root of a synthetic 4-ary path: at each level the running node sits at position `digit` among its three siblings
+    (N1, N2, N3), arrangements of gadget_vsmt_4.rs:176-181"""
+    cur = leaf
+    for d, (n1, n2, n3) in zip(digits, siblings3):
+        children = [n1, n2, n3]
+        children.insert(d, cur)
+        cur = poseidon_hash_4(children, params, INVERSE)
+    return cur
+
+
 def vsmt_root_from_path(leaf, bits, siblings, params):
     """Native root for a synthetic path, orientation of gadget_vsmt_2.rs:134-147 / :192-200."""
     cur = leaf

@@ -151,6 +151,90 @@ def test_batch_aux_inputs_bound_check(api, gens):
     assert wl.circuit.verify_batch(gens, wl.label, V2, proofs2, bad["entropy"]).tolist()[0] == 3
 
 
+def test_vsmt4_membership(api, gens, levels=2, params=(6, 2, 2, 3), count=3):
+    """4-ary sparse Merkle membership (reference src/gadget_vsmt_4.rs:199-312, Poseidon 4:1 of src/gadget_poseidon.rs:488-551):
+    native root equal to the oracle's, commitments and proof bytes equal to the oracle's prover running the oracle's restatement
+    of the gadget, verifier accepts, wrong root and wrong index digit rejected"""
+    from bulletproofs_r1cs_gadgets_b200 import workloads
+    pp, opp = api.PoseidonParams(*params), G.PoseidonParams(*params)
+    wl = workloads.Vsmt4(gens, levels=levels, params=pp)
+    assert wl.circuit.num_aux == 4 * levels and wl.circuit.num_public == 1 and wl.circuit.m == 2 + 3 * levels + 2
+    inp = wl.inputs(0, count)
+    V, P, st = wl.circuit.prove_batch(gens, wl.label, inp["v"], inp["v_blinding"], inp["entropy"], aux=inp["aux"], pub=inp["pub"])
+    assert not st.any()
+    cap = 1
+    while cap < wl.circuit.n:
+        cap *= 2
+    for i in range(count):
+        leaf, digits, sibs = wl.witness_values(i)
+        root = G.vsmt4_root_from_path(leaf, digits, sibs, opp)
+        assert root == int.from_bytes(inp["pub"][i, 0].tobytes(), "little")
+        op = R.Prover(R.PedersenGens(), R.Transcript(b"VSMT"))
+        ops = [op.commit(int.from_bytes(inp["v"][i][j].tobytes(), "little"), int.from_bytes(inp["v_blinding"][i][j].tobytes(), "little")) for j in range(wl.circuit.m)]
+        vs = [o[1] for o in ops]
+        G.vanilla_merkle_tree_4_verif_gadget(op, levels, root, vs[0], vs[1], digits, vs[2:2 + 3 * levels], vs[2 + 3 * levels:], opp)
+        assert (len(op.aL), op.num_constraints()) == (wl.circuit.n, wl.circuit.q)
+        assert b"".join(o[0] for o in ops) == V[i].tobytes()
+        assert R.proof_to_bytes(op.prove(R.BulletproofGens(cap), inp["entropy"][i].tobytes())) == P[i].tobytes()
+    assert not wl.circuit.verify_batch(gens, wl.label, V, P, inp["entropy"], pub=inp["pub"]).any()
+    bad = inp["pub"].copy(); bad[1, 0, 0] ^= 1
+    assert wl.circuit.verify_batch(gens, wl.label, V, P, inp["entropy"], pub=bad).tolist() == [0, 3] + [0] * (count - 2)
+    # a prover lying about one index digit (its bits still sum to the committed index only if unchanged): rejected
+    aux2 = inp["aux"].copy(); aux2[0, 0, 0] ^= 1; aux2[0, 1, 0] ^= 1
+    V2, P2, st2 = wl.circuit.prove_batch(gens, wl.label, inp["v"], inp["v_blinding"], inp["entropy"], aux=aux2, pub=inp["pub"])
+    assert wl.circuit.verify_batch(gens, wl.label, V2, P2, inp["entropy"], pub=inp["pub"])[0] == 3
+    # tier 1: the same gadget through the one-at-a-time Prover / Verifier mirror
+    leaf, digits, sibs = wl.witness_values(0)
+    root = int.from_bytes(inp["pub"][0, 0].tobytes(), "little")
+    pr = api.Prover(gens, b"VSMT")
+    pv = [pr.commit(int.from_bytes(inp["v"][0][j].tobytes(), "little"), int.from_bytes(inp["v_blinding"][0][j].tobytes(), "little"))[1] for j in range(wl.circuit.m)]
+    pr.vsmt4_verif_gadget(pp, levels, root, pv[0], pv[1], digits, pv[2:2 + 3 * levels], pv[2 + 3 * levels:])
+    assert pr.prove(inp["entropy"][0].tobytes()) == P[0].tobytes()
+
+
+def test_sparse_merkle_tree_and_membership_from_a_real_tree(api, gens):
+    """the reference's two VSMT tests (src/gadget_vsmt_2.rs:223-259 data structure, :262-399 membership proof) at a small depth:
+    update/get/verify_proof of the HashMap tree, then a membership proof whose witness comes from the tree instead of a synthetic path"""
+    from bulletproofs_r1cs_gadgets_b200 import trees
+    pp, opp = api.PoseidonParams(6, 2, 2, 3), G.PoseidonParams(6, 2, 2, 3)
+    depth = 6
+    tree = trees.VanillaSparseMerkleTree(pp, depth)
+    # empty-subtree recurrence equals the oracle's native hash
+    e = 0
+    for i in range(depth):
+        e = G.poseidon_hash_2(e, e, opp, G.INVERSE)
+        assert tree.empty_tree_hashes[i + 1] == e
+    vals = {k: H.rand_scalars(40 + k, 1)[0] for k in (1, 2, 7, 33, 63)}
+    for k, v in vals.items():
+        tree.update(k, v)
+    for k, v in vals.items():
+        proof = []
+        assert tree.get(k, proof) == v and len(proof) == depth
+        assert tree.verify_proof(k, v, proof) and tree.verify_proof(k, v, proof, tree.root)
+        assert not tree.verify_proof(k, (v + 1) % L, proof)
+    assert tree.get(5) == 0  # untouched leaf
+    # membership proof for key 7 (reference test flow: commit leaf, index bits LSB first, siblings leaf level first, statics)
+    k = 7; proof = []; leaf = tree.get(k, proof); proof.reverse()
+    bits = [(k >> i) & 1 for i in range(depth)]
+    pr = api.Prover(gens, b"VSMT")
+    bl = H.rand_scalars(77, 1 + 2 * depth)
+    cvars = [pr.commit(x, b)[1] for x, b in zip([leaf] + bits + proof, bl)]
+    statics = pr.allocate_statics(4)
+    pr.vsmt2_verif_gadget(pp, depth, tree.root, cvars[0], cvars[1:1 + depth], cvars[1 + depth:], statics)
+    Vs = pr.commitments()
+    pf = pr.prove(bytes(range(32)))
+    vf = api.Verifier(gens, b"VSMT")
+    vv = [vf.commit(V) for V in Vs[:1 + 2 * depth]]
+    vst = vf.allocate_statics(4)
+    vf.vsmt2_verif_gadget(pp, depth, tree.root, vv[0], vv[1:1 + depth], vv[1 + depth:], vst)
+    assert vf.verify(pf, bytes(32)) == 0
+    vf2 = api.Verifier(gens, b"VSMT")
+    vv2 = [vf2.commit(V) for V in Vs[:1 + 2 * depth]]
+    vst2 = vf2.allocate_statics(4)
+    vf2.vsmt2_verif_gadget(pp, depth, (tree.root + 1) % L, vv2[0], vv2[1:1 + depth], vv2[1 + depth:], vst2)
+    assert vf2.verify(pf, bytes(32)) == 3
+
+
 def test_explicit_witness_equals_witness_program(api, gens, oracle_lib):
     from bulletproofs_r1cs_gadgets_b200 import workloads
     wl = workloads.Mimc(gens, rounds=6)
