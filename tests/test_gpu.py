@@ -54,7 +54,8 @@ def test_msm_path_choice_is_invisible(api, gens, monkeypatch): E.test_msm_path_c
 def test_combined_verification(api, gens): E.test_combined_verification(api, gens)
 def test_wire_format(api, gens): E.test_wire_format(api, gens)
 def test_vsmt4_membership_small(api, gens): E.test_vsmt4_membership(api, gens)
-def test_vsmt4_membership_reference_parameters(api, gens_big): E.test_vsmt4_membership(api, gens_big, levels=3, params=(6, 4, 4, 140), count=2)
+def test_vsmt4_membership_reference_parameters(api, gens_big, oracle_lib): E.test_vsmt4_membership(api, gens_big, levels=3, params=(6, 4, 4, 140), count=2, c_oracle_prover=True)
+def test_sparse_merkle_tree_and_membership_from_a_real_tree(api, gens): E.test_sparse_merkle_tree_and_membership_from_a_real_tree(api, gens)
 def test_error_codes(api, gens): E.test_error_codes(api, gens)
 def test_single_multiplier_and_allocate_single(api, gens): E.test_single_multiplier_and_allocate_single(api, gens)
 

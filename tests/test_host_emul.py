@@ -151,7 +151,7 @@ def test_batch_aux_inputs_bound_check(api, gens):
     assert wl.circuit.verify_batch(gens, wl.label, V2, proofs2, bad["entropy"]).tolist()[0] == 3
 
 
-def test_vsmt4_membership(api, gens, levels=2, params=(6, 2, 2, 3), count=3):
+def test_vsmt4_membership(api, gens, levels=2, params=(6, 2, 2, 3), count=3, c_oracle_prover=False):
     """4-ary sparse Merkle membership (reference src/gadget_vsmt_4.rs:199-312, Poseidon 4:1 of src/gadget_poseidon.rs:488-551):
     native root equal to the oracle's, commitments and proof bytes equal to the oracle's prover running the oracle's restatement
     of the gadget, verifier accepts, wrong root and wrong index digit rejected"""
@@ -175,7 +175,14 @@ def test_vsmt4_membership(api, gens, levels=2, params=(6, 2, 2, 3), count=3):
         G.vanilla_merkle_tree_4_verif_gadget(op, levels, root, vs[0], vs[1], digits, vs[2:2 + 3 * levels], vs[2 + 3 * levels:], opp)
         assert (len(op.aL), op.num_constraints()) == (wl.circuit.n, wl.circuit.q)
         assert b"".join(o[0] for o in ops) == V[i].tobytes()
-        assert R.proof_to_bytes(op.prove(R.BulletproofGens(cap), inp["entropy"][i].tobytes())) == P[i].tobytes()
+        if c_oracle_prover:
+            # large circuits: the Python oracle records the circuit and the witness, the C oracle (fast) produces the proof
+            oc = CO.Circuit.from_cs(op, wl.circuit.m)
+            rc, oV, oP = CO.prove(oc, api.scalars_to_array(op.aL), api.scalars_to_array(op.aR), api.scalars_to_array(op.aO), inp["v"][i], inp["v_blinding"][i],
+                                  b"VSMT", inp["entropy"][i].tobytes(), cap)
+            assert rc == 0 and oV.tobytes() == V[i].tobytes() and oP == P[i].tobytes()
+        else:
+            assert R.proof_to_bytes(op.prove(R.BulletproofGens(cap), inp["entropy"][i].tobytes())) == P[i].tobytes()
     assert not wl.circuit.verify_batch(gens, wl.label, V, P, inp["entropy"], pub=inp["pub"]).any()
     bad = inp["pub"].copy(); bad[1, 0, 0] ^= 1
     assert wl.circuit.verify_batch(gens, wl.label, V, P, inp["entropy"], pub=bad).tolist() == [0, 3] + [0] * (count - 2)
@@ -197,14 +204,14 @@ def test_sparse_merkle_tree_and_membership_from_a_real_tree(api, gens):
     update/get/verify_proof of the HashMap tree, then a membership proof whose witness comes from the tree instead of a synthetic path"""
     from bulletproofs_r1cs_gadgets_b200 import trees
     pp, opp = api.PoseidonParams(6, 2, 2, 3), G.PoseidonParams(6, 2, 2, 3)
-    depth = 6
+    depth = 3  # 3 x (4 + 81) multipliers fit the 256 generators of the test fixture
     tree = trees.VanillaSparseMerkleTree(pp, depth)
     # empty-subtree recurrence equals the oracle's native hash
     e = 0
     for i in range(depth):
         e = G.poseidon_hash_2(e, e, opp, G.INVERSE)
         assert tree.empty_tree_hashes[i + 1] == e
-    vals = {k: H.rand_scalars(40 + k, 1)[0] for k in (1, 2, 7, 33, 63)}
+    vals = {k: H.rand_scalars(40 + k, 1)[0] for k in (1, 2, 7, 4)}
     for k, v in vals.items():
         tree.update(k, v)
     for k, v in vals.items():
@@ -218,21 +225,22 @@ def test_sparse_merkle_tree_and_membership_from_a_real_tree(api, gens):
     bits = [(k >> i) & 1 for i in range(depth)]
     pr = api.Prover(gens, b"VSMT")
     bl = H.rand_scalars(77, 1 + 2 * depth)
-    cvars = [pr.commit(x, b)[1] for x, b in zip([leaf] + bits + proof, bl)]
+    com = [pr.commit(x, b) for x, b in zip([leaf] + bits + proof, bl)]
+    Vs, cvars = [c[0] for c in com], [c[1] for c in com]
     statics = pr.allocate_statics(4)
     pr.vsmt2_verif_gadget(pp, depth, tree.root, cvars[0], cvars[1:1 + depth], cvars[1 + depth:], statics)
-    Vs = pr.commitments()
     pf = pr.prove(bytes(range(32)))
-    vf = api.Verifier(gens, b"VSMT")
-    vv = [vf.commit(V) for V in Vs[:1 + 2 * depth]]
-    vst = vf.allocate_statics(4)
-    vf.vsmt2_verif_gadget(pp, depth, tree.root, vv[0], vv[1:1 + depth], vv[1 + depth:], vst)
-    assert vf.verify(pf, bytes(32)) == 0
-    vf2 = api.Verifier(gens, b"VSMT")
-    vv2 = [vf2.commit(V) for V in Vs[:1 + 2 * depth]]
-    vst2 = vf2.allocate_statics(4)
-    vf2.vsmt2_verif_gadget(pp, depth, (tree.root + 1) % L, vv2[0], vv2[1:1 + depth], vv2[1 + depth:], vst2)
-    assert vf2.verify(pf, bytes(32)) == 3
+    for root, ok in ((tree.root, True), ((tree.root + 1) % L, False)):
+        vf = api.Verifier(gens, b"VSMT")
+        vv = [vf.commit(V) for V in Vs]
+        vst = vf.allocate_statics(4)
+        vf.vsmt2_verif_gadget(pp, depth, root, vv[0], vv[1:1 + depth], vv[1 + depth:], vst)
+        if ok:
+            assert vf.verify(pf, bytes(32))
+        else:
+            with pytest.raises(api.R1CSError) as e:
+                vf.verify(pf, bytes(32))
+            assert e.value.code == 3
 
 
 def test_explicit_witness_equals_witness_program(api, gens, oracle_lib):
