@@ -61,6 +61,7 @@ int bp_device_init() {
   return BP_OK;
 }
 
+static const int SG_SPARE = 8;  // spare generator slots of the shift table (padding sums of up to 8 circuit shapes)
 template <class T>
 static int dalloc(T **p, size_t count) { return dev_malloc((void **)p, count * sizeof(T)); }
 
@@ -143,7 +144,7 @@ int gens_create(uint32_t capacity, BpGens **out) {
   }
   // shift table of the sorted-bucket MSM (SB_WINDOWS x 96 B per generator): kept up to 16 GB, i.e. capacity 2^22
   if (!getenv("BP_B200_NO_TABLE") && !getenv("BP_B200_NO_SORTED") && ngen * SB_WINDOWS * sizeof(ge_niels) <= ((size_t)16 << 30)) {
-    if (dalloc(&g->sg, ngen * SB_WINDOWS)) { gens_free(g); return BP_ERR_OOM; }
+    if (dalloc(&g->sg, (ngen + SG_SPARE) * SB_WINDOWS)) { gens_free(g); return BP_ERR_OOM; }
     CK(launch((long)ngen, s, KShiftTableBuild{g->G_p3, g->H_p3, g->pc, (long)capacity, g->sg}));
     CK(dev_sync(s));
   }
@@ -282,8 +283,8 @@ static long msm_target_warps() { return 148L * 8 * 4; }
 // device bytes ensure_workspace() + ensure_front() allocate per proof of a chunk (the MSM bucket floor of small chunks aside)
 double engine_workspace_bytes_per_proof(const BpCircuit *c) {
   const double n = c->n, N = c->N, m = c->m, q = c->q, k = c->k;
-  const double rows = std::max(std::max(5 * n + 3, 2 * (N + 1)), 2 * N + m + 13 + 2 * k + 2);
-  const double items = std::max(2 * n + 1, N + 1) * SB_WINDOWS, slices = SB_BUCKETS + items / SB_SEG + 2;
+  const double rows = std::max(std::max(5 * n + 3, 2 * (N + 2)), 2 * N + m + 13 + 2 * k + 2);
+  const double items = std::max(2 * n + 1, N + 2) * SB_WINDOWS, slices = SB_BUCKETS + items / SB_SEG + 2;
   const double nch = std::max(n, N) / CH_DOT + 2;
   double b = 0;
   b += sizeof(scm) * ((double)c->nslots + (q + 1) + 4 * N + (2 * k + 2) + 40 + nch * 6 + (c->npub + 1));  // w_all, zpow, ypow, yinvpow, a, b, ...
@@ -301,11 +302,11 @@ static int ensure_workspace(BpCircuit *c, int B) {
   const size_t n = c->n, N = c->N, m = c->m, q = c->q, Bz = (size_t)B;
   const size_t k = c->k;
   size_t nchunks = (std::max(n, N) + CH_DOT - 1) / CH_DOT + 1;
-  size_t rows_as = (2 * n + 1) + (n + 1) + (2 * n + 1), rows_ipa = 2 * (N + 1), rows_ver = 2 * N + m + 13 + 2 * k + 2;
+  size_t rows_as = (2 * n + 1) + (n + 1) + (2 * n + 1), rows_ipa = 2 * (N + 2), rows_ver = 2 * N + m + 13 + 2 * k + 2;
   w->dig_bytes = std::max(std::max(rows_as, rows_ipa), rows_ver) * SB_ROW_BYTES * Bz;  // sized for the wider 13-bit rows
   // bucket slots: enough for one MSM launch at the largest split the launcher will pick
   size_t max_warps = (size_t)std::max<long>(msm_target_warps(), 2L * B) + B;
-  w->items_cap = (size_t)std::max(2 * n + 1, N + 1) * SB_WINDOWS;  // items of one instance
+  w->items_cap = (size_t)std::max(2 * n + 1, N + 2) * SB_WINDOWS;  // items of one instance
   w->slices_cap = SB_BUCKETS + w->items_cap / SB_SEG + 2;  // partial sums: one per (bucket, segment) crossing
   w->bucket_slots = std::max(max_warps * MSM_WINDOWS * MSM_BUCKETS, Bz * w->slices_cap);
   int bad = 0;
@@ -406,6 +407,29 @@ static void base_transcript(strobe128 &t, const uint8_t *label, int label_len) {
   ts_init(t, label, label_len);
   const uint8_t r1[7] = {'r', '1', 'c', 's', ' ', 'v', '1'};
   ts_append(t, "dom-sep", r1, 7);
+}
+
+// Round 0 of a padded circuit: the N - n H-rows of L_0 whose partner index is a padding index all carry the scalar -y^h
+// (KRecodeUnfolded13), so their generators are summed ONCE per (generators, n, N) into a spare slot of the shift table.
+// Returns the generator index of the slot, or -1 when there is no padding / no spare slot (then the rows are kept).
+static long ensure_pad_generator(BpGens *g, long n, long N, dev_stream s) {
+  if (!g->sg || n >= N || getenv("BP_B200_NO_PADSUM")) return -1;
+  for (int k = 0; k < g->pad_count; k++) if (g->pad_n[k] == n && g->pad_N[k] == N) return 2L * g->capacity + 2 + k;
+  if (g->pad_count >= SG_SPARE) return -1;
+  const long h = N / 2, first = n - h, count = h - first;  // H_first .. H_{h-1}
+  if (first < 0 || count <= 0) return -1;
+  const long T = count < 256 ? count : 256;
+  ge_p3 *tmp = nullptr;
+  if (dalloc(&tmp, (size_t)T + 1)) return -1;
+  int bad = launch(T, s, KSumPointsStrided{g->H_p3 + first, count, T, tmp});
+  bad |= launch(1, s, KSumPointsStrided{tmp, T, 1, tmp + T});
+  const int k = g->pad_count;
+  bad |= launch(1, s, KShiftTableOne{tmp + T, 2L * g->capacity + 2 + k, g->sg});
+  bad |= dev_sync(s);
+  dev_free(tmp);
+  if (bad) return -1;
+  g->pad_n[k] = n; g->pad_N[k] = N; g->pad_count = k + 1;
+  return 2L * g->capacity + 2 + k;
 }
 
 // ------------------------------------------------------------------------------------------------ prover
@@ -584,9 +608,15 @@ static int prove_phase_b(const BpGens *g, BpCircuit *c, Front &f, const ProveArg
       const int cur = round & 1;
       RowMap rl{1, nullptr, (long)g->capacity, N, len, h}, rr{2, nullptr, (long)g->capacity, N, len, h};
       if (sorted) {
-        CK(launch((N / 2) * B, s, KRecodeUnfolded13{w->a, w->b, UG[cur], UH[cur], w->yinvpow, ch_u, w->clr, ch_w, N, len, h, n, B, dL, dR, rows * rb}));
-        rc = run_msm_sorted(g, w, rl, rows, B, dL, rows * rb, A.proofs + 448 + 64 * round, plen, s); if (rc) return rc;
-        rc = run_msm_sorted(g, w, rr, rows, B, dR, rows * rb, A.proofs + 448 + 64 * round + 32, plen, s); if (rc) return rc;
+        // round 0 of a padded circuit: one extra row (N + 1) stands for the N - n H-rows of L_0 that share the scalar -y^h
+        const long pad_gen = (round == 0 && (size_t)(N + 2) * SB_WINDOWS <= w->items_cap) ? ensure_pad_generator(const_cast<BpGens *>(g), n, N, s) : -1;
+        const long srows = pad_gen >= 0 ? rows + 1 : rows;
+        int8_t *dRs = w->dig + srows * rb * B;
+        rl.pad_gen = rr.pad_gen = pad_gen;
+        CK(launch((N / 2) * B, s, KRecodeUnfolded13{w->a, w->b, UG[cur], UH[cur], w->yinvpow, ch_u, w->clr, ch_w, N, len, h, n, B, dL, dRs, srows * rb,
+                                                    pad_gen >= 0 ? 1 : 0, w->ypow + h * B}));
+        rc = run_msm_sorted(g, w, rl, srows, B, dL, srows * rb, A.proofs + 448 + 64 * round, plen, s); if (rc) return rc;
+        rc = run_msm_sorted(g, w, rr, srows, B, dRs, srows * rb, A.proofs + 448 + 64 * round + 32, plen, s); if (rc) return rc;
       } else {
         CK(launch((N / 2) * B, s, KRecodeUnfolded{w->a, w->b, UG[cur], UH[cur], w->yinvpow, ch_u, w->clr, ch_w, N, len, h, n, B, dL, dR, rows * rb}));
         rc = run_msm_table(g, w, rl, rows, B, dL, rows * rb, A.proofs + 448 + 64 * round, plen, s); if (rc) return rc;

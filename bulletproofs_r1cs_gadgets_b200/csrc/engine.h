@@ -15,7 +15,8 @@ struct BpGens {
   ge_p3 *pc;            // B, B_blinding
   ge_niels *pc_niels;
   ge_niels *pc_table;   // [2][64][16]
-  ge_niels *sg;         // shift table [(2cap+2)][20]: 2^(13w) * P (sorted-bucket MSM); NULL when disabled
+  ge_niels *sg;         // shift table [(2cap+2) + SG_SPARE][SB_WINDOWS]: 2^(15w) * P (sorted-bucket MSM); NULL when disabled
+  long pad_n[8], pad_N[8]; int pad_count;  // spare shift-table slots holding sum_{i=n-N/2}^{N/2-1} H_i of the circuits seen (see engine.cu)
   ge_niels *table;      // fixed-base tables [(2cap+2)][32][128] (see KTableBuild); NULL when disabled
   uint8_t pc_c[64];     // compressed B, B_blinding (host copy)
   struct Workspace *msm_ws; uint32_t msm_ws_n;  // scratch of the MSM microbenchmark entry

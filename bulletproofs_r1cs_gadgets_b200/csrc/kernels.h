@@ -1138,13 +1138,14 @@ struct KTableBuild {
 
 // row -> generator index.  mode 0: explicit map; 1/2: the L / R multiscalar multiplication of an UNFOLDED inner-product
 // round over the original generators (nj = current vector length, h = nj/2, N rows of G then H, last row = B).
-struct RowMap { int mode; const uint32_t *map; long cap, N, nj, h; long inst_off; };  // inst_off: generator offset per instance (split MSM)
+struct RowMap { int mode; const uint32_t *map; long cap, N, nj, h; long inst_off; long pad_gen; };  // inst_off: generator offset per instance (split MSM); pad_gen: generator index of row N + 1 (modes 1, 2)
 HD long row_gen(const RowMap &m, long r) {
   if (m.mode == 0) return m.map[r];
   if (m.mode == 3) return r;  // (global) row r is generator r; sub-instance `inst` of a split MSM covers rows inst * inst_off ..
   if (m.mode == 4) return r == 0 ? 2 * m.cap + m.nj : m.nj * m.cap + (r - 1);  // verifier half nj (0: B, G_i; 1: B_blinding, H_i)
   if (m.mode == 5) return r < m.N ? r : (r < 2 * m.N ? m.cap + (r - m.N) : 2 * m.cap + (r - 2 * m.N));  // combined check: G_0.., H_0.., B, B_blinding
   if (r == m.N) return 2 * m.cap;  // B
+  if (r == m.N + 1) return m.pad_gen;  // sum of the padding generators (round 0, see KRecodeUnfolded13)
   const long half = m.N / 2;
   const bool isH = r >= half;
   const long rr = isH ? r - half : r, blk = rr / m.h, i = rr % m.h;
@@ -1368,6 +1369,19 @@ struct KShiftTableBuild {
     }
   }
 };
+// shift-table rows of ONE extra point (a circuit's sum of padding generators) at generator slot `gen`
+struct KShiftTableOne {
+  static constexpr int kBlock = 32, kMinBlocks = 1;
+  static constexpr const char *kName = "KShiftTableOne";
+  const ge_p3 *pt; long gen; ge_niels *sg;
+  HD void operator()(long) const {
+    ge_p3 P; load_struct(P, pt);
+    for (int w = 0; w < SB_WINDOWS; w++) {
+      ge_niels nl; ge_to_niels(nl, P); store_struct(&sg[gen * SB_WINDOWS + w], nl);
+      for (int i = 0; i < SB_BITS; i++) ge_dbl(P, P);
+    }
+  }
+};
 // src [cnt][B] (optionally times mul[p]) -> 13-bit digit rows row0.. of each instance
 struct KRecode13 {
   static constexpr int kBlock = 128, kMinBlocks = 1;
@@ -1386,7 +1400,12 @@ struct KRecodeUnfolded13 {
   static constexpr int kBlock = 128, kMinBlocks = 1;
   static constexpr const char *kName = "KRecodeUnfolded13";
   const scm *a, *b, *UG, *UH, *yinvpow, *ufac, *clr, *w; long N, nj, h, n; int B; int8_t *digL, *digR; long inst_stride;
+  // Round 0 of a padded circuit (n < N): the padded entries of r are -y^i, so every H-row of L whose partner index h + i is
+  // >= n carries the SAME scalar y^-i * (-y^(h+i)) = -y^h.  With pad_rows set those N - n rows are left empty and one extra
+  // row N + 1 holds -y^h for the precomputed point sum_{i = n-h}^{h-1} H_i (ypow_h = y^h per proof).
+  int pad_rows; const scm *ypow_h;
   HD void put(int8_t *base, long row, const scm &v) const { int16_t d[SB_WINDOWS]; sc_recode13(d, v); store_digits13(base + row * SB_ROW_BYTES, d); }
+  HD void put_zero(int8_t *base, long row) const { int16_t d[SB_WINDOWS]; for (int i = 0; i < SB_WINDOWS; i++) d[i] = 0; store_digits13(base + row * SB_ROW_BYTES, d); }
   HD void operator()(long tid) const {
     int p = (int)(tid % B); long rr = tid / B;
     const long blk = rr / h, i = rr % h;
@@ -1397,10 +1416,14 @@ struct KRecodeUnfolded13 {
     int8_t *L = digL + (long)p * inst_stride, *R = digR + (long)p * inst_stride;
     const long half = N / 2;
     put(L, rr, sc_mul(sc_mul(ug, gf_hi), a_lo));
-    put(L, half + rr, sc_mul(sc_mul(sc_mul(uh, yinvpow[lo * B + p]), gf_lo), b_hi));
+    if (pad_rows && hi >= n) put_zero(L, half + rr);
+    else put(L, half + rr, sc_mul(sc_mul(sc_mul(uh, yinvpow[lo * B + p]), gf_lo), b_hi));
     put(R, rr, sc_mul(sc_mul(ug, gf_lo), a_hi));
     put(R, half + rr, sc_mul(sc_mul(sc_mul(uh, yinvpow[hi * B + p]), gf_hi), b_lo));
-    if (rr == 0) { put(L, N, sc_mul(clr[p], w[p])); put(R, N, sc_mul(clr[B + p], w[p])); }
+    if (rr == 0) {
+      put(L, N, sc_mul(clr[p], w[p])); put(R, N, sc_mul(clr[B + p], w[p]));
+      if (pad_rows) { put(L, N + 1, sc_neg(ypow_h[p])); put_zero(R, N + 1); }
+    }
   }
 };
 // item = (generator*20 + window) | sign << 31
