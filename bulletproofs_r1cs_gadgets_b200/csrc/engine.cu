@@ -90,12 +90,13 @@ struct Workspace {
   ge_p3 *wsum = 0, *Q = 0, *Gt = 0, *Ht = 0, *pts = 0;
   int8_t *naf = 0; int *naf_top = 0;
   scm *utab = 0; uint32_t *rg_as = 0; long rg_cap = -1;
+  uint32_t *rg_ai = 0; uint8_t *skip_ai = 0; long rg_ai_cap = -1;  // A_I row map / skip flags with the merged S-box rows
   uint32_t *rg_ver = 0; long rg_ver_cap = -1, rg_ver_N = -1;
   uint32_t *items = 0, *boff = 0, *soff = 0; size_t items_cap = 0, slices_cap = 0; ge_p3 *seg = 0;
   void release() {
     for (Front &f : fronts) f.release();
     fronts.clear();
-    void *ps[] = {items, boff, soff, seg, rg_ver, utab, rg_as, vpub, uj, w_all, zpow, ypow, yinvpow, a, b, chal, t, tb, clr, part, dig, buckets, wsum, Q, Gt, Ht, pts, naf, naf_top};
+    void *ps[] = {items, boff, soff, seg, rg_ver, utab, rg_as, rg_ai, skip_ai, vpub, uj, w_all, zpow, ypow, yinvpow, a, b, chal, t, tb, clr, part, dig, buckets, wsum, Q, Gt, Ht, pts, naf, naf_top};
     for (void *p : ps) dev_free(p);
     *this = Workspace();
   }
@@ -144,7 +145,8 @@ int gens_create(uint32_t capacity, BpGens **out) {
   }
   // shift table of the sorted-bucket MSM (SB_WINDOWS x 96 B per generator): kept up to 16 GB, i.e. capacity 2^22
   if (!getenv("BP_B200_NO_TABLE") && !getenv("BP_B200_NO_SORTED") && ngen * SB_WINDOWS * sizeof(ge_niels) <= ((size_t)16 << 30)) {
-    if (dalloc(&g->sg, (ngen + SG_SPARE) * SB_WINDOWS)) { gens_free(g); return BP_ERR_OOM; }
+    g->merge_slots = capacity < 16384 ? capacity : 16384;
+    if (dalloc(&g->sg, (ngen + SG_SPARE + g->merge_slots) * SB_WINDOWS)) { gens_free(g); return BP_ERR_OOM; }
     CK(launch((long)ngen, s, KShiftTableBuild{g->G_p3, g->H_p3, g->pc, (long)capacity, g->sg}));
     CK(dev_sync(s));
   }
@@ -179,6 +181,7 @@ int circuit_create(uint32_t n, uint32_t m, uint32_t npub, uint32_t q, const uint
   if (rc) return rc;
   BpCircuit *c = new BpCircuit();
   memset(c, 0, sizeof *c);
+  { static uint64_t next_serial = 0; c->serial = ++next_serial; }
   c->n = n; c->m = m; c->q = q; c->N = next_pow2(n ? n : 1); c->k = ilog2(c->N);
   c->nnz = cons_ptr[q]; c->nslots = 3 * n + m + 1 + npub; c->naux = naux; c->npub = npub;
   // validate + transpose to slot-major
@@ -249,6 +252,19 @@ int circuit_create(uint32_t n, uint32_t m, uint32_t npub, uint32_t q, const uint
       CK(dev_h2d(c->d_pos_rk, ptape->round_keys, ptape->nkeys * sizeof(scm), s));
       CK(dev_h2d(c->d_pos_mds, ptape->mds, POSEIDON_WIDTH * POSEIDON_WIDTH * sizeof(scm), s));
       c->pos = PoseidonDev{c->d_pos_rk, c->d_pos_mds, ptape->full_b, ptape->partial, ptape->full_e};
+      // inverse S-box multipliers (x, 1/x, .), (x, 0, .), (x, 1/x, .) written by the block op: the three left wires are equal and
+      // so are the first and third right wires -> A_I can use the SUM of their generators (one row per group)
+      c->merge_src = new std::vector<uint32_t>();
+      for (uint32_t b = 0; b < ptape->nblocks; b++) {
+        const PoseidonBlock &pb = ptape->blocks[b];
+        if (pb.sbox != 1) continue;
+        const uint32_t sboxes = POSEIDON_WIDTH * (ptape->full_b + ptape->full_e) + ptape->partial;
+        for (uint32_t sb = 0; sb < sboxes; sb++) {
+          const uint32_t m0 = pb.first_mult + 3 * sb;
+          c->merge_src->insert(c->merge_src->end(), {m0, m0 + 1, m0 + 2});                       // left wires: G_m0 + G_m0+1 + G_m0+2
+          c->merge_src->insert(c->merge_src->end(), {n + m0, n + m0 + 2, 0xffffffffu});          // right wires: H_m0 + H_m0+2
+        }
+      }
     }
   }
   CK(dev_sync(s));
@@ -260,6 +276,7 @@ void circuit_free(BpCircuit *c) {
   if (!c) return;
   dev_free(c->d_slot_ptr); dev_free(c->d_tq); dev_free(c->d_tcoeff); dev_free(c->d_tape); dev_free(c->d_wptr); dev_free(c->d_wkind);
   dev_free(c->d_widx); dev_free(c->d_wcoeff); dev_free(c->d_pblocks); dev_free(c->d_pos_rk); dev_free(c->d_pos_mds);
+  delete c->merge_src;
   if (c->ws) { c->ws->release(); delete c->ws; }
   delete c;
 }
@@ -321,7 +338,7 @@ static int ensure_workspace(BpCircuit *c, int B) {
   bad |= dalloc(&w->naf, 4 * 256 * Bz); bad |= dalloc(&w->naf_top, 4 * Bz);
   bad |= dalloc(&w->items, w->items_cap * Bz); bad |= dalloc(&w->boff, (size_t)(SB_BUCKETS + 1) * Bz); bad |= dalloc(&w->soff, (size_t)(SB_BUCKETS + 1) * Bz);
   bad |= dalloc(&w->seg, (size_t)SB_SEGS * 2 * Bz);
-  bad |= dalloc(&w->utab, 4 * (size_t)(1 << UNFOLD_MAX) * Bz + 4 * Bz); bad |= dalloc(&w->rg_as, 2 * n + 2);
+  bad |= dalloc(&w->utab, 4 * (size_t)(1 << UNFOLD_MAX) * Bz + 4 * Bz); bad |= dalloc(&w->rg_as, 2 * n + 2); bad |= dalloc(&w->rg_ai, 2 * n + 2); bad |= dalloc(&w->skip_ai, 2 * n + 2);
   if (bad) { w->release(); return BP_ERR_OOM; }
   w->B = B;
   return BP_OK;
@@ -432,6 +449,44 @@ static long ensure_pad_generator(BpGens *g, long n, long N, dev_stream s) {
   return 2L * g->capacity + 2 + k;
 }
 
+// A_I with merged rows: builds (once per generators / circuit pair) the generator sums of the circuit's equal-scalar groups in
+// the merge slots of the shift table, the row -> generator map that points each group's first row at its sum, and the skip flags
+// of the other rows.  Returns 1 when the merged map is usable.
+static int ensure_merged_ai(BpGens *g, BpCircuit *c, dev_stream s) {
+  Workspace *w = c->ws;
+  if (!g->sg || !c->merge_src || c->merge_src->empty() || getenv("BP_B200_NO_MERGE")) return 0;
+  const long groups = (long)c->merge_src->size() / 3, n = c->n, cap = g->capacity;
+  if (groups > g->merge_slots) return 0;
+  const long slot0 = 2 * cap + 2 + SG_SPARE;
+  if (g->merge_owner != c->serial) {
+    std::vector<uint32_t> src(*c->merge_src);
+    for (uint32_t &x : src) if (x != 0xffffffffu) x = x < (uint32_t)n ? x : (uint32_t)(cap + (x - n));  // circuit index -> generator index
+    uint32_t *d_src = nullptr;
+    if (dalloc(&d_src, src.size())) return 0;
+    int bad = dev_h2d(d_src, src.data(), src.size() * sizeof(uint32_t), s);
+    bad |= launch(groups, s, KMergeGens{g->G_p3, g->H_p3, cap, d_src, slot0, g->sg});
+    bad |= dev_sync(s);
+    dev_free(d_src);
+    if (bad) return 0;
+    g->merge_owner = c->serial;
+    w->rg_ai_cap = -1;
+  }
+  if (w->rg_ai_cap != cap) {
+    std::vector<uint32_t> rg(2 * n + 1);
+    std::vector<uint8_t> skip(2 * n + 1, 0);
+    rg[0] = 2 * cap + 1;
+    for (long i = 0; i < n; i++) { rg[1 + i] = (uint32_t)i; rg[1 + n + i] = (uint32_t)(cap + i); }
+    for (long j = 0; j < groups; j++) {
+      const uint32_t lead = (*c->merge_src)[3 * j];
+      rg[1 + lead] = (uint32_t)(slot0 + j);  // rows are 1 + circuit index (left wires 0..n-1, right wires n..2n-1)
+      for (int t = 1; t < 3; t++) { const uint32_t o = (*c->merge_src)[3 * j + t]; if (o != 0xffffffffu) skip[1 + o] = 1; }
+    }
+    if (dev_h2d(w->rg_ai, rg.data(), rg.size() * sizeof(uint32_t), s) || dev_h2d(w->skip_ai, skip.data(), skip.size(), s) || dev_sync(s)) return 0;
+    w->rg_ai_cap = cap;
+  }
+  return 1;
+}
+
 // ------------------------------------------------------------------------------------------------ prover
 // Phase A of one chunk (SURVEY A.3 steps 1-3 + witness): everything here is a one-thread-per-proof sequential chain
 // (Keccak permutations, field inversions), i.e. latency-bound and nearly free in throughput terms.  It runs on the chunk's
@@ -514,15 +569,18 @@ static int prove_phase_b(const BpGens *g, BpCircuit *c, Front &f, const ProveArg
     const bool sorted = g->sg != nullptr && rowsI >= SORTED_MIN_ROWS;
     const long rb = sorted ? SB_ROW_BYTES : 32;
     int8_t *dI = w->dig, *dO = dI + rowsI * rb * B, *dS = dO + rowsO * rb * B;
+    // witness written by the tape's Poseidon block op: rows with equal scalars by construction share one (summed) generator
+    const int merged = (sorted && !A.aL) ? ensure_merged_ai(const_cast<BpGens *>(g), c, s) : 0;
+    const uint8_t *skipI = merged ? w->skip_ai : nullptr;
     if (sorted) {
-      CK(launch(B, s, KRecode13{i_b, nullptr, 1, B, dI, rowsI * rb, 0}));
-      CK(launch(n * B, s, KRecode13{aL, nullptr, (int)n, B, dI, rowsI * rb, 1}));
-      CK(launch(n * B, s, KRecode13{aR, nullptr, (int)n, B, dI, rowsI * rb, (int)(1 + n)}));
+      CK(launch(B, s, KRecode13{i_b, nullptr, 1, B, dI, rowsI * rb, 0, nullptr}));
+      CK(launch(n * B, s, KRecode13{aL, nullptr, (int)n, B, dI, rowsI * rb, 1, skipI}));
+      CK(launch(n * B, s, KRecode13{aR, nullptr, (int)n, B, dI, rowsI * rb, (int)(1 + n), skipI}));
       CK(launch(B, s, KRecode{i_b + B, nullptr, 1, B, dO, rowsO * 32, 0}));   // A_O stays on the direct tables: its scalars are 0/1
       CK(launch(n * B, s, KRecode{aO, nullptr, (int)n, B, dO, rowsO * 32, 1}));
-      CK(launch(B, s, KRecode13{i_b + 2L * B, nullptr, 1, B, dS, rowsI * rb, 0}));
-      CK(launch(n * B, s, KRecode13{sL, nullptr, (int)n, B, dS, rowsI * rb, 1}));
-      CK(launch(n * B, s, KRecode13{sR, nullptr, (int)n, B, dS, rowsI * rb, (int)(1 + n)}));
+      CK(launch(B, s, KRecode13{i_b + 2L * B, nullptr, 1, B, dS, rowsI * rb, 0, nullptr}));
+      CK(launch(n * B, s, KRecode13{sL, nullptr, (int)n, B, dS, rowsI * rb, 1, nullptr}));
+      CK(launch(n * B, s, KRecode13{sR, nullptr, (int)n, B, dS, rowsI * rb, (int)(1 + n), nullptr}));
     } else {
       CK(launch(B, s, KRecode{i_b, nullptr, 1, B, dI, rowsI * rb, 0}));
       CK(launch(n * B, s, KRecode{aL, nullptr, (int)n, B, dI, rowsI * rb, 1}));
@@ -543,7 +601,8 @@ static int prove_phase_b(const BpGens *g, BpCircuit *c, Front &f, const ProveArg
       }
       RowMap rm{0, w->rg_as, (long)g->capacity, 0, 0, 0};
       if (sorted) {
-        rc = run_msm_sorted(g, w, rm, rowsI, B, dI, rowsI * rb, A.proofs + 0, plen, s); if (rc) return rc;
+        RowMap rmI{0, merged ? w->rg_ai : w->rg_as, (long)g->capacity, 0, 0, 0};
+        rc = run_msm_sorted(g, w, rmI, rowsI, B, dI, rowsI * rb, A.proofs + 0, plen, s); if (rc) return rc;
         rc = run_msm_table(g, w, rm, rowsO, B, dO, rowsO * 32, A.proofs + 32, plen, s); if (rc) return rc;
         rc = run_msm_sorted(g, w, rm, rowsI, B, dS, rowsI * rb, A.proofs + 64, plen, s); if (rc) return rc;
       } else {
@@ -721,7 +780,7 @@ static int sorted_split_msm(BpGens *g, long nrows, const uint8_t *d_bytes, const
   }
   CK(dev_memset(w->dig, 0, (size_t)S * R * SB_ROW_BYTES, s));  // rows past nrows stay all-zero digits
   if (d_bytes) { CK(launch(nrows, s, KLoadScalars{d_bytes, w->a, (int)nrows, 1})); d_scm = w->a; }
-  CK(launch(nrows, s, KRecode13{d_scm, nullptr, (int)nrows, 1, w->dig, 0, 0}));  // B = 1: row i at dig + i * SB_ROW_BYTES = sub-instance i / R, row i % R
+  CK(launch(nrows, s, KRecode13{d_scm, nullptr, (int)nrows, 1, w->dig, 0, 0, nullptr}));  // B = 1: row i at dig + i * SB_ROW_BYTES = sub-instance i / R, row i % R
   RowMap rm{mode, nullptr, (long)g->capacity, mapN, 0, 0, R};
   CK(launch_sort_buckets(rm, w->dig, R * SB_ROW_BYTES, R, S, w->items, (long)w->items_cap, w->boff, w->soff, s));
   SortedView sv{w->items, w->boff, w->soff, (long)w->items_cap, (long)w->slices_cap};

@@ -16,7 +16,8 @@ struct BpGens {
   ge_niels *pc_niels;
   ge_niels *pc_table;   // [2][64][16]
   ge_niels *sg;         // shift table [(2cap+2) + SG_SPARE][SB_WINDOWS]: 2^(15w) * P (sorted-bucket MSM); NULL when disabled
-  long pad_n[8], pad_N[8]; int pad_count;  // spare shift-table slots holding sum_{i=n-N/2}^{N/2-1} H_i of the circuits seen (see engine.cu)
+  long pad_n[8], pad_N[8]; int pad_count;
+  long merge_slots; uint64_t merge_owner;  // slots after the spare ones hold the generator sums of ONE circuit at a time (KMergeGens)  // spare shift-table slots holding sum_{i=n-N/2}^{N/2-1} H_i of the circuits seen (see engine.cu)
   ge_niels *table;      // fixed-base tables [(2cap+2)][32][128] (see KTableBuild); NULL when disabled
   uint8_t pc_c[64];     // compressed B, B_blinding (host copy)
   struct Workspace *msm_ws; uint32_t msm_ws_n;  // scratch of the MSM microbenchmark entry
@@ -33,6 +34,8 @@ struct BpCircuit {
   int has_tape;
   TapeOp *d_tape; uint32_t *d_wptr; uint8_t *d_wkind; uint32_t *d_widx; scm *d_wcoeff;
   PoseidonBlock *d_pblocks; scm *d_pos_rk, *d_pos_mds; PoseidonDev pos;
+  uint64_t serial;                   // unique per circuit_create (a freed circuit's address may be reused)
+  std::vector<uint32_t> *merge_src;  // host: groups of A_I rows with equal scalars, 3 generator indices each (G index, or n + H index; ~0 unused)
   Workspace *ws;
 };
 

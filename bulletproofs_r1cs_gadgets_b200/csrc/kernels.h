@@ -1387,12 +1387,40 @@ struct KRecode13 {
   static constexpr int kBlock = 128, kMinBlocks = 1;
   static constexpr const char *kName = "KRecode13";
   const scm *src; const scm *mul; int cnt, B; int8_t *dig; long inst_stride; int row0;
+  const uint8_t *skip;  // optional, indexed by row: rows merged into another row's generator sum get all-zero digits
   HD void operator()(long tid) const {
     int p = (int)(tid % B); long i = tid / B;
-    scm s = src[i * B + p];
-    if (mul) s = sc_mul(s, mul[p]);
-    int16_t d[SB_WINDOWS]; sc_recode13(d, s);
+    int16_t d[SB_WINDOWS];
+    if (skip && skip[row0 + i]) {
+#pragma unroll
+      for (int j = 0; j < SB_WINDOWS; j++) d[j] = 0;
+    } else {
+      scm s = src[i * B + p];
+      if (mul) s = sc_mul(s, mul[p]);
+      sc_recode13(d, s);
+    }
     store_digits13(dig + (long)p * inst_stride + (row0 + i) * SB_ROW_BYTES, d);
+  }
+};
+// shift-table rows of generator SUMS: group j = sum of `cnt[j]` generators src[j][0..] (indices into the G | H space) at slot
+// slot0 + j.  Used for multipliers whose values are equal by construction (the three left wires and the two non-zero right
+// wires of an inverse S-box), so that A_I pays one row per group.
+struct KMergeGens {
+  static constexpr int kBlock = 64, kMinBlocks = 1;
+  static constexpr const char *kName = "KMergeGens";
+  const ge_p3 *G, *H; long cap; const uint32_t *src; long slot0; ge_niels *sg;  // src[3*j + {0,1,2}], 0xffffffff = unused
+  HD void operator()(long j) const {
+    ge_p3 P; ge_identity(P);
+    for (int t = 0; t < 3; t++) {
+      const uint32_t gidx = src[3 * j + t];
+      if (gidx == 0xffffffffu) continue;
+      ge_p3 Q; load_struct(Q, gidx < cap ? &G[gidx] : &H[gidx - cap]);
+      ge_add(P, P, Q);
+    }
+    for (int w = 0; w < SB_WINDOWS; w++) {
+      ge_niels nl; ge_to_niels(nl, P); store_struct(&sg[(slot0 + j) * SB_WINDOWS + w], nl);
+      for (int i = 0; i < SB_BITS; i++) ge_dbl(P, P);
+    }
   }
 };
 // same scalars as KRecodeUnfolded, 13-bit rows

@@ -270,20 +270,26 @@ def test_chunking_is_invisible(api, gens, monkeypatch):
 
 def test_msm_path_choice_is_invisible(api, gens, monkeypatch):
     """the direct 8-bit tables (small instances) and the sorted-bucket path on the 15-bit shift table (>= 8192 rows per
-    instance by default) must give the same proof bytes and the same verdicts: force each path on a small circuit"""
+    instance by default) must give the same proof bytes and the same verdicts: force each path on small circuits.  The
+    sorted path also collapses the padding rows of L_0 into one row and, for inverse-S-box Poseidon circuits proven from the
+    witness program, the equal-scalar rows of A_I into generator sums -- both are covered here."""
     from bulletproofs_r1cs_gadgets_b200 import workloads
-    wl = workloads.Mimc(gens, rounds=5)
-    inp = wl.inputs(0, 3)
-    outs = []
-    for min_rows in ("1000000000", "0"):
-        monkeypatch.setenv("BP_B200_SORTED_MIN_ROWS", min_rows)
+    for wl in (workloads.Mimc(gens, rounds=5), workloads.PoseidonHash2(gens, api.SBOX_INVERSE, params=api.PoseidonParams(6, 2, 2, 3))):
+        inp = wl.inputs(0, 3)
+        outs = []
+        for min_rows in ("1000000000", "0"):
+            monkeypatch.setenv("BP_B200_SORTED_MIN_ROWS", min_rows)
+            V, P, st = wl.circuit.prove_batch(gens, wl.label, inp["v"], inp["v_blinding"], inp["entropy"], pub=inp["pub"])
+            assert not st.any()
+            assert not wl.circuit.verify_batch(gens, wl.label, V, P, inp["entropy"], pub=inp["pub"]).any()
+            bad = inp["pub"].copy(); bad[1, 0, 0] ^= 1
+            assert wl.circuit.verify_batch(gens, wl.label, V, P, inp["entropy"], pub=bad).tolist() == [0, 3, 0]
+            outs.append((V.tobytes(), P.tobytes()))
+        assert outs[0] == outs[1], wl.name
+        monkeypatch.setenv("BP_B200_NO_MERGE", "1"); monkeypatch.setenv("BP_B200_NO_PADSUM", "1")
         V, P, st = wl.circuit.prove_batch(gens, wl.label, inp["v"], inp["v_blinding"], inp["entropy"], pub=inp["pub"])
-        assert not st.any()
-        assert not wl.circuit.verify_batch(gens, wl.label, V, P, inp["entropy"], pub=inp["pub"]).any()
-        bad = inp["pub"].copy(); bad[1, 0, 0] ^= 1
-        assert wl.circuit.verify_batch(gens, wl.label, V, P, inp["entropy"], pub=bad).tolist() == [0, 3, 0]
-        outs.append((V.tobytes(), P.tobytes()))
-    assert outs[0] == outs[1]
+        assert (V.tobytes(), P.tobytes()) == outs[0]
+        monkeypatch.delenv("BP_B200_NO_MERGE"); monkeypatch.delenv("BP_B200_NO_PADSUM")
 
 
 def test_combined_verification(api, gens):
