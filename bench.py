@@ -288,11 +288,14 @@ def main():
     # measured peak of the same addition in isolation (profiles/r01_field_microbench_3way.jsonl, ge_madd, 32 warps/SM)
     roofline_int = None
     if "KBucketAccumulate" in prof:
-        adds = float(terms_sorted) * SB_WINDOWS * B * args.steps  # one addition per non-zero digit (upper bound: zero scalars add nothing)
+        # rows that actually reach the kernel: the three equal left wires / two equal right wires of every inverse S-box share one
+        # row of A_I (188 S-boxes per level), and the N - n padding rows of L_0 are one row
+        rows_sorted = terms_sorted - 3 * 188 * args.depth - (N - n - 1)
+        adds = float(rows_sorted) * SB_WINDOWS * B * args.steps  # one addition per non-zero digit (upper bound: zero scalars add nothing)
         ach = adds / (prof["KBucketAccumulate"][1] / 1000.0) / 1e9
         roofline_int = {"kernel": "KBucketAccumulate", "bound": "integer pipe (IMAD.WIDE)", "achieved": ach, "peak": 12.57, "unit": "G mixed additions/s",
                         "frac": ach / 12.57, "peak_source": "measured: ge_madd microbenchmark on this pool (tools/fe_bench2)",
-                        "note": "additions counted as terms x 17 windows; rows with a zero scalar contribute none, so this is an upper bound"}
+                        "note": "additions counted as rows x 17 windows; rows with a zero scalar (a third of a_R, the padded half of round 0) contribute none, so this is an upper bound"}
 
     # ---- cpu_baseline: the oracle port on a bounded sample of the same workload ----
     cpu = None
