@@ -13,7 +13,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "_obj")
 SO = os.path.join(PKG, "libbp_b200.so")
-UNITS = ["engine", "gadgets", "capi", "k_msm", "k_fold", "k_points", "k_transcript", "k_scalar", "k_table", "k_sorted"]
+UNITS = ["engine", "gadgets", "capi", "tree", "k_msm", "k_fold", "k_points", "k_transcript", "k_scalar", "k_table", "k_sorted"]
 NVCC = os.environ.get("NVCC", "nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]

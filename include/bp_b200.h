@@ -218,6 +218,35 @@ int32_t bp_verify_batch_combined_device(const bp_gens *g, bp_circuit *c, uint32_
 int64_t bp_proof_to_wire(const uint8_t *proof, size_t proof_len, uint8_t *out, size_t out_cap);
 int64_t bp_proof_from_wire(const uint8_t *wire, size_t wire_len, uint8_t *proof_out, size_t out_cap);
 
+/* ---- device-side sparse Merkle tree (the step before the hot path) ----------------
+ * Batched VanillaSparseMerkleTree (reference src/gadget_vsmt_2.rs:27-166) with every Poseidon hash on the GPU.  Leaf indices
+ * are uint64 (depth <= 63; the reference's TreeDepth = 253 stays with the host mirror); values are 32-byte LE scalars.
+ * Nodes are stored by position, so the tree keeps its latest state only (the reference's content-addressed map also
+ * keeps every older node; `get`, `update` and `root` cannot tell the difference). */
+typedef struct bp_vsmt2 bp_vsmt2;
+/* VanillaSparseMerkleTree::new (src/gadget_vsmt_2.rs:36-61): empty-subtree hashes, root of the empty tree.  The reference
+ * always hashes with SboxType::Inverse (:45,79,85). */
+int32_t bp_vsmt2_new(const bp_poseidon_params *p, uint32_t depth, int32_t sbox, bp_vsmt2 **out);
+void bp_vsmt2_free(bp_vsmt2 *t);
+uint32_t bp_vsmt2_depth(const bp_vsmt2 *t);
+uint64_t bp_vsmt2_num_nodes(const bp_vsmt2 *t); /* stored (non-empty) nodes of all levels */
+int32_t bp_vsmt2_root(const bp_vsmt2 *t, uint8_t root[32]);
+int32_t bp_vsmt2_empty_hashes(const bp_vsmt2 *t, uint8_t *out /* [depth+1][32], [0] = leaf level */);
+/* count x VanillaSparseMerkleTree::update (src/gadget_vsmt_2.rs:63-98) in one pass: level by level, one hash per DISTINCT
+ * parent.  A repeated index keeps its last value, as sequential updates would.  root_out may be NULL. */
+int32_t bp_vsmt2_update_batch(bp_vsmt2 *t, uint32_t count, const uint64_t *idx, const uint8_t *vals, uint8_t root_out[32]);
+/* count x VanillaSparseMerkleTree::get (src/gadget_vsmt_2.rs:101-131): leaves [count][32], proofs [count][depth][32] with
+ * the siblings root -> leaf, the order `get` pushes them */
+int32_t bp_vsmt2_get_batch(const bp_vsmt2 *t, uint32_t count, const uint64_t *idx, uint8_t *leaves, uint8_t *proofs);
+/* committed values of count membership proofs in the commit order of the reference's prover (src/gadget_vsmt_2.rs:296-330):
+ * v [count][2*depth+5][32] = leaf, index bits LSB first, siblings leaf level first, statics 0,101,0,0 -- the `v` argument of
+ * bp_prove_batch[_device] for the circuit of bp_gadget_vsmt2_verif_public; pub [count][32] = the root (may be NULL).
+ * _device: device pointers (idx uint64 [count]), asynchronous on `stream`. */
+int32_t bp_vsmt2_witness_batch(const bp_vsmt2 *t, uint32_t count, const uint64_t *idx, uint8_t *v, uint8_t *pub);
+int32_t bp_vsmt2_witness_batch_device(const bp_vsmt2 *t, uint32_t count, const uint64_t *d_idx, uint8_t *d_v, uint8_t *d_pub, void *stream);
+/* Poseidon_hash_2 (src/gadget_poseidon.rs:428-443) of count independent pairs on the device; host buffers [count][32] */
+int32_t bp_poseidon_hash_2_batch(const bp_poseidon_params *p, int32_t sbox, uint32_t count, const uint8_t *xl, const uint8_t *xr, uint8_t *out);
+
 /* ---- MSM microbenchmark entry (BASELINE.json config 3) -------------------------------------------
  * result = sum_i scalars[i] * points[i] over ristretto255; points are the first n generators of chain G.
  * d_scalars: device, [n][32] canonical LE.  out: device, 32 bytes. */

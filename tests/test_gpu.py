@@ -56,6 +56,11 @@ def test_wire_format(api, gens): E.test_wire_format(api, gens)
 def test_vsmt4_membership_small(api, gens): E.test_vsmt4_membership(api, gens)
 def test_vsmt4_membership_reference_parameters(api, gens_big, oracle_lib): E.test_vsmt4_membership(api, gens_big, levels=3, params=(6, 4, 4, 140), count=2, c_oracle_prover=True)
 def test_sparse_merkle_tree_and_membership_from_a_real_tree(api, gens): E.test_sparse_merkle_tree_and_membership_from_a_real_tree(api, gens)
+def test_device_tree_small(api, gens): E.test_device_tree(api, gens)
+def test_device_tree_depth5(api, gens): E.test_device_tree_depth5(api, gens)
+def test_device_tree_reference_parameters(api, gens_big, oracle_lib):
+    """depth 32, Poseidon 4+140+4 inverse: device tree vs the oracle's one-key-at-a-time tree hashing with the C oracle; membership proofs from the tree"""
+    E.test_device_tree(api, gens_big, oracle_lib=oracle_lib, depth=32, params=(6, 4, 4, 140), nkeys=24, prove=True, seed=901)
 def test_error_codes(api, gens): E.test_error_codes(api, gens)
 def test_single_multiplier_and_allocate_single(api, gens): E.test_single_multiplier_and_allocate_single(api, gens)
 
@@ -242,3 +247,43 @@ def test_vsmt2_depth32_batch_properties(api, gens_big):
     assert not ok.any()
     assert len({P[i].tobytes() for i in range(B)}) == B  # distinct statements, distinct proofs
     assert P.shape[1] == 1472 and all(P[i, 96:192].tobytes() == bytes(96) for i in range(B))  # single-phase: A_I2, A_O2, S2 are the identity
+
+
+def test_device_tree_large_batch_properties(api, oracle_lib):
+    """2^14 random updates at depth 32 (full Poseidon): the root does not depend on how the updates are batched, get returns what
+    update stored, paths fetched from the device verify against the device root under the ORACLE's verify_proof, and the witness
+    rows written into device buffers equal the host-buffer ones"""
+    import random
+    import torch
+    from bulletproofs_r1cs_gadgets_b200 import trees
+    from oracle import tree_pyref as TP
+    depth, K = 32, 1 << 14
+    pp = api.PoseidonParams()
+    rnd = random.Random(4242)
+    keys = [rnd.randrange(2 ** depth) for _ in range(K)]
+    keys[100] = keys[7]  # one repeated key
+    vals = api.scalars_to_array(H.rand_scalars(4243, K))
+    one = trees.DeviceVsmt2(pp, depth)
+    r_one = one.update_batch(keys, vals)
+    parts = trees.DeviceVsmt2(pp, depth)
+    for a in range(0, K, 5000):
+        r_parts = parts.update_batch(keys[a:a + 5000], vals[a:a + 5000])
+    assert r_one == r_parts == one.root == parts.root
+    assert one.num_nodes == parts.num_nodes and K * (depth - 14) < one.num_nodes <= K * (depth + 1)
+    leaves, proofs = one.get_batch(keys)
+    last = {k: i for i, k in enumerate(keys)}
+    assert all(leaves[i].tobytes() == vals[last[k]].tobytes() for i, k in enumerate(keys))
+    oracle_lib.poseidon_set_params(H.POSEIDON_BLOB)
+    checker = TP.VanillaSparseMerkleTree.__new__(TP.VanillaSparseMerkleTree)
+    checker.depth, checker.hash2, checker.root = depth, TP.c_oracle_hash2(oracle_lib, 1), r_one
+    for i in (0, 7, 100, K - 1):
+        path = [int.from_bytes(proofs[i, j].tobytes(), "little") for j in range(depth)]
+        assert checker.verify_proof(keys[i], int.from_bytes(leaves[i].tobytes(), "little"), path)
+        assert not checker.verify_proof(keys[i] ^ 1, int.from_bytes(leaves[i].tobytes(), "little"), path)
+    v, pub = one.witness_rows(keys[:64])
+    d_idx = torch.tensor(keys[:64], dtype=torch.int64, device="cuda")
+    d_v = torch.zeros((64, 2 * depth + 5, 32), dtype=torch.uint8, device="cuda")
+    d_pub = torch.zeros((64, 1, 32), dtype=torch.uint8, device="cuda")
+    one.witness_rows_device(d_idx, d_v, d_pub, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert d_v.cpu().numpy().tobytes() == v.tobytes() and d_pub.cpu().numpy().tobytes() == pub.tobytes()

@@ -243,6 +243,83 @@ def test_sparse_merkle_tree_and_membership_from_a_real_tree(api, gens):
             assert e.value.code == 3
 
 
+def test_device_tree_depth5(api, gens): test_device_tree(api, gens, depth=5, nkeys=11, prove=False)
+
+
+def test_device_tree(api, gens, oracle_lib=None, depth=3, params=(6, 2, 2, 3), nkeys=6, prove=True, seed=900):
+    """device-side batched sparse Merkle tree (bp_vsmt2_*) against the oracle's restatement of the reference's
+    VanillaSparseMerkleTree (oracle/tree_pyref.py, reference src/gadget_vsmt_2.rs:27-166) applied one key at a time:
+    empty-subtree hashes, roots after batched updates (with a repeated key and a later overwrite), get (leaf + siblings root -> leaf),
+    an untouched key, verify_proof on the device's paths, the circuit's witness rows, and a membership proof driven from the tree"""
+    import random
+    from bulletproofs_r1cs_gadgets_b200 import trees, workloads
+    from oracle import tree_pyref as TP
+    pp = api.PoseidonParams(*params)
+    if oracle_lib is not None and params == (6, 4, 4, 140):  # full-size permutation: the C oracle's hash (the Python one takes ~0.1 s)
+        oracle_lib.poseidon_set_params(H.POSEIDON_BLOB)
+        h2 = TP.c_oracle_hash2(oracle_lib, 1)
+    else:
+        opp = G.PoseidonParams(*params)
+        h2 = lambda a, b: G.poseidon_hash_2(a, b, opp, G.INVERSE)
+    ref = TP.VanillaSparseMerkleTree(h2, depth)
+    dev = trees.DeviceVsmt2(pp, depth)
+    assert dev.empty_tree_hashes == ref.empty_tree_hashes and dev.root == ref.root and dev.num_nodes == 0
+    rnd = random.Random(seed)
+    keys = [0, 2 ** depth - 1, 1] + [rnd.randrange(2 ** depth) for _ in range(nkeys - 3)]
+    vals = H.rand_scalars(seed, len(keys))
+    keys.append(keys[4]); vals.append(vals[0] + 5)  # a repeated key inside one batch: the last value stays
+    first = len(keys) // 2
+    for a, b in ((0, first), (first, len(keys))):
+        for k, v in zip(keys[a:b], vals[a:b]):
+            ref.update(k, v)
+        assert dev.update_batch(keys[a:b], vals[a:b]) == ref.root == dev.root
+    over = {keys[1]: 7, keys[5]: 0}  # overwrite existing leaves (one with the empty value)
+    for k, v in over.items():
+        ref.update(k, v)
+    assert dev.update_batch(list(over), list(over.values())) == ref.root
+    assert dev.update_batch([], []) == ref.root
+    n_before = dev.num_nodes
+    assert dev.update_batch(list(over), list(over.values())) == ref.root and dev.num_nodes == n_before  # idempotent, no new nodes
+    untouched = next(k for k in range(2 ** depth) if k not in keys)
+    q = sorted(set(keys)) + [untouched]
+    leaves, proofs = dev.get_batch(q)
+    for i, k in enumerate(q):
+        path = []
+        assert int.from_bytes(leaves[i].tobytes(), "little") == ref.get(k, path)
+        got = [int.from_bytes(proofs[i, j].tobytes(), "little") for j in range(depth)]
+        assert got == path
+        assert ref.verify_proof(k, ref.get(k), got)
+    assert int.from_bytes(leaves[-1].tobytes(), "little") == 0
+    plist = []
+    assert dev.get(q[2], plist) == ref.get(q[2]) and len(plist) == depth
+    # witness rows = the reference prover's commit order: leaf, bits LSB first, siblings leaf level first, statics
+    v, pub = dev.witness_rows(q)
+    for i, k in enumerate(q):
+        path = []; leaf = ref.get(k, path); path.reverse()
+        want = [leaf] + [(k >> j) & 1 for j in range(depth)] + path + [0, 101, 0, 0]
+        assert v[i].tobytes() == api.scalars_to_array(want).tobytes()
+        assert pub[i, 0].tobytes() == api.scalar_bytes(ref.root)
+    with pytest.raises(api.R1CSError):
+        dev.update_batch([2 ** depth], [1])
+    # batched hash entry
+    xs, ys = H.rand_scalars(seed + 1, 5), H.rand_scalars(seed + 2, 5)
+    hb = trees.poseidon_hash_2_batch(pp, [0] + xs, [0] + ys)
+    assert [int.from_bytes(hb[i].tobytes(), "little") for i in range(6)] == [h2(a, b) for a, b in zip([0] + xs, [0] + ys)]
+    if not prove:
+        return
+    # membership proofs straight from the device tree: rows -> prove_batch -> verify_batch (root as the public input)
+    wl = workloads.Vsmt2(gens, depth=depth, params=pp)
+    B = 3
+    vb = api.scalars_to_array(H.rand_scalars(seed + 3, B * wl.circuit.m)).reshape(B, wl.circuit.m, 32)
+    vb[:, -4:] = 0  # statics are committed with blinding 0 (reference src/gadget_poseidon.rs:556-571)
+    ent = np.frombuffer(bytes(range(B * 32)), dtype=np.uint8).reshape(B, 32)
+    V, P, st = wl.circuit.prove_batch(gens, wl.label, v[:B], vb, ent, pub=pub[:B])
+    assert not st.any()
+    assert not wl.circuit.verify_batch(gens, wl.label, V, P, ent, pub=pub[:B]).any()
+    bad = pub[:B].copy(); bad[1, 0, 0] ^= 1
+    assert wl.circuit.verify_batch(gens, wl.label, V, P, ent, pub=bad).tolist() == [0, 3, 0]
+
+
 def test_explicit_witness_equals_witness_program(api, gens, oracle_lib):
     from bulletproofs_r1cs_gadgets_b200 import workloads
     wl = workloads.Mimc(gens, rounds=6)
