@@ -6,8 +6,11 @@
 
 A step = one pass of the prover over one batch of `--batch` synthetic proofs per GPU (BASELINE.json
 config 5 shape: depth 32, inverse S-box, n = 18176 multipliers, N = 32768, m = 69 commitments).
-`value` = proofs/s with inputs resident in HBM; `e2e` = the same through the host-buffer C-ABI call
-(bp_prove_batch: H2D of inputs and D2H of commitments + proofs inside the timed region).
+Batches are streamed with two in flight (bp_prove_stream_*): a step enqueues the first phase of the next batch and
+the MSM / inner-product phase of the current one, so every timed step holds one whole batch of work.
+`value` = proofs/s with inputs resident in HBM; `e2e` = the same through the host-buffer C-ABI calls
+(bp_prove_stream_begin_host / _finish_host: H2D of inputs and D2H of commitments + proofs inside the timed region);
+`single_call_value` = one plain bp_prove_batch_device call (nothing overlapped across batches).
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -168,9 +171,10 @@ def main():
     pin = {k: torch.from_numpy(v).pin_memory() for k, v in inp.items() if k in ("v", "v_blinding", "entropy")}
     d = {k: t.to(dev) for k, t in pin.items()}
     m, plen = circ.m, circ.proof_len
-    d_V = torch.empty((B, m, 32), dtype=torch.uint8, device=dev)
-    d_P = torch.empty((B, plen), dtype=torch.uint8, device=dev)
-    d_S = torch.empty((B,), dtype=torch.int32, device=dev)
+    # two sets of output buffers: two batches are in flight (bp_prove_stream_*, include/bp_b200.h)
+    outs = [(torch.empty((B, m, 32), dtype=torch.uint8, device=dev), torch.empty((B, plen), dtype=torch.uint8, device=dev),
+             torch.empty((B,), dtype=torch.int32, device=dev)) for _ in range(2)]
+    d_V, d_P, d_S = outs[0]
     gathered = torch.empty((world * B, plen), dtype=torch.uint8, device=dev) if world > 1 else None
     label = b"VSMT"
     lbuf = api._buf(label)
@@ -178,14 +182,32 @@ def main():
     def ptr(t):
         return C.c_void_p(t.data_ptr())
 
-    def step_device():
+    def begin(slot):
         stream = torch.cuda.current_stream().cuda_stream
-        rc = lib.bp_prove_batch_device(gens._h, circ._h, C.c_uint32(B), lbuf, C.c_size_t(len(label)), ptr(d["v"]), ptr(d["v_blinding"]), ptr(d["entropy"]),
-                                       None, None, None, None, None, ptr(d_V), ptr(d_P), ptr(d_S), C.c_void_p(stream))
+        o = outs[slot]
+        rc = lib.bp_prove_stream_begin(gens._h, circ._h, C.c_int32(slot), C.c_uint32(B), lbuf, C.c_size_t(len(label)), ptr(d["v"]), ptr(d["v_blinding"]),
+                                       ptr(d["entropy"]), None, None, None, None, None, ptr(o[0]), ptr(o[1]), ptr(o[2]), C.c_void_p(stream))
         if rc != 0:
-            raise api.R1CSError(rc, "bp_prove_batch_device")
+            raise api.R1CSError(rc, "bp_prove_stream_begin")
+
+    def finish(slot):
+        stream = torch.cuda.current_stream().cuda_stream
+        rc = lib.bp_prove_stream_finish(gens._h, circ._h, C.c_int32(slot), C.c_void_p(stream))
+        if rc != 0:
+            raise api.R1CSError(rc, "bp_prove_stream_finish")
         if world > 1:  # the one collective of the path: gather the fixed-size proof records
-            dist.all_gather_into_tensor(gathered, d_P)
+            dist.all_gather_into_tensor(gathered, outs[slot][1])
+
+    # One step = one whole batch: the first phase (commitments, witness program, blinding draws) of the NEXT batch is enqueued,
+    # then the rest (every MSM, the inner-product argument) of the CURRENT one.  K steps hold K first phases and K second phases.
+    seq = [0]
+    begin(0)
+
+    def step_device():
+        k = seq[0]
+        begin((k + 1) % 2)
+        finish(k % 2)
+        seq[0] = k + 1
 
     def barrier():
         if world > 1:
@@ -215,23 +237,44 @@ def main():
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    status = d_S.cpu().numpy()
-    assert not status.any(), "prover status %s" % status[:8]
+    finish(seq[0] % 2)  # drain the batch whose first phase the last step enqueued
+    barrier()
+    for o in outs:
+        assert not o[2].cpu().numpy().any(), "prover status %s" % o[2][:8]
+    assert torch.equal(outs[0][1], outs[1][1]), "the two stream slots disagree"
     value = world * B * args.steps / (ms / 1000.0)
+    # the same batch as ONE plain call (no overlap between batches), for comparison
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d_P1 = torch.empty_like(d_P)
+    g0.record()
+    rc = lib.bp_prove_batch_device(gens._h, circ._h, C.c_uint32(B), lbuf, C.c_size_t(len(label)), ptr(d["v"]), ptr(d["v_blinding"]), ptr(d["entropy"]),
+                                   None, None, None, None, None, ptr(outs[1][0]), ptr(d_P1), ptr(outs[1][2]), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    g1.record()
+    barrier()
+    assert rc == 0 and torch.equal(d_P1, d_P), "streamed and plain calls disagree"
+    single_call_value = B / (g0.elapsed_time(g1) / 1000.0)
+    del d_P1
 
     # ---- e2e: the host-buffer C-ABI call (H2D inputs + D2H outputs inside the timed region) ----
     e2e = None
     if not args.no_e2e:
-        hv, hvb, hent = inp["v"], inp["v_blinding"], inp["entropy"]
+        # pinned host buffers in, pinned host buffers out; every step copies its inputs H2D and its results D2H and waits for them
+        hin = [pin[k].numpy() for k in ("v", "v_blinding", "entropy")]
+        hout = [(torch.empty((B, m, 32), dtype=torch.uint8).pin_memory().numpy(), torch.empty((B, plen), dtype=torch.uint8).pin_memory().numpy(),
+                 torch.empty((B,), dtype=torch.int32).pin_memory().numpy()) for _ in range(2)]
+        ps = api.ProveStream(circ, gens, label, stream=torch.cuda.current_stream().cuda_stream)
         e2e_steps = 2  # the device path above already warmed every kernel, table and workspace
+        ps.begin(0, *hin)
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
-        for _ in range(e2e_steps):
-            V_h, P_h, S_h = circ.prove_batch(gens, label, hv, hvb, hent)
+        for k in range(e2e_steps):
+            ps.begin((k + 1) % 2, *hin)
+            V_h, P_h, S_h = ps.finish(k % 2, out=hout[k % 2])
         f1.record()
         barrier()
         ems = f0.elapsed_time(f1)
+        ps.finish(e2e_steps % 2, out=hout[e2e_steps % 2])
         if world > 1:
             t = torch.tensor([ems], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -239,7 +282,8 @@ def main():
         assert not S_h.any()
         assert P_h.tobytes() == d_P.cpu().numpy().tobytes(), "host-buffer and device-buffer paths disagree"
         e2e = {"value": world * B * e2e_steps / (ems / 1000.0), "unit": UNIT, "steps": e2e_steps,
-               "h2d_bytes_per_step": int(hv.nbytes + hvb.nbytes + hent.nbytes), "d2h_bytes_per_step": int(V_h.nbytes + P_h.nbytes + S_h.nbytes)}
+               "h2d_bytes_per_step": int(sum(a.nbytes for a in hin)), "d2h_bytes_per_step": int(V_h.nbytes + P_h.nbytes + S_h.nbytes),
+               "api": "bp_prove_stream_begin_host / _finish_host (pinned host buffers; H2D of the inputs and D2H of V, proofs, status every step)"}
 
     if rank != 0:
         if world > 1:
@@ -314,8 +358,10 @@ def main():
             "config": {"workload": "gadget_vsmt_2 depth-%d membership proofs, inverse S-box (n=%d, N=%d, m=%d, q=%d)" % (args.depth, circ.n, N, circ.m, circ.q),
                        "proofs_per_gpu_per_step": B, "global_proofs_per_step": world * B,
                        "note": "BASELINE config 5 is 65536 proofs over 8 GPUs = 8192 per GPU; a step is one GPU's share", "parallelism": "proofs sharded over %d GPU(s), NCCL all-gather of proof bytes" % world,
+                       "pipeline": "two batches in flight per GPU: a step enqueues the first phase (commitments, witness program, blinding draws) of batch k+1, "
+                                   "then the MSM / inner-product phase of batch k (bp_prove_stream_begin / _finish); single_call_value = one plain bp_prove_batch_device call",
                        "l2": "per-step working set (GBs of scalars, digits, buckets, folded generators) exceeds the 126 MB L2"},
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_msm": roof("KBucketAccumulate"), "roofline_int": roofline_int,
+            "single_call_value": single_call_value, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_msm": roof("KBucketAccumulate"), "roofline_int": roofline_int,
             "kernel_time_shares": shares, "kernel_ms_per_step": {kn: round(v[1] / args.steps, 3) for kn, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:12]},
             "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)

@@ -474,6 +474,42 @@ class Circuit:
         return status
 
 
+class ProveStream:
+    """Pipeline of batches over one circuit (bp_prove_stream_* of include/bp_b200.h): `begin(slot, ...)` launches the
+    latency-bound first phase of a batch, `finish(slot)` the rest.  Enqueue begin(batch k+1) before finish(batch k) and the first
+    phase of the next batch runs beside the MSM phase of the current one.  Host buffers (numpy, or pinned torch tensors' numpy
+    views); the device-pointer form is bp_prove_stream_begin / _finish."""
+
+    def __init__(self, circuit, gens, label, stream=None):
+        self.circuit, self.gens, self.label, self.stream = circuit, gens, bytes(label), stream
+        self._shape = [None, None]
+
+    def begin(self, slot, v, v_blinding, entropy, aux=None, pub=None):
+        v, v_blinding, entropy = _np_u8(v), _np_u8(v_blinding), _np_u8(entropy)
+        aux = _np_u8(aux) if aux is not None else None
+        pub = _np_u8(pub) if pub is not None else None
+        B = entropy.shape[0]
+        p = lambda a: a.ctypes.data_as(u8p) if a is not None else None
+        _check(load().bp_prove_stream_begin_host(self.gens._h, self.circuit._h, C.c_int32(slot), C.c_uint32(B), _buf(self.label) if self.label else None,
+                                                 C.c_size_t(len(self.label)), p(v), p(v_blinding), p(entropy), p(aux), p(pub),
+                                                 C.c_void_p(self.stream) if self.stream else None), "prove_stream_begin_host")
+        self._shape[slot] = (B, (v, v_blinding, entropy, aux, pub))  # keeps the host buffers alive until finish
+
+    def finish(self, slot, out=None):
+        """returns (V, proofs, status) of the slot's batch; `out` = preallocated (V, proofs, status) arrays"""
+        if self._shape[slot] is None:
+            raise R1CSError(6, "prove_stream_finish_host: slot not begun")
+        B = self._shape[slot][0]
+        c = self.circuit
+        V, proofs, status = out if out is not None else (np.zeros((B, c.m, 32), dtype=np.uint8), np.zeros((B, c.proof_len), dtype=np.uint8),
+                                                         np.zeros(B, dtype=np.int32))
+        _check(load().bp_prove_stream_finish_host(self.gens._h, c._h, C.c_int32(slot), V.ctypes.data_as(u8p), proofs.ctypes.data_as(u8p),
+                                                  status.ctypes.data_as(C.POINTER(C.c_int32)), C.c_void_p(self.stream) if self.stream else None),
+               "prove_stream_finish_host")
+        self._shape[slot] = None
+        return V, proofs, status
+
+
 def _verify_batch_combined(self, gens, label, V, proofs, entropy, pub=None):
     """cross-proof batched verification: returns (status [B] of the structural checks, combined verdict 0 / 3)"""
     V, proofs, entropy = _np_u8(V), _np_u8(proofs), _np_u8(entropy)

@@ -3,7 +3,13 @@
 #include <algorithm>
 #include <memory>
 
-struct bp_circuit { BpCircuit *c; };
+// device staging of one stream slot of the host-buffer streaming entry points (bp_prove_stream_*_host)
+struct HostStage {
+  uint8_t *v = nullptr, *vb = nullptr, *e = nullptr, *aux = nullptr, *pub = nullptr, *V = nullptr, *P = nullptr; int32_t *S = nullptr;
+  uint32_t cap = 0, B = 0; bool active = false;
+  void release() { void *ps[] = {v, vb, e, aux, pub, V, P, S}; for (void *p : ps) dev_free(p); *this = HostStage(); }
+};
+struct bp_circuit { BpCircuit *c; HostStage stage[2]; };
 
 static scm load_scalar(const uint8_t *b) { return sc_from_bytes_mod_order(b); }
 static LC lc_from_terms(const bp_term *t, size_t n) {
@@ -370,7 +376,7 @@ int32_t bp_circuit_from_arrays(uint32_t n, uint32_t m, uint32_t q, const uint32_
   *out = new bp_circuit{c};
   return BP_OK;
 }
-void bp_circuit_free(bp_circuit *c) { if (c) { circuit_free(c->c); delete c; } }
+void bp_circuit_free(bp_circuit *c) { if (c) { c->stage[0].release(); c->stage[1].release(); circuit_free(c->c); delete c; } }
 uint32_t bp_circuit_num_multipliers(const bp_circuit *c) { return c ? c->c->n : 0; }
 uint32_t bp_circuit_num_constraints(const bp_circuit *c) { return c ? c->c->q : 0; }
 uint32_t bp_circuit_num_commitments(const bp_circuit *c) { return c ? c->c->m : 0; }
@@ -394,23 +400,96 @@ static uint32_t chunk_size(const BpCircuit *c, uint32_t B) {
   return ch;
 }
 
-int32_t bp_prove_batch_device(const bp_gens *g, bp_circuit *c, uint32_t B, const uint8_t *label, size_t label_len, const uint8_t *d_v,
-                              const uint8_t *d_vb, const uint8_t *d_entropy, const uint8_t *d_aux, const uint8_t *d_pub, const uint8_t *d_aL,
-                              const uint8_t *d_aR, const uint8_t *d_aO, uint8_t *d_V, uint8_t *d_proofs, int32_t *d_status, void *stream) {
-  if (!g || !c || !d_v || !d_vb || !d_entropy || !d_V || !d_proofs || !d_status || (label_len && !label)) return BP_ERR_INVALID_ARGUMENT;
+static int prove_args_device(const bp_circuit *c, uint32_t B, const uint8_t *label, size_t label_len, const uint8_t *d_v, const uint8_t *d_vb,
+                             const uint8_t *d_entropy, const uint8_t *d_aux, const uint8_t *d_pub, const uint8_t *d_aL, const uint8_t *d_aR,
+                             const uint8_t *d_aO, uint8_t *d_V, uint8_t *d_proofs, int32_t *d_status, ProveArgs &a) {
+  if (!c || !d_v || !d_vb || !d_entropy || !d_V || !d_proofs || !d_status || (label_len && !label)) return BP_ERR_INVALID_ARGUMENT;
   BpCircuit *cc = c->c;
   if ((d_aL || d_aR || d_aO) && !(d_aL && d_aR && d_aO)) return BP_ERR_INVALID_ARGUMENT;
   if (!d_aL && !cc->has_tape) return BP_ERR_MISSING_ASSIGNMENT;
   if (!d_aL && cc->naux && !d_aux) return BP_ERR_MISSING_ASSIGNMENT;
-#ifndef BP_HOST_EMUL
-  dev_stream s = (dev_stream)stream;
-#else
-  dev_stream s = 0; (void)stream;
-#endif
-  ProveArgs a{}; a.B = (int)B; a.label = label; a.label_len = (int)label_len;
+  a = ProveArgs{}; a.B = (int)B; a.label = label; a.label_len = (int)label_len;
   a.v = d_v; a.vbl = d_vb; a.entropy = d_entropy; a.aux = d_aux; a.pub = d_pub; a.aL = d_aL; a.aR = d_aR; a.aO = d_aO;
   a.V_out = d_V; a.proofs = d_proofs; a.status = d_status;
-  return engine_prove(g->g, cc, a, (int)chunk_size(cc, B), s);
+  return BP_OK;
+}
+static dev_stream to_stream(void *stream) {
+#ifndef BP_HOST_EMUL
+  return (dev_stream)stream;
+#else
+  (void)stream; return 0;
+#endif
+}
+
+int32_t bp_prove_batch_device(const bp_gens *g, bp_circuit *c, uint32_t B, const uint8_t *label, size_t label_len, const uint8_t *d_v,
+                              const uint8_t *d_vb, const uint8_t *d_entropy, const uint8_t *d_aux, const uint8_t *d_pub, const uint8_t *d_aL,
+                              const uint8_t *d_aR, const uint8_t *d_aO, uint8_t *d_V, uint8_t *d_proofs, int32_t *d_status, void *stream) {
+  if (!g) return BP_ERR_INVALID_ARGUMENT;
+  ProveArgs a;
+  int rc = prove_args_device(c, B, label, label_len, d_v, d_vb, d_entropy, d_aux, d_pub, d_aL, d_aR, d_aO, d_V, d_proofs, d_status, a);
+  if (rc) return rc;
+  return engine_prove(g->g, c->c, a, (int)chunk_size(c->c, B), to_stream(stream));
+}
+
+// streaming form: see include/bp_b200.h
+int32_t bp_prove_stream_begin(const bp_gens *g, bp_circuit *c, int32_t slot, uint32_t B, const uint8_t *label, size_t label_len, const uint8_t *d_v,
+                              const uint8_t *d_vb, const uint8_t *d_entropy, const uint8_t *d_aux, const uint8_t *d_pub, const uint8_t *d_aL,
+                              const uint8_t *d_aR, const uint8_t *d_aO, uint8_t *d_V, uint8_t *d_proofs, int32_t *d_status, void *stream) {
+  if (!g || B == 0) return BP_ERR_INVALID_ARGUMENT;
+  ProveArgs a;
+  int rc = prove_args_device(c, B, label, label_len, d_v, d_vb, d_entropy, d_aux, d_pub, d_aL, d_aR, d_aO, d_V, d_proofs, d_status, a);
+  if (rc) return rc;
+  return engine_prove_begin(g->g, c->c, slot, a, (int)chunk_size(c->c, B), to_stream(stream));
+}
+int32_t bp_prove_stream_finish(const bp_gens *g, bp_circuit *c, int32_t slot, void *stream) {
+  if (!g || !c) return BP_ERR_INVALID_ARGUMENT;
+  return engine_prove_finish(g->g, c->c, slot, to_stream(stream));
+}
+
+// host buffers (pinned for the copies to be asynchronous); witness from the circuit's program only
+int32_t bp_prove_stream_begin_host(const bp_gens *g, bp_circuit *c, int32_t slot, uint32_t B, const uint8_t *label, size_t label_len, const uint8_t *v,
+                                   const uint8_t *vb, const uint8_t *entropy, const uint8_t *aux, const uint8_t *pub, void *stream) {
+  if (!g || !c || !v || !vb || !entropy || B == 0 || slot < 0 || slot > 1 || (label_len && !label)) return BP_ERR_INVALID_ARGUMENT;
+  BpCircuit *cc = c->c;
+  if (!cc->has_tape || (cc->naux && !aux)) return BP_ERR_MISSING_ASSIGNMENT;
+  HostStage &st = c->stage[slot];
+  if (st.active) return BP_ERR_INVALID_ARGUMENT;
+  const size_t m = cc->m, plen = circuit_proof_len(cc), na = cc->naux, np_ = cc->npub;
+  dev_stream s = to_stream(stream);
+  if (st.cap < B) {
+    if (dev_sync(s)) return BP_ERR_CUDA;
+    st.release();
+    int bad = 0;
+    bad |= dev_malloc((void **)&st.v, B * m * 32); bad |= dev_malloc((void **)&st.vb, B * m * 32); bad |= dev_malloc((void **)&st.e, (size_t)B * 32);
+    bad |= dev_malloc((void **)&st.aux, B * na * 32); bad |= dev_malloc((void **)&st.pub, B * np_ * 32); bad |= dev_malloc((void **)&st.V, B * m * 32);
+    bad |= dev_malloc((void **)&st.P, B * plen); bad |= dev_malloc((void **)&st.S, B * sizeof(int32_t));
+    if (bad) { st.release(); return BP_ERR_OOM; }
+    st.cap = B;
+  }
+  int bad = 0;
+  bad |= dev_h2d(st.v, v, B * m * 32, s); bad |= dev_h2d(st.vb, vb, B * m * 32, s); bad |= dev_h2d(st.e, entropy, (size_t)B * 32, s);
+  if (na) bad |= dev_h2d(st.aux, aux, B * na * 32, s);
+  if (np_ && pub) bad |= dev_h2d(st.pub, pub, B * np_ * 32, s);
+  if (bad) return BP_ERR_CUDA;
+  int rc = bp_prove_stream_begin(g, c, slot, B, label, label_len, st.v, st.vb, st.e, na ? st.aux : nullptr, (np_ && pub) ? st.pub : nullptr, nullptr, nullptr,
+                                 nullptr, st.V, st.P, st.S, stream);
+  if (rc) return rc;
+  st.B = B; st.active = true;
+  return BP_OK;
+}
+// runs the rest of the slot's batch, copies commitments / proofs / status to the host buffers and waits for them
+int32_t bp_prove_stream_finish_host(const bp_gens *g, bp_circuit *c, int32_t slot, uint8_t *V_out, uint8_t *proofs, int32_t *status, void *stream) {
+  if (!g || !c || !V_out || !proofs || !status || slot < 0 || slot > 1 || !c->stage[slot].active) return BP_ERR_INVALID_ARGUMENT;
+  HostStage &st = c->stage[slot];
+  st.active = false;
+  int rc = bp_prove_stream_finish(g, c, slot, stream);
+  if (rc) return rc;
+  dev_stream s = to_stream(stream);
+  const size_t B = st.B, m = c->c->m, plen = circuit_proof_len(c->c);
+  int bad = 0;
+  bad |= dev_d2h(V_out, st.V, B * m * 32, s); bad |= dev_d2h(proofs, st.P, B * plen, s); bad |= dev_d2h(status, st.S, B * sizeof(int32_t), s);
+  bad |= dev_sync(s);
+  return bad ? BP_ERR_CUDA : BP_OK;
 }
 
 int32_t bp_prove_batch(const bp_gens *g, bp_circuit *c, uint32_t B, const uint8_t *label, size_t label_len, const uint8_t *v, const uint8_t *vb,

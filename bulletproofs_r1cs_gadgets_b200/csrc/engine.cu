@@ -80,9 +80,12 @@ struct Front {
     *this = Front();
   }
 };
+// a batch between engine_prove_begin and engine_prove_finish: its arguments (label copied) and chunking
+struct PendingProve { bool active = false; ProveArgs a{}; int chunk = 0; std::vector<uint8_t> label; };
 struct Workspace {
   int B = 0;
-  std::vector<Front> fronts;
+  std::vector<Front> fronts[2];  // two slots: phase A of the next batch of a stream runs beside phase B of the current one
+  PendingProve pending[2];
   scm *vpub = 0, *uj = 0, *w_all = 0, *zpow = 0, *ypow = 0, *yinvpow = 0, *a = 0, *b = 0, *chal = 0, *t = 0, *tb = 0,
       *clr = 0, *part = 0;
   int8_t *dig = 0; size_t dig_bytes = 0;
@@ -94,8 +97,7 @@ struct Workspace {
   uint32_t *rg_ver = 0; long rg_ver_cap = -1, rg_ver_N = -1;
   uint32_t *items = 0, *boff = 0, *soff = 0; size_t items_cap = 0, slices_cap = 0; ge_p3 *seg = 0;
   void release() {
-    for (Front &f : fronts) f.release();
-    fronts.clear();
+    for (auto &fs : fronts) { for (Front &f : fs) f.release(); fs.clear(); }
     void *ps[] = {items, boff, soff, seg, rg_ver, utab, rg_as, rg_ai, skip_ai, vpub, uj, w_all, zpow, ypow, yinvpow, a, b, chal, t, tb, clr, part, dig, buckets, wsum, Q, Gt, Ht, pts, naf, naf_top};
     for (void *p : ps) dev_free(p);
     *this = Workspace();
@@ -315,6 +317,7 @@ double engine_workspace_bytes_per_proof(const BpCircuit *c) {
 static int ensure_workspace(BpCircuit *c, int B) {
   Workspace *w = c->ws;
   if (w->B >= B) return BP_OK;
+  if (w->pending[0].active || w->pending[1].active) return BP_ERR_INVALID_ARGUMENT;  // growing would free the fronts of a batch in flight
   w->release();
   const size_t n = c->n, N = c->N, m = c->m, q = c->q, Bz = (size_t)B;
   const size_t k = c->k;
@@ -344,10 +347,10 @@ static int ensure_workspace(BpCircuit *c, int B) {
   return BP_OK;
 }
 
-static int ensure_front(BpCircuit *c, size_t idx, int B) {
+static int ensure_front(BpCircuit *c, int slot, size_t idx, int B) {
   Workspace *w = c->ws;
-  if (w->fronts.size() <= idx) w->fronts.resize(idx + 1);
-  Front &f = w->fronts[idx];
+  if (w->fronts[slot].size() <= idx) w->fronts[slot].resize(idx + 1);
+  Front &f = w->fronts[slot][idx];
   if (f.B >= B) return BP_OK;
   f.release();
   const size_t n = c->n, m = c->m, Bz = (size_t)B;
@@ -517,39 +520,64 @@ static int prove_phase_a(const BpGens *g, BpCircuit *c, Front &f, const ProveArg
 
 static int prove_phase_b(const BpGens *g, BpCircuit *c, Front &f, const ProveArgs &A, dev_stream s);
 
-// Whole batch: phase A of every chunk first (all chunks concurrently), then phase B chunk by chunk on the caller's stream.
-int engine_prove(const BpGens *g, BpCircuit *c, const ProveArgs &A, int chunk, dev_stream s) {
+// Whole batch in two calls.  begin: phase A of every chunk (all chunks concurrently, on the slot's side streams, ordered after
+// what is already enqueued on s).  finish: phase B chunk by chunk on the caller's stream.  With two slots the caller can
+// enqueue begin(batch k+1) before finish(batch k): the latency-bound phase A of the next batch then overlaps the
+// throughput-bound phase B of the current one instead of being exposed at the head of every batch.
+static ProveArgs prove_slice(const BpCircuit *c, const ProveArgs &A, int chunk, int ci) {
+  const size_t m = c->m, n = c->n, plen = circuit_proof_len(c);
+  ProveArgs a = A;
+  const size_t p0 = (size_t)ci * chunk;
+  a.B = (int)std::min<size_t>(chunk, A.B - p0);
+  a.v = A.v + p0 * m * 32; a.vbl = A.vbl + p0 * m * 32; a.entropy = A.entropy + p0 * 32;
+  a.aux = A.aux ? A.aux + p0 * c->naux * 32 : nullptr; a.pub = A.pub ? A.pub + p0 * c->npub * 32 : nullptr;
+  if (A.aL) { a.aL = A.aL + p0 * n * 32; a.aR = A.aR + p0 * n * 32; a.aO = A.aO + p0 * n * 32; }
+  a.V_out = A.V_out + p0 * m * 32; a.proofs = A.proofs + p0 * plen; a.status = A.status + p0;
+  return a;
+}
+int engine_prove_begin(const BpGens *g, BpCircuit *c, int slot, const ProveArgs &A, int chunk, dev_stream s) {
   const int B = A.B;
-  if (B <= 0) return BP_OK;
+  if (slot < 0 || slot > 1 || B <= 0) return BP_ERR_INVALID_ARGUMENT;
   if (g->capacity < c->n || g->capacity < c->N) return BP_ERR_INVALID_GENERATORS_LENGTH;
   if (!A.aL && !c->has_tape) return BP_ERR_MISSING_ASSIGNMENT;
+  if (c->ws->pending[slot].active) return BP_ERR_INVALID_ARGUMENT;
   if (chunk <= 0 || chunk > B) chunk = B;
   int rc = ensure_workspace(c, chunk);
   if (rc) return rc;
-  const size_t m = c->m, n = c->n, plen = circuit_proof_len(c);
   const int nchunks = (B + chunk - 1) / chunk;
-  auto slice = [&](int ci) {
-    ProveArgs a = A;
-    const size_t p0 = (size_t)ci * chunk;
-    a.B = (int)std::min<size_t>(chunk, B - p0);
-    a.v = A.v + p0 * m * 32; a.vbl = A.vbl + p0 * m * 32; a.entropy = A.entropy + p0 * 32;
-    a.aux = A.aux ? A.aux + p0 * c->naux * 32 : nullptr; a.pub = A.pub ? A.pub + p0 * c->npub * 32 : nullptr;
-    if (A.aL) { a.aL = A.aL + p0 * n * 32; a.aR = A.aR + p0 * n * 32; a.aO = A.aO + p0 * n * 32; }
-    a.V_out = A.V_out + p0 * m * 32; a.proofs = A.proofs + p0 * plen; a.status = A.status + p0;
-    return a;
-  };
+  PendingProve &P = c->ws->pending[slot];
+  P.label.assign(A.label, A.label + A.label_len);
+  P.a = A; P.a.label = P.label.data(); P.chunk = chunk;
+  for (int ci = 0; ci < nchunks; ci++) {
+    rc = ensure_front(c, slot, ci, chunk); if (rc) return rc;
+    rc = prove_phase_a(g, c, c->ws->fronts[slot][ci], prove_slice(c, P.a, chunk, ci), s); if (rc) return rc;
+  }
+  P.active = true;
+  return BP_OK;
+}
+int engine_prove_finish(const BpGens *g, BpCircuit *c, int slot, dev_stream s) {
+  if (slot < 0 || slot > 1 || !c->ws->pending[slot].active) return BP_ERR_INVALID_ARGUMENT;
+  PendingProve &P = c->ws->pending[slot];
+  P.active = false;
+  const ProveArgs &A = P.a;
+  const int B = A.B, chunk = P.chunk, nchunks = (B + chunk - 1) / chunk;
+  const size_t plen = circuit_proof_len(c);
+  int rc;
   CK(dev_memset(A.status, 0, sizeof(int) * B, s));
   CK(dev_memset(A.proofs, 0, plen * B, s));
   for (int ci = 0; ci < nchunks; ci++) {
-    rc = ensure_front(c, ci, chunk); if (rc) return rc;
-    rc = prove_phase_a(g, c, c->ws->fronts[ci], slice(ci), s); if (rc) return rc;
-  }
-  for (int ci = 0; ci < nchunks; ci++) {
-    Front &f = c->ws->fronts[ci];
+    Front &f = c->ws->fronts[slot][ci];
     dev_side_join(f.sideR, s); dev_side_join(f.sideW, s);
-    rc = prove_phase_b(g, c, f, slice(ci), s); if (rc) return rc;
+    rc = prove_phase_b(g, c, f, prove_slice(c, A, chunk, ci), s); if (rc) return rc;
   }
   return BP_OK;
+}
+int engine_prove(const BpGens *g, BpCircuit *c, const ProveArgs &A, int chunk, dev_stream s) {
+  if (A.B <= 0) return BP_OK;
+  const int slot = c->ws->pending[0].active ? 1 : 0;  // a streamed batch may be in flight in the other slot
+  int rc = engine_prove_begin(g, c, slot, A, chunk, s);
+  if (rc) return rc;
+  return engine_prove_finish(g, c, slot, s);
 }
 
 static int prove_phase_b(const BpGens *g, BpCircuit *c, Front &f, const ProveArgs &A, dev_stream s) {

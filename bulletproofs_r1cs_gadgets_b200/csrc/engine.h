@@ -66,6 +66,9 @@ struct ProveArgs {
 };
 // proves a.B statements; `chunk` = proofs per device chunk (<= 0: one chunk)
 int engine_prove(const BpGens *g, BpCircuit *c, const ProveArgs &a, int chunk, dev_stream s);
+// the same in two calls, two batches (slot 0 / 1) in flight per circuit: begin = phase A on internal streams, finish = phase B on s
+int engine_prove_begin(const BpGens *g, BpCircuit *c, int slot, const ProveArgs &a, int chunk, dev_stream s);
+int engine_prove_finish(const BpGens *g, BpCircuit *c, int slot, dev_stream s);
 
 struct VerifyArgs {
   int B;

@@ -76,7 +76,7 @@ class DeviceVsmt2:
         api._check(api.load().bp_vsmt2_new(hash_params._h, C.c_uint32(depth), C.c_int32(sbox), C.byref(self._h)), "vsmt2_new")
 
     def __del__(self):
-        if api._lib is not None and getattr(self, "_h", None):
+        if api is not None and api._lib is not None and getattr(self, "_h", None):
             api._lib.bp_vsmt2_free.restype = None
             api._lib.bp_vsmt2_free(self._h)
             self._h = None

@@ -190,6 +190,27 @@ int32_t bp_prove_batch_device(const bp_gens *g, bp_circuit *c, uint32_t B, const
                               const uint8_t *d_v, const uint8_t *d_v_blinding, const uint8_t *d_entropy, const uint8_t *d_aux,
                               const uint8_t *d_pub, const uint8_t *d_aL, const uint8_t *d_aR, const uint8_t *d_aO, uint8_t *d_V_out,
                               uint8_t *d_proofs, int32_t *d_status, void *stream);
+/* Streaming form of bp_prove_batch_device for a pipeline of batches (same arguments, same bytes).  _begin launches the
+ * latency-bound first phase of the batch -- commitments V, the witness program, the 2n+3 sequential blinding draws of the
+ * transcript RNG -- on internal streams ordered after the work already enqueued on `stream`, and returns.  _finish enqueues
+ * the rest (every MSM, the inner-product argument) on `stream`.  A circuit has two slots (0, 1): enqueueing begin(batch k+1)
+ * BEFORE finish(batch k) lets the first phase of the next batch run beside the MSM phase of the current one instead of
+ * idling the GPU at the head of every batch.  The buffers of a slot belong to the library from _begin until the work of
+ * its _finish has completed.  begin(s) + finish(s) == bp_prove_batch_device. */
+int32_t bp_prove_stream_begin(const bp_gens *g, bp_circuit *c, int32_t slot, uint32_t B, const uint8_t *label, size_t label_len,
+                              const uint8_t *d_v, const uint8_t *d_v_blinding, const uint8_t *d_entropy, const uint8_t *d_aux,
+                              const uint8_t *d_pub, const uint8_t *d_aL, const uint8_t *d_aR, const uint8_t *d_aO, uint8_t *d_V,
+                              uint8_t *d_proofs, int32_t *d_status, void *stream);
+int32_t bp_prove_stream_finish(const bp_gens *g, bp_circuit *c, int32_t slot, void *stream);
+/* the same with HOST buffers (pinned memory makes the copies asynchronous): _begin_host copies the inputs to per-slot device
+ * staging and begins; _finish_host finishes, copies V / proofs / status back and waits for them.  Witness from the circuit's
+ * witness program only. */
+int32_t bp_prove_stream_begin_host(const bp_gens *g, bp_circuit *c, int32_t slot, uint32_t B, const uint8_t *label, size_t label_len,
+                                   const uint8_t *v, const uint8_t *v_blinding, const uint8_t *entropy, const uint8_t *aux,
+                                   const uint8_t *pub, void *stream);
+int32_t bp_prove_stream_finish_host(const bp_gens *g, bp_circuit *c, int32_t slot, uint8_t *V_out, uint8_t *proofs, int32_t *status,
+                                    void *stream);
+
 /* B independent verifications of proofs over the same circuit; status[p] = BP_OK or BP_ERR_VERIFICATION / BP_ERR_FORMAT */
 int32_t bp_verify_batch(const bp_gens *g, bp_circuit *c, uint32_t B, const uint8_t *label, size_t label_len, const uint8_t *V,
                         const uint8_t *proofs, const uint8_t *entropy, const uint8_t *pub, int32_t *status);

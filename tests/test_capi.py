@@ -18,7 +18,7 @@ def test_header_declares_the_boundary():
     names = declared_functions()
     for must in ("bp_gens_new", "bp_prover_new", "bp_prover_commit", "bp_verifier_commit", "bp_cs_multiply", "bp_cs_allocate_multiplier",
                  "bp_cs_allocate_single", "bp_cs_evaluate_lc", "bp_cs_constrain", "bp_cs_num_constraints", "bp_cs_num_multipliers",
-                 "bp_prover_prove", "bp_verifier_verify", "bp_circuit_compile", "bp_prove_batch", "bp_verify_batch", "bp_verify_batch_combined", "bp_verify_batch_combined_device", "bp_proof_to_wire", "bp_proof_from_wire", "bp_gadget_vsmt4_verif", "bp_gadget_poseidon_hash_4", "bp_poseidon_hash_4", "bp_prove_batch_device", "bp_vsmt2_new", "bp_vsmt2_free", "bp_vsmt2_depth", "bp_vsmt2_num_nodes", "bp_vsmt2_root", "bp_vsmt2_empty_hashes", "bp_vsmt2_update_batch", "bp_vsmt2_get_batch", "bp_vsmt2_witness_batch", "bp_vsmt2_witness_batch_device", "bp_poseidon_hash_2_batch",
+                 "bp_prover_prove", "bp_verifier_verify", "bp_circuit_compile", "bp_prove_batch", "bp_verify_batch", "bp_verify_batch_combined", "bp_verify_batch_combined_device", "bp_proof_to_wire", "bp_proof_from_wire", "bp_gadget_vsmt4_verif", "bp_gadget_poseidon_hash_4", "bp_poseidon_hash_4", "bp_prove_batch_device", "bp_prove_stream_begin", "bp_prove_stream_finish", "bp_prove_stream_begin_host", "bp_prove_stream_finish_host", "bp_vsmt2_new", "bp_vsmt2_free", "bp_vsmt2_depth", "bp_vsmt2_num_nodes", "bp_vsmt2_root", "bp_vsmt2_empty_hashes", "bp_vsmt2_update_batch", "bp_vsmt2_get_batch", "bp_vsmt2_witness_batch", "bp_vsmt2_witness_batch_device", "bp_poseidon_hash_2_batch",
                  "bp_msm_gens_device"):
         assert must in names
 

@@ -333,6 +333,42 @@ def test_explicit_witness_equals_witness_program(api, gens, oracle_lib):
     assert not wl.circuit.verify_batch(gens, wl.label, V1, P1, inp["entropy"], pub=inp["pub"]).any()
 
 
+def test_streamed_batches_equal_plain_batches(api, gens):
+    """bp_prove_stream_*: two batches in flight (begin 0, begin 1, finish 0, begin 0 again, finish 1, finish 0) give the bytes of
+    three plain bp_prove_batch calls; a slot cannot be begun twice or finished when idle; chunked batches stream too"""
+    import os
+    from bulletproofs_r1cs_gadgets_b200 import workloads
+    wl = workloads.Mimc(gens, rounds=6)
+    batches = [wl.inputs(10 * i, 3 + i) for i in range(3)]
+    plain = [wl.circuit.prove_batch(gens, wl.label, b["v"], b["v_blinding"], b["entropy"], pub=b["pub"]) for b in batches]
+    for chunk in (None, "2"):
+        if chunk:
+            os.environ["BP_B200_CHUNK"] = chunk
+        try:
+            st = api.ProveStream(wl.circuit, gens, wl.label)
+            args = lambda b: (b["v"], b["v_blinding"], b["entropy"], None, b["pub"])
+            st.begin(0, *args(batches[0]))
+            st.begin(1, *args(batches[1]))
+            with pytest.raises(api.R1CSError):
+                st.begin(1, *args(batches[2]))
+            got0 = st.finish(0)
+            st.begin(0, *args(batches[2]))
+            got1 = st.finish(1)
+            got2 = st.finish(0)
+            with pytest.raises(api.R1CSError):
+                st.finish(0)
+        finally:
+            os.environ.pop("BP_B200_CHUNK", None)
+        for got, want in zip((got0, got1, got2), plain):
+            assert got[0].tobytes() == want[0].tobytes() and got[1].tobytes() == want[1].tobytes() and not got[2].any()
+    # a plain call while a streamed batch is in flight uses the other slot
+    st = api.ProveStream(wl.circuit, gens, wl.label)
+    st.begin(0, batches[0]["v"], batches[0]["v_blinding"], batches[0]["entropy"], None, batches[0]["pub"])
+    again = wl.circuit.prove_batch(gens, wl.label, batches[1]["v"], batches[1]["v_blinding"], batches[1]["entropy"], pub=batches[1]["pub"])
+    assert again[1].tobytes() == plain[1][1].tobytes()
+    assert st.finish(0)[1].tobytes() == plain[0][1].tobytes()
+
+
 def test_chunking_is_invisible(api, gens, monkeypatch):
     from bulletproofs_r1cs_gadgets_b200 import workloads
     wl = workloads.Mimc(gens, rounds=3)
