@@ -414,7 +414,9 @@ static int run_msm_table(const BpGens *g, Workspace *w, const RowMap &rmap, long
 static int run_msm_sorted(const BpGens *g, Workspace *w, const RowMap &rmap, long rows, long ninst, const int8_t *dig, long dig_inst_stride,
                           uint8_t *out, long out_stride, dev_stream s) {
   if ((size_t)rows * SB_WINDOWS > w->items_cap || (size_t)ninst * w->slices_cap > w->bucket_slots) return BP_ERR_OOM;
-  CK(launch_sort_buckets(rmap, dig, dig_inst_stride, rows, ninst, w->items, (long)w->items_cap, w->boff, w->soff, s));
+  // the partial-sum buffer is dead until KBucketAccumulate below writes it: scratch of the two-pass sort
+  CK(launch_sort_buckets(rmap, dig, dig_inst_stride, rows, ninst, w->items, (long)w->items_cap, w->boff, w->soff, (uint32_t *)w->buckets,
+                         w->bucket_slots * sizeof(ge_p3), 2L * g->capacity + 2 + SG_SPARE + g->merge_slots, s));
   SortedView sv{w->items, w->boff, w->soff, (long)w->items_cap, (long)w->slices_cap};
   const long segs = (rows * SB_WINDOWS + SB_SEG - 1) / SB_SEG;  // segments of this launch's longest possible item list
   CK(launch(ninst * segs, s, KBucketAccumulate{g->sg, sv, w->buckets, segs}));
@@ -810,7 +812,7 @@ static int sorted_split_msm(BpGens *g, long nrows, const uint8_t *d_bytes, const
   if (d_bytes) { CK(launch(nrows, s, KLoadScalars{d_bytes, w->a, (int)nrows, 1})); d_scm = w->a; }
   CK(launch(nrows, s, KRecode13{d_scm, nullptr, (int)nrows, 1, w->dig, 0, 0, nullptr}));  // B = 1: row i at dig + i * SB_ROW_BYTES = sub-instance i / R, row i % R
   RowMap rm{mode, nullptr, (long)g->capacity, mapN, 0, 0, R};
-  CK(launch_sort_buckets(rm, w->dig, R * SB_ROW_BYTES, R, S, w->items, (long)w->items_cap, w->boff, w->soff, s));
+  CK(launch_sort_buckets(rm, w->dig, R * SB_ROW_BYTES, R, S, w->items, (long)w->items_cap, w->boff, w->soff, nullptr, 0, 0, s));
   SortedView sv{w->items, w->boff, w->soff, (long)w->items_cap, (long)w->slices_cap};
   const long segs = (R * SB_WINDOWS + SB_SEG - 1) / SB_SEG;
   ge_p3 *partial = w->buckets + (size_t)S * w->slices_cap;
@@ -974,7 +976,7 @@ int engine_verify(const BpGens *g, BpCircuit *c, const VerifyArgs &A, dev_stream
     for (int half = 0; half < 2; half++) {
       RowMap rm{4, nullptr, (long)g->capacity, 0, half, 0, 0};
       const int8_t *dg = half ? wideH : wideG;
-      CK(launch_sort_buckets(rm, dg, (N + 1) * SB_ROW_BYTES, N + 1, B, w->items, (long)w->items_cap, w->boff, w->soff, s));
+      CK(launch_sort_buckets(rm, dg, (N + 1) * SB_ROW_BYTES, N + 1, B, w->items, (long)w->items_cap, w->boff, w->soff, nullptr, 0, 0, s));
       SortedView sv{w->items, w->boff, w->soff, (long)w->items_cap, (long)w->slices_cap};
       const long segs = ((N + 1) * SB_WINDOWS + SB_SEG - 1) / SB_SEG;
       CK(launch(B * segs, s, KBucketAccumulate{g->sg, sv, w->buckets, segs}));

@@ -146,29 +146,187 @@ __global__ void __launch_bounds__(SORT_THREADS, 1) sort_buckets_direct_kernel(Ro
     }
   }
 }
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Two-pass (most-significant-digit first) variant, the default.  The one-pass kernels above append 4-byte items to 16384
+// bucket regions per instance; with ~1 item per bucket and tile that is one partial 32-byte sector per item, and the ncu
+// capture (profiles/) shows it: 37.7 GB of DRAM traffic for 8.4 GB of digits + items, at the ~2 TB/s that scattered
+// sectors reach.  Here pass 1 partitions the items of an instance into SORT_GROUPS coarse groups of SORT_FINE buckets (runs
+// of ~70 items per group and tile leave shared memory as whole lines) and pass 2 sorts one coarse group per block inside
+// shared memory and writes it back linearly.  Every global access is coalesced; items cross HBM three times instead of
+// being read-modified-written sector by sector.  The low bucket bits ride in bits 22..28 of the intermediate item, so
+// generator slot * SB_WINDOWS must stay below 2^22 (the launcher falls back to the staged kernel otherwise).
+#define SORT2_THREADS 512
+#define SORT2_WARPS (SORT2_THREADS / 32)
+#define SORT_FINE_BITS 7
+#define SORT_FINE (1 << SORT_FINE_BITS)
+#define SORT_GROUPS (SB_BUCKETS / SORT_FINE)
+#define SORT2_TILE_ITEMS (SORT2_THREADS * SB_WINDOWS)
+#define SORT2_BUF_WORDS (SB_BUCKETS > SORT2_TILE_ITEMS ? SB_BUCKETS : SORT2_TILE_ITEMS)
+#define SORT2_SMEM_BYTES ((SORT2_BUF_WORDS + SORT_GROUPS * SORT2_WARPS + SORT_GROUPS + 8) * 4)
+#define SORT_ITEM_BITS 22
+#define SORT_ITEM_MASK (0x80000000u | ((1u << SORT_ITEM_BITS) - 1))
+#define SORT_FINE_CAP 12160  // items of one coarse group sorted inside shared memory (larger groups scatter directly)
+
+// in-place exclusive scan of THREADS * PER counters, thread-contiguous; returns the total to every thread
+template <int PER, int THREADS>
+__device__ __forceinline__ uint32_t block_scan_excl(uint32_t *c, uint32_t *warp_tot) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  uint32_t sum = 0;
+#pragma unroll 4
+  for (int i = 0; i < PER; i++) sum += c[tid * PER + i];
+  uint32_t incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  if (lane == 31) warp_tot[tid >> 5] = incl;
+  __syncthreads();
+  if (tid < 32) {
+    uint32_t v = tid < THREADS / 32 ? warp_tot[tid] : 0, inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (tid >= o) inc += t; }
+    if (tid < THREADS / 32) warp_tot[tid] = inc - v;
+    if (tid == 31) warp_tot[32] = inc;
+  }
+  __syncthreads();
+  uint32_t run = warp_tot[tid >> 5] + (incl - sum);
+#pragma unroll 4
+  for (int i = 0; i < PER; i++) { const uint32_t v = c[tid * PER + i]; c[tid * PER + i] = run; run += v; }
+  const uint32_t total = warp_tot[32];
+  __syncthreads();
+  return total;
+}
+
+__global__ void __launch_bounds__(SORT2_THREADS, 2) sort_coarse_kernel(RowMap rmap, const int8_t *dig, long dig_inst_stride, long rows,
+                                                                      uint32_t *tmp, long items_stride, uint32_t *boff) {
+  extern __shared__ uint32_t sort_sm[];
+  uint32_t *buf = sort_sm;                                  // pass 0: SB_BUCKETS fine counters; afterwards the tile's staged items
+  uint32_t *wc = sort_sm + SORT2_BUF_WORDS;                 // [SORT_GROUPS][SORT2_WARPS] items of (coarse group, warp) in the tile
+  uint32_t *ccur = wc + SORT_GROUPS * SORT2_WARPS;          // [SORT_GROUPS] next free slot of every coarse group's region
+  __shared__ uint32_t warp_tot[33];
+  const long inst = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int8_t *drow = dig + inst * dig_inst_stride;
+  uint32_t *out = tmp + inst * items_stride;
+  // pass 0: fine histogram of the whole instance -> bucket offsets (global) and coarse cursors
+  for (int b = tid; b < SB_BUCKETS; b += SORT2_THREADS) buf[b] = 0;
+  __syncthreads();
+  for (long r = tid; r < rows; r += SORT2_THREADS) {
+    int16_t d[24]; load_digits13(d, drow + r * SB_ROW_BYTES);
+#pragma unroll
+    for (int w = 0; w < SB_WINDOWS; w++) if (d[w]) atomicAdd(&buf[(d[w] < 0 ? -d[w] : d[w]) - 1], 1u);
+  }
+  __syncthreads();
+  {
+    const uint32_t total = block_scan_excl<SB_BUCKETS / SORT2_THREADS, SORT2_THREADS>(buf, warp_tot);
+    uint32_t *off = boff + inst * (SB_BUCKETS + 1);
+    for (int b = tid; b < SB_BUCKETS; b += SORT2_THREADS) off[b] = buf[b];
+    if (tid == 0) off[SB_BUCKETS] = total;
+    if (tid < SORT_GROUPS) ccur[tid] = buf[tid * SORT_FINE];
+  }
+  __syncthreads();
+  // pass 1: tiles of SORT2_THREADS rows, one row per thread
+  for (long t0 = 0; t0 < rows; t0 += SORT2_THREADS) {
+    for (int i = tid; i < SORT_GROUPS * SORT2_WARPS; i += SORT2_THREADS) wc[i] = 0;
+    __syncthreads();
+    const long r = t0 + tid;
+    uint32_t code[SB_WINDOWS];  // sign << 31 | bucket << 16 | rank within (tile, coarse group, warp); ~0 = no item
+#pragma unroll
+    for (int w = 0; w < SB_WINDOWS; w++) code[w] = 0xffffffffu;
+    if (r < rows) {
+      int16_t d[24]; load_digits13(d, drow + r * SB_ROW_BYTES);
+#pragma unroll
+      for (int w = 0; w < SB_WINDOWS; w++) if (d[w]) {
+        const uint32_t neg = d[w] < 0; const uint32_t b = (uint32_t)(neg ? -d[w] : d[w]) - 1;
+        code[w] = (neg << 31) | (b << 16) | atomicAdd(&wc[(b >> SORT_FINE_BITS) * SORT2_WARPS + wid], 1u);
+      }
+    }
+    __syncthreads();
+    const uint32_t ttotal = block_scan_excl<SORT_GROUPS * SORT2_WARPS / SORT2_THREADS, SORT2_THREADS>(wc, warp_tot);
+    if (r < rows) {
+      const uint32_t g = (uint32_t)row_gen(rmap, r + inst * rmap.inst_off) * SB_WINDOWS;
+#pragma unroll
+      for (int w = 0; w < SB_WINDOWS; w++) if (code[w] != 0xffffffffu) {
+        const uint32_t b = (code[w] >> 16) & 0x7fffu;
+        buf[wc[(b >> SORT_FINE_BITS) * SORT2_WARPS + wid] + (code[w] & 0xffffu)] =
+            (g + w) | ((b & (SORT_FINE - 1)) << SORT_ITEM_BITS) | (code[w] & 0x80000000u);
+      }
+    }
+    __syncthreads();
+    // copy-out: one warp per coarse group, the group's run of the tile leaves as consecutive 128-byte lines
+    for (int c = wid; c < SORT_GROUPS; c += SORT2_WARPS) {
+      const uint32_t s0 = wc[c * SORT2_WARPS], s1 = c + 1 < SORT_GROUPS ? wc[(c + 1) * SORT2_WARPS] : ttotal, dst = ccur[c];
+      for (uint32_t j = lane; j < s1 - s0; j += 32) out[dst + j] = buf[s0 + j];
+      __syncwarp();
+      if (lane == 0) ccur[c] = dst + (s1 - s0);
+    }
+    __syncthreads();
+  }
+}
+// pass 2: block (instance, coarse group) orders the group's items by their low bucket bits
+__global__ void __launch_bounds__(256, 4) sort_fine_kernel(const uint32_t *tmp, uint32_t *items, long items_stride, const uint32_t *boff) {
+  __shared__ uint32_t cur[SORT_FINE];
+  __shared__ uint32_t stage[SORT_FINE_CAP];
+  const long inst = blockIdx.x / SORT_GROUPS; const int c = (int)(blockIdx.x % SORT_GROUPS);
+  const int tid = threadIdx.x;
+  const uint32_t *off = boff + inst * (SB_BUCKETS + 1) + c * SORT_FINE;
+  const uint32_t start = off[0], n = off[SORT_FINE] - start;
+  if (n == 0) return;
+  if (tid < SORT_FINE) cur[tid] = off[tid] - start;
+  __syncthreads();
+  const uint32_t *in = tmp + inst * items_stride + start;
+  uint32_t *out = items + inst * items_stride + start;
+  if (n <= SORT_FINE_CAP) {
+    for (uint32_t k = tid; k < n; k += 256) {
+      const uint32_t x = in[k];
+      stage[atomicAdd(&cur[(x >> SORT_ITEM_BITS) & (SORT_FINE - 1)], 1u)] = x & SORT_ITEM_MASK;
+    }
+    __syncthreads();
+    for (uint32_t k = tid; k < n; k += 256) out[k] = stage[k];
+  } else {
+    for (uint32_t k = tid; k < n; k += 256) {
+      const uint32_t x = in[k];
+      out[atomicAdd(&cur[(x >> SORT_ITEM_BITS) & (SORT_FINE - 1)], 1u)] = x & SORT_ITEM_MASK;
+    }
+  }
+}
 #endif
 
 int launch_sort_buckets(const RowMap &rmap, const int8_t *dig, long dig_inst_stride, long rows, long ninst, uint32_t *items, long items_stride,
-                        uint32_t *boff, uint32_t *soff, dev_stream s) {
+                        uint32_t *boff, uint32_t *soff, uint32_t *tmp, size_t tmp_bytes, long gen_slots, dev_stream s) {
 #ifndef BP_HOST_EMUL
   if (ninst <= 0) return 0;
-  if (g_profile_on) profile_begin("sort_buckets_kernel", ninst * SORT_THREADS, s);
-  static int mode = -1;  // 0: staged tiles (default), 1: direct scatter (BP_B200_SORT=direct)
+  static int mode = -1;  // 2: two-pass radix (default), 0: staged tiles (BP_B200_SORT=staged), 1: direct scatter (BP_B200_SORT=direct)
   if (mode < 0) {
     const char *e = getenv("BP_B200_SORT");
-    mode = e ? (e[0] == 'd') : 0;  // measured at batch 8192: staged 855 ms, direct 1102 ms per step
+    mode = e ? (e[0] == 'd' ? 1 : (e[0] == 's' ? 0 : 2)) : 2;
     cudaFuncSetAttribute(sort_buckets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM_BYTES);
     cudaFuncSetAttribute(sort_buckets_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM_BYTES);
+    cudaFuncSetAttribute(sort_coarse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT2_SMEM_BYTES);
   }
-  // the direct variant asks for the same (large) shared-memory carve-out on purpose: one block per SM bounds the open sectors
-  if (mode) sort_buckets_direct_kernel<<<(unsigned)ninst, SORT_THREADS, SORT_SMEM_BYTES, s>>>(rmap, dig, dig_inst_stride, rows, items, items_stride, boff);
-  else sort_buckets_kernel<<<(unsigned)ninst, SORT_THREADS, SORT_SMEM_BYTES, s>>>(rmap, dig, dig_inst_stride, rows, items, items_stride, boff);
-  if (g_profile_on) profile_end(s);
-  g_launch_count++;
+  // the two-pass form needs scratch for the coarse-partitioned items and 22 bits for generator slot * SB_WINDOWS + window
+  const bool radix = mode == 2 && tmp && tmp_bytes >= (size_t)ninst * items_stride * sizeof(uint32_t) && gen_slots > 0 &&
+                     (size_t)gen_slots * SB_WINDOWS < (1u << SORT_ITEM_BITS) && ninst * SORT_GROUPS < (1L << 31);
+  if (radix) {
+    if (g_profile_on) profile_begin("sort_coarse_kernel", ninst * SORT2_THREADS, s);
+    sort_coarse_kernel<<<(unsigned)ninst, SORT2_THREADS, SORT2_SMEM_BYTES, s>>>(rmap, dig, dig_inst_stride, rows, tmp, items_stride, boff);
+    if (g_profile_on) profile_end(s);
+    if (g_profile_on) profile_begin("sort_fine_kernel", ninst * SORT_GROUPS * 256, s);
+    sort_fine_kernel<<<(unsigned)(ninst * SORT_GROUPS), 256, 0, s>>>(tmp, items, items_stride, boff);
+    if (g_profile_on) profile_end(s);
+    g_launch_count += 2;
+  } else {
+    if (g_profile_on) profile_begin("sort_buckets_kernel", ninst * SORT_THREADS, s);
+    // the direct variant asks for the same (large) shared-memory carve-out on purpose: one block per SM bounds the open sectors
+    if (mode == 1) sort_buckets_direct_kernel<<<(unsigned)ninst, SORT_THREADS, SORT_SMEM_BYTES, s>>>(rmap, dig, dig_inst_stride, rows, items, items_stride, boff);
+    else sort_buckets_kernel<<<(unsigned)ninst, SORT_THREADS, SORT_SMEM_BYTES, s>>>(rmap, dig, dig_inst_stride, rows, items, items_stride, boff);
+    if (g_profile_on) profile_end(s);
+    g_launch_count++;
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { fprintf(stderr, "bp_b200: sort_buckets launch failed: %s\n", cudaGetErrorString(e)); return 1; }
   return 0;
 #else
+  (void)tmp; (void)tmp_bytes; (void)gen_slots;
   return launch(ninst, s, KSortBucketsSerial{rmap, dig, dig_inst_stride, rows, items, items_stride, boff, soff});
 #endif
 }

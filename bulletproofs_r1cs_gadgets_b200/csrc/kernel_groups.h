@@ -29,5 +29,6 @@ KGROUP_SCALAR(KDECL_EXTERN)
 #endif
 
 // block-cooperative counting sort of digit items by bucket (k_sorted.cu)
+// tmp (optional): scratch of ninst * items_stride words for the two-pass form; gen_slots: generator slots of the shift table
 int launch_sort_buckets(const RowMap &rmap, const int8_t *dig, long dig_inst_stride, long rows, long ninst, uint32_t *items, long items_stride,
-                        uint32_t *boff, uint32_t *soff, dev_stream s);
+                        uint32_t *boff, uint32_t *soff, uint32_t *tmp, size_t tmp_bytes, long gen_slots, dev_stream s);
