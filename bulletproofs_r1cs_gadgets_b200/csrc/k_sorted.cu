@@ -163,10 +163,13 @@ __global__ void __launch_bounds__(SORT_THREADS, 1) sort_buckets_direct_kernel(Ro
 #define SORT_GROUPS (SB_BUCKETS / SORT_FINE)
 #define SORT2_TILE_ITEMS (SORT2_THREADS * SB_WINDOWS)
 #define SORT2_BUF_WORDS (SB_BUCKETS > SORT2_TILE_ITEMS ? SB_BUCKETS : SORT2_TILE_ITEMS)
-#define SORT2_SMEM_BYTES ((SORT2_BUF_WORDS + SORT_GROUPS * SORT2_WARPS + SORT_GROUPS + 8) * 4)
+#define SORT2_WC_STRIDE (SORT2_WARPS + 1)  // odd stride: the 32 lanes of a warp (same warp slot, different groups) hit different banks
+#define SORT2_WC_PER ((SORT_GROUPS * SORT2_WC_STRIDE + SORT2_THREADS - 1) / SORT2_THREADS)
+#define SORT2_WC_WORDS (SORT2_WC_PER * SORT2_THREADS)
+#define SORT2_SMEM_BYTES ((SORT2_BUF_WORDS + SORT2_WC_WORDS + SORT_GROUPS + 8) * 4)
 #define SORT_ITEM_BITS 22
 #define SORT_ITEM_MASK (0x80000000u | ((1u << SORT_ITEM_BITS) - 1))
-#define SORT_FINE_CAP 12160  // items of one coarse group sorted inside shared memory (larger groups scatter directly)
+#define SORT_FINE_CAP 6016   // items of one coarse group sorted inside shared memory (larger groups scatter directly)
 
 // in-place exclusive scan of THREADS * PER counters, thread-contiguous; returns the total to every thread
 template <int PER, int THREADS>
@@ -200,8 +203,8 @@ __global__ void __launch_bounds__(SORT2_THREADS, 2) sort_coarse_kernel(RowMap rm
                                                                       uint32_t *tmp, long items_stride, uint32_t *boff) {
   extern __shared__ uint32_t sort_sm[];
   uint32_t *buf = sort_sm;                                  // pass 0: SB_BUCKETS fine counters; afterwards the tile's staged items
-  uint32_t *wc = sort_sm + SORT2_BUF_WORDS;                 // [SORT_GROUPS][SORT2_WARPS] items of (coarse group, warp) in the tile
-  uint32_t *ccur = wc + SORT_GROUPS * SORT2_WARPS;          // [SORT_GROUPS] next free slot of every coarse group's region
+  uint32_t *wc = sort_sm + SORT2_BUF_WORDS;                 // [SORT_GROUPS][SORT2_WC_STRIDE] items of (coarse group, warp) in the tile
+  uint32_t *ccur = wc + SORT2_WC_WORDS;                     // [SORT_GROUPS] next free slot of every coarse group's region
   __shared__ uint32_t warp_tot[33];
   const long inst = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -226,7 +229,7 @@ __global__ void __launch_bounds__(SORT2_THREADS, 2) sort_coarse_kernel(RowMap rm
   __syncthreads();
   // pass 1: tiles of SORT2_THREADS rows, one row per thread
   for (long t0 = 0; t0 < rows; t0 += SORT2_THREADS) {
-    for (int i = tid; i < SORT_GROUPS * SORT2_WARPS; i += SORT2_THREADS) wc[i] = 0;
+    for (int i = tid; i < SORT2_WC_WORDS; i += SORT2_THREADS) wc[i] = 0;
     __syncthreads();
     const long r = t0 + tid;
     uint32_t code[SB_WINDOWS];  // sign << 31 | bucket << 16 | rank within (tile, coarse group, warp); ~0 = no item
@@ -237,24 +240,24 @@ __global__ void __launch_bounds__(SORT2_THREADS, 2) sort_coarse_kernel(RowMap rm
 #pragma unroll
       for (int w = 0; w < SB_WINDOWS; w++) if (d[w]) {
         const uint32_t neg = d[w] < 0; const uint32_t b = (uint32_t)(neg ? -d[w] : d[w]) - 1;
-        code[w] = (neg << 31) | (b << 16) | atomicAdd(&wc[(b >> SORT_FINE_BITS) * SORT2_WARPS + wid], 1u);
+        code[w] = (neg << 31) | (b << 16) | atomicAdd(&wc[(b >> SORT_FINE_BITS) * SORT2_WC_STRIDE + wid], 1u);
       }
     }
     __syncthreads();
-    const uint32_t ttotal = block_scan_excl<SORT_GROUPS * SORT2_WARPS / SORT2_THREADS, SORT2_THREADS>(wc, warp_tot);
+    const uint32_t ttotal = block_scan_excl<SORT2_WC_PER, SORT2_THREADS>(wc, warp_tot);
     if (r < rows) {
       const uint32_t g = (uint32_t)row_gen(rmap, r + inst * rmap.inst_off) * SB_WINDOWS;
 #pragma unroll
       for (int w = 0; w < SB_WINDOWS; w++) if (code[w] != 0xffffffffu) {
         const uint32_t b = (code[w] >> 16) & 0x7fffu;
-        buf[wc[(b >> SORT_FINE_BITS) * SORT2_WARPS + wid] + (code[w] & 0xffffu)] =
+        buf[wc[(b >> SORT_FINE_BITS) * SORT2_WC_STRIDE + wid] + (code[w] & 0xffffu)] =
             (g + w) | ((b & (SORT_FINE - 1)) << SORT_ITEM_BITS) | (code[w] & 0x80000000u);
       }
     }
     __syncthreads();
     // copy-out: one warp per coarse group, the group's run of the tile leaves as consecutive 128-byte lines
     for (int c = wid; c < SORT_GROUPS; c += SORT2_WARPS) {
-      const uint32_t s0 = wc[c * SORT2_WARPS], s1 = c + 1 < SORT_GROUPS ? wc[(c + 1) * SORT2_WARPS] : ttotal, dst = ccur[c];
+      const uint32_t s0 = wc[c * SORT2_WC_STRIDE], s1 = c + 1 < SORT_GROUPS ? wc[(c + 1) * SORT2_WC_STRIDE] : ttotal, dst = ccur[c];
       for (uint32_t j = lane; j < s1 - s0; j += 32) out[dst + j] = buf[s0 + j];
       __syncwarp();
       if (lane == 0) ccur[c] = dst + (s1 - s0);
@@ -263,7 +266,7 @@ __global__ void __launch_bounds__(SORT2_THREADS, 2) sort_coarse_kernel(RowMap rm
   }
 }
 // pass 2: block (instance, coarse group) orders the group's items by their low bucket bits
-__global__ void __launch_bounds__(256, 4) sort_fine_kernel(const uint32_t *tmp, uint32_t *items, long items_stride, const uint32_t *boff) {
+__global__ void __launch_bounds__(256, 8) sort_fine_kernel(const uint32_t *tmp, uint32_t *items, long items_stride, const uint32_t *boff) {
   __shared__ uint32_t cur[SORT_FINE];
   __shared__ uint32_t stage[SORT_FINE_CAP];
   const long inst = blockIdx.x / SORT_GROUPS; const int c = (int)(blockIdx.x % SORT_GROUPS);
@@ -276,9 +279,12 @@ __global__ void __launch_bounds__(256, 4) sort_fine_kernel(const uint32_t *tmp, 
   const uint32_t *in = tmp + inst * items_stride + start;
   uint32_t *out = items + inst * items_stride + start;
   if (n <= SORT_FINE_CAP) {
-    for (uint32_t k = tid; k < n; k += 256) {
-      const uint32_t x = in[k];
-      stage[atomicAdd(&cur[(x >> SORT_ITEM_BITS) & (SORT_FINE - 1)], 1u)] = x & SORT_ITEM_MASK;
+    for (uint32_t k0 = 0; k0 < n; k0 += 4 * 256) {  // four independent loads in flight per thread
+      uint32_t x[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) { const uint32_t k = k0 + j * 256 + tid; x[j] = k < n ? in[k] : 0xffffffffu; }
+#pragma unroll
+      for (int j = 0; j < 4; j++) if (k0 + j * 256 + tid < n) stage[atomicAdd(&cur[(x[j] >> SORT_ITEM_BITS) & (SORT_FINE - 1)], 1u)] = x[j] & SORT_ITEM_MASK;
     }
     __syncthreads();
     for (uint32_t k = tid; k < n; k += 256) out[k] = stage[k];
