@@ -10,7 +10,7 @@ Batches are streamed with two in flight (bp_prove_stream_*): a step enqueues the
 the MSM / inner-product phase of the current one, so every timed step holds one whole batch of work.
 `value` = proofs/s with inputs resident in HBM; `e2e` = the same through the host-buffer C-ABI calls
 (bp_prove_stream_begin_host / _finish_host: H2D of inputs and D2H of commitments + proofs inside the timed region);
-`single_call_value` = one plain bp_prove_batch_device call (nothing overlapped across batches).
+`single_call_value_per_gpu` = one plain bp_prove_batch_device call on rank 0 (nothing overlapped across batches).
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -359,9 +359,9 @@ def main():
                        "proofs_per_gpu_per_step": B, "global_proofs_per_step": world * B,
                        "note": "BASELINE config 5 is 65536 proofs over 8 GPUs = 8192 per GPU; a step is one GPU's share", "parallelism": "proofs sharded over %d GPU(s), NCCL all-gather of proof bytes" % world,
                        "pipeline": "two batches in flight per GPU: a step enqueues the first phase (commitments, witness program, blinding draws) of batch k+1, "
-                                   "then the MSM / inner-product phase of batch k (bp_prove_stream_begin / _finish); single_call_value = one plain bp_prove_batch_device call",
+                                   "then the MSM / inner-product phase of batch k (bp_prove_stream_begin / _finish); single_call_value_per_gpu = one plain bp_prove_batch_device call on rank 0",
                        "l2": "per-step working set (GBs of scalars, digits, buckets, folded generators) exceeds the 126 MB L2"},
-            "single_call_value": single_call_value, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_msm": roof("KBucketAccumulate"), "roofline_int": roofline_int,
+            "single_call_value_per_gpu": single_call_value, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_msm": roof("KBucketAccumulate"), "roofline_int": roofline_int,
             "kernel_time_shares": shares, "kernel_ms_per_step": {kn: round(v[1] / args.steps, 3) for kn, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:12]},
             "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
