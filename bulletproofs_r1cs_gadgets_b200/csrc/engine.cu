@@ -303,7 +303,7 @@ static long msm_target_warps() { return 148L * 8 * 4; }
 double engine_workspace_bytes_per_proof(const BpCircuit *c) {
   const double n = c->n, N = c->N, m = c->m, q = c->q, k = c->k;
   const double rows = std::max(std::max(5 * n + 3, 2 * (N + 2)), 2 * N + m + 13 + 2 * k + 2);
-  const double items = std::max(2 * n + 1, N + 2) * SB_WINDOWS, slices = SB_BUCKETS + items / SB_SEG + 2;
+  const double items = std::max(2 * n + 1, N + 2) * SB_WINDOWS, slices = std::max(SB_BUCKETS + items / SB_SEG + 2, items * 4 / sizeof(ge_p3) + 1);
   const double nch = std::max(n, N) / CH_DOT + 2;
   double b = 0;
   b += sizeof(scm) * ((double)c->nslots + (q + 1) + 4 * N + (2 * k + 2) + 40 + nch * 6 + (c->npub + 1));  // w_all, zpow, ypow, yinvpow, a, b, ...
@@ -329,6 +329,8 @@ static int ensure_workspace(BpCircuit *c, int B) {
   w->items_cap = (size_t)std::max(2 * n + 1, N + 2) * SB_WINDOWS;  // items of one instance
   w->slices_cap = SB_BUCKETS + w->items_cap / SB_SEG + 2;  // partial sums: one per (bucket, segment) crossing
   w->bucket_slots = std::max(max_warps * MSM_WINDOWS * MSM_BUCKETS, Bz * w->slices_cap);
+  // the buffer doubles as the scratch of the two-pass bucket sort (one 4-byte item per digit)
+  w->bucket_slots = std::max(w->bucket_slots, Bz * ((w->items_cap * sizeof(uint32_t) + sizeof(ge_p3) - 1) / sizeof(ge_p3)));
   int bad = 0;
   bad |= dalloc(&w->vpub, (size_t)(c->npub + 1) * Bz); bad |= dalloc(&w->uj, (2 * k + 2) * Bz);
   bad |= dalloc(&w->w_all, (size_t)c->nslots * Bz);

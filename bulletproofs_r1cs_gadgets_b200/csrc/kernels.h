@@ -1496,7 +1496,9 @@ struct KSortBucketsSerial {
 // sizes, and needed a slice table for buckets holding thousands of identical digits).  A segment that crosses a bucket
 // boundary stores its partial sum and starts a new one: partial (bucket b, segment s) lives at psum[b + s], which is
 // unique because buckets and segments are both ordered along the list.
+#ifndef SB_SEG
 #define SB_SEG 128
+#endif
 struct KBucketAccumulate {
   static constexpr int kBlock = 128, kMinBlocks = 1;
   static constexpr const char *kName = "KBucketAccumulate";
