@@ -721,6 +721,12 @@ struct WitnessLcs { const uint32_t *ptr; const uint8_t *kind; const uint32_t *id
 struct PoseidonBlock { uint32_t in_lc[6]; uint32_t sbox; uint32_t first_mult; };
 struct PoseidonDev { const scm *round_keys; const scm *mds; uint32_t full_b, partial, full_e; };
 #define POSEIDON_WIDTH 6
+// keeps a loop rolled on the device so that its body (an inlined Montgomery multiplication) exists once in the instruction stream
+#if defined(__CUDA_ARCH__)
+#define POSEIDON_ROLLED _Pragma("unroll 1")
+#else
+#define POSEIDON_ROLLED
+#endif
 
 struct KWitnessTape {
   static constexpr int kBlock = 32, kMinBlocks = 1;
@@ -731,14 +737,16 @@ struct KWitnessTape {
     scm acc = sc_zero();
     for (uint32_t t = lcs.ptr[lc]; t < lcs.ptr[lc + 1]; t++) {
       scm c = lcs.coeff[t]; long at = (long)lcs.idx[t] * B + p;
+      const scm *src;  // one multiplication site for every variable kind (instruction-cache footprint)
       switch (lcs.kind[t]) {
-        case 0: acc = sc_add(acc, sc_mul(c, v[at])); break;
-        case 1: acc = sc_add(acc, sc_mul(c, aL[at])); break;
-        case 2: acc = sc_add(acc, sc_mul(c, aR[at])); break;
-        case 3: acc = sc_add(acc, sc_mul(c, aO[at])); break;
-        case 5: acc = sc_add(acc, sc_mul(c, pub[at])); break;
-        default: acc = sc_add(acc, c); break;
+        case 0: src = v; break;
+        case 1: src = aL; break;
+        case 2: src = aR; break;
+        case 3: src = aO; break;
+        case 5: src = pub; break;
+        default: src = nullptr; break;
       }
+      acc = sc_add(acc, src ? sc_mul(c, src[at]) : c);
     }
     return acc;
   }
@@ -762,29 +770,35 @@ struct KWitnessTape {
       const bool full = rnd < pos.full_b || rnd >= pos.full_b + pos.partial;
       for (int i = 0; i < POSEIDON_WIDTH; i++) st[i] = sc_add(st[i], pos.round_keys[off + i]);
       off += POSEIDON_WIDTH;
-      if (full && blk.sbox == 1) {
-        // six inversions with one field inversion (Montgomery's trick); zero inputs map to zero as Scalar::invert does
+      if (blk.sbox == 1) {
+        // the inversions of a round (six lanes of a full round, the last lane of a partial one) with ONE field inversion
+        // (Montgomery's trick); zero inputs map to zero as Scalar::invert does
+        const int first = full ? 0 : POSEIDON_WIDTH - 1;
         scm x[POSEIDON_WIDTH], pre[POSEIDON_WIDTH], acc = sc_one();
-        for (int i = 0; i < POSEIDON_WIDTH; i++) { x[i] = sc_is_zero(st[i]) ? sc_one() : st[i]; pre[i] = acc; acc = sc_mul(acc, x[i]); }
+        POSEIDON_ROLLED
+        for (int i = first; i < POSEIDON_WIDTH; i++) { x[i] = sc_is_zero(st[i]) ? sc_one() : st[i]; pre[i] = acc; acc = sc_mul(acc, x[i]); }
         scm inv = sc_invert(acc);
-        for (int i = POSEIDON_WIDTH - 1; i >= 0; i--) {
+        POSEIDON_ROLLED
+        for (int i = POSEIDON_WIDTH - 1; i >= first; i--) {
           scm xi = sc_mul(inv, pre[i]); inv = sc_mul(inv, x[i]);
           if (sc_is_zero(st[i])) xi = sc_zero();
           x[i] = xi;
         }
-        for (int i = 0; i < POSEIDON_WIDTH; i++) {
+        POSEIDON_ROLLED
+        for (int i = first; i < POSEIDON_WIDTH; i++) {
           scm o = sc_is_zero(st[i]) ? sc_zero() : sc_one();
           put(at, p, st[i], x[i], o); put(at + 1, p, st[i], sc_zero(), sc_zero()); put(at + 2, p, st[i], x[i], o);
           at += 3; st[i] = x[i];
         }
-      } else if (full) {
-        for (int i = 0; i < POSEIDON_WIDTH; i++) at = sbox_out(at, p, st[i], blk.sbox);
       } else {
-        at = sbox_out(at, p, st[POSEIDON_WIDTH - 1], blk.sbox);
+        POSEIDON_ROLLED
+        for (int i = full ? 0 : POSEIDON_WIDTH - 1; i < POSEIDON_WIDTH; i++) at = sbox_out(at, p, st[i], 0);
       }
       scm nx[POSEIDON_WIDTH];
+      POSEIDON_ROLLED
       for (int i = 0; i < POSEIDON_WIDTH; i++) {
         scm acc = sc_zero();
+        POSEIDON_ROLLED
         for (int j = 0; j < POSEIDON_WIDTH; j++) acc = sc_add(acc, sc_mul(st[j], pos.mds[i * POSEIDON_WIDTH + j]));
         nx[i] = acc;
       }
