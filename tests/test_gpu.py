@@ -62,6 +62,8 @@ def test_device_tree_reference_parameters(api, gens_big, oracle_lib):
     """depth 32, Poseidon 4+140+4 inverse: device tree vs the oracle's one-key-at-a-time tree hashing with the C oracle; membership proofs from the tree"""
     E.test_device_tree(api, gens_big, oracle_lib=oracle_lib, depth=32, params=(6, 4, 4, 140), nkeys=24, prove=True, seed=901)
 def test_streamed_batches_equal_plain_batches(api, gens): E.test_streamed_batches_equal_plain_batches(api, gens)
+def test_skewed_digit_distributions_small(api, gens, oracle_lib): E.test_skewed_digit_distributions(api, gens, oracle_lib)
+def test_skewed_digit_distributions_sorted_path(api, gens_big, oracle_lib): E.test_skewed_digit_distributions(api, gens_big, oracle_lib, n=6000, cap=8192)
 def test_error_codes(api, gens): E.test_error_codes(api, gens)
 def test_single_multiplier_and_allocate_single(api, gens): E.test_single_multiplier_and_allocate_single(api, gens)
 

@@ -369,6 +369,28 @@ def test_streamed_batches_equal_plain_batches(api, gens):
     assert st.finish(0)[1].tobytes() == plain[0][1].tobytes()
 
 
+def test_skewed_digit_distributions(api, gens, oracle_lib, n=100, cap=256):
+    """explicit witnesses whose scalars all share their digits (every row of A_I lands in one or two buckets of the sorted-bucket
+    MSM: the single-coarse-group path of the two-pass sort at n >= 4096 on the GPU), negative digits only, and zeros; proof bytes
+    against the C oracle's prover on the same (unsatisfied -- the prover does not care) circuit"""
+    kind, idx = [1, 0, 2, 3], [0, 0, n - 1, n // 2]
+    coeff = api.scalars_to_array([1, L - 1, 7, 9])
+    cons_ptr = [0, 2, 4]
+    circ = api.Circuit.from_arrays(n, 1, cons_ptr, kind, idx, coeff)
+    oc = CO.Circuit(n, 1, cons_ptr, kind, idx, coeff)
+    rows = [([5] * n, [7] * n, [35] * n), ([2 ** 120 + 3] * n, [L - 1] * n, [0] * n), ([0] * n, [1] * n, [2 ** 252] * n)]
+    B = len(rows)
+    wit = [np.stack([api.scalars_to_array(r[j]) for r in rows]) for j in range(3)]
+    v = api.scalars_to_array(H.rand_scalars(31, B)).reshape(B, 1, 32)
+    vb = api.scalars_to_array(H.rand_scalars(32, B)).reshape(B, 1, 32)
+    ent = np.frombuffer(bytes(range(100, 100 + 32 * B)), dtype=np.uint8).reshape(B, 32)
+    V, P, st = circ.prove_batch(gens, b"skew", v, vb, ent, witness=tuple(wit))
+    assert not st.any()
+    for i in range(B):
+        rc, oV, oP = CO.prove(oc, wit[0][i], wit[1][i], wit[2][i], v[i], vb[i], b"skew", ent[i].tobytes(), cap)
+        assert rc == 0 and oV.tobytes() == V[i].tobytes() and oP == P[i].tobytes(), i
+
+
 def test_chunking_is_invisible(api, gens, monkeypatch):
     from bulletproofs_r1cs_gadgets_b200 import workloads
     wl = workloads.Mimc(gens, rounds=3)
