@@ -58,6 +58,7 @@ def test_vsmt4_membership_reference_parameters(api, gens_big, oracle_lib): E.tes
 def test_sparse_merkle_tree_and_membership_from_a_real_tree(api, gens): E.test_sparse_merkle_tree_and_membership_from_a_real_tree(api, gens)
 def test_device_tree_small(api, gens): E.test_device_tree(api, gens)
 def test_device_tree_depth5(api, gens): E.test_device_tree_depth5(api, gens)
+def test_device_tree_depth63(api, gens): E.test_device_tree_depth63(api, gens)
 def test_device_tree_reference_parameters(api, gens_big, oracle_lib):
     """depth 32, Poseidon 4+140+4 inverse: device tree vs the oracle's one-key-at-a-time tree hashing with the C oracle; membership proofs from the tree"""
     E.test_device_tree(api, gens_big, oracle_lib=oracle_lib, depth=32, params=(6, 4, 4, 140), nkeys=24, prove=True, seed=901)
