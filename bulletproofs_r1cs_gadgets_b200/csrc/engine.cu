@@ -718,9 +718,11 @@ static int prove_phase_b(const BpGens *g, BpCircuit *c, Front &f, const ProveArg
       CK(launch(h * B, s, KFoldAB{w->a, w->b, ipa_u, ipa_uinv, (int)h, B}));
       CK(launch((2L << round) * B, s, KIpaUTable{ipa_u, ipa_uinv, UG[cur], UH[cur], UG[cur ^ 1], UH[cur ^ 1], B}));
       if (round == J - 1 && h > 1) {
-        // true folded generators of level J straight from the tables; alpha = beta = 1 and the y^-i factors are inside
+        // folded generators of level J straight from the tables: H side true (beta = 1, the y^-i factors are inside), G side
+        // divided by UG[0] so that the first of its 2^J terms is the generator itself; alpha = UG[0] carries the factor
         CK(launch(N * B, s, KRecodeFoldTable{UG[cur ^ 1], UH[cur ^ 1], w->yinvpow, ch_u, N, h, n, B, w->dig, 2 * N * 32}));
-        CK(launch(2 * h * B, s, KFoldTable{g->table, (long)g->capacity, N, h, w->dig, 2 * N * 32, w->Gt, w->Ht, gs}));
+        CK(launch(2 * h * B, s, KFoldTable{g->table, (long)g->capacity, N, h, w->dig, 2 * N * 32, w->Gt, w->Ht, gs, g->G_n}));
+        CK(dev_d2d(alpha, UG[cur ^ 1], sizeof(scm) * B, s));
         yfree = 1;
       }
       len = h;

@@ -1319,7 +1319,10 @@ struct KRecodeUnfolded {
     }
   }
 };
-// digit rows for materialising the TRUE folded generators at level J: row idx (G) = UG[b]*gf(idx), row N+idx (H) = UH[b]*y^-idx*gf(idx)
+// digit rows for materialising the folded generators at level J: row idx (G) = UG[b]*gf(idx) / UG[0], row N+idx (H) = UH[b]*y^-idx*gf(idx).
+// The G side is kept un-normalised by the factor UG[0] (it becomes alpha, see KTsIpaRound): block 0 of every G output then carries the
+// scalar 1 -- its row is all zeros here and KFoldTable adds the generator itself, one addition instead of 32.  (The H side has no
+// common factor: its block-0 scalar UH[0]*y^-i depends on the output index.)  UG[0]^-1 = UH[0] (KIpaUTable).
 struct KRecodeFoldTable {
   static constexpr int kBlock = 128, kMinBlocks = 1;
   static constexpr const char *kName = "KRecodeFoldTable";
@@ -1330,19 +1333,21 @@ struct KRecodeFoldTable {
     scm gf = idx >= n ? ufac[p] : sc_one();
     int8_t d[32];
     int8_t *row = dig + (long)p * inst_stride;
-    sc_recode_bytes(d, sc_mul(UG[blk * B + p], gf)); store_digits(row + idx * 32, d);
+    sc_recode_bytes(d, blk == 0 ? sc_zero() : sc_mul(sc_mul(UG[blk * B + p], gf), UH[p])); store_digits(row + idx * 32, d);
     sc_recode_bytes(d, sc_mul(sc_mul(UH[blk * B + p], yinvpow[idx * B + p]), gf)); store_digits(row + (N + idx) * 32, d);
   }
 };
-// G_J[i] = sum_b (row b*nJ+i) * G_{b*nJ+i}, H_J[i] likewise: the folded generators after J rounds, straight from the tables
+// G_J[i] = G_i + sum_{b>0} (row b*nJ+i) * G_{b*nJ+i} (un-normalised, see KRecodeFoldTable), H_J[i] = sum_b (row N+b*nJ+i) * H_{b*nJ+i}:
+// the folded generators after J rounds, straight from the tables
 struct KFoldTable {
   static constexpr int kBlock = 128, kMinBlocks = BP_OCC_TABLE;
   static constexpr const char *kName = "KFoldTable";
-  const ge_niels *table; long cap, N, nJ; const int8_t *dig; long dig_inst_stride; ge_p3 *dstG, *dstH; long dst_stride;
+  const ge_niels *table; long cap, N, nJ; const int8_t *dig; long dig_inst_stride; ge_p3 *dstG, *dstH; long dst_stride; const ge_niels *Gn;
   HD void operator()(long tid) const {
     long p = tid / (2 * nJ); long r = tid % (2 * nJ); int which = (int)(r / nJ); long i = r % nJ;
     const int8_t *drow = dig + p * dig_inst_stride + (which ? N * 32 : 0);
     ge_p3 acc; ge_identity(acc);
+    if (!which) { ge_niels q; load_struct(q, &Gn[i]); ge_madd(acc, acc, q, 0); }
     for (long blk = 0; blk < N / nJ; blk++) {
       long idx = blk * nJ + i;
       const int8_t *d = drow + idx * 32;
