@@ -8,6 +8,7 @@ import pytest
 
 import helpers as H
 import test_host_emul as E
+import test_libsodium_pin as S
 from helpers import R, G, CO, L
 
 pytestmark = pytest.mark.gpu
@@ -43,6 +44,14 @@ def _msm_device_pointers(api, gens, arr):
 
 
 def test_msm_entry(api, gens): E.test_msm_entry(api, gens, call=_msm_device_pointers)
+
+
+# third-party pin (libsodium, tests/test_libsodium_pin.py): device scalar field, Pedersen commitments, and the MSM kernels of
+# both paths (direct tables at 200 rows; sort / KBucketAccumulate / KBucketReduce at 40000 rows, ragged last sub-instance)
+def test_libsodium_scalar_field(api): S.check_device_scalar_field(api, 1000)
+def test_libsodium_commit_and_one_way_map(api, gens): S.check_device_from_uniform_and_commit(api, gens, 16)
+def test_libsodium_msm_table_path(api, gens): S.check_device_msm(api, gens, 200, _msm_device_pointers)
+def test_libsodium_msm_sorted_path(api): S.check_device_msm(api, api.Gens(1 << 16), 40000, _msm_device_pointers)
 def test_golden_proofs_tier1(api, gens): E.test_golden_proofs_tier1(api, gens)
 def test_python_gadget_code_drives_product_cs(api, gens): E.test_python_gadget_code_drives_product_cs(api, gens)
 def test_verifier_rejects_tampering(api, gens): E.test_verifier_rejects_tampering(api, gens)
