@@ -721,7 +721,7 @@ static int prove_phase_b(const BpGens *g, BpCircuit *c, Front &f, const ProveArg
         // folded generators of level J straight from the tables: H side true (beta = 1, the y^-i factors are inside), G side
         // divided by UG[0] so that the first of its 2^J terms is the generator itself; alpha = UG[0] carries the factor
         CK(launch(N * B, s, KRecodeFoldTable{UG[cur ^ 1], UH[cur ^ 1], w->yinvpow, ch_u, N, h, n, B, w->dig, 2 * N * 32}));
-        CK(launch(2 * h * B, s, KFoldTable{g->table, (long)g->capacity, N, h, w->dig, 2 * N * 32, w->Gt, w->Ht, gs, g->G_n}));
+        CK(launch(2 * h * B, s, KFoldTable{g->table, (long)g->capacity, N, h, w->dig, 2 * N * 32, w->Gt, w->Ht, gs, g->G_p3}));
         CK(dev_d2d(alpha, UG[cur ^ 1], sizeof(scm) * B, s));
         yfree = 1;
       }

@@ -358,6 +358,20 @@ HD void fe_sq(fe &out, const fe &f) {
 #endif
 }
 HD void fe_sq2(fe &out, const fe &f) { fe t; fe_sq(t, f); fe_add(out, t, t); }
+// Call-or-inline choice per use.  A call moves its 16 + 8 operand registers with IMAD.MOV -- which issues on the same
+// multiplier pipe as the IMAD.WIDE of the product itself -- so the point operations of the hot loops expand the field
+// multiplications in place (INL = true: +16 % mixed additions per second, profiles/r02_field_call_vs_inline.jsonl) while
+// everything with many multiplication sites (inversions, encodings, set-up) keeps the calls and a small instruction footprint.
+#ifndef BP_GE_INLINE
+#define BP_GE_INLINE 1  // 0: every multiplication is a call (the round-1 build), for A/B runs
+#endif
+template <bool INL> HD void fe_mul_x(fe &out, const fe &f, const fe &g) {
+  if constexpr (INL && BP_GE_INLINE) fe_mul_inl(out, f, g); else fe_mul(out, f, g);
+}
+template <bool INL> HD void fe_sq_x(fe &out, const fe &f) {
+  if constexpr (INL && BP_GE_INLINE) fe_sq_inl(out, f); else fe_sq(out, f);
+}
+template <bool INL> HD void fe_sq2_x(fe &out, const fe &f) { fe t; fe_sq_x<INL>(t, f); fe_add(out, t, t); }
 HD void fe_sqn(fe &out, const fe &f, int n) {
   fe_sq(out, f);
   for (int i = 1; i < n; i++) fe_sq(out, out);

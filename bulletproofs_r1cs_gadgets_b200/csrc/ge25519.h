@@ -14,71 +14,105 @@ struct ge_p1p1 { fe X, Y, Z, T; };
 HD void ge_identity(ge_p3 &p) { fe_0(p.X); fe_1(p.Y); fe_1(p.Z); fe_0(p.T); }
 HD void ge_niels_identity(ge_niels &n) { fe_1(n.ypx); fe_1(n.ymx); fe_0(n.xy2d); }
 
-HD void ge_p1p1_to_p3(ge_p3 &r, const ge_p1p1 &p) {
-  fe_mul(r.X, p.X, p.T); fe_mul(r.Y, p.Y, p.Z); fe_mul(r.Z, p.Z, p.T); fe_mul(r.T, p.X, p.Y);
+// INL: expand the field multiplications in place (hot loops) instead of calling them, see fe_mul_x
+template <bool INL = false> HD void ge_p1p1_to_p3(ge_p3 &r, const ge_p1p1 &p) {
+  fe_mul_x<INL>(r.X, p.X, p.T); fe_mul_x<INL>(r.Y, p.Y, p.Z); fe_mul_x<INL>(r.Z, p.Z, p.T); fe_mul_x<INL>(r.T, p.X, p.Y);
 }
 // projective result only (T not produced): valid input for a following doubling
-HD void ge_p1p1_to_p2(ge_p3 &r, const ge_p1p1 &p) {
-  fe_mul(r.X, p.X, p.T); fe_mul(r.Y, p.Y, p.Z); fe_mul(r.Z, p.Z, p.T);
+template <bool INL = false> HD void ge_p1p1_to_p2(ge_p3 &r, const ge_p1p1 &p) {
+  fe_mul_x<INL>(r.X, p.X, p.T); fe_mul_x<INL>(r.Y, p.Y, p.Z); fe_mul_x<INL>(r.Z, p.Z, p.T);
 }
-HD void ge_to_cached(ge_cached &c, const ge_p3 &p) {
+template <bool INL = false> HD void ge_to_cached(ge_cached &c, const ge_p3 &p) {
   fe d2; FE_2D(d2);
-  fe_add(c.YpX, p.Y, p.X); fe_sub(c.YmX, p.Y, p.X); c.Z = p.Z; fe_mul(c.T2d, p.T, d2);
+  fe_add(c.YpX, p.Y, p.X); fe_sub(c.YmX, p.Y, p.X); c.Z = p.Z; fe_mul_x<INL>(c.T2d, p.T, d2);
 }
 // kept for the call sites written for the lazy 10-limb form: saturated limbs carry nothing over
 HD void fe_carry(fe &) {}
 
 // r = p + (neg ? -q : q), q affine niels.  7 multiplications after completion.
-HD void ge_madd_p1p1(ge_p1p1 &r, const ge_p3 &p, const ge_niels &q, int neg) {
+template <bool INL = false> HD void ge_madd_p1p1(ge_p1p1 &r, const ge_p3 &p, const ge_niels &q, int neg) {
   fe a, b, t0, qp, qm, qt;
   fe_select(qp, q.ypx, q.ymx, neg);
   fe_select(qm, q.ymx, q.ypx, neg);
   fe_cneg(qt, q.xy2d, neg);
   fe_add(a, p.Y, p.X); fe_sub(b, p.Y, p.X);
-  fe_mul(r.Z, a, qp);      // A
-  fe_mul(r.Y, b, qm);      // B
-  fe_mul(r.T, qt, p.T);    // C
-  fe_add(t0, p.Z, p.Z);    // D
+  fe_mul_x<INL>(r.Z, a, qp);      // A
+  fe_mul_x<INL>(r.Y, b, qm);      // B
+  fe_mul_x<INL>(r.T, qt, p.T);    // C
+  fe_add(t0, p.Z, p.Z);           // D
   fe_sub(r.X, r.Z, r.Y); fe_add(r.Y, r.Z, r.Y);
   fe_add(r.Z, t0, r.T); fe_sub(r.T, t0, r.T);
 }
-HD void ge_madd(ge_p3 &r, const ge_p3 &p, const ge_niels &q, int neg) {
-  ge_p1p1 t; ge_madd_p1p1(t, p, q, neg); ge_p1p1_to_p3(r, t);
+template <bool INL = false> HD void ge_madd(ge_p3 &r, const ge_p3 &p, const ge_niels &q, int neg) {
+  ge_p1p1 t; ge_madd_p1p1<INL>(t, p, q, neg); ge_p1p1_to_p3<INL>(r, t);
 }
 // r = p + (neg ? -q : q), q cached
-HD void ge_add_cached_p1p1(ge_p1p1 &r, const ge_p3 &p, const ge_cached &q, int neg) {
+template <bool INL = false> HD void ge_add_cached_p1p1(ge_p1p1 &r, const ge_p3 &p, const ge_cached &q, int neg) {
   fe a, b, t0, qp, qm, qt;
   fe_select(qp, q.YpX, q.YmX, neg);
   fe_select(qm, q.YmX, q.YpX, neg);
   fe_cneg(qt, q.T2d, neg);
   fe_add(a, p.Y, p.X); fe_sub(b, p.Y, p.X);
-  fe_mul(r.Z, a, qp);
-  fe_mul(r.Y, b, qm);
-  fe_mul(r.T, qt, p.T);
-  fe_mul(r.X, p.Z, q.Z);
+  fe_mul_x<INL>(r.Z, a, qp);
+  fe_mul_x<INL>(r.Y, b, qm);
+  fe_mul_x<INL>(r.T, qt, p.T);
+  fe_mul_x<INL>(r.X, p.Z, q.Z);
   fe_add(t0, r.X, r.X);
   fe_sub(r.X, r.Z, r.Y); fe_add(r.Y, r.Z, r.Y);
   fe_add(r.Z, t0, r.T); fe_sub(r.T, t0, r.T);
 }
-HD void ge_add_cached(ge_p3 &r, const ge_p3 &p, const ge_cached &q, int neg) {
-  ge_p1p1 t; ge_add_cached_p1p1(t, p, q, neg); ge_p1p1_to_p3(r, t);
+template <bool INL = false> HD void ge_add_cached(ge_p3 &r, const ge_p3 &p, const ge_cached &q, int neg) {
+  ge_p1p1 t; ge_add_cached_p1p1<INL>(t, p, q, neg); ge_p1p1_to_p3<INL>(r, t);
 }
-HD void ge_add(ge_p3 &r, const ge_p3 &p, const ge_p3 &q) {
-  ge_cached c; ge_to_cached(c, q); ge_add_cached(r, p, c, 0);
+template <bool INL = false> HD void ge_add(ge_p3 &r, const ge_p3 &p, const ge_p3 &q) {
+  ge_cached c; ge_to_cached<INL>(c, q); ge_add_cached<INL>(r, p, c, 0);
 }
-HD void ge_sub(ge_p3 &r, const ge_p3 &p, const ge_p3 &q) {
-  ge_cached c; ge_to_cached(c, q); ge_add_cached(r, p, c, 1);
+template <bool INL = false> HD void ge_sub(ge_p3 &r, const ge_p3 &p, const ge_p3 &q) {
+  ge_cached c; ge_to_cached<INL>(c, q); ge_add_cached<INL>(r, p, c, 1);
 }
 // doubling; only X, Y, Z of p are read
-HD void ge_dbl_p1p1(ge_p1p1 &r, const ge_p3 &p) {
+template <bool INL = false> HD void ge_dbl_p1p1(ge_p1p1 &r, const ge_p3 &p) {
   fe t0;
-  fe_sq(r.X, p.X); fe_sq(r.Z, p.Y); fe_sq2(r.T, p.Z);
-  fe_add(r.Y, p.X, p.Y); fe_sq(t0, r.Y);
+  fe_sq_x<INL>(r.X, p.X); fe_sq_x<INL>(r.Z, p.Y); fe_sq2_x<INL>(r.T, p.Z);
+  fe_add(r.Y, p.X, p.Y); fe_sq_x<INL>(t0, r.Y);
   fe_add(r.Y, r.Z, r.X); fe_sub(r.Z, r.Z, r.X);
   fe_sub(r.X, t0, r.Y); fe_sub(r.T, r.T, r.Z);
 }
-HD void ge_dbl(ge_p3 &r, const ge_p3 &p) { ge_p1p1 t; ge_dbl_p1p1(t, p); ge_p1p1_to_p3(r, t); }
-HD void ge_dbl_p2(ge_p3 &r, const ge_p3 &p) { ge_p1p1 t; ge_dbl_p1p1(t, p); ge_p1p1_to_p2(r, t); }
+template <bool INL = false> HD void ge_dbl(ge_p3 &r, const ge_p3 &p) { ge_p1p1 t; ge_dbl_p1p1<INL>(t, p); ge_p1p1_to_p3<INL>(r, t); }
+template <bool INL = false> HD void ge_dbl_p2(ge_p3 &r, const ge_p3 &p) { ge_p1p1 t; ge_dbl_p1p1<INL>(t, p); ge_p1p1_to_p2<INL>(r, t); }
+// Point-level device functions for kernels with SEVERAL addition / doubling sites (generator fold, per-proof bucket method,
+// bucket reduction): one copy of the expanded field arithmetic per kernel, operands and result in registers.
+#if defined(__CUDACC__)
+static __device__ __noinline__ ge_p3 ge_add_cached_fn(ge_p3 p, ge_cached q, int neg) { ge_p3 r; ge_add_cached<true>(r, p, q, neg); return r; }
+static __device__ __noinline__ ge_p3 ge_dbl_fn(ge_p3 p, int need_t) {
+  ge_p1p1 t; ge_dbl_p1p1<true>(t, p);
+  ge_p3 r; ge_p1p1_to_p2<true>(r, t);
+  if (need_t) fe_mul_x<true>(r.T, t.X, t.Y); else r.T = p.T;
+  return r;
+}
+#endif
+HD void ge_add_cached_f(ge_p3 &r, const ge_p3 &p, const ge_cached &q, int neg) {
+#if defined(__CUDA_ARCH__) && BP_GE_INLINE
+  r = ge_add_cached_fn(p, q, neg);
+#else
+  ge_add_cached(r, p, q, neg);
+#endif
+}
+HD void ge_add_f(ge_p3 &r, const ge_p3 &p, const ge_p3 &q) { ge_cached c; ge_to_cached<true>(c, q); ge_add_cached_f(r, p, c, 0); }
+HD void ge_dbl_f(ge_p3 &r, const ge_p3 &p) {
+#if defined(__CUDA_ARCH__) && BP_GE_INLINE
+  r = ge_dbl_fn(p, 1);
+#else
+  ge_dbl(r, p);
+#endif
+}
+HD void ge_dbl_p2_f(ge_p3 &r, const ge_p3 &p) {
+#if defined(__CUDA_ARCH__) && BP_GE_INLINE
+  r = ge_dbl_fn(p, 0);
+#else
+  ge_dbl_p2(r, p);
+#endif
+}
 HD void ge_neg(ge_p3 &r, const ge_p3 &p) { fe_neg(r.X, p.X); r.Y = p.Y; r.Z = p.Z; fe_neg(r.T, p.T); }
 
 // affine normalisation -> niels form (one inversion)

@@ -189,7 +189,7 @@ struct KMsmAccumulate {
             int neg = d < 0; int idx = (neg ? -d : d) - 1;
             ge_niels qn; load_struct(qn, &bases[t]);
             ge_p3 acc; load_struct(acc, &bk[idx]);
-            ge_madd(acc, acc, qn, neg);
+            ge_madd(acc, acc, qn, neg);  // shared generators without tables: not a hot configuration, keeps the called multiplications
             store_struct(&bk[idx], acc);
           }
         }
@@ -200,9 +200,9 @@ struct KMsmAccumulate {
           if (d != 0) {
             int neg = d < 0; int idx = (neg ? -d : d) - 1;
             ge_p3 qp; load_struct(qp, &bases[t]);
-            ge_cached c; ge_to_cached(c, qp);
+            ge_cached c; ge_to_cached<true>(c, qp);
             ge_p3 acc; load_struct(acc, &bk[idx]);
-            ge_add_cached(acc, acc, c, neg);
+            ge_add_cached_f(acc, acc, c, neg);
             store_struct(&bk[idx], acc);
           }
         }
@@ -213,8 +213,8 @@ struct KMsmAccumulate {
     ge_p3 run, tot; ge_identity(run); ge_identity(tot);
     for (int d = MSM_BUCKETS - 1; d >= 0; d--) {
       ge_p3 b; load_struct(b, &bk[d]);
-      ge_add(run, run, b);
-      ge_add(tot, tot, run);
+      ge_add_f(run, run, b);
+      ge_add_f(tot, tot, run);
     }
     store_struct(&wsum[tid], tot);
   }
@@ -628,21 +628,21 @@ struct KFoldGens {
       ge_cached c[4];
       {
         ge_p3 h2, t; ge_cached c2;
-        ge_dbl(h2, hi); ge_to_cached(c2, h2);
-        ge_to_cached(c[0], hi);
-        ge_add_cached(t, hi, c2, 0); ge_to_cached(c[1], t);
-        ge_add_cached(t, t, c2, 0); ge_to_cached(c[2], t);
-        ge_add_cached(t, t, c2, 0); ge_to_cached(c[3], t);
+        ge_dbl_f(h2, hi); ge_to_cached<true>(c2, h2);
+        ge_to_cached<true>(c[0], hi);
+        ge_add_cached_f(t, hi, c2, 0); ge_to_cached<true>(c[1], t);
+        ge_add_cached_f(t, t, c2, 0); ge_to_cached<true>(c[2], t);
+        ge_add_cached_f(t, t, c2, 0); ge_to_cached<true>(c[3], t);
       }
       ge_identity(acc);
       for (int bit = top; bit >= 0; bit--) {
         int d = nf[bit];
         // T is only needed when an addition follows (a digit here, or the final + lo)
-        if (bit != top) { if (d != 0 || bit == 0) ge_dbl(acc, acc); else ge_dbl_p2(acc, acc); }
-        if (d != 0) { const int neg = d < 0; const int idx = ((neg ? -d : d) - 1) >> 1; ge_add_cached(acc, acc, c[idx], neg); }
+        if (bit != top) { if (d != 0 || bit == 0) ge_dbl_f(acc, acc); else ge_dbl_p2_f(acc, acc); }
+        if (d != 0) { const int neg = d < 0; const int idx = ((neg ? -d : d) - 1) >> 1; ge_add_cached_f(acc, acc, c[idx], neg); }
       }
-      ge_cached cl; ge_to_cached(cl, lo);
-      ge_add_cached(acc, acc, cl, 0);
+      ge_cached cl; ge_to_cached<true>(cl, lo);
+      ge_add_cached_f(acc, acc, cl, 0);
     }
     store_struct(&dst[i], acc);
   }
@@ -1185,13 +1185,13 @@ struct KMsmTable {
       memcpy(d, drow + r * 32, 32);
 #endif
       const ge_niels *tg = table + row_gen(rmap, r) * (long)(TBL_W * TBL_E);
-#pragma unroll 4
-      for (int w = 0; w < TBL_W; w++) {
+#pragma unroll 1
+      for (int w = 0; w < TBL_W; w++) {  // rolled: ONE addition site, its field multiplications expanded in place
         int dv = d[w];
         if (dv != 0) {
           int neg = dv < 0; int e = (neg ? -dv : dv) - 1;
           ge_niels q; load_struct(q, &tg[w * TBL_E + e]);
-          ge_madd(acc, acc, q, neg);
+          ge_madd<true>(acc, acc, q, neg);
         }
       }
     }
@@ -1342,23 +1342,21 @@ struct KRecodeFoldTable {
 struct KFoldTable {
   static constexpr int kBlock = 128, kMinBlocks = BP_OCC_TABLE;
   static constexpr const char *kName = "KFoldTable";
-  const ge_niels *table; long cap, N, nJ; const int8_t *dig; long dig_inst_stride; ge_p3 *dstG, *dstH; long dst_stride; const ge_niels *Gn;
+  const ge_niels *table; long cap, N, nJ; const int8_t *dig; long dig_inst_stride; ge_p3 *dstG, *dstH; long dst_stride; const ge_p3 *G;
   HD void operator()(long tid) const {
     long p = tid / (2 * nJ); long r = tid % (2 * nJ); int which = (int)(r / nJ); long i = r % nJ;
     const int8_t *drow = dig + p * dig_inst_stride + (which ? N * 32 : 0);
-    ge_p3 acc; ge_identity(acc);
-    if (!which) { ge_niels q; load_struct(q, &Gn[i]); ge_madd(acc, acc, q, 0); }
-    for (long blk = 0; blk < N / nJ; blk++) {
-      long idx = blk * nJ + i;
-      const int8_t *d = drow + idx * 32;
-      const ge_niels *tg = table + ((which ? cap : 0) + idx) * (long)(TBL_W * TBL_E);
-      for (int w = 0; w < TBL_W; w++) {
-        int dv = d[w];
-        if (dv != 0) {
-          int neg = dv < 0; int e = (neg ? -dv : dv) - 1;
-          ge_niels q; load_struct(q, &tg[w * TBL_E + e]);
-          ge_madd(acc, acc, q, neg);
-        }
+    ge_p3 acc;
+    if (which) ge_identity(acc); else load_struct(acc, &G[i]);  // G side: block 0 carries the scalar 1 (see KRecodeFoldTable)
+    const long terms = (N / nJ) * TBL_W;
+#pragma unroll 1
+    for (long t = 0; t < terms; t++) {  // one flat loop over (block, window): ONE addition site, field multiplications expanded in place
+      const long idx = (t / TBL_W) * nJ + i; const int w = (int)(t % TBL_W);
+      const int dv = drow[idx * 32 + w];
+      if (dv != 0) {
+        int neg = dv < 0; int e = (neg ? -dv : dv) - 1;
+        ge_niels q; load_struct(q, &table[(((which ? cap : 0) + idx) * TBL_W + w) * (long)TBL_E + e]);
+        ge_madd<true>(acc, acc, q, neg);
       }
     }
     store_struct(&(which ? dstH : dstG)[p * dst_stride + i], acc);
@@ -1518,8 +1516,11 @@ struct KSortBucketsSerial {
 #ifndef SB_SEG
 #define SB_SEG 128
 #endif
+#ifndef BP_OCC_SORTED
+#define BP_OCC_SORTED 4
+#endif
 struct KBucketAccumulate {
-  static constexpr int kBlock = 128, kMinBlocks = 1;
+  static constexpr int kBlock = 128, kMinBlocks = BP_OCC_SORTED;
   static constexpr const char *kName = "KBucketAccumulate";
   const ge_niels *sg; SortedView sv; ge_p3 *psum; long segs_cap;  // psum[inst*slices_cap + b + s]
   HD void operator()(long tid) const {
@@ -1545,7 +1546,7 @@ struct KBucketAccumulate {
       }
       const uint32_t cur = item; const ge_niels qc = q;
       if (k + 1 < k1) { item = it[k + 1]; load_struct(q, &sg[item & 0x7fffffffu]); }
-      ge_madd(acc, acc, qc, (int)(cur >> 31));
+      ge_madd<true>(acc, acc, qc, (int)(cur >> 31));  // the kernel's one addition site: field multiplications expanded in place
     }
     store_struct(&ps[b], acc);
   }
@@ -1565,9 +1566,9 @@ struct KBucketReduce {
       const uint32_t o0 = off[b], o1 = off[b + 1];
       if (o1 > o0) {
         const uint32_t s0 = o0 / SB_SEG, s1 = (o1 - 1) / SB_SEG;
-        for (uint32_t sj = s0; sj <= s1; sj++) { ge_p3 t; load_struct(t, &ps[b + sj]); ge_add(run, run, t); }
+        for (uint32_t sj = s0; sj <= s1; sj++) { ge_p3 t; load_struct(t, &ps[b + sj]); ge_add_f(run, run, t); }
       }
-      ge_add(tot, tot, run);
+      ge_add_f(tot, tot, run);
     }
     store_struct(&seg[tid * 2], run); store_struct(&seg[tid * 2 + 1], tot);
   }
