@@ -11,7 +11,9 @@ the MSM / inner-product phase of the current one, so every timed step holds one 
 `value` = proofs/s with inputs resident in HBM; `e2e` = the same through the host-buffer C-ABI calls
 (bp_prove_stream_begin_host / _finish_host: H2D of inputs and D2H of commitments + proofs inside the timed region);
 `single_call_value_per_gpu` = one plain bp_prove_batch_device call on rank 0 (nothing overlapped across batches).
-Prints ONE JSON line on rank 0.
+After the timed region every proof of the last batch goes through the cross-proof combined verifier (`verified`), and the other
+BASELINE.json configurations are measured (`configs`: Poseidon 2:1 x 1024 cube / inverse, MiMC 8192 per GPU -- 32768 over 4 GPUs
+under torchrun --, the MSM sweep 2^10..2^22, per-proof and combined verification).  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -40,6 +42,8 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="proofs in the cpu_baseline sample (0 = one per host core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configs / verifier measurements after the headline")
+    ap.add_argument("--no-verify", action="store_true", help="skip the combined verification of the whole timed batch")
     return ap.parse_args()
 
 
@@ -139,6 +143,156 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def _ptr(t):
+    import ctypes as C
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def timed_device_batches(lib, api, gens, wl, inp_np, reps, dev):
+    """one plain bp_prove_batch_device call per rep on device-resident inputs: (ms per call, V, proofs) -- the small configurations"""
+    import ctypes as C
+    import torch
+    circ = wl.circuit
+    B = inp_np["entropy"].shape[0]
+    d = {k: torch.from_numpy(a).to(dev) for k, a in inp_np.items()}
+    dV = torch.empty((B, circ.m, 32), dtype=torch.uint8, device=dev)
+    dP = torch.empty((B, circ.proof_len), dtype=torch.uint8, device=dev)
+    dS = torch.empty(B, dtype=torch.int32, device=dev)
+
+    def run():
+        rc = lib.bp_prove_batch_device(gens._h, circ._h, C.c_uint32(B), api._buf(wl.label), C.c_size_t(len(wl.label)), _ptr(d["v"]), _ptr(d["v_blinding"]),
+                                       _ptr(d["entropy"]), _ptr(d.get("aux")), _ptr(d.get("pub")), None, None, None, _ptr(dV), _ptr(dP), _ptr(dS),
+                                       C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0, rc
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    assert not dS.cpu().numpy().any()
+    return e0.elapsed_time(e1) / reps, dV, dP
+
+
+def combined_verify_device(lib, api, gens, circ, label, dV, dP, dE, dPub, dev, piece=2048):
+    """cross-proof combined verification of device-resident proofs in pieces that fit one device chunk: (all combined verdicts 0, structural statuses all 0)"""
+    import ctypes as C
+    import torch
+    B = dP.shape[0]
+    dS = torch.zeros(B, dtype=torch.int32, device=dev)
+    dC = torch.zeros(1, dtype=torch.int32, device=dev)
+    ok = True
+    for a in range(0, B, piece):
+        b = min(B, a + piece)
+        rc = lib.bp_verify_batch_combined_device(gens._h, circ._h, C.c_uint32(b - a), api._buf(label), C.c_size_t(len(label)), _ptr(dV[a:b]), _ptr(dP[a:b]), _ptr(dE[a:b]),
+                                                 _ptr(dPub[a:b]) if dPub is not None else None, _ptr(dS[a:b]), _ptr(dC), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0, rc
+        torch.cuda.synchronize()
+        ok = ok and int(dC.item()) == 0
+    return ok, not bool(dS.cpu().numpy().any())
+
+
+def extra_configs(args, lib, api, workloads, parallel, gens32k, wl5, dev, world, rank, dist, hbm_peak):
+    """BASELINE.json configs 2, 3, 4 and the verifier, measured after the headline (device-resident inputs, CUDA events).
+    Config 4 is sharded like the headline (8192 MiMC proofs per GPU: 32768 over 4 GPUs under torchrun --gpus 4); the rest runs on rank 0."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    out = {}
+    g2k = api.Gens(2048)
+    # config 4: gadget_mimc, 8192 proofs per GPU (reference src/gadget_mimc.rs:92-175)
+    wl = workloads.Mimc(g2k)
+    a, b = parallel.shard_range(rank, world, world * 8192)
+    inp = wl.inputs(a, b - a)
+    if world > 1:
+        dist.barrier()
+    ms, dV, dP = timed_device_batches(lib, api, g2k, wl, inp, 3, dev)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    okc, oks = combined_verify_device(lib, api, g2k, wl.circuit, wl.label, dV, dP, torch.from_numpy(inp["entropy"]).to(dev), torch.from_numpy(inp["pub"]).to(dev), dev, piece=8192)
+    out["mimc_8192_per_gpu"] = {"proofs_per_s": world * 8192 / ms * 1e3, "ms_per_step": ms, "proofs_per_step": world * 8192, "n": wl.circuit.n, "gpus": world,
+                                "verified_combined_rank0": bool(okc and oks)}
+    if rank != 0:
+        return out
+    # config 2: gadget_poseidon 2:1 preimage, 1024 proofs, both S-boxes (reference src/gadget_poseidon.rs:691-785)
+    for sbox, nm in ((api.SBOX_CUBE, "cube"), (api.SBOX_INVERSE, "inverse")):
+        wl = workloads.PoseidonHash2(g2k, sbox)
+        inp = wl.inputs(0, 1024)
+        ms, dV, dP = timed_device_batches(lib, api, g2k, wl, inp, 3, dev)
+        okc, oks = combined_verify_device(lib, api, g2k, wl.circuit, wl.label, dV, dP, torch.from_numpy(inp["entropy"]).to(dev), torch.from_numpy(inp["pub"]).to(dev), dev, piece=1024)
+        out["poseidon_1024_" + nm] = {"proofs_per_s": 1024 / ms * 1e3, "ms_per_step": ms, "n": wl.circuit.n, "verified_combined": bool(okc and oks)}
+    del g2k
+    # verifier on depth-32 membership proofs: per-proof (Verifier::verify, reference src/gadget_vsmt_2.rs:395) and cross-proof combined
+    Bv = 1024
+    inp = wl5.inputs(0, Bv, with_root=False)
+    pub = wl5.roots_batch(inp["v"])
+    d = {k: torch.from_numpy(v).to(dev) for k, v in inp.items() if k in ("v", "v_blinding", "entropy")}
+    dV = torch.empty((Bv, wl5.circuit.m, 32), dtype=torch.uint8, device=dev)
+    dP = torch.empty((Bv, wl5.circuit.proof_len), dtype=torch.uint8, device=dev)
+    dS = torch.empty(Bv, dtype=torch.int32, device=dev)
+    dC = torch.zeros(1, dtype=torch.int32, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    lbl, ll = api._buf(wl5.label), C.c_size_t(len(wl5.label))
+    assert lib.bp_prove_batch_device(gens32k._h, wl5.circuit._h, C.c_uint32(Bv), lbl, ll, _ptr(d["v"]), _ptr(d["v_blinding"]), _ptr(d["entropy"]), None, None,
+                                     None, None, None, _ptr(dV), _ptr(dP), _ptr(dS), st) == 0
+    dpub = torch.from_numpy(pub).to(dev)
+    dbad = dpub.clone()
+    dbad[Bv // 2, 0, 0] ^= 1
+
+    def per_proof(p_):
+        assert lib.bp_verify_batch_device(gens32k._h, wl5.circuit._h, C.c_uint32(Bv), lbl, ll, _ptr(dV), _ptr(dP), _ptr(d["entropy"]), _ptr(p_), _ptr(dS), st) == 0
+
+    def comb(p_):
+        assert lib.bp_verify_batch_combined_device(gens32k._h, wl5.circuit._h, C.c_uint32(Bv), lbl, ll, _ptr(dV), _ptr(dP), _ptr(d["entropy"]), _ptr(p_), _ptr(dS), _ptr(dC), st) == 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for name, fn in (("verify_per_proof", per_proof), ("verify_combined", comb)):
+        fn(dpub)
+        torch.cuda.synchronize()
+        e0.record()
+        fn(dpub)
+        fn(dpub)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 2
+        good = (not dS.cpu().numpy().any()) and (name == "verify_per_proof" or int(dC.item()) == 0)
+        fn(dbad)
+        torch.cuda.synchronize()
+        sb = dS.cpu().numpy()
+        rejected = (sb[Bv // 2] == 3 and not np.delete(sb, Bv // 2).any()) if name == "verify_per_proof" else int(dC.item()) == 3
+        out[name] = {"verifications_per_s": Bv / ms * 1e3, "ms_per_step": ms, "batch": Bv, "depth": 32, "all_valid_accepted": bool(good), "one_wrong_root_rejected": bool(rejected)}
+    del d, dV, dP, dpub, dbad
+    # config 3: ristretto MSM microbenchmark, one instance over the first 2^k generators of chain G, uniform scalars
+    import hashlib
+    msm = {}
+    gbig = api.Gens(1 << 22)
+    for lg in (10, 12, 14, 16, 18, 20, 22):
+        n = 1 << lg
+        raw = np.frombuffer(hashlib.shake_256(b"msm-bench/%d" % n).digest(32 * n), dtype=np.uint8).reshape(n, 32).copy()
+        raw[:, 31] &= 0x0f  # < 2^252 < l: canonical without a big-integer reduction
+        d_in = torch.from_numpy(raw).to(dev)
+        d_out = torch.zeros(32, dtype=torch.uint8, device=dev)
+        for _ in range(2):
+            assert lib.bp_msm_gens_device(gbig._h, n, _ptr(d_in), _ptr(d_out), st) == 0
+        torch.cuda.synchronize()
+        reps = 5 if lg <= 18 else 2
+        e0.record()
+        for _ in range(reps):
+            lib.bp_msm_gens_device(gbig._h, n, _ptr(d_in), _ptr(d_out), st)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        gbs = 64.0 * n / (ms / 1e3) / 1e9
+        msm["2^%d" % lg] = {"ms": round(ms, 4), "Mterms_per_s": round(n / ms / 1e3, 2), "GB_per_s": round(gbs, 3), "frac_of_hbm": round(gbs / hbm_peak, 6)}
+    out["msm_sweep"] = {"unit": "64 algorithmic bytes per term (32 B scalar + 32 B compressed point)", "hbm_peak_GB_per_s": hbm_peak, "sizes": msm}
+    del gbig
+    return out
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -147,7 +301,7 @@ def main():
     import numpy as np
     import torch
     import ctypes as C
-    from bulletproofs_r1cs_gadgets_b200 import api, workloads
+    from bulletproofs_r1cs_gadgets_b200 import api, workloads, parallel
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -166,8 +320,10 @@ def main():
     circ = wl.circuit
     if gens.capacity < wl.gens_capacity:
         gens = api.Gens(wl.gens_capacity)
-    # rank r proves proofs [r*B, (r+1)*B): independent statements, no exchange during proving
-    inp = wl.inputs(rank * B, B, with_root=False)
+    # rank r proves the statements parallel.shard_range(r, world, world * B): independent proofs, no exchange during proving
+    first, last = parallel.shard_range(rank, world, world * B)
+    assert last - first == B
+    inp = wl.inputs(first, B, with_root=False)
     pin = {k: torch.from_numpy(v).pin_memory() for k, v in inp.items() if k in ("v", "v_blinding", "entropy")}
     d = {k: t.to(dev) for k, t in pin.items()}
     m, plen = circ.m, circ.proof_len
@@ -175,12 +331,10 @@ def main():
     outs = [(torch.empty((B, m, 32), dtype=torch.uint8, device=dev), torch.empty((B, plen), dtype=torch.uint8, device=dev),
              torch.empty((B,), dtype=torch.int32, device=dev)) for _ in range(2)]
     d_V, d_P, d_S = outs[0]
-    gathered = torch.empty((world * B, plen), dtype=torch.uint8, device=dev) if world > 1 else None
+    gathered = [None]
     label = b"VSMT"
     lbuf = api._buf(label)
-
-    def ptr(t):
-        return C.c_void_p(t.data_ptr())
+    ptr = _ptr
 
     def begin(slot):
         stream = torch.cuda.current_stream().cuda_stream
@@ -195,8 +349,8 @@ def main():
         rc = lib.bp_prove_stream_finish(gens._h, circ._h, C.c_int32(slot), C.c_void_p(stream))
         if rc != 0:
             raise api.R1CSError(rc, "bp_prove_stream_finish")
-        if world > 1:  # the one collective of the path: gather the fixed-size proof records
-            dist.all_gather_into_tensor(gathered, outs[slot][1])
+        if world > 1:  # the one collective of the path: every rank receives all records {commitments || proof || status}
+            gathered[0] = parallel.gather_records(parallel.pack_records(*outs[slot]), world * B)
 
     # One step = one whole batch: the first phase (commitments, witness program, blinding draws) of the NEXT batch is enqueued,
     # then the rest (every MSM, the inner-product argument) of the CURRENT one.  K steps hold K first phases and K second phases.
@@ -232,6 +386,7 @@ def main():
     clocks = sampler.stop()
     launches = api.launch_count() - l0
     prof = api.profile_report()
+    sorted_items = prof.pop("@sorted_items", (0, 0.0, 0.0))[2]
     ms = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([ms], device=dev)
@@ -242,6 +397,11 @@ def main():
     for o in outs:
         assert not o[2].cpu().numpy().any(), "prover status %s" % o[2][:8]
     assert torch.equal(outs[0][1], outs[1][1]), "the two stream slots disagree"
+    if world > 1:  # the gathered records hold this rank's proofs at its own index range
+        gV, gP, gS = parallel.unpack_records(gathered[0], m, plen)
+        assert torch.equal(gP[first:last], outs[seq[0] % 2][1]) and torch.equal(gV[first:last], outs[seq[0] % 2][0]) and not gS.cpu().numpy().any()
+        del gV, gP, gS
+        gathered[0] = None
     value = world * B * args.steps / (ms / 1000.0)
     # the same batch as ONE plain call (no overlap between batches), for comparison
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -255,7 +415,26 @@ def main():
     single_call_value = B / (g0.elapsed_time(g1) / 1000.0)
     del d_P1
 
-    # ---- e2e: the host-buffer C-ABI call (H2D inputs + D2H outputs inside the timed region) ----
+    # ---- every proof of the timed batch through the cross-proof combined verifier (roots hashed on the device, level by level) ----
+    verified = None
+    if not args.no_verify:
+        tv = time.time()
+        d_pub = torch.from_numpy(wl.roots_batch(inp["v"])).to(dev)
+        okc, oks = combined_verify_device(lib, api, gens, circ, label, d_V, d_P, d["entropy"], d_pub, dev)
+        d_bad = d_pub.clone()
+        d_bad[B // 3, 0, 0] ^= 1
+        piece = (B // 3) // 2048 * 2048
+        badc, _ = combined_verify_device(lib, api, gens, circ, label, d_V[piece:piece + 2048], d_P[piece:piece + 2048], d["entropy"][piece:piece + 2048],
+                                         d_bad[piece:piece + 2048], dev)
+        verified = {"proofs": B, "combined_ok": bool(okc), "structural_status_clean": bool(oks), "wrong_root_rejected": bool(not badc),
+                    "api": "bp_verify_batch_combined_device in pieces of 2048 proofs", "seconds": round(time.time() - tv, 2)}
+        if world > 1:
+            t = torch.tensor([1 if (okc and oks and not badc) else 0], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            verified["all_ranks_ok"] = bool(int(t.item()))
+        del d_pub, d_bad
+
+    # ---- e2e: the host-buffer C-ABI call (H2D inputs + D2H outputs inside the timed region), over the same number of steps ----
     e2e = None
     if not args.no_e2e:
         # pinned host buffers in, pinned host buffers out; every step copies its inputs H2D and its results D2H and waits for them
@@ -263,7 +442,7 @@ def main():
         hout = [(torch.empty((B, m, 32), dtype=torch.uint8).pin_memory().numpy(), torch.empty((B, plen), dtype=torch.uint8).pin_memory().numpy(),
                  torch.empty((B,), dtype=torch.int32).pin_memory().numpy()) for _ in range(2)]
         ps = api.ProveStream(circ, gens, label, stream=torch.cuda.current_stream().cuda_stream)
-        e2e_steps = 2  # the device path above already warmed every kernel, table and workspace
+        e2e_steps = args.steps
         ps.begin(0, *hin)
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -284,22 +463,31 @@ def main():
         e2e = {"value": world * B * e2e_steps / (ems / 1000.0), "unit": UNIT, "steps": e2e_steps,
                "h2d_bytes_per_step": int(sum(a.nbytes for a in hin)), "d2h_bytes_per_step": int(V_h.nbytes + P_h.nbytes + S_h.nbytes),
                "api": "bp_prove_stream_begin_host / _finish_host (pinned host buffers; H2D of the inputs and D2H of V, proofs, status every step)"}
+        del hout
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(HERE, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
+
+    # ---- the other BASELINE configs and the verifier (all ranks take part in the sharded MiMC run) ----
+    configs = None
+    if not args.no_extras:
+        # release the prover's per-chunk workspace first?  It stays: 72 GB of 180, the extras need < 40 GB
+        configs = extra_configs(args, lib, api, workloads, parallel, gens, wl, dev, world, rank, dist, hbm_peak)
+        if world > 1:
+            dist.barrier()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel and of the MSM kernel (algorithmic bytes: DESIGN.md section 4) ----
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(HERE, "MEASURED_PEAKS.json")))
-    except OSError:
-        pass
-    hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    # ---- roofline of the dominant kernel (algorithmic bytes: DESIGN.md section 4) ----
     n, N, k = circ.n, 1 << (circ.n - 1).bit_length(), (circ.n - 1).bit_length()
     J = min(int(os.environ.get("BP_B200_UNFOLD", "4")), k)  # unfold_rounds() in csrc/engine.cu
-    SB_WINDOWS = 17                                          # 15-bit windows (csrc/kernels.h)
     # algorithmic bytes: 64 B per multiscalar term (32 B scalar + 32 B compressed point), 96 B per folded point
     terms_sorted = 2 * (2 * n + 1) + J * 2 * (N + 1)                              # A_I, S + the unfolded rounds, per proof (sorted-bucket MSM)
     terms_table = n + 1                                                           # A_O (0/1 scalars, direct tables)
@@ -312,10 +500,12 @@ def main():
     shares = {kname: round(v[1] / total_kernel_ms, 4) for kname, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:8]}
     # DRAM traffic per launch of the same launch geometry from the committed ncu --set full capture (profiles/), if there is one
     traffic = {}
-    try:
-        traffic = json.load(open(os.path.join(HERE, "profiles", "r01_ncu_traffic.json")))
-    except (OSError, ValueError):
-        pass
+    for fn in ("r02_ncu_traffic.json", "r01_ncu_traffic.json"):
+        try:
+            traffic = json.load(open(os.path.join(HERE, "profiles", fn)))
+            break
+        except (OSError, ValueError):
+            pass
 
     def roof(kname):
         if kname not in prof or kname not in alg_bytes:
@@ -328,18 +518,26 @@ def main():
                 "peak_source": peak_src, "launches": launches_k, "avg_launch_ms": ms_k / launches_k, "share_of_step": shares.get(kname)}
     dominant = max(((kn, v) for kn, v in prof.items() if kn in alg_bytes), key=lambda kv: kv[1][1])[0] if prof else None
     roofline = roof(dominant) or roof("KBucketAccumulate")
-    # the roof that actually binds these kernels is the integer pipe: mixed point additions per second against the
-    # measured peak of the same addition in isolation (profiles/r01_field_microbench_3way.jsonl, ge_madd, 32 warps/SM)
+    # What binds these kernels is the multiplier pipe.  Numerator: the EXACT number of point additions the kernel did (length of the
+    # sorted item lists, counted on the device) x 504 IMAD.WIDE per addition (7 field multiplications x 72, csrc/fe25519.h);
+    # denominator: the instruction peak measured on this pool (tools/intpipe_bench.cu, profiles/r01_intpipe_peak.jsonl).
     roofline_int = None
-    if "KBucketAccumulate" in prof:
-        # rows that actually reach the kernel: the three equal left wires / two equal right wires of every inverse S-box share one
-        # row of A_I (188 S-boxes per level), and the N - n padding rows of L_0 are one row
-        rows_sorted = terms_sorted - 3 * 188 * args.depth - (N - n - 1)
-        adds = float(rows_sorted) * SB_WINDOWS * B * args.steps  # one addition per non-zero digit (upper bound: zero scalars add nothing)
-        ach = adds / (prof["KBucketAccumulate"][1] / 1000.0) / 1e9
-        roofline_int = {"kernel": "KBucketAccumulate", "bound": "integer pipe (IMAD.WIDE)", "achieved": ach, "peak": 12.57, "unit": "G mixed additions/s",
-                        "frac": ach / 12.57, "peak_source": "measured: ge_madd microbenchmark on this pool (tools/fe_bench2)",
-                        "note": "additions counted as rows x 17 windows; rows with a zero scalar (a third of a_R, the padded half of round 0) contribute none, so this is an upper bound"}
+    if "KBucketAccumulate" in prof and sorted_items:
+        imad_peak = 8.171e12
+        try:
+            for line in open(os.path.join(HERE, "profiles", "r01_intpipe_peak.jsonl")):
+                r = json.loads(line)
+                if "carry chains" in r.get("op", ""):
+                    imad_peak = r["Tops_per_s"] * 1e12
+        except (OSError, ValueError):
+            pass
+        t_s = prof["KBucketAccumulate"][1] / 1000.0
+        ach = sorted_items * 504.0 / t_s
+        roofline_int = {"kernel": "KBucketAccumulate", "bound": "multiplier pipe (IMAD.WIDE.U32)", "achieved": ach / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD.WIDE/s",
+                        "frac": ach / imad_peak, "additions": int(sorted_items), "G_additions_per_s": sorted_items / t_s / 1e9,
+                        "peak_source": "measured instruction peak, mad.lo.cc/madc.hi.cc carry chains (profiles/r01_intpipe_peak.jsonl)",
+                        "note": "additions counted exactly on the device (one per non-zero digit); 7 field multiplications x 72 IMAD.WIDE each; "
+                                "the pipe also issues the kernel's IMAD.MOV / IMAD.X, which this numerator leaves out"}
 
     # ---- cpu_baseline: the oracle port on a bounded sample of the same workload ----
     cpu = None
@@ -357,13 +555,14 @@ def main():
             "data": "synthetic",
             "config": {"workload": "gadget_vsmt_2 depth-%d membership proofs, inverse S-box (n=%d, N=%d, m=%d, q=%d)" % (args.depth, circ.n, N, circ.m, circ.q),
                        "proofs_per_gpu_per_step": B, "global_proofs_per_step": world * B,
-                       "note": "BASELINE config 5 is 65536 proofs over 8 GPUs = 8192 per GPU; a step is one GPU's share", "parallelism": "proofs sharded over %d GPU(s), NCCL all-gather of proof bytes" % world,
+                       "note": "BASELINE config 5 is 65536 proofs over 8 GPUs = 8192 per GPU; a step is one GPU's share",
+                       "parallelism": "proofs sharded over %d GPU(s) (parallel.shard_range), one NCCL all-gather of the records {V || proof || status} per step" % world,
                        "pipeline": "two batches in flight per GPU: a step enqueues the first phase (commitments, witness program, blinding draws) of batch k+1, "
                                    "then the MSM / inner-product phase of batch k (bp_prove_stream_begin / _finish); single_call_value_per_gpu = one plain bp_prove_batch_device call on rank 0",
                        "l2": "per-step working set (GBs of scalars, digits, buckets, folded generators) exceeds the 126 MB L2"},
             "single_call_value_per_gpu": single_call_value, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_msm": roof("KBucketAccumulate"), "roofline_int": roofline_int,
             "kernel_time_shares": shares, "kernel_ms_per_step": {kn: round(v[1] / args.steps, 3) for kn, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:12]},
-            "cpu_baseline": cpu}
+            "verified": verified, "configs": configs, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

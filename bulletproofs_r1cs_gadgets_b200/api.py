@@ -92,6 +92,16 @@ def _np_u8(a):
     return np.ascontiguousarray(a, dtype=np.uint8)
 
 
+def _want(a, shape, what, code=6):
+    """the C-ABI takes plain pointers and sizes: a wrongly shaped array would be an out-of-bounds access inside the library, so
+    shapes are checked here (FormatError for proof bytes, InvalidArgument otherwise)"""
+    if a is None:
+        raise R1CSError(4, "%s is required" % what)
+    if tuple(a.shape) != tuple(shape):
+        raise R1CSError(code, "%s has shape %s, expected %s" % (what, tuple(a.shape), tuple(shape)))
+    return a
+
+
 def scalars_to_array(vals):
     """iterable of ints -> uint8 [len][32]"""
     vals = list(vals)
@@ -202,6 +212,16 @@ class PoseidonParams:
         out = (C.c_uint8 * 32)()
         _check(load().bp_poseidon_hash_2(self._h, _buf(scalar_bytes(xl)), _buf(scalar_bytes(xr)), sbox, out))
         return int.from_bytes(bytes(out), "little")
+
+    def hash_2_batch(self, xl, xr, sbox):
+        """Poseidon_hash_2 of `count` independent pairs on the device; xl, xr: uint8 [count][32] -> uint8 [count][32]"""
+        xl, xr = _np_u8(xl), _np_u8(xr)
+        _want(xl, (xl.shape[0], 32), "xl"); _want(xr, xl.shape, "xr")
+        out = np.zeros_like(xl)
+        if xl.shape[0]:
+            _check(load().bp_poseidon_hash_2_batch(self._h, C.c_int32(sbox), C.c_uint32(xl.shape[0]), xl.ctypes.data_as(u8p), xr.ctypes.data_as(u8p),
+                                                   out.ctypes.data_as(u8p)), "poseidon_hash_2_batch")
+        return out
 
     def hash_4(self, xs, sbox):
         """Poseidon_hash_4 (reference src/gadget_poseidon.rs:488-503)"""
@@ -458,15 +478,32 @@ class Circuit:
         aux = _np_u8(aux) if aux is not None else None
         pub = _np_u8(pub) if pub is not None else None
         wl = [_np_u8(w) for w in witness] if witness is not None else [None, None, None]
+        self._check_prover_shapes(B, v, v_blinding, entropy, aux, pub, wl)
         _check(load().bp_prove_batch(gens._h, self._h, C.c_uint32(B), _buf(label) if label else None, C.c_size_t(len(label)), p(v), p(v_blinding),
                                      p(entropy), p(aux), p(pub), p(wl[0]), p(wl[1]), p(wl[2]), p(V), p(proofs), status.ctypes.data_as(C.POINTER(C.c_int32))),
                "prove_batch")
         return V, proofs, status
 
+    def _check_prover_shapes(self, B, v, v_blinding, entropy, aux, pub, wl):
+        _want(entropy, (B, 32), "entropy"); _want(v, (B, self.m, 32), "v"); _want(v_blinding, (B, self.m, 32), "v_blinding")
+        if wl[0] is not None:
+            for w, name in zip(wl, ("aL", "aR", "aO")):
+                _want(w, (B, self.n, 32), name)
+        elif self.num_aux:
+            _want(aux, (B, self.num_aux, 32), "aux")
+        if pub is not None:
+            _want(pub, (B, self.num_public, 32), "pub")
+
+    def _check_verifier_shapes(self, B, V, proofs, entropy, pub):
+        _want(entropy, (B, 32), "entropy"); _want(V, (B, self.m, 32), "V"); _want(proofs, (B, self.proof_len), "proofs", code=2)
+        if self.num_public:
+            _want(pub, (B, self.num_public, 32), "pub")
+
     def verify_batch(self, gens, label, V, proofs, entropy, pub=None):
         V, proofs, entropy = _np_u8(V), _np_u8(proofs), _np_u8(entropy)
         pub = _np_u8(pub) if pub is not None else None
         B = entropy.shape[0]
+        self._check_verifier_shapes(B, V, proofs, entropy, pub)
         status = np.zeros(B, dtype=np.int32)
         _check(load().bp_verify_batch(gens._h, self._h, C.c_uint32(B), _buf(label) if label else None, C.c_size_t(len(label)), V.ctypes.data_as(u8p),
                                       proofs.ctypes.data_as(u8p), entropy.ctypes.data_as(u8p), pub.ctypes.data_as(u8p) if pub is not None else None,
@@ -489,6 +526,7 @@ class ProveStream:
         aux = _np_u8(aux) if aux is not None else None
         pub = _np_u8(pub) if pub is not None else None
         B = entropy.shape[0]
+        self.circuit._check_prover_shapes(B, v, v_blinding, entropy, aux, pub, [None, None, None])
         p = lambda a: a.ctypes.data_as(u8p) if a is not None else None
         _check(load().bp_prove_stream_begin_host(self.gens._h, self.circuit._h, C.c_int32(slot), C.c_uint32(B), _buf(self.label) if self.label else None,
                                                  C.c_size_t(len(self.label)), p(v), p(v_blinding), p(entropy), p(aux), p(pub),
@@ -503,6 +541,9 @@ class ProveStream:
         c = self.circuit
         V, proofs, status = out if out is not None else (np.zeros((B, c.m, 32), dtype=np.uint8), np.zeros((B, c.proof_len), dtype=np.uint8),
                                                          np.zeros(B, dtype=np.int32))
+        _want(V, (B, c.m, 32), "out V"); _want(proofs, (B, c.proof_len), "out proofs"); _want(status, (B,), "out status")
+        if V.dtype != np.uint8 or proofs.dtype != np.uint8 or status.dtype != np.int32 or not (V.flags.c_contiguous and proofs.flags.c_contiguous):
+            raise R1CSError(6, "out buffers must be contiguous uint8 / int32 arrays")
         _check(load().bp_prove_stream_finish_host(self.gens._h, c._h, C.c_int32(slot), V.ctypes.data_as(u8p), proofs.ctypes.data_as(u8p),
                                                   status.ctypes.data_as(C.POINTER(C.c_int32)), C.c_void_p(self.stream) if self.stream else None),
                "prove_stream_finish_host")
@@ -515,6 +556,7 @@ def _verify_batch_combined(self, gens, label, V, proofs, entropy, pub=None):
     V, proofs, entropy = _np_u8(V), _np_u8(proofs), _np_u8(entropy)
     pub = _np_u8(pub) if pub is not None else None
     B = entropy.shape[0]
+    self._check_verifier_shapes(B, V, proofs, entropy, pub)
     status = np.zeros(B, dtype=np.int32)
     combined = C.c_int32(0)
     f = load().bp_verify_batch_combined
@@ -560,7 +602,8 @@ def profile_enable(on=True):
 
 
 def profile_report():
-    """{kernel: (launches, total_ms, threads)} since the last report; call after a device synchronise"""
+    """{kernel: (launches, total_ms, threads)} since the last report; call after a device synchronise.
+    The pseudo-kernel "@sorted_items" carries, in the `threads` field, the exact number of point additions KBucketAccumulate did."""
     buf = C.create_string_buffer(1 << 16)
     n = load().bp_profile_report(buf, C.c_size_t(len(buf)))
     out = {}

@@ -140,22 +140,33 @@ static int32_t compile_cs(const bp_cs *cs, bool with_tape, BpCircuit **out) {
   size_t nnz = cs->terms.size();
   std::vector<uint8_t> kind(nnz ? nnz : 1); std::vector<uint32_t> idx(nnz ? nnz : 1); std::vector<scm> co(nnz ? nnz : 1);
   for (size_t t = 0; t < nnz; t++) { kind[t] = (uint8_t)cs->terms[t].var.kind; idx[t] = cs->terms[t].var.index; co[t] = cs->terms[t].coeff; }
-  if (!with_tape || cs->pending >= 0)
-    return circuit_create(cs->num_mult, (uint32_t)cs->V.size(), (uint32_t)cs->pub.size(), (uint32_t)cs->num_constraints(), cs->cons_ptr.data(), kind.data(), idx.data(),
-                          co.data(), nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, out);
+  if (!with_tape || cs->pending >= 0) {
+    int rc = circuit_create(cs->num_mult, (uint32_t)cs->V.size(), (uint32_t)cs->pub.size(), (uint32_t)cs->num_constraints(), cs->cons_ptr.data(), kind.data(), idx.data(),
+                            co.data(), nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, out);
+    if (!rc && !cs->fixed_idx.empty()) {
+      rc = circuit_set_fixed_commitments(*out, (uint32_t)cs->fixed_idx.size(), cs->fixed_idx.data(), cs->fixed_V[0].data());
+      if (rc) { circuit_free(*out); *out = nullptr; }
+    }
+    return rc;
+  }
   size_t wn = cs->wlc_terms.size();
   std::vector<uint8_t> wkind(wn ? wn : 1); std::vector<uint32_t> widx(wn ? wn : 1); std::vector<scm> wco(wn ? wn : 1);
   for (size_t t = 0; t < wn; t++) { wkind[t] = (uint8_t)cs->wlc_terms[t].var.kind; widx[t] = cs->wlc_terms[t].var.index; wco[t] = cs->wlc_terms[t].coeff; }
   HostPoseidonTape pt{}; std::vector<scm> mds;
   if (!cs->pblocks.empty()) {
-    const bp_poseidon_params *pp = cs->pparams;
+    const bp_poseidon_params *pp = cs->pparams.get();
     for (auto &row : pp->mds) mds.insert(mds.end(), row.begin(), row.end());
     pt = HostPoseidonTape{cs->pblocks.data(), (uint32_t)cs->pblocks.size(), pp->round_keys.data(), (uint32_t)pp->round_keys.size(), mds.data(),
                           pp->full_rounds_beginning, pp->partial_rounds, pp->full_rounds_end};
   }
-  return circuit_create(cs->num_mult, (uint32_t)cs->V.size(), (uint32_t)cs->pub.size(), (uint32_t)cs->num_constraints(), cs->cons_ptr.data(), kind.data(), idx.data(),
-                        co.data(), cs->tape.data(), cs->naux, (uint32_t)cs->wlc_ptr.size() - 1, cs->wlc_ptr.data(), wkind.data(), widx.data(),
-                        wco.data(), cs->pblocks.empty() ? nullptr : &pt, out);
+  int rc = circuit_create(cs->num_mult, (uint32_t)cs->V.size(), (uint32_t)cs->pub.size(), (uint32_t)cs->num_constraints(), cs->cons_ptr.data(), kind.data(), idx.data(),
+                          co.data(), cs->tape.data(), cs->naux, (uint32_t)cs->wlc_ptr.size() - 1, cs->wlc_ptr.data(), wkind.data(), widx.data(),
+                          wco.data(), cs->pblocks.empty() ? nullptr : &pt, out);
+  if (!rc && !cs->fixed_idx.empty()) {
+    rc = circuit_set_fixed_commitments(*out, (uint32_t)cs->fixed_idx.size(), cs->fixed_idx.data(), cs->fixed_V[0].data());
+    if (rc) { circuit_free(*out); *out = nullptr; }
+  }
+  return rc;
 }
 
 struct DevBuf {
@@ -250,9 +261,13 @@ int32_t bp_gadget_allocate_statics(bp_cs *cs, uint32_t num_statics, bp_var *out_
   for (uint32_t i = 0; i < num_statics; i++) {
     const uint8_t *val = i == 1 ? pad : zero;
     int rc;
-    if (cs->is_prover) { uint8_t V[32]; rc = bp_prover_commit(cs, val, zero, V, &out_vars[i]); }
-    else { uint8_t V[32]; rc = engine_commit(cs->gens->g, 1, val, zero, V); if (!rc) rc = bp_verifier_commit(cs, V, &out_vars[i]); }
+    uint8_t V[32];
+    if (cs->is_prover) rc = bp_prover_commit(cs, val, zero, V, &out_vars[i]);
+    else { rc = engine_commit(cs->gens->g, 1, val, zero, V); if (!rc) rc = bp_verifier_commit(cs, V, &out_vars[i]); }
     if (rc) return rc;
+    // a compiled circuit remembers these slots: its batch verifiers reject a proof whose caller-supplied V differs here
+    cs->fixed_idx.push_back(out_vars[i].index);
+    std::array<uint8_t, 32> fv; memcpy(fv.data(), V, 32); cs->fixed_V.push_back(fv);
   }
   return BP_OK;
 }

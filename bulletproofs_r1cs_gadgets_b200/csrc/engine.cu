@@ -20,6 +20,21 @@ void profile_begin(const char *name, long threads, dev_stream s) {
   g_prof.push_back(r);
 }
 void profile_end(dev_stream s) { cudaEventRecord(g_prof.back().e1, s); }
+// exact number of point additions of the sorted-bucket path while profiling: sum over instances of the item-list lengths
+// (one item = one non-zero digit = one addition in KBucketAccumulate).  Reported as the pseudo-kernel "@sorted_items".
+static unsigned long long *g_items_dev = nullptr;
+static long g_items_launches = 0;
+__global__ void count_items_kernel(const uint32_t *boff, long ninst, unsigned long long *out) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long v = i < ninst ? boff[i * (SB_BUCKETS + 1) + SB_BUCKETS] : 0;
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0 && v) atomicAdd(out, v);
+}
+static void profile_count_items(const uint32_t *boff, long ninst, dev_stream s) {
+  if (!g_items_dev) { if (cudaMalloc(&g_items_dev, 8) != cudaSuccess) { g_items_dev = nullptr; return; } cudaMemsetAsync(g_items_dev, 0, 8, s); }
+  count_items_kernel<<<(unsigned)((ninst + 127) / 128), 128, 0, s>>>(boff, ninst, g_items_dev);
+  g_items_launches++;
+}
 void engine_profile_enable(int on) { g_profile_on = on; }
 // writes "name launches total_ms threads\n" lines; clears the records.  Caller must have synchronised.
 int engine_profile_report(char *buf, size_t cap) {
@@ -32,6 +47,13 @@ int engine_profile_report(char *buf, size_t cap) {
   }
   g_prof.clear();
   size_t off = 0;
+  if (g_items_dev && g_items_launches) {
+    unsigned long long items = 0;
+    cudaMemcpy(&items, g_items_dev, 8, cudaMemcpyDeviceToHost); cudaMemset(g_items_dev, 0, 8);
+    int w = snprintf(buf, cap, "@sorted_items %ld 0.000000 %llu\n", g_items_launches, items);
+    if (w > 0 && (size_t)w < cap) off = (size_t)w;
+    g_items_launches = 0;
+  }
   for (auto &kv : agg) {
     int w = snprintf(buf + off, off < cap ? cap - off : 0, "%s %ld %.6f %.0f\n", kv.first.c_str(), kv.second.launches, kv.second.ms, kv.second.threads);
     if (w < 0 || off + (size_t)w >= cap) break;
@@ -213,13 +235,15 @@ int circuit_create(uint32_t n, uint32_t m, uint32_t npub, uint32_t q, const uint
       tc[at] = co;
     }
   dev_stream s = 0;
+#define CKC(x) do { if (x) { fprintf(stderr, "bp_b200: %s failed at %s:%d\n", #x, __FILE__, __LINE__); circuit_free(c); return BP_ERR_CUDA; } } while (0)
   if (dalloc(&c->d_slot_ptr, c->nslots + 1) || dalloc(&c->d_tq, tq.size()) || dalloc(&c->d_tcoeff, tc.size())) { circuit_free(c); return BP_ERR_OOM; }
-  CK(dev_h2d(c->d_slot_ptr, slot_cnt.data(), (c->nslots + 1) * sizeof(uint32_t), s));
-  CK(dev_h2d(c->d_tq, tq.data(), tq.size() * sizeof(uint32_t), s));
-  CK(dev_h2d(c->d_tcoeff, tc.data(), tc.size() * sizeof(scm), s));
+  CKC(dev_h2d(c->d_slot_ptr, slot_cnt.data(), (c->nslots + 1) * sizeof(uint32_t), s));
+  CKC(dev_h2d(c->d_tq, tq.data(), tq.size() * sizeof(uint32_t), s));
+  CKC(dev_h2d(c->d_tcoeff, tc.data(), tc.size() * sizeof(scm), s));
   if (tape) {
     c->has_tape = 1;
     uint32_t wn = wlc_ptr[nwlc];
+    for (uint32_t t = 0; t < wn; t++) if (wkind[t] == 5) c->wit_uses_pub = 1;
     for (uint32_t t = 0; t < wn; t++) {
       uint32_t lim = wkind[t] == 0 ? m : (wkind[t] == 4 ? 1 : (wkind[t] == 5 ? npub : n));
       if (wkind[t] > 5 || widx[t] >= lim) { circuit_free(c); return BP_ERR_INVALID_ARGUMENT; }
@@ -234,11 +258,11 @@ int circuit_create(uint32_t n, uint32_t m, uint32_t npub, uint32_t q, const uint
     }
     if (dalloc(&c->d_tape, n ? n : 1) || dalloc(&c->d_wptr, nwlc + 1) || dalloc(&c->d_wkind, wn ? wn : 1) || dalloc(&c->d_widx, wn ? wn : 1) ||
         dalloc(&c->d_wcoeff, wn ? wn : 1)) { circuit_free(c); return BP_ERR_OOM; }
-    CK(dev_h2d(c->d_tape, tape, n * sizeof(TapeOp), s));
-    CK(dev_h2d(c->d_wptr, wlc_ptr, (nwlc + 1) * sizeof(uint32_t), s));
-    CK(dev_h2d(c->d_wkind, wkind, wn, s));
-    CK(dev_h2d(c->d_widx, widx, wn * sizeof(uint32_t), s));
-    CK(dev_h2d(c->d_wcoeff, wcoeff, wn * sizeof(scm), s));
+    CKC(dev_h2d(c->d_tape, tape, n * sizeof(TapeOp), s));
+    CKC(dev_h2d(c->d_wptr, wlc_ptr, (nwlc + 1) * sizeof(uint32_t), s));
+    CKC(dev_h2d(c->d_wkind, wkind, wn, s));
+    CKC(dev_h2d(c->d_widx, widx, wn * sizeof(uint32_t), s));
+    CKC(dev_h2d(c->d_wcoeff, wcoeff, wn * sizeof(scm), s));
     if (ptape && ptape->nblocks) {
       const uint32_t total = ptape->full_b + ptape->partial + ptape->full_e;
       if (ptape->nkeys < total * POSEIDON_WIDTH) { circuit_free(c); return BP_ERR_INVALID_ARGUMENT; }
@@ -250,9 +274,9 @@ int circuit_create(uint32_t n, uint32_t m, uint32_t npub, uint32_t q, const uint
         if (!ok) { circuit_free(c); return BP_ERR_INVALID_ARGUMENT; }
       }
       if (dalloc(&c->d_pblocks, ptape->nblocks) || dalloc(&c->d_pos_rk, ptape->nkeys) || dalloc(&c->d_pos_mds, POSEIDON_WIDTH * POSEIDON_WIDTH)) { circuit_free(c); return BP_ERR_OOM; }
-      CK(dev_h2d(c->d_pblocks, ptape->blocks, ptape->nblocks * sizeof(PoseidonBlock), s));
-      CK(dev_h2d(c->d_pos_rk, ptape->round_keys, ptape->nkeys * sizeof(scm), s));
-      CK(dev_h2d(c->d_pos_mds, ptape->mds, POSEIDON_WIDTH * POSEIDON_WIDTH * sizeof(scm), s));
+      CKC(dev_h2d(c->d_pblocks, ptape->blocks, ptape->nblocks * sizeof(PoseidonBlock), s));
+      CKC(dev_h2d(c->d_pos_rk, ptape->round_keys, ptape->nkeys * sizeof(scm), s));
+      CKC(dev_h2d(c->d_pos_mds, ptape->mds, POSEIDON_WIDTH * POSEIDON_WIDTH * sizeof(scm), s));
       c->pos = PoseidonDev{c->d_pos_rk, c->d_pos_mds, ptape->full_b, ptape->partial, ptape->full_e};
       // inverse S-box multipliers (x, 1/x, .), (x, 0, .), (x, 1/x, .) written by the block op: the three left wires are equal and
       // so are the first and third right wires -> A_I can use the SUM of their generators (one row per group)
@@ -269,13 +293,23 @@ int circuit_create(uint32_t n, uint32_t m, uint32_t npub, uint32_t q, const uint
       }
     }
   }
-  CK(dev_sync(s));
+  CKC(dev_sync(s));
   c->ws = new Workspace();
   *out = c;
   return BP_OK;
 }
+int circuit_set_fixed_commitments(BpCircuit *c, uint32_t n, const uint32_t *idx, const uint8_t *V) {
+  for (uint32_t i = 0; i < n; i++) if (idx[i] >= c->m) return BP_ERR_INVALID_ARGUMENT;
+  dev_free(c->d_fixed_idx); dev_free(c->d_fixed_V); c->d_fixed_idx = nullptr; c->d_fixed_V = nullptr; c->nfixed = 0;
+  if (!n) return BP_OK;
+  if (dalloc(&c->d_fixed_idx, n) || dalloc(&c->d_fixed_V, (size_t)n * 32)) return BP_ERR_OOM;
+  CK(dev_h2d(c->d_fixed_idx, idx, n * sizeof(uint32_t), 0)); CK(dev_h2d(c->d_fixed_V, V, (size_t)n * 32, 0)); CK(dev_sync(0));
+  c->nfixed = n;
+  return BP_OK;
+}
 void circuit_free(BpCircuit *c) {
   if (!c) return;
+  dev_free(c->d_fixed_idx); dev_free(c->d_fixed_V);
   dev_free(c->d_slot_ptr); dev_free(c->d_tq); dev_free(c->d_tcoeff); dev_free(c->d_tape); dev_free(c->d_wptr); dev_free(c->d_wkind);
   dev_free(c->d_widx); dev_free(c->d_wcoeff); dev_free(c->d_pblocks); dev_free(c->d_pos_rk); dev_free(c->d_pos_mds);
   delete c->merge_src;
@@ -421,6 +455,9 @@ static int run_msm_sorted(const BpGens *g, Workspace *w, const RowMap &rmap, lon
                          w->bucket_slots * sizeof(ge_p3), 2L * g->capacity + 2 + SG_SPARE + g->merge_slots, s));
   SortedView sv{w->items, w->boff, w->soff, (long)w->items_cap, (long)w->slices_cap};
   const long segs = (rows * SB_WINDOWS + SB_SEG - 1) / SB_SEG;  // segments of this launch's longest possible item list
+#ifndef BP_HOST_EMUL
+  if (g_profile_on) profile_count_items(w->boff, ninst, s);
+#endif
   CK(launch(ninst * segs, s, KBucketAccumulate{g->sg, sv, w->buckets, segs}));
   CK(launch(ninst * SB_SEGS, s, KBucketReduce{w->buckets, sv, w->seg}));
   CK(launch(ninst, s, KBucketFinish{w->seg, out, out_stride, nullptr}));
@@ -513,6 +550,7 @@ static int prove_phase_a(const BpGens *g, BpCircuit *c, Front &f, const ProveArg
   } else {
     if (c->naux) CK(launch((long)c->naux * B, sW, KLoadScalars{A.aux, f.aux, (int)c->naux, B}));
     if (c->npub && A.pub) CK(launch((long)c->npub * B, sW, KLoadScalars{A.pub, f.pub, (int)c->npub, B}));
+    else if (c->npub) CK(dev_memset(f.pub, 0, sizeof(scm) * (size_t)c->npub * B, sW));  // unread (wit_uses_pub checked by the caller), but never uninitialised
     CK(launch(B, sW, KWitnessTape{c->d_tape, WitnessLcs{c->d_wptr, c->d_wkind, c->d_widx, c->d_wcoeff}, c->d_pblocks, c->pos, (int)n, B, f.v, f.aux, f.pub, aL, aR, aO}));
   }
   CK(launch(m * B, sR, KCommit{f.v, f.vbl, (int)m, B, g->pc_table, A.V_out, m * 32, 32, nullptr}));
@@ -544,6 +582,7 @@ int engine_prove_begin(const BpGens *g, BpCircuit *c, int slot, const ProveArgs 
   if (slot < 0 || slot > 1 || B <= 0) return BP_ERR_INVALID_ARGUMENT;
   if (g->capacity < c->n || g->capacity < c->N) return BP_ERR_INVALID_GENERATORS_LENGTH;
   if (!A.aL && !c->has_tape) return BP_ERR_MISSING_ASSIGNMENT;
+  if (!A.aL && c->wit_uses_pub && !A.pub) return BP_ERR_MISSING_ASSIGNMENT;  // the witness program reads public inputs nobody supplied
   if (c->ws->pending[slot].active) return BP_ERR_INVALID_ARGUMENT;
   if (chunk <= 0 || chunk > B) chunk = B;
   int rc = ensure_workspace(c, chunk);
@@ -892,10 +931,14 @@ int engine_verify_combined(BpGens *g, BpCircuit *c, const VerifyArgs &A, int *d_
   if (dig8_bytes + (size_t)(2 * N + 2) * sizeof(scm) > w->dig_bytes) return BP_ERR_OOM;
   scm *partG = w->b, *partH = w->ypow, *rows = (scm *)(w->dig + dig8_bytes);
   CK(dev_memset(A.status, 0, sizeof(int) * B, s));
+  if (c->nfixed) CK(launch((long)c->nfixed * B, s, KCheckFixedCommitments{A.V, (int)m, B, c->d_fixed_idx, c->d_fixed_V, (int)c->nfixed, A.status}));
   strobe128 base; base_transcript(base, A.label, A.label_len);
-  CK(launch(B, s, KTsVerify{base, A.V, (int)m, B, (int)k, (unsigned)N, A.proofs, plen, A.entropy, w->chal, uj, ujinv, A.status, 1}));
+  // per-proof digests and the batch seed live in the (not yet used) partial-sum buffer
+  uint8_t *digest = (uint8_t *)w->part, *seed = digest + (size_t)B * 32;
+  CK(launch(B, s, KTsVerify{base, A.V, (int)m, B, (int)k, (unsigned)N, A.proofs, plen, A.entropy, w->chal, uj, ujinv, A.status, digest, A.pub, (int)c->npub}));
   CK(launch(npts * B, s, KVerifyDecompress{A.V, A.proofs, plen, (int)m, (int)k, B, w->pts, npts, A.status}));
-  CK(launch(B, s, KVerifyMaskRho{A.status, rho}));
+  CK(launch(1, s, KBatchSeed{digest, B, seed}));
+  CK(launch(B, s, KVerifyRho{seed, A.status, rho}));
   CK(launch(((q + CH_POW - 1) / CH_POW) * B, s, KPowers{ch_z, w->zpow, (int)q, B, 1, CH_POW}));
   CK(launch(((N + CH_POW - 1) / CH_POW) * B, s, KPowers{ch_yinv, w->yinvpow, (int)N, B, 0, CH_POW}));
   CK(launch((long)c->nslots * B, s, KFlatten{c->d_slot_ptr, c->d_tq, c->d_tcoeff, w->zpow, w->w_all, B}));
@@ -945,8 +988,9 @@ int engine_verify(const BpGens *g, BpCircuit *c, const VerifyArgs &A, dev_stream
   scm *ch_z = w->chal + B, *ch_yinv = w->chal + 2L * B;
   scm *uj = w->uj, *ujinv = w->uj + (k + 1) * B;
   CK(dev_memset(A.status, 0, sizeof(int) * B, s));
+  if (c->nfixed) CK(launch((long)c->nfixed * B, s, KCheckFixedCommitments{A.V, (int)m, B, c->d_fixed_idx, c->d_fixed_V, (int)c->nfixed, A.status}));
   strobe128 base; base_transcript(base, A.label, A.label_len);
-  CK(launch(B, s, KTsVerify{base, A.V, (int)m, B, (int)k, (unsigned)N, A.proofs, plen, A.entropy, w->chal, uj, ujinv, A.status, 0}));
+  CK(launch(B, s, KTsVerify{base, A.V, (int)m, B, (int)k, (unsigned)N, A.proofs, plen, A.entropy, w->chal, uj, ujinv, A.status, nullptr, nullptr, 0}));
   CK(launch(((q + CH_POW - 1) / CH_POW) * B, s, KPowers{ch_z, w->zpow, (int)q, B, 1, CH_POW}));
   CK(launch(((N + CH_POW - 1) / CH_POW) * B, s, KPowers{ch_yinv, w->yinvpow, (int)N, B, 0, CH_POW}));
   CK(launch((long)c->nslots * B, s, KFlatten{c->d_slot_ptr, c->d_tq, c->d_tcoeff, w->zpow, w->w_all, B}));

@@ -34,6 +34,8 @@ struct BpCircuit {
   int has_tape;
   TapeOp *d_tape; uint32_t *d_wptr; uint8_t *d_wkind; uint32_t *d_widx; scm *d_wcoeff;
   PoseidonBlock *d_pblocks; scm *d_pos_rk, *d_pos_mds; PoseidonDev pos;
+  uint32_t nfixed; uint32_t *d_fixed_idx; uint8_t *d_fixed_V;  // commitments the circuit fixes (statics): slot indices, expected bytes
+  int wit_uses_pub;                  // the witness program reads public inputs
   uint64_t serial;                   // unique per circuit_create (a freed circuit's address may be reused)
   std::vector<uint32_t> *merge_src;  // host: groups of A_I rows with equal scalars, 3 generator indices each (G index, or n + H index; ~0 unused)
   Workspace *ws;
@@ -48,6 +50,8 @@ int gens_export(const BpGens *g, int which, uint32_t count, uint8_t *out);  // w
 int circuit_create(uint32_t n, uint32_t m, uint32_t npub, uint32_t q, const uint32_t *cons_ptr, const uint8_t *kind, const uint32_t *idx,
                    const scm *coeff, const TapeOp *tape, uint32_t naux, uint32_t nwlc, const uint32_t *wlc_ptr,
                    const uint8_t *wkind, const uint32_t *widx, const scm *wcoeff, const struct HostPoseidonTape *ptape, BpCircuit **out);
+// commitment slots whose compressed value is fixed by the circuit (idx[n], V[n][32], host pointers); checked by the verifiers
+int circuit_set_fixed_commitments(BpCircuit *c, uint32_t n, const uint32_t *idx, const uint8_t *V);
 void circuit_free(BpCircuit *c);
 size_t circuit_proof_len(const BpCircuit *c);
 double engine_workspace_bytes_per_proof(const BpCircuit *c);

@@ -146,14 +146,23 @@ static int synthesize_sbox(bp_cs &cs, const LC &input, const scm &round_key, int
   out = var_r;
   return BP_OK;
 }
+// block ops of one constraint system share one set of parameters: equal content, whatever object the caller passes
+static bool poseidon_params_equal(const bp_poseidon_params &a, const bp_poseidon_params &b) {
+  if (a.width != b.width || a.full_rounds_beginning != b.full_rounds_beginning || a.full_rounds_end != b.full_rounds_end ||
+      a.partial_rounds != b.partial_rounds || a.round_keys.size() != b.round_keys.size() || a.mds.size() != b.mds.size()) return false;
+  if (memcmp(a.round_keys.data(), b.round_keys.data(), a.round_keys.size() * sizeof(scm))) return false;
+  for (size_t i = 0; i < a.mds.size(); i++)
+    if (a.mds[i].size() != b.mds[i].size() || memcmp(a.mds[i].data(), b.mds[i].data(), a.mds[i].size() * sizeof(scm))) return false;
+  return true;
+}
 int poseidon_permutation_constraints(bp_cs &cs, const bp_poseidon_params &p, std::vector<LC> &st, int sbox) {  // gadget_poseidon.rs:282-399
   const uint32_t w = p.width, total = p.full_rounds_beginning + p.partial_rounds + p.full_rounds_end;
   if (st.size() != w) return BP_ERR_GADGET;
   // witness program: the whole permutation becomes one block op when it has the standard shape
-  const bool block = w == POSEIDON_WIDTH && cs.pending < 0 && (cs.pparams == nullptr || cs.pparams == &p);
+  const bool block = w == POSEIDON_WIDTH && cs.pending < 0 && (cs.pparams == nullptr || poseidon_params_equal(*cs.pparams, p));
   PoseidonBlock blk{};
   if (block) {
-    cs.pparams = &p;
+    if (!cs.pparams) cs.pparams = std::make_shared<const bp_poseidon_params>(p);
     for (uint32_t i = 0; i < w; i++) blk.in_lc[i] = cs.add_wlc(st[i]);
     blk.sbox = (uint32_t)sbox; blk.first_mult = cs.num_mult;
   }

@@ -892,7 +892,12 @@ struct KTsVerify {
   static constexpr int kBlock = 64, kMinBlocks = 1;
   static constexpr const char *kName = "KTsVerify";
   strobe128 base; const uint8_t *V; int m, B, k; unsigned N; const uint8_t *proofs; long proof_stride; const uint8_t *entropy;
-  scm *chal; scm *uj, *ujinv; int *status; int combined;  // combined: also draw the batching weight rho_p (chal slot 7)
+  scm *chal; scm *uj, *ujinv; int *status;
+  // combined (cross-proof) mode: digest[p] = 32 bytes bound to EVERYTHING the verification of proof p reads -- its whole
+  // transcript (V, every proof element), the inner-product scalars a and b (which the transcript never absorbs), the
+  // public inputs and the verifier's entropy.  The batching weights are derived from the digests of ALL proofs (KBatchSeed,
+  // KVerifyRho), so no weight can be known before every proof of the batch is fixed.
+  uint8_t *digest; const uint8_t *pub; int npub;
   HD static int is_zero32(const uint8_t *b) { uint8_t nz = 0; for (int i = 0; i < 32; i++) nz |= b[i]; return nz == 0; }
   HD void operator()(long p) const {
     strobe128 t; strobe_load(t, &base);
@@ -930,8 +935,27 @@ struct KTsVerify {
     trng_finalize(t, entropy + p * 32);
     { uint8_t b[64]; trng_fill(t, b, 64); r = sc_from_bytes_wide(b); }
     chal[p] = y; chal[B + p] = z; chal[2L * B + p] = sc_invert(y); chal[3L * B + p] = u; chal[4L * B + p] = x; chal[5L * B + p] = w; chal[6L * B + p] = r;
-    if (combined) { uint8_t b[64]; trng_fill(t, b, 64); chal[7L * B + p] = sc_from_bytes_wide(b); }
+    if (digest) {
+      ts_append(t, "ipp-a", pf + 448 + 64 * k, 32); ts_append(t, "ipp-b", pf + 480 + 64 * k, 32);
+      for (int j = 0; j < npub; j++) ts_append(t, "pub", pub + ((long)p * npub + j) * 32, 32);
+      ts_challenge_bytes(t, "batch-digest", digest + p * 32, 32);
+    }
     if (st) status[p] = st;
+  }
+};
+// Commitments whose value the circuit fixes (the Poseidon "statics" 0, 101, 0, 0 committed with blinding 0): the reference's
+// verifier computes them itself (allocate_statics_for_verifier, src/gadget_poseidon.rs:580-608); a batch verifier takes V from
+// the caller, so it compares those slots with the bytes recorded when the circuit was built.  thread = (fixed slot, proof)
+struct KCheckFixedCommitments {
+  static constexpr int kBlock = 128, kMinBlocks = 1;
+  static constexpr const char *kName = "KCheckFixedCommitments";
+  const uint8_t *V; int m, B; const uint32_t *idx; const uint8_t *expect; int nfixed; int *status;
+  HD void operator()(long tid) const {
+    const long p = tid / nfixed; const int j = (int)(tid % nfixed);
+    const uint8_t *got = V + (p * m + idx[j]) * 32, *want = expect + 32 * j;
+    uint8_t diff = 0;
+    for (int i = 0; i < 32; i++) diff |= got[i] ^ want[i];
+    if (diff) status[p] = BP_ERR_VERIFICATION_;
   }
 };
 // s_i = prod_j u_j^(+1 if bit (k-1-j) of i else -1)
@@ -1048,12 +1072,36 @@ struct KVerifyCombineRows {
     rows[r] = acc;
   }
 };
-// combined mode: proofs that failed a structural check (status != 0) take no part in the combination
-struct KVerifyMaskRho {
-  static constexpr int kBlock = 128, kMinBlocks = 1;
-  static constexpr const char *kName = "KVerifyMaskRho";
-  const int *status; scm *rho;
-  HD void operator()(long p) const { if (status[p] != 0) rho[p] = sc_zero(); }
+// combined mode, weights.  seed = transcript over the digests of all B proofs, in order (one thread: B x 32 bytes through the
+// sponge, ~B / 5 permutations); rho_p = challenge of (seed, p).  A weight therefore depends on every byte of every proof, every
+// commitment, every public input and every entropy value of the batch: submitting one proof twice, reusing entropy between
+// slots, or knowing the entropy does not let a prover predict or equalise weights (each rho_p is a random-oracle output of the
+// finished batch).  Proofs that failed a structural check (status != 0) take no part in the combination.
+struct KBatchSeed {
+  static constexpr int kBlock = 32, kMinBlocks = 1;
+  static constexpr const char *kName = "KBatchSeed";
+  const uint8_t *digest; int B; uint8_t *seed;
+  HD void operator()(long) const {
+    const uint8_t lbl[24] = {'b', 'p', '-', 'b', '2', '0', '0', ' ', 'c', 'o', 'm', 'b', 'i', 'n', 'e', 'd', ' ', 'v', 'e', 'r', 'i', 'f', 'y', '2'};
+    strobe128 t; ts_init(t, lbl, 24);
+    ts_append_u64(t, "batch", (uint64_t)B);
+    for (int p = 0; p < B; p++) ts_append(t, "digest", digest + (long)p * 32, 32);
+    ts_challenge_bytes(t, "seed", seed, 32);
+  }
+};
+struct KVerifyRho {
+  static constexpr int kBlock = 64, kMinBlocks = 1;
+  static constexpr const char *kName = "KVerifyRho";
+  const uint8_t *seed; const int *status; scm *rho;
+  HD void operator()(long p) const {
+    if (status[p] != 0) { rho[p] = sc_zero(); return; }
+    const uint8_t lbl[23] = {'b', 'p', '-', 'b', '2', '0', '0', ' ', 'b', 'a', 't', 'c', 'h', ' ', 'w', 'e', 'i', 'g', 'h', 't', ' ', 'v', '2'};
+    strobe128 t; ts_init(t, lbl, 23);
+    ts_append(t, "seed", seed, 32);
+    ts_append_u64(t, "index", (uint64_t)p);
+    scm r; TS_CHALLENGE(t, "rho", r);
+    rho[p] = r;
+  }
 };
 // remaining scalars: rows 0,1 (B, B_blinding) and the per-proof points after the generators:
 // A_I1 A_O1 S1 A_I2 A_O2 S2 | V_0..V_{m-1} | T_1 T_3 T_4 T_5 T_6 | L_0.. | R_0..

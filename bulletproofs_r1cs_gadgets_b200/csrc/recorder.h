@@ -4,6 +4,7 @@
 // a witness program; all group arithmetic and the proof itself happen on the device (engine.h).
 #pragma once
 #include <array>
+#include <memory>
 #include <string>
 #include <vector>
 #include "../../include/bp_b200.h"
@@ -53,7 +54,11 @@ struct bp_cs {
   uint32_t naux = 0;
   std::vector<scm> pub;                          // public inputs (values for this cs; zero when recording only)
   std::vector<PoseidonBlock> pblocks;            // block ops of the witness program
-  const struct bp_poseidon_params *pparams = nullptr;  // parameters shared by every block op
+  std::shared_ptr<const struct bp_poseidon_params> pparams;  // OWN copy of the parameters shared by every block op (the caller may free its object before compiling)
+  // commitments whose value the circuit fixes (allocate_statics: the reference's verifier computes them itself,
+  // src/gadget_poseidon.rs:580-608): index among the committed variables and the expected compressed point
+  std::vector<uint32_t> fixed_idx;
+  std::vector<std::array<uint8_t, 32>> fixed_V;
 
 
   uint32_t add_wlc(const LC &lc) {

@@ -54,7 +54,7 @@ class Vsmt2(Workload):
         leaf = rec.commit(zero)
         bits = [rec.commit(zero) for _ in range(depth)]
         nodes = [rec.commit(zero) for _ in range(depth)]
-        statics = [rec.commit(zero) for _ in range(4)]
+        statics = rec.allocate_statics(4)  # the verifier computes these four commitments itself (reference src/gadget_poseidon.rs:580-608)
         root = rec.public_input()
         rec.vsmt2_verif_gadget(self.params, depth, root, leaf, bits, nodes, statics)
         circ = rec.compile()
@@ -73,6 +73,17 @@ class Vsmt2(Workload):
         for b, s in zip(bits, sibs):
             cur = self.params.hash_2(s, cur, api.SBOX_INVERSE) if b else self.params.hash_2(cur, s, api.SBOX_INVERSE)
         return cur
+
+    def roots_batch(self, v):
+        """Merkle roots of a batch of committed-value rows v [count][m][32] (leaf, bits, siblings, statics), every level hashed
+        as one device batch: the public inputs the verifier needs when `inputs(..., with_root=False)` skipped them"""
+        d = self.depth
+        cur = np.ascontiguousarray(v[:, 0])
+        for i in range(d):
+            bit = (v[:, 1 + i, 0] & 1).astype(bool)[:, None]
+            sib = v[:, 1 + d + i]
+            cur = self.params.hash_2_batch(np.where(bit, sib, cur), np.where(bit, cur, sib), api.SBOX_INVERSE)
+        return cur.reshape(-1, 1, 32)
 
     def inputs(self, first, count, with_root=True):
         d, m = self.depth, self.circuit.m
@@ -106,7 +117,7 @@ class Vsmt4(Workload):
         leaf = rec.commit(zero)
         index = rec.commit(zero)
         nodes = [rec.commit(zero) for _ in range(3 * levels)]
-        statics = [rec.commit(zero) for _ in range(2)]
+        statics = rec.allocate_statics(2)
         root = rec.public_input()
         rec.vsmt4_verif_gadget(self.params, levels, root, leaf, index, None, nodes, statics)
         circ = rec.compile()
@@ -167,7 +178,7 @@ class PoseidonHash2(Workload):
         rec = api.Verifier(gens_for_recording, label)
         zero = bytes(32)
         xs = [rec.commit(zero) for _ in range(2)]
-        statics = [rec.commit(zero) for _ in range(4)]
+        statics = rec.allocate_statics(4)
         h = rec.public_input()
         rec.poseidon_hash_2_gadget(self.params, xs[0], xs[1], statics, sbox, h)
         circ = rec.compile()

@@ -2,6 +2,7 @@
 import ctypes as C
 import os
 import re
+import subprocess
 
 import pytest
 
@@ -60,3 +61,37 @@ def test_python_layer_requires_the_library(tmp_path, monkeypatch):
     with pytest.raises(RuntimeError):
         api.load()
     api._lib = saved
+
+
+def _build_and_run_smoke(tmp_path, so):
+    """tests/capi_smoke.c: a C11 translation unit that includes include/bp_b200.h, compiled with -Wall -Wextra -Werror and linked
+    against `so` -- the header's prototypes and the library's entry points have to agree for this to compile, link and pass"""
+    exe = str(tmp_path / "capi_smoke")
+    d, name = os.path.dirname(so), os.path.basename(so)
+    cmd = ["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "capi_smoke.c"), "-o", exe,
+           "-L" + d, "-l:" + name, "-Wl,-rpath," + d]
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    return subprocess.run([exe], capture_output=True, text=True)
+
+
+def test_c_translation_unit_against_the_kernel_bodies(tmp_path, emul_so):
+    r = _build_and_run_smoke(tmp_path, emul_so)
+    assert r.returncode == 0 and "capi_smoke ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_c_translation_unit_links_against_the_product(tmp_path, product_so):
+    """on the CPU box the product library links and runs up to its first device call, which must report BP_ERR_NO_DEVICE (7)"""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present: tests/test_gpu.py runs the full program")
+    except ImportError:
+        pass
+    r = _build_and_run_smoke(tmp_path, product_so)
+    assert r.returncode == 1 and "bp_gens_new(16, &g) -> 7" in r.stderr, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_c_translation_unit_on_the_device(tmp_path, product_so):
+    r = _build_and_run_smoke(tmp_path, product_so)
+    assert r.returncode == 0 and "capi_smoke ok" in r.stdout, r.stdout + r.stderr

@@ -62,6 +62,7 @@ def test_chunking_is_invisible(api, gens, monkeypatch): E.test_chunking_is_invis
 def test_msm_path_choice_is_invisible(api, gens, monkeypatch): E.test_msm_path_choice_is_invisible(api, gens, monkeypatch)
 def test_combined_verification(api, gens): E.test_combined_verification(api, gens)
 def test_wire_format(api, gens): E.test_wire_format(api, gens)
+def test_static_commitments_are_checked_by_the_batch_verifiers(api, gens): E.test_static_commitments_are_checked_by_the_batch_verifiers(api, gens)
 def test_vsmt4_membership_small(api, gens): E.test_vsmt4_membership(api, gens)
 def test_vsmt4_membership_reference_parameters(api, gens_big, oracle_lib): E.test_vsmt4_membership(api, gens_big, levels=3, params=(6, 4, 4, 140), count=2, c_oracle_prover=True)
 def test_sparse_merkle_tree_and_membership_from_a_real_tree(api, gens): E.test_sparse_merkle_tree_and_membership_from_a_real_tree(api, gens)
@@ -260,6 +261,77 @@ def test_vsmt2_depth32_batch_properties(api, gens_big):
     assert not ok.any()
     assert len({P[i].tobytes() for i in range(B)}) == B  # distinct statements, distinct proofs
     assert P.shape[1] == 1472 and all(P[i, 96:192].tobytes() == bytes(96) for i in range(B))  # single-phase: A_I2, A_O2, S2 are the identity
+
+
+def test_vsmt2_depth32_chunk_border_vs_c_oracle(api, gens_big, oracle_lib, monkeypatch):
+    """depth-32 parity on a batch of 64 proofs that crosses device-chunk borders (chunks of 24, 24, 16): every
+    proof and every commitment byte-equal to the C oracle's (native witness + prove, all host cores), on the streamed entry points
+    the bench uses as well as on the plain call (reference flow src/gadget_vsmt_2.rs:262-399)"""
+    import torch
+    from bulletproofs_r1cs_gadgets_b200 import workloads
+    oracle_lib.poseidon_set_params(H.POSEIDON_BLOB)
+    wl = workloads.Vsmt2(gens_big, depth=32)
+    B = 64
+    inp = wl.inputs(5000, B, with_root=False)
+    pp = G.PoseidonParams()
+    oc = _oracle_circuit(lambda cs, v: G.vanilla_merkle_tree_verif_gadget(cs, 32, 0, v[0], v[1:33], v[33:65], v[65:], pp), 69, wl.label)
+    st_o, V_o, P_o = CO.prove_batch(oc, B, inp["v"], inp["v_blinding"], inp["entropy"], wl.label, 32768, os.cpu_count() or 1, witness_kind=1, depth=32)
+    assert not st_o.any()
+    monkeypatch.setenv("BP_B200_CHUNK", "24")
+    V, P, st = wl.circuit.prove_batch(gens_big, wl.label, inp["v"], inp["v_blinding"], inp["entropy"])
+    assert not st.any()
+    assert V.tobytes() == V_o.tobytes(), "commitments differ from the C oracle"
+    bad = [i for i in range(B) if P[i].tobytes() != P_o[i].tobytes()]
+    assert not bad, "proofs differ from the C oracle: %s" % bad
+    ps = api.ProveStream(wl.circuit, gens_big, wl.label)
+    ps.begin(0, inp["v"][:40], inp["v_blinding"][:40], inp["entropy"][:40])
+    ps.begin(1, inp["v"][40:], inp["v_blinding"][40:], inp["entropy"][40:])
+    Va, Pa, sa = ps.finish(0)
+    Vb, Pb, sb = ps.finish(1)
+    assert not sa.any() and not sb.any()
+    assert Pa.tobytes() + Pb.tobytes() == P_o.tobytes() and Va.tobytes() + Vb.tobytes() == V_o.tobytes()
+    # the whole batch through both verifiers with device-hashed roots; one wrong root is found by each
+    pub = wl.roots_batch(inp["v"])
+    assert pub[:2].tobytes() == wl.inputs(5000, 2)["pub"].tobytes()  # device-batched roots = the host's level-by-level hashing
+    assert not wl.circuit.verify_batch(gens_big, wl.label, V, P, inp["entropy"], pub=pub).any()
+    stc, comb = wl.circuit.verify_batch_combined(gens_big, wl.label, V, P, inp["entropy"], pub=pub)
+    assert comb == 0 and not stc.any()
+    badpub = pub.copy(); badpub[41, 0, 3] ^= 0x10
+    assert wl.circuit.verify_batch(gens_big, wl.label, V, P, inp["entropy"], pub=badpub).tolist() == [0] * 41 + [3] + [0] * 22
+    stc, comb = wl.circuit.verify_batch_combined(gens_big, wl.label, V, P, inp["entropy"], pub=badpub)
+    assert comb == 3 and not stc.any()
+
+
+def test_msm_2_pow_20_linearity_and_splitting(api):
+    """MSM parity at the benchmarked size (BASELINE config 3, 2^20 generators): linear in the scalars, and equal to the sum of
+    the results over two halves of the rows (the second half shifted in by zero scalars) -- size-independent properties"""
+    import torch
+    n = 1 << 20
+    g = api.Gens(n)
+    import hashlib
+
+    def scal(tag):
+        raw = np.frombuffer(hashlib.shake_256(b"msm-2^20/" + tag).digest(32 * n), dtype=np.uint8).reshape(n, 32).copy()
+        raw[:, 31] &= 0x0f
+        return raw
+
+    def msm(arr):
+        d_in = torch.from_numpy(np.ascontiguousarray(arr)).cuda()
+        d_out = torch.zeros(32, dtype=torch.uint8, device="cuda")
+        assert api.load().bp_msm_gens_device(g._h, arr.shape[0], C.c_void_p(d_in.data_ptr()), C.c_void_p(d_out.data_ptr()), None) == 0
+        torch.cuda.synchronize()
+        return d_out.cpu().numpy().tobytes()
+    a, b = scal(b"a"), scal(b"b")
+    ia = [int.from_bytes(a[i].tobytes(), "little") for i in range(n)]
+    ib = [int.from_bytes(b[i].tobytes(), "little") for i in range(n)]
+    s = api.scalars_to_array([(x + y) % L for x, y in zip(ia, ib)])
+    Pa, Pb, Ps = msm(a), msm(b), msm(s)
+    add = lambda x, y: R.ristretto_encode(R.pt_add(R.ristretto_decode(x), R.ristretto_decode(y)))
+    assert add(Pa, Pb) == Ps
+    lo, hi = a.copy(), a.copy()
+    lo[n // 2:] = 0; hi[:n // 2] = 0
+    assert add(msm(lo), msm(hi)) == Pa
+    assert msm(a[:n // 2]) == msm(lo)  # trailing zero rows change nothing
 
 
 def test_device_tree_large_batch_properties(api, oracle_lib):

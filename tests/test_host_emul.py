@@ -456,6 +456,50 @@ def test_combined_verification(api, gens):
     # single proof
     st, comb = wl.circuit.verify_batch_combined(gens, wl.label, V[:1], P[:1], inp["entropy"][:1], pub=inp["pub"][:1])
     assert comb == 0 and not st.any()
+    # Forgery regression: one valid proof submitted twice with the inner-product scalar a moved by +d and -d,
+    # the SAME verifier entropy in both slots.  Weights drawn from each proof's own transcript RNG were equal for the two slots
+    # (a and b are never absorbed by the transcript) and the two errors cancelled; weights derived from the digest of the whole
+    # batch differ per slot and depend on a, so the combination must fail -- as each proof does on its own.
+    off = wl.circuit.proof_len - 64  # the proof ends with a, b
+    a = int.from_bytes(P[0, off:off + 32].tobytes(), "little")
+    d = 0x1234567
+    Pf = np.stack([P[0], P[0]]).copy()
+    Pf[0, off:off + 32] = np.frombuffer(((a + d) % L).to_bytes(32, "little"), np.uint8)
+    Pf[1, off:off + 32] = np.frombuffer(((a - d) % L).to_bytes(32, "little"), np.uint8)
+    Vf, pubf, entf = np.stack([V[0], V[0]]), np.stack([inp["pub"][0], inp["pub"][0]]), np.stack([inp["entropy"][0], inp["entropy"][0]])
+    assert wl.circuit.verify_batch(gens, wl.label, Vf, Pf, entf, pub=pubf).tolist() == [3, 3]
+    st, comb = wl.circuit.verify_batch_combined(gens, wl.label, Vf, Pf, entf, pub=pubf)
+    assert comb == 3
+    # the same two slots holding the untouched proof pass; weights differ between slots although entropy and proof are equal
+    st, comb = wl.circuit.verify_batch_combined(gens, wl.label, Vf, np.stack([P[0], P[0]]), entf, pub=pubf)
+    assert comb == 0 and not st.any()
+
+
+def test_static_commitments_are_checked_by_the_batch_verifiers(api, gens):
+    """the Poseidon statics (0, 101, 0, 0 with blinding 0) are commitments the reference's verifier computes
+    itself (allocate_statics_for_verifier, src/gadget_poseidon.rs:580-608).  A prover who chooses other values for those slots
+    gets a proof that is VALID for its own V -- the batch verifiers must reject it because V differs from the fixed bytes."""
+    from bulletproofs_r1cs_gadgets_b200 import workloads
+    pp = api.PoseidonParams(6, 2, 2, 3)
+    wl = workloads.PoseidonHash2(gens, sbox=api.SBOX_INVERSE, params=pp)
+    inp = wl.inputs(0, 3)
+    v, pub = inp["v"].copy(), inp["pub"].copy()
+    v[1, 3] = api.scalars_to_array([77])[0]          # proof 1: padding lane 77 instead of 101 ...
+    xl, xr = (int.from_bytes(v[1, j].tobytes(), "little") for j in (0, 1))
+    image = G.poseidon_permutation([0, xl, xr, 77, 0, 0], G.PoseidonParams(6, 2, 2, 3), G.INVERSE)[1]
+    pub[1, 0] = api.scalars_to_array([image])[0]     # ... and the image that goes with it: a true statement about a DIFFERENT hash
+    V, P, st = wl.circuit.prove_batch(gens, wl.label, v, inp["v_blinding"], inp["entropy"], pub=pub)
+    assert not st.any()
+    assert V[0, 3].tobytes() == gens.commit(101, 0) and V[1, 3].tobytes() == gens.commit(77, 0)
+    # the proof itself is sound for its own commitments: a verifier told nothing about fixed slots accepts it
+    loose = api.Verifier(gens, wl.label)
+    lv = [loose.commit(bytes(32)) for _ in range(6)]
+    loose.poseidon_hash_2_gadget(pp, lv[0], lv[1], lv[2:6], api.SBOX_INVERSE, loose.public_input())
+    assert loose.compile().verify_batch(gens, wl.label, V, P, inp["entropy"], pub=pub).tolist() == [0, 0, 0]
+    # the circuit built with allocate_statics knows what slots 2..5 must hold
+    assert wl.circuit.verify_batch(gens, wl.label, V, P, inp["entropy"], pub=pub).tolist() == [0, 3, 0]
+    st, comb = wl.circuit.verify_batch_combined(gens, wl.label, V, P, inp["entropy"], pub=pub)
+    assert st.tolist() == [0, 3, 0] and comb == 0   # reported per proof, left out of the combination
 
 
 def test_wire_format(api, gens):
@@ -504,6 +548,22 @@ def test_error_codes(api, gens):
     vf = api.Verifier(gens, b"lin"); b = vf.commit(V); vf.constrain(b - 8)
     with pytest.raises(api.R1CSError):
         vf.verify(proof, bytes(32))
+    # wrongly shaped batch arrays are refused by the host layer (the C-ABI takes bare pointers): proof bytes -> FormatError,
+    # everything else -> InvalidArgument; a witness program that reads public inputs refuses to run without them
+    from bulletproofs_r1cs_gadgets_b200 import workloads
+    wl = workloads.Mimc(gens, rounds=3)
+    inp = wl.inputs(0, 2)
+    V2, P2, st = wl.circuit.prove_batch(gens, wl.label, inp["v"], inp["v_blinding"], inp["entropy"], pub=inp["pub"])
+    assert not st.any()
+    for kw, code in ((dict(V=V2[:, :1]), 6), (dict(proofs=P2[:, :-32]), 2), (dict(pub=inp["pub"][:1]), 6), (dict(V=V2[:1]), 6)):
+        args = dict(V=V2, proofs=P2, pub=inp["pub"]); args.update(kw)
+        for fn in (wl.circuit.verify_batch, wl.circuit.verify_batch_combined):
+            with pytest.raises(api.R1CSError) as e:
+                fn(gens, wl.label, args["V"], args["proofs"], inp["entropy"], pub=args["pub"])
+            assert e.value.code == code
+    with pytest.raises(api.R1CSError) as e:
+        wl.circuit.prove_batch(gens, wl.label, inp["v"][:, :1], inp["v_blinding"], inp["entropy"], pub=inp["pub"])
+    assert e.value.code == 6
 
 
 def test_single_multiplier_and_allocate_single(api, gens):
