@@ -52,6 +52,43 @@ HD void keccak_f1600(uint64_t st[25]) {
   for (int i = 0; i < 25; i++) st[i] = a[i];
 }
 
+// The same permutation on 25 named lanes, always inlined, every index a compile-time constant: the state never leaves the
+// register file.  Used by the steady state of the transcript RNG (KRngDraw), where the STROBE operations of one draw touch
+// fixed byte positions and nothing needs byte addressing.
+HD void keccak_f1600_lanes(uint64_t (&a)[25]) {
+  const uint64_t RC[24] = {
+      0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808AULL, 0x8000000080008000ULL,
+      0x000000000000808BULL, 0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL,
+      0x000000000000008AULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000AULL,
+      0x000000008000808BULL, 0x800000000000008BULL, 0x8000000000008089ULL, 0x8000000000008003ULL,
+      0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800AULL, 0x800000008000000AULL,
+      0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  for (int r = 0; r < 24; r++) {
+    uint64_t c[5], d[5], b[25];
+#pragma unroll
+    for (int x = 0; x < 5; x++) c[x] = a[x] ^ a[x + 5] ^ a[x + 10] ^ a[x + 15] ^ a[x + 20];
+#pragma unroll
+    for (int x = 0; x < 5; x++) d[x] = c[(x + 4) % 5] ^ rol64(c[(x + 1) % 5], 1);
+#pragma unroll
+    for (int i = 0; i < 25; i++) a[i] ^= d[i % 5];
+    b[0] = a[0];
+    b[10] = rol64(a[1], 1);   b[20] = rol64(a[2], 62);  b[5] = rol64(a[3], 28);   b[15] = rol64(a[4], 27);
+    b[16] = rol64(a[5], 36);  b[1] = rol64(a[6], 44);   b[11] = rol64(a[7], 6);   b[21] = rol64(a[8], 55);  b[6] = rol64(a[9], 20);
+    b[7] = rol64(a[10], 3);   b[17] = rol64(a[11], 10); b[2] = rol64(a[12], 43);  b[12] = rol64(a[13], 25); b[22] = rol64(a[14], 39);
+    b[23] = rol64(a[15], 41); b[8] = rol64(a[16], 45);  b[18] = rol64(a[17], 15); b[3] = rol64(a[18], 21);  b[13] = rol64(a[19], 8);
+    b[14] = rol64(a[20], 18); b[24] = rol64(a[21], 2);  b[9] = rol64(a[22], 61);  b[19] = rol64(a[23], 56); b[4] = rol64(a[24], 14);
+#pragma unroll
+    for (int y = 0; y < 25; y += 5) {
+#pragma unroll
+      for (int x = 0; x < 5; x++) a[y + x] = b[y + x] ^ ((~b[y + (x + 1) % 5]) & b[y + (x + 2) % 5]);
+    }
+    a[0] ^= RC[r];
+  }
+}
+
 // ---------------------------------------------------------------- byte access into a lane array
 HD uint8_t st_get(const uint64_t *st, int pos) { return (uint8_t)(st[pos >> 3] >> (8 * (pos & 7))); }
 HD void st_xor(uint64_t *st, int pos, uint8_t b) { st[pos >> 3] ^= (uint64_t)b << (8 * (pos & 7)); }

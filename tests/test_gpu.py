@@ -291,6 +291,7 @@ def test_vsmt2_depth32_chunk_border_vs_c_oracle(api, gens_big, oracle_lib, monke
     assert not sa.any() and not sb.any()
     assert Pa.tobytes() + Pb.tobytes() == P_o.tobytes() and Va.tobytes() + Vb.tobytes() == V_o.tobytes()
     # the whole batch through both verifiers with device-hashed roots; one wrong root is found by each
+    monkeypatch.delenv("BP_B200_CHUNK")  # one combination per call: the 64 proofs must share a device chunk
     pub = wl.roots_batch(inp["v"])
     assert pub[:2].tobytes() == wl.inputs(5000, 2)["pub"].tobytes()  # device-batched roots = the host's level-by-level hashing
     assert not wl.circuit.verify_batch(gens_big, wl.label, V, P, inp["entropy"], pub=pub).any()
