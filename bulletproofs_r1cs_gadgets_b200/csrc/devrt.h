@@ -20,14 +20,18 @@ extern long g_launch_count;
 // optional per-kernel timing (bp_profile_*): CUDA events recorded on the launching stream around every kernel
 extern int g_profile_on;
 void profile_begin(const char *name, long threads, dev_stream s);
+bool profile_selected(const char *name);
 void profile_end(dev_stream s);
 template <class K>
 int launch(long n, dev_stream s, const K &k) {
   if (n <= 0) return 0;
   long blocks = (n + K::kBlock - 1) / K::kBlock;
-  if (g_profile_on) profile_begin(K::kName, n, s);
+  // g_profile_on: 1 = every launch, 2 = only the launches of profile_selected() kernels (the events around ALL ~700 launches of a
+  // step cost ~2.5 % of the step; the timed region of bench.py brackets the dominant kernel only)
+  const bool prof = g_profile_on == 1 || (g_profile_on == 2 && profile_selected(K::kName));
+  if (prof) profile_begin(K::kName, n, s);
   run_kernel<K><<<(unsigned)blocks, K::kBlock, 0, s>>>(n, k);
-  if (g_profile_on) profile_end(s);
+  if (prof) profile_end(s);
   g_launch_count++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { fprintf(stderr, "bp_b200: launch failed: %s\n", cudaGetErrorString(e)); return 1; }
@@ -43,7 +47,12 @@ inline int dev_memset(void *d, int v, size_t n, dev_stream s) { return n ? cudaM
 struct dev_side { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
 inline int dev_side_init(dev_side &d) {
   if (d.s) return 0;
-  if (cudaStreamCreateWithFlags(&d.s, cudaStreamNonBlocking) != cudaSuccess) return 1;
+  // highest priority: the side streams carry the latency chains of a batch's first phase (a few hundred small blocks that run
+  // for most of a second); the block scheduler must place them as soon as an SM has room, ahead of the queued blocks of the
+  // throughput kernels on the caller's stream -- otherwise they wait for a grid's tail and the next batch stalls on them
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  if (cudaStreamCreateWithPriority(&d.s, cudaStreamNonBlocking, hi) != cudaSuccess) return 1;
   if (cudaEventCreateWithFlags(&d.fork, cudaEventDisableTiming) != cudaSuccess) return 1;
   if (cudaEventCreateWithFlags(&d.join, cudaEventDisableTiming) != cudaSuccess) return 1;
   return 0;

@@ -20,6 +20,7 @@ void profile_begin(const char *name, long threads, dev_stream s) {
   g_prof.push_back(r);
 }
 void profile_end(dev_stream s) { cudaEventRecord(g_prof.back().e1, s); }
+bool profile_selected(const char *name) { return strcmp(name, "KBucketAccumulate") == 0; }
 // exact number of point additions of the sorted-bucket path while profiling: sum over instances of the item-list lengths
 // (one item = one non-zero digit = one addition in KBucketAccumulate).  Reported as the pseudo-kernel "@sorted_items".
 static unsigned long long *g_items_dev = nullptr;
@@ -343,7 +344,7 @@ double engine_workspace_bytes_per_proof(const BpCircuit *c) {
   b += sizeof(scm) * ((double)c->nslots + (q + 1) + 4 * N + (2 * k + 2) + 40 + nch * 6 + (c->npub + 1));  // w_all, zpow, ypow, yinvpow, a, b, ...
   b += rows * SB_ROW_BYTES;                                                      // digit rows
   b += sizeof(ge_p3) * (slices + 2 * (N / 2 + 1) + (m + 12 + 2 * k) + 2 * SB_SEGS + 1 + 2 * MSM_WINDOWS);  // partial sums, folded generators, ...
-  b += 4 * items + 8 * (SB_BUCKETS + 1) + 4 * 256 + 16;                          // sorted items, offsets, NAFs
+  b += 4 * items + 8 * (SB_BUCKETS + 1) + 8 * 256 + 32;                          // sorted items, offsets, NAFs
   b += sizeof(scm) * (2 * (m + 1) + (c->naux + 1) + (c->npub + 1) + 3 * (n + 1) + (3 + 2 * n)) + 2 * sizeof(strobe128);  // front
   return b;
 }
@@ -374,7 +375,7 @@ static int ensure_workspace(BpCircuit *c, int B) {
   bad |= dalloc(&w->dig, w->dig_bytes); bad |= dalloc(&w->buckets, w->bucket_slots); bad |= dalloc(&w->wsum, (max_warps + (size_t)B + 64) * MSM_WINDOWS);
   bad |= dalloc(&w->Q, Bz); bad |= dalloc(&w->Gt, (N / 2 + 1) * Bz); bad |= dalloc(&w->Ht, (N / 2 + 1) * Bz);
   bad |= dalloc(&w->pts, (m + 11 + 2 * k + 1) * Bz);
-  bad |= dalloc(&w->naf, 4 * 256 * Bz); bad |= dalloc(&w->naf_top, 4 * Bz);
+  bad |= dalloc(&w->naf, 8 * 256 * Bz); bad |= dalloc(&w->naf_top, 8 * Bz);
   bad |= dalloc(&w->items, w->items_cap * Bz); bad |= dalloc(&w->boff, (size_t)(SB_BUCKETS + 1) * Bz); bad |= dalloc(&w->soff, (size_t)(SB_BUCKETS + 1) * Bz);
   bad |= dalloc(&w->seg, (size_t)SB_SEGS * 2 * Bz);
   bad |= dalloc(&w->utab, 4 * (size_t)(1 << UNFOLD_MAX) * Bz + 4 * Bz); bad |= dalloc(&w->rg_as, 2 * n + 2); bad |= dalloc(&w->rg_ai, 2 * n + 2); bad |= dalloc(&w->skip_ai, 2 * n + 2);
@@ -610,7 +611,13 @@ int engine_prove_finish(const BpGens *g, BpCircuit *c, int slot, dev_stream s) {
   CK(dev_memset(A.proofs, 0, plen * B, s));
   for (int ci = 0; ci < nchunks; ci++) {
     Front &f = c->ws->fronts[slot][ci];
+#ifndef BP_HOST_EMUL
+    if (g_profile_on == 1) profile_begin("@wait_first_phase", 0, s);  // pseudo-kernel: time the caller's stream spends waiting for this chunk's first phase
+#endif
     dev_side_join(f.sideR, s); dev_side_join(f.sideW, s);
+#ifndef BP_HOST_EMUL
+    if (g_profile_on == 1) profile_end(s);
+#endif
     rc = prove_phase_b(g, c, f, prove_slice(c, A, chunk, ci), s); if (rc) return rc;
   }
   return BP_OK;

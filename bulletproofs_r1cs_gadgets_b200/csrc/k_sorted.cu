@@ -313,19 +313,19 @@ int launch_sort_buckets(const RowMap &rmap, const int8_t *dig, long dig_inst_str
   const bool radix = mode == 2 && tmp && tmp_bytes >= (size_t)ninst * items_stride * sizeof(uint32_t) && gen_slots > 0 &&
                      (size_t)gen_slots * SB_WINDOWS < (1u << SORT_ITEM_BITS) && ninst * SORT_GROUPS < (1L << 31);
   if (radix) {
-    if (g_profile_on) profile_begin("sort_coarse_kernel", ninst * SORT2_THREADS, s);
+    if (g_profile_on == 1) profile_begin("sort_coarse_kernel", ninst * SORT2_THREADS, s);
     sort_coarse_kernel<<<(unsigned)ninst, SORT2_THREADS, SORT2_SMEM_BYTES, s>>>(rmap, dig, dig_inst_stride, rows, tmp, items_stride, boff);
-    if (g_profile_on) profile_end(s);
-    if (g_profile_on) profile_begin("sort_fine_kernel", ninst * SORT_GROUPS * 256, s);
+    if (g_profile_on == 1) profile_end(s);
+    if (g_profile_on == 1) profile_begin("sort_fine_kernel", ninst * SORT_GROUPS * 256, s);
     sort_fine_kernel<<<(unsigned)(ninst * SORT_GROUPS), 256, 0, s>>>(tmp, items, items_stride, boff);
-    if (g_profile_on) profile_end(s);
+    if (g_profile_on == 1) profile_end(s);
     g_launch_count += 2;
   } else {
-    if (g_profile_on) profile_begin("sort_buckets_kernel", ninst * SORT_THREADS, s);
+    if (g_profile_on == 1) profile_begin("sort_buckets_kernel", ninst * SORT_THREADS, s);
     // the direct variant asks for the same (large) shared-memory carve-out on purpose: one block per SM bounds the open sectors
     if (mode == 1) sort_buckets_direct_kernel<<<(unsigned)ninst, SORT_THREADS, SORT_SMEM_BYTES, s>>>(rmap, dig, dig_inst_stride, rows, items, items_stride, boff);
     else sort_buckets_kernel<<<(unsigned)ninst, SORT_THREADS, SORT_SMEM_BYTES, s>>>(rmap, dig, dig_inst_stride, rows, items, items_stride, boff);
-    if (g_profile_on) profile_end(s);
+    if (g_profile_on == 1) profile_end(s);
     g_launch_count++;
   }
   cudaError_t e = cudaGetLastError();

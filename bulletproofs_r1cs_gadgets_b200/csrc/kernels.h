@@ -279,8 +279,11 @@ struct KTsStart {
   }
 };
 // draws `count` uniform scalars (64 bytes each, wide reduction) into dst[i*B+p]
+// Blocks of 128 threads (one warp per SM sub-partition): these latency chains run beside the throughput kernels of the previous
+// chunk, whose blocks hold 16 K registers each -- a 128-thread block here displaces about one of them, where four 32-thread
+// blocks spread over four SMs would each strand most of a 16 K slot.
 struct KRngDraw {
-  static constexpr int kBlock = 32, kMinBlocks = 1;
+  static constexpr int kBlock = 128, kMinBlocks = 1;
   static constexpr const char *kName = "KRngDraw";
   strobe128 *rng; scm *dst; int count, B;
   // One draw of 64 bytes (merlin TranscriptRng::fill_bytes) is: meta_ad(u32le(64)), begin_op(PRF) -> pad + permute, squeeze 64.
@@ -369,11 +372,11 @@ struct KTsPhase4 {
   }
 };
 
-// width-4 non-adjacent form of a canonical scalar: digits in {+-1, +-3, +-5, +-7}, at most one non-zero digit in any four
-// consecutive positions (about 253/5 = 51 additions per scalar instead of 253/3 = 84 for the plain NAF);
+// width-4 non-adjacent form of a 256-bit integer: digits in {+-1, +-3, +-5, +-7}, at most one non-zero digit in any four
+// consecutive positions (about one addition per five bits instead of one per three for the plain NAF);
 // returns the index of the top non-zero digit (or -1)
-HD int sc_naf(int8_t naf[256], const scm &s) {
-  uint64_t k[4]; sc_to_canonical(k, s);
+HD int naf_words(int8_t naf[256], const uint64_t k_in[4]) {
+  uint64_t k[4] = {k_in[0], k_in[1], k_in[2], k_in[3]};
   int top = -1;
   for (int i = 0; i < 256; i++) {
     int8_t z = 0;
@@ -394,19 +397,87 @@ HD int sc_naf(int8_t naf[256], const scm &s) {
   }
   return top;
 }
+HD int sc_naf(int8_t naf[256], const scm &s) { uint64_t k[4]; sc_to_canonical(k, s); return naf_words(naf, k); }
+
+// Half-size decomposition of a fold scalar.  The generator fold G' = G_lo + e G_hi is only needed up to a known factor (the
+// factor is carried in the scalars, see KTsIpaRound), so instead of one 253-bit scalar we look for c with BOTH c and
+// d = c e mod l short: the extended Euclidean algorithm on (l, e) produces remainders r_i = t_i e (mod l) with |t_i| r_{i-1} <= l;
+// stopping at the first r_i < 2^127 gives |c| = |t_i| <= 2^126, 0 <= d = r_i < 2^127.  Then c G_lo + d G_hi = c (G_lo + e G_hi)
+// costs ~128 shared doublings and two ~26-addition digit strings instead of 253 doublings and ~51 additions.
+// Quotients are taken bit by bit (shift-and-subtract); a remainder moves to r1 only when fully reduced, so (t1, r1) is always
+// a true step of the Euclidean sequence.  c comes back as sign + magnitude.
+HD int u256_bitlen(const uint64_t a[4]) {
+  for (int i = 3; i >= 0; i--) if (a[i]) { int b = 63; while (!((a[i] >> b) & 1)) b--; return 64 * i + b + 1; }
+  return 0;
+}
+HD void u256_shl(uint64_t r[4], const uint64_t a[4], int k) {
+  const int ws = k >> 6, bs = k & 63;
+  for (int i = 3; i >= 0; i--) {
+    uint64_t v = 0;
+    if (i - ws >= 0) { v = a[i - ws] << bs; if (bs && i - ws - 1 >= 0) v |= a[i - ws - 1] >> (64 - bs); }
+    r[i] = v;
+  }
+}
+HD int u256_ge(const uint64_t a[4], const uint64_t b[4]) {
+  for (int i = 3; i >= 0; i--) { if (a[i] != b[i]) return a[i] > b[i]; }
+  return 1;
+}
+HD void u256_sub(uint64_t r[4], const uint64_t a[4], const uint64_t b[4]) {  // mod 2^256 (two's complement for the cofactors)
+  uint64_t br = 0;
+  for (int i = 0; i < 4; i++) { const uint64_t t = a[i] - b[i], t2 = t - br; br = (uint64_t)((a[i] < b[i]) | (t < br)); r[i] = t2; }
+}
+HD void sc_half_size(uint64_t cmag[4], int &cneg, uint64_t d[4], const scm &e) {
+  uint64_t r0[4] = SC_L_LIMBS, r1[4], t0[4] = {0, 0, 0, 0}, t1[4] = {1, 0, 0, 0};
+  sc_to_canonical(r1, e);
+  while (u256_bitlen(r1) > 127) {
+    int k = u256_bitlen(r0) - u256_bitlen(r1);
+    uint64_t sh[4]; u256_shl(sh, r1, k);
+    if (!u256_ge(r0, sh)) { k--; u256_shl(sh, r1, k); }
+    uint64_t ts[4]; u256_shl(ts, t1, k);
+    u256_sub(r0, r0, sh); u256_sub(t0, t0, ts);
+    if (!u256_ge(r0, r1)) {
+      for (int i = 0; i < 4; i++) { uint64_t x = r0[i]; r0[i] = r1[i]; r1[i] = x; x = t0[i]; t0[i] = t1[i]; t1[i] = x; }
+    }
+  }
+  cneg = (int)(t1[3] >> 63);
+  if (cneg) { const uint64_t z[4] = {0, 0, 0, 0}; u256_sub(cmag, z, t1); } else { for (int i = 0; i < 4; i++) cmag[i] = t1[i]; }
+  for (int i = 0; i < 4; i++) d[i] = r1[i];
+}
+HD scm sc_from_u256_small(const uint64_t w[4]) { scm x; x.v[0] = w[0]; x.v[1] = w[1]; x.v[2] = w[2]; x.v[3] = w[3]; return sc_montmul_any(x, sc_r2()); }  // w < l
 
 // One inner-product round, transcript side (A.4): append L,R, draw u; derive everything the
 // scalar fold and the generator fold of this round need.
 //   folded generators are kept un-normalised:  G_true[i] = alpha * Gt[i],  H_true[i] = beta * y^-i * Ht[i]
-//   Gt'[i] = Gt[i] + eG * Gt[h+i],  eG = u^2          (times the G-factor class of index h+i in round 0)
-//   Ht'[i] = Ht[i] + eH * Ht[h+i],  eH = u^-2 * y^-h  (same class factor)
-//   alpha' = alpha * u^-1,  beta' = beta * u
+//   Gt'[i] = cG (Gt[i] + eG * Gt[h+i]) = cG Gt[i] + dG Gt[h+i],  eG = u^2   (times the G-factor class of index h+i in round 0)
+//   Ht'[i] = cH (Ht[i] + eH * Ht[h+i]) = cH Ht[i] + dH Ht[h+i],  eH = u^-2 * y^-h  (same class factor)
+//   (c, d) = half-size decomposition of e (sc_half_size); round 0 with its two classes keeps c = 1, d = e
+//   alpha' = alpha * u^-1 / cG,  beta' = beta * u / cH
+// NAF layout: naf[((p*4 + which*2 + cls)*2 + {0: c on the low point, 1: d on the high point}) * 256], tops likewise.
 struct KTsIpaRound {
   static constexpr int kBlock = 64, kMinBlocks = 1;
   static constexpr const char *kName = "KTsIpaRound";
   strobe128 *ts; const uint8_t *proofs; long proof_stride; int round; int B; int h;
   const scm *yinvpow; const scm *ufac;  // y^-i table [N][B]; the r1cs challenge u (class factor, round 0 only)
   scm *u, *uinv, *alpha, *beta; int8_t *naf; int *naf_top; int *status; int verifier; int yfree;  // yfree: generators already carry y^-i
+  HD void put_naf(long p, int slot, int which, const uint64_t k[4], int neg) const {
+    int8_t nf[256];
+    const int top = naf_words(nf, k);
+    int8_t *dst = naf + ((p * 4 + slot) * 2 + which) * 256;
+    for (int i = 0; i <= top; i++) dst[i] = neg ? (int8_t)-nf[i] : nf[i];
+    naf_top[(p * 4 + slot) * 2 + which] = top;
+  }
+  HD void full_size(long p, int slot, const scm &e) const {
+    const uint64_t one[4] = {1, 0, 0, 0};
+    uint64_t k[4]; sc_to_canonical(k, e);
+    put_naf(p, slot, 0, one, 0); put_naf(p, slot, 1, k, 0);
+  }
+  HD scm half_size(long p, int slot, const scm &e) const {  // writes both digit strings, returns c as a scalar
+    uint64_t cm[4], d[4]; int cneg;
+    sc_half_size(cm, cneg, d, e);
+    put_naf(p, slot, 0, cm, cneg); put_naf(p, slot, 1, d, 0);
+    scm c = sc_from_u256_small(cm);
+    return cneg ? sc_neg(c) : c;
+  }
   HD void operator()(long p) const {
     strobe128 t; strobe_load(t, &ts[p]);
     const uint8_t *pf = proofs + p * proof_stride + 448 + 64 * round;
@@ -421,17 +492,15 @@ struct KTsIpaRound {
     if (verifier) return;
     scm eG = sc_sqr(uu), eH = sc_sqr(ui);
     if (!yfree) eH = sc_mul(eH, yinvpow[(long)h * B + p]);
-    int8_t nf[256];
-    int8_t *dst = naf + p * 4 * 256;
-    int top;
-    top = sc_naf(nf, eG); for (int i = 0; i < 256; i++) dst[i] = nf[i]; naf_top[p * 4 + 0] = top;
-    top = sc_naf(nf, eH); for (int i = 0; i < 256; i++) dst[512 + i] = nf[i]; naf_top[p * 4 + 2] = top;
+    scm cG = sc_one(), cH = sc_one();
     if (round == 0) {
       scm f = ufac[p];
-      top = sc_naf(nf, sc_mul(eG, f)); for (int i = 0; i < 256; i++) dst[256 + i] = nf[i]; naf_top[p * 4 + 1] = top;
-      top = sc_naf(nf, sc_mul(eH, f)); for (int i = 0; i < 256; i++) dst[768 + i] = nf[i]; naf_top[p * 4 + 3] = top;
+      full_size(p, 0, eG); full_size(p, 1, sc_mul(eG, f));
+      full_size(p, 2, eH); full_size(p, 3, sc_mul(eH, f));
+    } else {
+      cG = half_size(p, 0, eG); cH = half_size(p, 2, eH);
     }
-    alpha[p] = sc_mul(alpha[p], ui); beta[p] = sc_mul(beta[p], uu);
+    alpha[p] = sc_mul(sc_mul(alpha[p], ui), sc_invert(cG)); beta[p] = sc_mul(sc_mul(beta[p], uu), sc_invert(cH));
   }
 };
 
@@ -627,8 +696,8 @@ struct KStoreAB {
 };
 
 // ------------------------------------------------------------------------------------------------
-// generator fold: dst[p][i] = lo[i] + e * hi[i],  e given in NAF (shared by all i of a proof and class)
-// thread order is proof-major so a warp walks one NAF (uniform branches).
+// generator fold: dst[p][i] = c * lo[i] + d * hi[i], (c, d) given as two NAFs shared by all i of a proof and class (KTsIpaRound):
+// one doubling chain for both digit strings (Straus), thread order proof-major so a warp walks the same digits (uniform branches).
 // ------------------------------------------------------------------------------------------------
 struct KFoldGens {
   static constexpr int kBlock = 128, kMinBlocks = BP_OCC_FOLD;
@@ -636,42 +705,38 @@ struct KFoldGens {
   const ge_p3 *srcG, *srcH; long src_stride;  // round 0: shared generators (stride 0); later: per-proof
   ge_p3 *dstG, *dstH; long dst_stride;
   const int8_t *naf; const int *naf_top; int h, n, round;
+  // odd multiples 1, 3, 5, 7 of a point (one doubling, three additions)
+  HD static void odd_multiples(ge_cached c[4], const ge_p3 &pt) {
+    ge_p3 p2, t; ge_cached c2;
+    ge_dbl_f(p2, pt); ge_to_cached<true>(c2, p2);
+    ge_to_cached<true>(c[0], pt);
+    ge_add_cached_f(t, pt, c2, 0); ge_to_cached<true>(c[1], t);
+    ge_add_cached_f(t, t, c2, 0); ge_to_cached<true>(c[2], t);
+    ge_add_cached_f(t, t, c2, 0); ge_to_cached<true>(c[3], t);
+  }
   HD void operator()(long tid) const {
     long p = tid / (2 * h); int r = (int)(tid % (2 * h)); int which = r / h; int i = r % h;
     const ge_p3 *src = (which ? srcH : srcG) + p * src_stride;
     ge_p3 *dst = (which ? dstH : dstG) + p * dst_stride;
     int cls = (round == 0 && h + i >= n) ? 1 : 0;
-    const int8_t *nf = naf + (p * 4 + which * 2 + cls) * 256;
-    int top = naf_top[p * 4 + which * 2 + cls];
+    const long slot = (p * 4 + which * 2 + cls) * 2;
+    const int8_t *nfc = naf + slot * 256, *nfd = nfc + 256;
+    const int topc = naf_top[slot], topd = naf_top[slot + 1];
+    const int top = topc > topd ? topc : topd;
     ge_p3 lo, hi; load_struct(lo, &src[i]); load_struct(hi, &src[h + i]);
-    ge_p3 acc;
-    if (top < 0) { acc = lo; }
-    else {
-      // odd multiples 1, 3, 5, 7 of the upper point (one doubling, three additions), then double-and-add over the digits
-      ge_cached c[4];
-      {
-        ge_p3 h2, t; ge_cached c2;
-        ge_dbl_f(h2, hi); ge_to_cached<true>(c2, h2);
-        ge_to_cached<true>(c[0], hi);
-        ge_add_cached_f(t, hi, c2, 0); ge_to_cached<true>(c[1], t);
-        ge_add_cached_f(t, t, c2, 0); ge_to_cached<true>(c[2], t);
-        ge_add_cached_f(t, t, c2, 0); ge_to_cached<true>(c[3], t);
+    ge_cached c[8];  // [0..4): odd multiples of lo, [4..8): of hi
+    odd_multiples(c, lo); odd_multiples(c + 4, hi);
+    ge_p3 acc; ge_identity(acc);
+    for (int bit = top; bit >= 0; bit--) {
+      const int dc = bit <= topc ? nfc[bit] : 0, dd = bit <= topd ? nfd[bit] : 0;
+      // the doubling is the hot operation: expanded in place, ONE site; T is only needed when an addition follows or at the end
+      if (bit != top) {
+        ge_p1p1 t; ge_dbl_p1p1<true>(t, acc);
+        ge_p1p1_to_p2<true>(acc, t);
+        if (dc != 0 || dd != 0 || bit == 0) fe_mul_x<true>(acc.T, t.X, t.Y);
       }
-      ge_identity(acc);
-      for (int bit = top; bit >= 0; bit--) {
-        int d = nf[bit];
-        // T is only needed when an addition follows (a digit here, or the final + lo)
-        // the doubling is the hot operation (253 per output against ~51 additions): expanded in place, ONE site; T is only
-        // needed when an addition follows (a digit here, or the final + lo)
-        if (bit != top) {
-          ge_p1p1 t; ge_dbl_p1p1<true>(t, acc);
-          ge_p1p1_to_p2<true>(acc, t);
-          if (d != 0 || bit == 0) fe_mul_x<true>(acc.T, t.X, t.Y);
-        }
-        if (d != 0) { const int neg = d < 0; const int idx = ((neg ? -d : d) - 1) >> 1; ge_add_cached_f(acc, acc, c[idx], neg); }
-      }
-      ge_cached cl; ge_to_cached<true>(cl, lo);
-      ge_add_cached_f(acc, acc, cl, 0);
+      if (dc != 0) { const int neg = dc < 0; ge_add_cached_f(acc, acc, c[((neg ? -dc : dc) - 1) >> 1], neg); }
+      if (dd != 0) { const int neg = dd < 0; ge_add_cached_f(acc, acc, c[4 + (((neg ? -dd : dd) - 1) >> 1)], neg); }
     }
     store_struct(&dst[i], acc);
   }
@@ -758,7 +823,7 @@ struct PoseidonDev { const scm *round_keys; const scm *mds; uint32_t full_b, par
 #endif
 
 struct KWitnessTape {
-  static constexpr int kBlock = 32, kMinBlocks = 1;
+  static constexpr int kBlock = 128, kMinBlocks = 1;  // see KRngDraw
   static constexpr const char *kName = "KWitnessTape";
   const TapeOp *tape; WitnessLcs lcs; const PoseidonBlock *pblocks; PoseidonDev pos; int n, B;
   const scm *v; const scm *aux; const scm *pub; scm *aL, *aR, *aO;

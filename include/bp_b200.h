@@ -60,7 +60,8 @@ typedef struct bp_circuit bp_circuit; /* a compiled constraint system for batche
 int32_t bp_version(void);
 /* number of CUDA kernels this library has launched in this process (bench.py reports it) */
 int64_t bp_launch_count(void);
-/* per-kernel device timing: while enabled every kernel launch is bracketed by CUDA events on its stream.
+/* per-kernel device timing: on = 1 brackets every kernel launch with CUDA events on its stream (about 2.5 % overhead on a
+ * depth-32 proving step), on = 2 only the launches of the dominant kernel (KBucketAccumulate), 0 = off.
  * bp_profile_report (after the caller synchronised) writes lines "kernel launches total_ms threads" and clears the records. */
 void bp_profile_enable(int32_t on);
 int32_t bp_profile_report(char *buf, size_t cap);
