@@ -163,7 +163,8 @@ int gens_create(uint32_t capacity, BpGens **out) {
   // direct 8-bit tables (384 KiB per generator); BP_B200_NO_TABLE=1 keeps the bucket-method-only pipeline
   const size_t ngen = 2 * (size_t)capacity + 2;
   const size_t table_bytes = ngen * TBL_W * TBL_E * sizeof(ge_niels);
-  if (!getenv("BP_B200_NO_TABLE") && table_bytes <= ((size_t)48 << 30)) {  // capacities above ~65k generators do without
+  // BP_B200_NO_DIRECT_TABLE=1: the configuration of capacities above ~65k generators (shift table only) at any size, for tests
+  if (!getenv("BP_B200_NO_TABLE") && !getenv("BP_B200_NO_DIRECT_TABLE") && table_bytes <= ((size_t)48 << 30)) {  // capacities above ~65k generators do without
     if (dalloc(&g->table, ngen * TBL_W * TBL_E)) { gens_free(g); return BP_ERR_OOM; }
     CK(launch((long)ngen * TBL_W, s, KTableBuild{g->G_p3, g->H_p3, g->pc, (long)capacity, g->table}));
     CK(dev_sync(s));
@@ -669,7 +670,7 @@ static int prove_phase_b(const BpGens *g, BpCircuit *c, Front &f, const ProveArg
       CK(launch(n * B, s, KRecode{sL, nullptr, (int)n, B, dS, rowsI * rb, 1}));
       CK(launch(n * B, s, KRecode{sR, nullptr, (int)n, B, dS, rowsI * rb, (int)(1 + n)}));
     }
-    if (g->table) {
+    if (g->table || sorted) {
       if (w->rg_cap != (long)g->capacity) {
         std::vector<uint32_t> rg(2 * n + 1);
         rg[0] = 2 * g->capacity + 1;
@@ -681,7 +682,13 @@ static int prove_phase_b(const BpGens *g, BpCircuit *c, Front &f, const ProveArg
       if (sorted) {
         RowMap rmI{0, merged ? w->rg_ai : w->rg_as, (long)g->capacity, 0, 0, 0};
         rc = run_msm_sorted(g, w, rmI, rowsI, B, dI, rowsI * rb, A.proofs + 0, plen, s); if (rc) return rc;
-        rc = run_msm_table(g, w, rm, rowsO, B, dO, rowsO * 32, A.proofs + 32, plen, s); if (rc) return rc;
+        if (g->table) { rc = run_msm_table(g, w, rm, rowsO, B, dO, rowsO * 32, A.proofs + 32, plen, s); if (rc) return rc; }
+        else {
+          // no direct tables (capacities above ~65k generators): A_O through the bucket method on the generators themselves
+          // (its scalars are 0 / 1: one non-zero digit per row)
+          MsmSeg segsO[2] = {{g->pc_niels + 1, 0, 0, 1}, {g->G_n, 0, 0, (int)n}};
+          rc = run_msm(w, segsO, 2, B, dO, rowsO * 32, A.proofs + 32, plen, 0, nullptr, s); if (rc) return rc;
+        }
         rc = run_msm_sorted(g, w, rm, rowsI, B, dS, rowsI * rb, A.proofs + 64, plen, s); if (rc) return rc;
       } else {
         rc = run_msm_table(g, w, rm, rowsI, B, dI, rowsI * rb, A.proofs + 0, plen, s); if (rc) return rc;

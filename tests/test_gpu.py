@@ -61,6 +61,7 @@ def test_explicit_witness_equals_witness_program(api, gens, oracle_lib): E.test_
 def test_chunking_is_invisible(api, gens, monkeypatch): E.test_chunking_is_invisible(api, gens, monkeypatch)
 def test_msm_path_choice_is_invisible(api, gens, monkeypatch): E.test_msm_path_choice_is_invisible(api, gens, monkeypatch)
 def test_combined_verification(api, gens): E.test_combined_verification(api, gens)
+def test_shift_table_only_generators(api, gens, monkeypatch): E.test_shift_table_only_generators(api, gens, monkeypatch)
 def test_wire_format(api, gens): E.test_wire_format(api, gens)
 def test_static_commitments_are_checked_by_the_batch_verifiers(api, gens): E.test_static_commitments_are_checked_by_the_batch_verifiers(api, gens)
 def test_vsmt4_membership_small(api, gens): E.test_vsmt4_membership(api, gens)
@@ -301,6 +302,36 @@ def test_vsmt2_depth32_chunk_border_vs_c_oracle(api, gens_big, oracle_lib, monke
     assert wl.circuit.verify_batch(gens_big, wl.label, V, P, inp["entropy"], pub=badpub).tolist() == [0] * 41 + [3] + [0] * 22
     stc, comb = wl.circuit.verify_batch_combined(gens_big, wl.label, V, P, inp["entropy"], pub=badpub)
     assert comb == 3 and not stc.any()
+
+
+def test_vsmt2_depth253_reference_configuration(api, oracle_lib):
+    """The reference's own test configuration (src/gadget_vsmt_2.rs:23,262-399): TreeDepth = 253, inverse S-box, 4+140+4 rounds,
+    n = 143704 multipliers -> N = 262144 generators (shift table only, no direct tables), m = 511 commitments, label b"VSMT".
+    Two proofs, byte-equal to the C oracle's; both verifiers accept them and reject a wrong root."""
+    from bulletproofs_r1cs_gadgets_b200 import workloads
+    oracle_lib.poseidon_set_params(H.POSEIDON_BLOB)
+    depth, B, cap = 253, 2, 1 << 18
+    g = api.Gens(cap)
+    wl = workloads.Vsmt2(g, depth=depth)
+    assert (wl.circuit.n, wl.circuit.q, wl.circuit.m, wl.circuit.proof_len) == (143704, 334973, 511, 1664)  # SURVEY section 8 table
+    inp = wl.inputs(7000, B, with_root=False)
+    pp = G.PoseidonParams()
+    oc = _oracle_circuit(lambda cs, v: G.vanilla_merkle_tree_verif_gadget(cs, depth, 0, v[0], v[1:1 + depth], v[1 + depth:1 + 2 * depth], v[1 + 2 * depth:], pp),
+                         2 * depth + 5, wl.label)
+    assert (oc.n, oc.q, oc.m) == (wl.circuit.n, wl.circuit.q, wl.circuit.m)
+    st_o, V_o, P_o = CO.prove_batch(oc, B, inp["v"], inp["v_blinding"], inp["entropy"], wl.label, cap, B, witness_kind=1, depth=depth)
+    assert not st_o.any()
+    V, P, st = wl.circuit.prove_batch(g, wl.label, inp["v"], inp["v_blinding"], inp["entropy"])
+    assert not st.any()
+    assert V.tobytes() == V_o.tobytes(), "commitments differ from the C oracle"
+    assert P.tobytes() == P_o.tobytes(), "proof bytes differ from the C oracle"
+    pub = wl.roots_batch(inp["v"])
+    assert not wl.circuit.verify_batch(g, wl.label, V, P, inp["entropy"], pub=pub).any()
+    stc, comb = wl.circuit.verify_batch_combined(g, wl.label, V, P, inp["entropy"], pub=pub)
+    assert comb == 0 and not stc.any()
+    bad = pub.copy(); bad[1, 0, 0] ^= 1
+    assert wl.circuit.verify_batch(g, wl.label, V, P, inp["entropy"], pub=bad).tolist() == [0, 3]
+    assert wl.circuit.verify_batch_combined(g, wl.label, V, P, inp["entropy"], pub=bad)[1] == 3
 
 
 def test_msm_2_pow_20_linearity_and_splitting(api):

@@ -428,6 +428,31 @@ def test_msm_path_choice_is_invisible(api, gens, monkeypatch):
         monkeypatch.delenv("BP_B200_NO_MERGE"); monkeypatch.delenv("BP_B200_NO_PADSUM")
 
 
+def test_shift_table_only_generators(api, gens, monkeypatch):
+    """Generators above ~65k capacity (the reference's own configuration, BulletproofGens::new(819200, 1) at
+    src/gadget_vsmt_2.rs:290, needs 262144) carry the 15-bit shift table but no direct 8-bit tables: commitments through the sorted
+    path, every inner-product round on folded generators.  Forced here at small capacity; the proofs must be the bytes the
+    fully tabulated generators produce."""
+    from bulletproofs_r1cs_gadgets_b200 import workloads
+    monkeypatch.setenv("BP_B200_NO_DIRECT_TABLE", "1")
+    lean = api.Gens(256)
+    monkeypatch.delenv("BP_B200_NO_DIRECT_TABLE")
+    for wl in (workloads.Mimc(gens, rounds=5), workloads.PoseidonHash2(gens, api.SBOX_INVERSE, params=api.PoseidonParams(6, 2, 2, 3)),
+               workloads.Vsmt2(gens, depth=2, params=api.PoseidonParams(6, 2, 2, 3))):
+        inp = wl.inputs(0, 3)
+        want = wl.circuit.prove_batch(gens, wl.label, inp["v"], inp["v_blinding"], inp["entropy"], pub=inp["pub"])
+        for min_rows in ("0", "1000000000"):  # sorted path for the commitments / bucket method on the generators
+            monkeypatch.setenv("BP_B200_SORTED_MIN_ROWS", min_rows)
+            V, P, st = wl.circuit.prove_batch(lean, wl.label, inp["v"], inp["v_blinding"], inp["entropy"], pub=inp["pub"])
+            assert not st.any() and V.tobytes() == want[0].tobytes() and P.tobytes() == want[1].tobytes(), (wl.name, min_rows)
+            assert not wl.circuit.verify_batch(lean, wl.label, V, P, inp["entropy"], pub=inp["pub"]).any()
+            stc, comb = wl.circuit.verify_batch_combined(lean, wl.label, V, P, inp["entropy"], pub=inp["pub"])
+            assert comb == 0 and not stc.any()
+            bad = inp["pub"].copy(); bad[2, 0, 1] ^= 2
+            assert wl.circuit.verify_batch(lean, wl.label, V, P, inp["entropy"], pub=bad).tolist() == [0, 0, 3]
+        monkeypatch.delenv("BP_B200_SORTED_MIN_ROWS")
+
+
 def test_combined_verification(api, gens):
     """cross-proof batched verification: one combined verdict for the batch, per-proof status for structural failures only"""
     from bulletproofs_r1cs_gadgets_b200 import workloads
