@@ -148,7 +148,7 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
-def timed_device_batches(lib, api, gens, wl, inp_np, reps, dev):
+def timed_device_batches(lib, api, gens, wl, inp_np, reps, dev, warm=3):
     """one plain bp_prove_batch_device call per rep on device-resident inputs: (ms per call, V, proofs) -- the small configurations"""
     import ctypes as C
     import torch
@@ -164,7 +164,7 @@ def timed_device_batches(lib, api, gens, wl, inp_np, reps, dev):
                                        _ptr(d["entropy"]), _ptr(d.get("aux")), _ptr(d.get("pub")), None, None, None, _ptr(dV), _ptr(dP), _ptr(dS),
                                        C.c_void_p(torch.cuda.current_stream().cuda_stream))
         assert rc == 0, rc
-    for _ in range(3):
+    for _ in range(warm):
         run()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -266,6 +266,18 @@ def extra_configs(args, lib, api, workloads, parallel, gens32k, wl5, dev, world,
         rejected = (sb[Bv // 2] == 3 and not np.delete(sb, Bv // 2).any()) if name == "verify_per_proof" else int(dC.item()) == 3
         out[name] = {"verifications_per_s": Bv / ms * 1e3, "ms_per_step": ms, "batch": Bv, "depth": 32, "all_valid_accepted": bool(good), "one_wrong_root_rejected": bool(rejected)}
     del d, dV, dP, dpub, dbad
+    # the reference's OWN test configuration (src/gadget_vsmt_2.rs:23,262-399): TreeDepth = 253, n = 143704, N = 262144 generators
+    # (shift table only), m = 511; byte parity with the C oracle is tests/test_gpu.py::test_vsmt2_depth253_reference_configuration
+    g18 = api.Gens(1 << 18)
+    wl253 = workloads.Vsmt2(g18, depth=253)
+    Bd = 64
+    inp = wl253.inputs(0, Bd, with_root=False)
+    ms, dV, dP = timed_device_batches(lib, api, g18, wl253, {k: inp[k] for k in ("v", "v_blinding", "entropy")}, 1, dev, warm=1)
+    pub = torch.from_numpy(wl253.roots_batch(inp["v"])).to(dev)
+    okc, oks = combined_verify_device(lib, api, g18, wl253.circuit, wl253.label, dV, dP, torch.from_numpy(inp["entropy"]).to(dev), pub, dev, piece=Bd)
+    out["vsmt2_depth253_reference_config"] = {"proofs_per_s": Bd / ms * 1e3, "ms_per_step": ms, "batch": Bd, "n": wl253.circuit.n, "N": 1 << 18, "m": wl253.circuit.m,
+                                               "proof_bytes": wl253.circuit.proof_len, "verified_combined": bool(okc and oks)}
+    del g18, wl253, dV, dP, pub
     # config 3: ristretto MSM microbenchmark, one instance over the first 2^k generators of chain G, uniform scalars
     import hashlib
     msm = {}
