@@ -211,12 +211,36 @@ __global__ void __launch_bounds__(SORT2_THREADS, 2) sort_coarse_kernel(RowMap rm
   const int8_t *drow = dig + inst * dig_inst_stride;
   uint32_t *out = tmp + inst * items_stride;
   // pass 0: fine histogram of the whole instance -> bucket offsets (global) and coarse cursors
+  // Both passes stream the instance's digit rows through shared memory in tiles of SORT2_THREADS rows (x 48 contiguous bytes):
+  // ONE asynchronous bulk copy per tile (cp.async.bulk, the TMA engine's 1-D form) issued by thread 0 and tracked by an
+  // mbarrier; the copy of the next tile is issued as soon as every thread has taken its row into registers, so it is in flight
+  // while the block works on the current one.
+  __shared__ alignas(128) int8_t trows[SORT2_THREADS * SB_ROW_BYTES];
+  __shared__ alignas(8) uint64_t tbar_mem;
+  const uint32_t tbar = smem_addr32(&tbar_mem), tdst = smem_addr32(trows);
+  uint32_t tphase = 0;
+  auto fetch_tile = [&](long t0) {  // thread 0 only
+    const long left = rows - t0, cnt = left < SORT2_THREADS ? left : SORT2_THREADS;
+    mbar_arrive_expect_tx(tbar, (uint32_t)(cnt * SB_ROW_BYTES));
+    bulk_copy_g2s(tdst, drow + t0 * SB_ROW_BYTES, (uint32_t)(cnt * SB_ROW_BYTES), tbar);
+  };
+  if (tid == 0) { mbar_init(tbar, 1); mbar_fence_init(); if (rows > 0) fetch_tile(0); }
   for (int b = tid; b < SB_BUCKETS; b += SORT2_THREADS) buf[b] = 0;
   __syncthreads();
-  for (long r = tid; r < rows; r += SORT2_THREADS) {
-    int16_t d[24]; load_digits13(d, drow + r * SB_ROW_BYTES);
+  for (long t0 = 0; t0 < rows; t0 += SORT2_THREADS) {
+    mbar_wait(tbar, tphase); tphase ^= 1;
+    int16_t d[24];
+    const bool have = t0 + tid < rows;
+    if (have) load_digits13(d, trows + (long)tid * SB_ROW_BYTES);
+    __syncthreads();  // rows are in registers: the buffer is free
+    if (tid == 0) {   // next tile of this pass, or the first tile of pass 1
+      fence_proxy_async_smem();
+      fetch_tile(t0 + SORT2_THREADS < rows ? t0 + SORT2_THREADS : 0);
+    }
+    if (have) {
 #pragma unroll
-    for (int w = 0; w < SB_WINDOWS; w++) if (d[w]) atomicAdd(&buf[(d[w] < 0 ? -d[w] : d[w]) - 1], 1u);
+      for (int w = 0; w < SB_WINDOWS; w++) if (d[w]) atomicAdd(&buf[(d[w] < 0 ? -d[w] : d[w]) - 1], 1u);
+    }
   }
   __syncthreads();
   {
@@ -227,7 +251,7 @@ __global__ void __launch_bounds__(SORT2_THREADS, 2) sort_coarse_kernel(RowMap rm
     if (tid < SORT_GROUPS) ccur[tid] = buf[tid * SORT_FINE];
   }
   __syncthreads();
-  // pass 1: tiles of SORT2_THREADS rows, one row per thread
+  // pass 1: tiles of SORT2_THREADS rows, one row per thread (the first tile's copy was issued at the end of pass 0)
   for (long t0 = 0; t0 < rows; t0 += SORT2_THREADS) {
     for (int i = tid; i < SORT2_WC_WORDS; i += SORT2_THREADS) wc[i] = 0;
     __syncthreads();
@@ -235,15 +259,17 @@ __global__ void __launch_bounds__(SORT2_THREADS, 2) sort_coarse_kernel(RowMap rm
     uint32_t code[SB_WINDOWS];  // sign << 31 | bucket << 16 | rank within (tile, coarse group, warp); ~0 = no item
 #pragma unroll
     for (int w = 0; w < SB_WINDOWS; w++) code[w] = 0xffffffffu;
+    mbar_wait(tbar, tphase); tphase ^= 1;
     if (r < rows) {
-      int16_t d[24]; load_digits13(d, drow + r * SB_ROW_BYTES);
+      int16_t d[24]; load_digits13(d, trows + (long)tid * SB_ROW_BYTES);
 #pragma unroll
       for (int w = 0; w < SB_WINDOWS; w++) if (d[w]) {
         const uint32_t neg = d[w] < 0; const uint32_t b = (uint32_t)(neg ? -d[w] : d[w]) - 1;
         code[w] = (neg << 31) | (b << 16) | atomicAdd(&wc[(b >> SORT_FINE_BITS) * SORT2_WC_STRIDE + wid], 1u);
       }
     }
-    __syncthreads();
+    __syncthreads();  // every row of the tile is in registers: the buffer is free for the next tile
+    if (tid == 0 && t0 + SORT2_THREADS < rows) { fence_proxy_async_smem(); fetch_tile(t0 + SORT2_THREADS); }
     const uint32_t ttotal = block_scan_excl<SORT2_WC_PER, SORT2_THREADS>(wc, warp_tot);
     if (r < rows) {
       const uint32_t g = (uint32_t)row_gen(rmap, r + inst * rmap.inst_off) * SB_WINDOWS;

@@ -1661,6 +1661,13 @@ struct KSortBucketsSerial {
 #ifndef BP_OCC_SORTED
 #define BP_OCC_SORTED 4
 #endif
+#ifndef BP_TMA_STAGE
+// 1: table entries staged in shared memory by per-lane cp.async.bulk copies.  MEASURED SLOWER (KBucketAccumulate 934 -> 1135 ms
+// per 2731-proof chunk, profiles/r02_tma_entry_staging_negative_result.json): UBLKCP is a warp-uniform instruction, so a per-lane
+// 96-byte gather becomes an ELECT loop of ~9 instructions per lane and item.  Kept for the record; the bulk-copy engine is used
+// where one thread moves a whole tile (the digit tiles of the bucket sort, k_sorted.cu).
+#define BP_TMA_STAGE 0
+#endif
 struct KBucketAccumulate {
   static constexpr int kBlock = 128, kMinBlocks = BP_OCC_SORTED;
   static constexpr const char *kName = "KBucketAccumulate";
@@ -1670,6 +1677,9 @@ struct KBucketAccumulate {
     const uint32_t *off = sv.boff + inst * (SB_BUCKETS + 1);
     const uint32_t total = off[SB_BUCKETS];
     const uint32_t k0 = s * SB_SEG;
+#if defined(__CUDA_ARCH__) && BP_TMA_STAGE
+    staged(inst, s, off, total, k0);
+#else
     if (k0 >= total) return;
     const uint32_t k1 = k0 + SB_SEG < total ? k0 + SB_SEG : total;
     int lo = 0, hi = SB_BUCKETS;  // largest b with off[b] <= k0 (then off[b + 1] > k0)
@@ -1691,7 +1701,68 @@ struct KBucketAccumulate {
       ge_madd<true>(acc, acc, qc, (int)(cur >> 31));  // the kernel's one addition site: field multiplications expanded in place
     }
     store_struct(&ps[b], acc);
+#endif
   }
+#if defined(__CUDA_ARCH__) && BP_TMA_STAGE
+  // Table entries staged in shared memory by the copy engine.  Each thread's next two entries (96 bytes each, at random rows of
+  // the shift table) are fetched by cp.async.bulk into a two-stage ring in shared memory and completion is tracked by one
+  // mbarrier per warp and stage; the addition of item k runs while the entries of items k+1 and k+2 are in flight.  Against the
+  // register-load form: the prefetch needs no registers (24 fewer live across the addition), it is two additions deep instead
+  // of one, and the LSU issues one bulk request per entry instead of six 16-byte loads.  Every lane of a warp makes exactly
+  // SB_SEG passes (lanes past the end of their list only arrive at the barriers), so barrier phases stay in step.
+  __device__ __forceinline__ void staged(long inst, uint32_t s, const uint32_t *off, uint32_t total, uint32_t k0) const {
+    __shared__ alignas(128) ge_niels stage[2][kBlock];
+    __shared__ alignas(8) uint64_t bars[2][kBlock / 32];
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned mask = __activemask();
+    const uint32_t bar0 = smem_addr32(&bars[0][warp]), bar1 = smem_addr32(&bars[1][warp]);
+    const uint32_t slot0 = smem_addr32(&stage[0][threadIdx.x]), slot1 = smem_addr32(&stage[1][threadIdx.x]);
+    if (lane == (unsigned)(__ffs(mask) - 1)) { mbar_init(bar0, __popc(mask)); mbar_init(bar1, __popc(mask)); mbar_fence_init(); }
+    __syncwarp(mask);
+    const uint32_t k1 = k0 >= total ? k0 : (k0 + SB_SEG < total ? k0 + SB_SEG : total);
+    uint32_t b = 0, next = 0;
+    if (k1 > k0) {
+      int lo = 0, hi = SB_BUCKETS;  // largest b with off[b] <= k0 (then off[b + 1] > k0)
+      while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (off[mid] <= k0) lo = mid; else hi = mid; }
+      b = (uint32_t)lo; next = off[b + 1];
+    }
+    const uint32_t *it = sv.items + inst * sv.items_stride;
+    ge_p3 *ps = psum + inst * sv.slices_cap + s;
+    ge_p3 acc; ge_identity(acc);
+    uint32_t item0 = 0, item1 = 0;  // items whose entries sit in stage 0 / 1
+    if (k0 < k1) { item0 = it[k0]; mbar_arrive_expect_tx(bar0, (uint32_t)sizeof(ge_niels)); bulk_copy_g2s(slot0, &sg[item0 & 0x7fffffffu], (uint32_t)sizeof(ge_niels), bar0); }
+    else mbar_arrive(bar0);
+    if (k0 + 1 < k1) { item1 = it[k0 + 1]; mbar_arrive_expect_tx(bar1, (uint32_t)sizeof(ge_niels)); bulk_copy_g2s(slot1, &sg[item1 & 0x7fffffffu], (uint32_t)sizeof(ge_niels), bar1); }
+    else mbar_arrive(bar1);
+#pragma unroll 1
+    for (uint32_t j = 0; j < SB_SEG; j++) {
+      const uint32_t k = k0 + j, st = j & 1;
+      const uint32_t bar = st ? bar1 : bar0, slot = st ? slot1 : slot0;
+      mbar_wait(bar, (j >> 1) & 1);
+      const uint32_t cur = st ? item1 : item0;
+      ge_niels qc;
+      if (k < k1) load_struct(qc, &stage[st][threadIdx.x]);
+      __syncwarp(mask);
+      fence_proxy_async_smem();  // the slot is about to be rewritten by the copy engine
+      if (k + 2 < k1) {
+        const uint32_t nx = it[k + 2];
+        if (st) item1 = nx; else item0 = nx;
+        mbar_arrive_expect_tx(bar, (uint32_t)sizeof(ge_niels));
+        bulk_copy_g2s(slot, &sg[nx & 0x7fffffffu], (uint32_t)sizeof(ge_niels), bar);
+      } else {
+        mbar_arrive(bar);
+      }
+      if (k < k1) {
+        if (k == next) {
+          store_struct(&ps[b], acc); ge_identity(acc);
+          do { b++; next = off[b + 1]; } while (next == k);
+        }
+        ge_madd<true>(acc, acc, qc, (int)(cur >> 31));  // the kernel's one addition site: field multiplications expanded in place
+      }
+    }
+    if (k1 > k0) store_struct(&ps[b], acc);
+  }
+#endif
 };
 // per group of 128 buckets: S = sum b_i, W = sum (local index + 1) * b_i   (running-sum trick); b_i = sum of its partials
 struct KBucketReduce {
