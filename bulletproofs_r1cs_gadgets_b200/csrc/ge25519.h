@@ -6,8 +6,8 @@
 #pragma once
 #include "fe25519.h"
 
-struct alignas(16) ge_p3 { fe X, Y, Z, T; };          // 128 B: x = X/Z, y = Y/Z, xy = T/Z
-struct alignas(16) ge_niels { fe ypx, ymx, xy2d; };   // affine: y+x, y-x, 2d*x*y   (96 B = three 32-byte sectors)
+struct alignas(32) ge_p3 { fe X, Y, Z, T; };          // 128 B: x = X/Z, y = Y/Z, xy = T/Z            (four 256-bit loads, hd.h)
+struct alignas(32) ge_niels { fe ypx, ymx, xy2d; };   // affine: y+x, y-x, 2d*x*y   (96 B = three 32-byte sectors = three 256-bit loads)
 struct ge_cached { fe YpX, YmX, Z, T2d; };
 struct ge_p1p1 { fe X, Y, Z, T; };
 

@@ -69,7 +69,37 @@ HD void store_struct(T *dst, const T &src) {
   *dst = src;
 #endif
 }
-
+// The same in 256-bit granules -- LDG.E.256 / STG.E.256, a width that exists from sm_100 on (PTX ld.global.v8.u32) -- for structs
+// of 32-byte alignment in GLOBAL memory.  Used where a kernel streams whole points through a read-modify-write (the per-proof
+// bucket kernel: -9 %); measured neutral for the table gathers of the sorted path and worse for the chained loads of the bucket
+// reduction, which keep the 128-bit form.
+template <typename T>
+HD void load_struct256(T &dst, const T *src) {
+#if defined(__CUDA_ARCH__)
+  static_assert(sizeof(T) % 32 == 0 && alignof(T) >= 32, "32-byte granules");
+  uint32_t *d = reinterpret_cast<uint32_t *>(&dst);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T) / 32); i++)
+    asm volatile("ld.global.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(d[8 * i]), "=r"(d[8 * i + 1]), "=r"(d[8 * i + 2]), "=r"(d[8 * i + 3]), "=r"(d[8 * i + 4]), "=r"(d[8 * i + 5]), "=r"(d[8 * i + 6]), "=r"(d[8 * i + 7])
+                 : "l"(reinterpret_cast<const char *>(src) + 32 * i) : "memory");
+#else
+  dst = *src;
+#endif
+}
+template <typename T>
+HD void store_struct256(T *dst, const T &src) {
+#if defined(__CUDA_ARCH__)
+  static_assert(sizeof(T) % 32 == 0 && alignof(T) >= 32, "32-byte granules");
+  const uint32_t *s = reinterpret_cast<const uint32_t *>(&src);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T) / 32); i++)
+    asm volatile("st.global.v8.u32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(reinterpret_cast<char *>(dst) + 32 * i), "r"(s[8 * i]), "r"(s[8 * i + 1]),
+                 "r"(s[8 * i + 2]), "r"(s[8 * i + 3]), "r"(s[8 * i + 4]), "r"(s[8 * i + 5]), "r"(s[8 * i + 6]), "r"(s[8 * i + 7]) : "memory");
+#else
+  *dst = src;
+#endif
+}
 // ---- asynchronous bulk copies (the TMA engine's 1-D form, cp.async.bulk) with mbarrier completion: sm_90+ PTX ----
 #if defined(__CUDACC__)
 __device__ __forceinline__ uint32_t smem_addr32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }

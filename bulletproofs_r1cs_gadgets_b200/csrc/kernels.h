@@ -171,7 +171,7 @@ struct KMsmAccumulate {
     ge_p3 *bk = buckets + tid * MSM_BUCKETS;
     {
       ge_p3 id; ge_identity(id);
-      for (int d = 0; d < MSM_BUCKETS; d++) store_struct(&bk[d], id);
+      for (int d = 0; d < MSM_BUCKETS; d++) store_struct256(&bk[d], id);
     }
     long total = 0;
     for (int s = 0; s < nseg; s++) total += seg[s].count;
@@ -199,11 +199,11 @@ struct KMsmAccumulate {
           int d = drow[(row + t) * 32];
           if (d != 0) {
             int neg = d < 0; int idx = (neg ? -d : d) - 1;
-            ge_p3 qp; load_struct(qp, &bases[t]);
+            ge_p3 qp; load_struct256(qp, &bases[t]);   // 256-bit loads / stores (hd.h): this loop is a read-modify-write of whole points
             ge_cached c; ge_to_cached<true>(c, qp);
-            ge_p3 acc; load_struct(acc, &bk[idx]);
+            ge_p3 acc; load_struct256(acc, &bk[idx]);
             ge_add_cached_f(acc, acc, c, neg);
-            store_struct(&bk[idx], acc);
+            store_struct256(&bk[idx], acc);
           }
         }
       }
@@ -212,7 +212,7 @@ struct KMsmAccumulate {
     // window sum = sum_d (d+1) * bucket[d] by the running-sum trick
     ge_p3 run, tot; ge_identity(run); ge_identity(tot);
     for (int d = MSM_BUCKETS - 1; d >= 0; d--) {
-      ge_p3 b; load_struct(b, &bk[d]);
+      ge_p3 b; load_struct256(b, &bk[d]);
       ge_add_f(run, run, b);
       ge_add_f(tot, tot, run);
     }
@@ -1741,7 +1741,7 @@ struct KBucketAccumulate {
       mbar_wait(bar, (j >> 1) & 1);
       const uint32_t cur = st ? item1 : item0;
       ge_niels qc;
-      if (k < k1) load_struct(qc, &stage[st][threadIdx.x]);
+      if (k < k1) qc = stage[st][threadIdx.x];  // shared memory: plain copy (load_struct is a global-memory load)
       __syncwarp(mask);
       fence_proxy_async_smem();  // the slot is about to be rewritten by the copy engine
       if (k + 2 < k1) {
