@@ -1,8 +1,9 @@
 // Device-side sparse Merkle tree: the batched analogue of VanillaSparseMerkleTree::{new,update,get}
 // (reference src/gadget_vsmt_2.rs:36-131).  The reference keeps a content-addressed HashMap hash -> (left, right) and walks
 // it one key at a time, 253 Poseidon hashes per update.  Here a node is addressed by its POSITION: heap key
-// 2^(depth-level) + (index >> level) (root = 1, leaves = 2^depth + index) in one open-addressing table in HBM
-// (8-byte key + 32-byte Montgomery scalar per slot); absent nodes are the empty-subtree hashes of their level.  A batch of
+// 2^(depth-level) + (index >> level) (root = 1, leaves = 2^depth + index) -- a 256-bit integer, since the reference's tree is
+// 253 levels deep (TreeDepth, src/gadget_vsmt_2.rs:23) -- in one open-addressing table in HBM (8-byte tag + 32-byte key +
+// 32-byte Montgomery scalar per slot); absent nodes are the empty-subtree hashes of their level.  A batch of
 // updates is hashed level by level, one thread per DISTINCT parent, so shared ancestors are hashed once; a batch of
 // lookups is one thread per (query, level) because every sibling's key is known from the index alone.
 #pragma once
@@ -60,29 +61,80 @@ HD scm poseidon_hash2_native(const PoseidonDev &pos, const scm &xl, const scm &x
 }
 
 // ------------------------------------------------------------------------------------------------ node table
-// open addressing, linear probing; key 0 = empty slot (heap keys are >= 1), capacity a power of two
-struct TreeTable { uint64_t *keys; scm *vals; uint64_t mask; };
-HD uint64_t tree_slot(uint64_t k, uint64_t mask) {  // splitmix64 finaliser
-  k ^= k >> 30; k *= 0xbf58476d1ce4e5b9ull; k ^= k >> 27; k *= 0x94d049bb133111ebull; k ^= k >> 31;
-  return k & mask;
+// 256-bit heap keys (little-endian words; bit 255 is never set: keys are below 2^254)
+struct tkey { uint64_t w[4]; };
+HD tkey tkey_leaf(const uint64_t idx[4], int depth) {  // 2^depth + idx
+  tkey k; for (int i = 0; i < 4; i++) k.w[i] = idx[i];
+  k.w[depth >> 6] |= 1ull << (depth & 63);
+  return k;
 }
-HD bool tree_lookup(const TreeTable &t, uint64_t key, scm &out) {
-  for (uint64_t s = tree_slot(key, t.mask);; s = (s + 1) & t.mask) {
-    uint64_t k = t.keys[s];
-    if (k == key) { load_struct(out, &t.vals[s]); return true; }
+HD tkey tkey_shr(const tkey &a, int n) {
+  tkey r; const int ws = n >> 6, bs = n & 63;
+  for (int i = 0; i < 4; i++) {
+    uint64_t v = i + ws < 4 ? a.w[i + ws] >> bs : 0;
+    if (bs && i + ws + 1 < 4) v |= a.w[i + ws + 1] << (64 - bs);
+    r.w[i] = v;
+  }
+  return r;
+}
+HD tkey tkey_child(const tkey &a, int right) {  // 2a + right
+  tkey r; r.w[3] = (a.w[3] << 1) | (a.w[2] >> 63); r.w[2] = (a.w[2] << 1) | (a.w[1] >> 63); r.w[1] = (a.w[1] << 1) | (a.w[0] >> 63);
+  r.w[0] = (a.w[0] << 1) | (uint64_t)right;
+  return r;
+}
+HD bool tkey_eq(const tkey &a, const tkey &b) { return a.w[0] == b.w[0] && a.w[1] == b.w[1] && a.w[2] == b.w[2] && a.w[3] == b.w[3]; }
+HD int tkey_bit(const uint64_t idx[4], int i) { return (int)((idx[i >> 6] >> (i & 63)) & 1); }
+HD uint64_t mix64(uint64_t k) {  // splitmix64 finaliser
+  k ^= k >> 30; k *= 0xbf58476d1ce4e5b9ull; k ^= k >> 27; k *= 0x94d049bb133111ebull; k ^= k >> 31;
+  return k;
+}
+HD uint64_t tkey_tag(const tkey &k) { return mix64(k.w[0] ^ mix64(k.w[1] ^ mix64(k.w[2] ^ mix64(k.w[3] + 0x9e3779b97f4a7c15ull)))) | 1ull; }  // never 0
+// Open addressing, linear probing, capacity a power of two.  A slot is claimed by a compare-and-swap on its 64-bit TAG (a hash of
+// the key, 0 = empty); the full key is stored beside it, its last word published LAST with TKEY_VALID set, so a reader that
+// meets an equal tag waits for the key before comparing (two different keys with equal tags are a 2^-64 event, handled).
+#define TKEY_VALID (1ull << 63)
+struct TreeTable { uint64_t *tags; tkey *keys; scm *vals; uint64_t mask; };
+HD bool tree_slot_holds(const TreeTable &t, uint64_t s, const tkey &key) {
+#if defined(__CUDA_ARCH__)
+  volatile uint64_t *kw = t.keys[s].w;
+  uint64_t w3;
+  while (!((w3 = kw[3]) & TKEY_VALID)) {}
+  return kw[0] == key.w[0] && kw[1] == key.w[1] && kw[2] == key.w[2] && (w3 & ~TKEY_VALID) == key.w[3];
+#else
+  const tkey &k = t.keys[s];
+  return k.w[0] == key.w[0] && k.w[1] == key.w[1] && k.w[2] == key.w[2] && (k.w[3] & ~TKEY_VALID) == key.w[3];
+#endif
+}
+HD bool tree_lookup(const TreeTable &t, const tkey &key, scm &out) {
+  const uint64_t tag = tkey_tag(key);
+  for (uint64_t s = tag & t.mask;; s = (s + 1) & t.mask) {
+    const uint64_t k = t.tags[s];
     if (k == 0) return false;
+    if (k == tag && tree_slot_holds(t, s, key)) { load_struct(out, &t.vals[s]); return true; }
   }
 }
 // returns 1 when the key was new.  Keys of one launch are distinct, so the value store needs no ordering.
-HD int tree_insert(const TreeTable &t, uint64_t key, const scm &v) {
-  for (uint64_t s = tree_slot(key, t.mask);; s = (s + 1) & t.mask) {
+HD int tree_insert(const TreeTable &t, const tkey &key, const scm &v) {
+  const uint64_t tag = tkey_tag(key);
+  for (uint64_t s = tag & t.mask;; s = (s + 1) & t.mask) {
 #if defined(__CUDA_ARCH__)
-    uint64_t old = atomicCAS((unsigned long long *)&t.keys[s], 0ull, (unsigned long long)key);
+    const uint64_t old = atomicCAS((unsigned long long *)&t.tags[s], 0ull, (unsigned long long)tag);
 #else
-    uint64_t old = t.keys[s];
-    if (old == 0) t.keys[s] = key;
+    const uint64_t old = t.tags[s];
+    if (old == 0) t.tags[s] = tag;
 #endif
-    if (old == 0 || old == key) { store_struct(&t.vals[s], v); return old == 0; }
+    if (old == 0) {
+      t.keys[s].w[0] = key.w[0]; t.keys[s].w[1] = key.w[1]; t.keys[s].w[2] = key.w[2];
+#if defined(__CUDA_ARCH__)
+      __threadfence();
+      *(volatile uint64_t *)&t.keys[s].w[3] = key.w[3] | TKEY_VALID;
+#else
+      t.keys[s].w[3] = key.w[3] | TKEY_VALID;
+#endif
+      store_struct(&t.vals[s], v);
+      return 1;
+    }
+    if (old == tag && tree_slot_holds(t, s, key)) { store_struct(&t.vals[s], v); return 0; }
   }
 }
 HD void tree_count_add(unsigned long long *c, unsigned long long n) {
@@ -116,12 +168,12 @@ struct KTreeHashLevel {
   static constexpr int kBlock = 64, kMinBlocks = 1;
   static constexpr const char *kName = "KTreeHashLevel";
   TreeTable t; PoseidonDev pos; int sbox;
-  const uint64_t *pk; const int32_t *li, *ri; const scm *child_vals; const scm *empty_child; scm *out;
+  const tkey *pk; const int32_t *li, *ri; const scm *child_vals; const scm *empty_child; scm *out;
   HD void operator()(long j) const {
-    const uint64_t key = pk[j];
+    const tkey key = pk[j];
     scm l, r;
-    if (li[j] >= 0) load_struct(l, &child_vals[li[j]]); else if (!tree_lookup(t, 2 * key, l)) l = *empty_child;
-    if (ri[j] >= 0) load_struct(r, &child_vals[ri[j]]); else if (!tree_lookup(t, 2 * key + 1, r)) r = *empty_child;
+    if (li[j] >= 0) load_struct(l, &child_vals[li[j]]); else if (!tree_lookup(t, tkey_child(key, 0), l)) l = *empty_child;
+    if (ri[j] >= 0) load_struct(r, &child_vals[ri[j]]); else if (!tree_lookup(t, tkey_child(key, 1), r)) r = *empty_child;
     scm h = poseidon_hash2_native(pos, l, r, sbox);
     store_struct(&out[j], h);
   }
@@ -129,7 +181,7 @@ struct KTreeHashLevel {
 struct KTreeInsert {
   static constexpr int kBlock = 128, kMinBlocks = 1;
   static constexpr const char *kName = "KTreeInsert";
-  TreeTable t; const uint64_t *keys; const scm *vals; unsigned long long *count;
+  TreeTable t; const tkey *keys; const scm *vals; unsigned long long *count;
   HD void operator()(long i) const {
     scm v; load_struct(v, &vals[i]);
     if (tree_insert(t, keys[i], v)) tree_count_add(count, 1);
@@ -140,8 +192,8 @@ struct KTreeRehash {  // thread per slot of the old table
   static constexpr const char *kName = "KTreeRehash";
   TreeTable from, to;
   HD void operator()(long s) const {
-    uint64_t k = from.keys[s];
-    if (k == 0) return;
+    if (from.tags[s] == 0) return;
+    tkey k = from.keys[s]; k.w[3] &= ~TKEY_VALID;
     scm v; load_struct(v, &from.vals[s]);
     tree_insert(to, k, v);
   }
@@ -152,17 +204,18 @@ struct KTreeRehash {  // thread per slot of the old table
 struct KTreeGet {
   static constexpr int kBlock = 128, kMinBlocks = 1;
   static constexpr const char *kName = "KTreeGet";
-  TreeTable t; const scm *empty; const uint64_t *idx; int depth, order; uint8_t *leaves, *proofs;
+  TreeTable t; const scm *empty; const uint64_t *idx; int depth, order; uint8_t *leaves, *proofs;  // idx: 4 little-endian words per query
   HD void operator()(long tid) const {
     const long q = tid / (depth + 1); const int l = (int)(tid % (depth + 1));
-    const uint64_t leaf_key = (1ull << depth) + idx[q];
+    const tkey leaf_key = tkey_leaf(idx + 4 * q, depth);
     scm v;
     if (l == depth) {
       if (!tree_lookup(t, leaf_key, v)) v = empty[0];
       sc_tobytes(leaves + 32 * q, v);
       return;
     }
-    if (!tree_lookup(t, (leaf_key >> l) ^ 1, v)) v = empty[l];
+    tkey sib = tkey_shr(leaf_key, l); sib.w[0] ^= 1;
+    if (!tree_lookup(t, sib, v)) v = empty[l];
     const int pos_ = order == 0 ? depth - 1 - l : l;
     sc_tobytes(proofs + 32 * (q * depth + pos_), v);
   }
@@ -178,16 +231,22 @@ struct KTreeWitnessRows {
   HD void operator()(long tid) const {
     const int m = 2 * depth + 5;
     const long q = tid / (m + 1); const int j = (int)(tid % (m + 1));
-    const uint64_t leaf_key = (1ull << depth) + idx[q];
+    const tkey leaf_key = tkey_leaf(idx + 4 * q, depth);
     if (j == m) { if (pub) sc_tobytes(pub + 32 * q, *root); return; }
     uint8_t *out = v + 32 * (q * m + j);
     scm val;
     if (j == 0) { if (!tree_lookup(t, leaf_key, val)) val = empty[0]; }
-    else if (j <= depth) val = ((idx[q] >> (j - 1)) & 1) ? sc_one() : sc_zero();
-    else if (j <= 2 * depth) { const int l = j - depth - 1; if (!tree_lookup(t, (leaf_key >> l) ^ 1, val)) val = empty[l]; }
+    else if (j <= depth) val = tkey_bit(idx + 4 * q, j - 1) ? sc_one() : sc_zero();
+    else if (j <= 2 * depth) { const int l = j - depth - 1; tkey sib = tkey_shr(leaf_key, l); sib.w[0] ^= 1; if (!tree_lookup(t, sib, val)) val = empty[l]; }
     else val = j == 2 * depth + 2 ? sc_from_u64(101) : sc_zero();
     sc_tobytes(out, val);
   }
+};
+struct KTreeWidenIndices {  // 64-bit indices -> 4-word indices
+  static constexpr int kBlock = 128, kMinBlocks = 1;
+  static constexpr const char *kName = "KTreeWidenIndices";
+  const uint64_t *in; uint64_t *out;
+  HD void operator()(long i) const { out[4 * i] = in[i]; out[4 * i + 1] = 0; out[4 * i + 2] = 0; out[4 * i + 3] = 0; }
 };
 // Poseidon_hash_2 of count independent pairs (tree building blocks; also the throughput probe of the hash itself)
 struct KPoseidonHash2Batch {

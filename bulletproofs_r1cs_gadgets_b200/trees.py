@@ -68,7 +68,8 @@ class DeviceVsmt2:
     """Batched VanillaSparseMerkleTree on the GPU (bp_vsmt2_* of include/bp_b200.h, kernels in csrc/tree_kernels.h):
     `update_batch` = many `update`s in one level-by-level pass, `get_batch` = many `get`s, `witness_rows` = the committed
     values of the membership circuit for a batch of leaves (reference src/gadget_vsmt_2.rs:63-131,296-330).  Indices are
-    integers below 2**depth, depth <= 63.  Same method names and orientation as the host mirror above."""
+    integers below 2**depth, depth <= 253 (the reference's TreeDepth; 256-bit keys through the *_wide entry points).  Same
+    method names and orientation as the host mirror above."""
 
     def __init__(self, hash_params, depth=32, sbox=api.SBOX_INVERSE):
         self.depth, self.hash_params = depth, hash_params
@@ -83,7 +84,11 @@ class DeviceVsmt2:
 
     @staticmethod
     def _idx(idx):
-        return np.ascontiguousarray(np.asarray(idx, dtype=np.uint64).reshape(-1))
+        """integers -> uint8 [count][32], little-endian 256-bit indices"""
+        idx = [int(i) for i in (idx.tolist() if isinstance(idx, np.ndarray) else idx)]
+        if not idx:
+            return np.zeros((0, 32), dtype=np.uint8)
+        return np.frombuffer(b"".join(i.to_bytes(32, "little") for i in idx), dtype=np.uint8).reshape(-1, 32).copy()
 
     @property
     def root(self):
@@ -112,8 +117,8 @@ class DeviceVsmt2:
         vals = api._np_u8(vals).reshape(-1, 32)
         assert len(vals) == len(idx)
         root = (C.c_uint8 * 32)()
-        api._check(api.load().bp_vsmt2_update_batch(self._h, C.c_uint32(len(idx)), idx.ctypes.data_as(C.POINTER(C.c_uint64)),
-                                                    vals.ctypes.data_as(api.u8p), root), "vsmt2_update_batch")
+        api._check(api.load().bp_vsmt2_update_batch_wide(self._h, C.c_uint32(len(idx)), idx.ctypes.data_as(api.u8p),
+                                                         vals.ctypes.data_as(api.u8p), root), "vsmt2_update_batch_wide")
         return int.from_bytes(bytes(root), "little")
 
     def update(self, idx, val):
@@ -124,8 +129,8 @@ class DeviceVsmt2:
         idx = self._idx(idx)
         leaves = np.zeros((len(idx), 32), dtype=np.uint8)
         proofs = np.zeros((len(idx), self.depth, 32), dtype=np.uint8)
-        api._check(api.load().bp_vsmt2_get_batch(self._h, C.c_uint32(len(idx)), idx.ctypes.data_as(C.POINTER(C.c_uint64)),
-                                                 leaves.ctypes.data_as(api.u8p), proofs.ctypes.data_as(api.u8p)), "vsmt2_get_batch")
+        api._check(api.load().bp_vsmt2_get_batch_wide(self._h, C.c_uint32(len(idx)), idx.ctypes.data_as(api.u8p),
+                                                      leaves.ctypes.data_as(api.u8p), proofs.ctypes.data_as(api.u8p)), "vsmt2_get_batch_wide")
         return leaves, proofs
 
     def get(self, idx, proof=None):
@@ -139,16 +144,18 @@ class DeviceVsmt2:
         idx = self._idx(idx)
         v = np.zeros((len(idx), 2 * self.depth + 5, 32), dtype=np.uint8)
         pub = np.zeros((len(idx), 1, 32), dtype=np.uint8)
-        api._check(api.load().bp_vsmt2_witness_batch(self._h, C.c_uint32(len(idx)), idx.ctypes.data_as(C.POINTER(C.c_uint64)),
-                                                     v.ctypes.data_as(api.u8p), pub.ctypes.data_as(api.u8p)), "vsmt2_witness_batch")
+        api._check(api.load().bp_vsmt2_witness_batch_wide(self._h, C.c_uint32(len(idx)), idx.ctypes.data_as(api.u8p),
+                                                          v.ctypes.data_as(api.u8p), pub.ctypes.data_as(api.u8p)), "vsmt2_witness_batch_wide")
         return v, pub
 
     def witness_rows_device(self, d_idx, d_v, d_pub=None, stream=None):
-        """device-resident variant: d_idx torch int64/uint64 [count], d_v torch uint8 [count][2*depth+5][32], d_pub uint8 [count][1][32]"""
-        count = int(d_idx.numel())
-        api._check(api.load().bp_vsmt2_witness_batch_device(self._h, C.c_uint32(count), C.c_void_p(d_idx.data_ptr()), C.c_void_p(d_v.data_ptr()),
-                                                            C.c_void_p(d_pub.data_ptr()) if d_pub is not None else None,
-                                                            C.c_void_p(stream) if stream else None), "vsmt2_witness_batch_device")
+        """device-resident variant: d_idx torch int64/uint64 [count] (depth <= 63) or uint8 [count][32] (256-bit little-endian indices),
+        d_v torch uint8 [count][2*depth+5][32], d_pub uint8 [count][1][32]"""
+        wide = d_idx.dim() == 2
+        count = int(d_idx.shape[0])
+        fn = api.load().bp_vsmt2_witness_batch_wide_device if wide else api.load().bp_vsmt2_witness_batch_device
+        api._check(fn(self._h, C.c_uint32(count), C.c_void_p(d_idx.data_ptr()), C.c_void_p(d_v.data_ptr()),
+                      C.c_void_p(d_pub.data_ptr()) if d_pub is not None else None, C.c_void_p(stream) if stream else None), "vsmt2_witness_batch_device")
 
 
 def poseidon_hash_2_batch(hash_params, xl, xr, sbox=api.SBOX_INVERSE):

@@ -266,6 +266,13 @@ int32_t bp_vsmt2_get_batch(const bp_vsmt2 *t, uint32_t count, const uint64_t *id
  * _device: device pointers (idx uint64 [count]), asynchronous on `stream`. */
 int32_t bp_vsmt2_witness_batch(const bp_vsmt2 *t, uint32_t count, const uint64_t *idx, uint8_t *v, uint8_t *pub);
 int32_t bp_vsmt2_witness_batch_device(const bp_vsmt2 *t, uint32_t count, const uint64_t *d_idx, uint8_t *d_v, uint8_t *d_pub, void *stream);
+/* The same with 256-bit indices, idx32 [count][32] little-endian integers below 2^depth: the reference's tree is TreeDepth = 253
+ * levels deep and keyed by Scalars (src/gadget_vsmt_2.rs:23,63-131); bp_vsmt2_new accepts depth <= 253.  The 64-bit forms above
+ * are conveniences for depth <= 63. */
+int32_t bp_vsmt2_update_batch_wide(bp_vsmt2 *t, uint32_t count, const uint8_t *idx32, const uint8_t *vals, uint8_t root_out[32]);
+int32_t bp_vsmt2_get_batch_wide(const bp_vsmt2 *t, uint32_t count, const uint8_t *idx32, uint8_t *leaves, uint8_t *proofs);
+int32_t bp_vsmt2_witness_batch_wide(const bp_vsmt2 *t, uint32_t count, const uint8_t *idx32, uint8_t *v, uint8_t *pub);
+int32_t bp_vsmt2_witness_batch_wide_device(const bp_vsmt2 *t, uint32_t count, const uint8_t *d_idx32, uint8_t *d_v, uint8_t *d_pub, void *stream);
 /* Poseidon_hash_2 (src/gadget_poseidon.rs:428-443) of count independent pairs on the device; host buffers [count][32] */
 int32_t bp_poseidon_hash_2_batch(const bp_poseidon_params *p, int32_t sbox, uint32_t count, const uint8_t *xl, const uint8_t *xr, uint8_t *out);
 

@@ -70,6 +70,11 @@ def test_sparse_merkle_tree_and_membership_from_a_real_tree(api, gens): E.test_s
 def test_device_tree_small(api, gens): E.test_device_tree(api, gens)
 def test_device_tree_depth5(api, gens): E.test_device_tree_depth5(api, gens)
 def test_device_tree_depth63(api, gens): E.test_device_tree_depth63(api, gens)
+def test_device_tree_depth253(api, gens): E.test_device_tree_depth253(api, gens)
+def test_device_tree_depth253_reference_parameters(api, gens, oracle_lib):
+    """the reference's own tree (TreeDepth = 253, src/gadget_vsmt_2.rs:23, Poseidon 4+140+4 inverse) on the device against the oracle's
+    one-key-at-a-time tree hashing with the C oracle: roots, leaves, sibling paths, witness rows"""
+    E.test_device_tree(api, gens, oracle_lib=oracle_lib, depth=253, params=(6, 4, 4, 140), nkeys=8, prove=False, seed=2530)
 def test_device_tree_reference_parameters(api, gens_big, oracle_lib):
     """depth 32, Poseidon 4+140+4 inverse: device tree vs the oracle's one-key-at-a-time tree hashing with the C oracle; membership proofs from the tree"""
     E.test_device_tree(api, gens_big, oracle_lib=oracle_lib, depth=32, params=(6, 4, 4, 140), nkeys=24, prove=True, seed=901)

@@ -244,7 +244,8 @@ def test_sparse_merkle_tree_and_membership_from_a_real_tree(api, gens):
 
 
 def test_device_tree_depth5(api, gens): test_device_tree(api, gens, depth=5, nkeys=11, prove=False)
-def test_device_tree_depth63(api, gens): test_device_tree(api, gens, depth=63, nkeys=9, prove=False, seed=77)  # widest index the device keys hold
+def test_device_tree_depth63(api, gens): test_device_tree(api, gens, depth=63, nkeys=9, prove=False, seed=77)  # widest index of the 64-bit entry points
+def test_device_tree_depth253(api, gens): test_device_tree(api, gens, depth=253, nkeys=9, prove=False, seed=253)  # the reference's TreeDepth: 256-bit keys
 
 
 def test_device_tree(api, gens, oracle_lib=None, depth=3, params=(6, 2, 2, 3), nkeys=6, prove=True, seed=900):
