@@ -46,6 +46,43 @@ u8p = C.POINTER(C.c_uint8)
 _lib = None
 
 
+_HEADER = os.path.join(_PKG, "..", "include", "bp_b200.h")
+_SCALAR_TYPES = {"int32_t": C.c_int32, "uint32_t": C.c_uint32, "int64_t": C.c_int64, "uint64_t": C.c_uint64, "size_t": C.c_size_t, "int": C.c_int}
+
+
+def header_prototypes(header=_HEADER):
+    """[(name, return type, [parameter type, ...])] of every function include/bp_b200.h declares, as C type strings"""
+    import re
+    src = re.sub(r"/\*.*?\*/", "", open(header).read(), flags=re.S)
+    out = []
+    for ret, name, args in re.findall(r"\n\s*([a-z0-9_]+(?:\s*\*)?)\s+(bp_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src):
+        params = []
+        for prm in args.split(","):
+            prm = " ".join(prm.split())
+            if prm in ("void", ""):
+                continue
+            if "*" in prm or "[" in prm:
+                params.append("pointer")
+            else:
+                params.append(prm.rsplit(" ", 1)[0].replace("const ", ""))
+        out.append((name, " ".join(ret.split()), params))
+    return out
+
+
+def _declare_prototypes(lib):
+    """restype / argtypes of every entry point, taken from the header itself: ctypes then converts and range-checks every scalar
+    argument (a bare Python int would otherwise travel as a C int) and refuses a call with the wrong number of arguments.
+    Pointers are declared as void* (arrays, ctypes pointers, integer addresses and None all convert)."""
+    if not os.path.exists(_HEADER):
+        raise RuntimeError("bp_b200: %s not found (the Python layer takes the C prototypes from it)" % _HEADER)
+    for name, ret, params in header_prototypes():
+        fn = getattr(lib, name, None)
+        if fn is None:
+            raise RuntimeError("bp_b200: %s is declared in include/bp_b200.h but missing from the library" % name)
+        fn.restype = None if ret == "void" else _SCALAR_TYPES[ret]
+        fn.argtypes = [C.c_void_p if p == "pointer" else (bp_var if p == "bp_var" else _SCALAR_TYPES[p]) for p in params]
+
+
 def load(path=None):
     """Load the shared library (once).  `path` is for the test-only emulation build."""
     global _lib
@@ -56,18 +93,7 @@ def load(path=None):
         raise RuntimeError("bp_b200: %s not found -- build it with `python -c 'import __graft_entry__ as g; g.build()'`; "
                            "there is no CPU fallback" % path)
     lib = C.CDLL(path)
-    lib.bp_launch_count.restype = C.c_int64
-    lib.bp_cs_num_constraints.restype = C.c_uint64
-    lib.bp_cs_num_multipliers.restype = C.c_uint64
-    lib.bp_cs_num_commitments.restype = C.c_uint64
-    lib.bp_cs_proof_len.restype = C.c_size_t
-    lib.bp_circuit_proof_len.restype = C.c_size_t
-    for f in ("bp_gens_capacity", "bp_circuit_num_multipliers", "bp_circuit_num_constraints", "bp_circuit_num_commitments", "bp_circuit_num_aux", "bp_circuit_num_public"):
-        getattr(lib, f).restype = C.c_uint32
-    lib.bp_gens_free.restype = None
-    lib.bp_cs_free.restype = None
-    lib.bp_circuit_free.restype = None
-    lib.bp_poseidon_params_free.restype = None
+    _declare_prototypes(lib)
     _lib = lib
     return lib
 

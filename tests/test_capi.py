@@ -31,6 +31,21 @@ def test_library_exports_every_declared_symbol(product_so):
     assert lib.bp_version() >= 1
 
 
+def test_python_layer_declares_every_prototype(product_so):
+    """the ctypes layer takes argtypes/restype from the header: every declared function is covered, arity is enforced"""
+    from bulletproofs_r1cs_gadgets_b200 import api
+    protos = api.header_prototypes()
+    assert sorted(n for n, _, _ in protos) == declared_functions()
+    lib = C.CDLL(product_so)
+    api._declare_prototypes(lib)
+    for name, ret, params in protos:
+        fn = getattr(lib, name)
+        assert fn.argtypes is not None and len(fn.argtypes) == len(params), name
+    assert lib.bp_launch_count.restype is C.c_int64 and lib.bp_vsmt2_free.restype is None
+    with pytest.raises((TypeError, C.ArgumentError)):
+        lib.bp_gens_new(16)  # wrong number of arguments is refused instead of reading a garbage pointer
+
+
 def test_emulation_build_is_not_the_product(product_so):
     """the product library is a CUDA binary for sm_100a (no host-emulation launcher inside)"""
     out = os.popen("cuobjdump -lelf %s 2>/dev/null" % product_so).read()
