@@ -177,6 +177,47 @@ def timed_device_batches(lib, api, gens, wl, inp_np, reps, dev, warm=3):
     return e0.elapsed_time(e1) / reps, dV, dP
 
 
+def streamed_device_batches(lib, api, gens, wl, inp_np, steps, dev, warm=1):
+    """the headline's pipeline for another circuit: two batches in flight (bp_prove_stream_begin / _finish), device-resident inputs;
+    (ms per batch, V, proofs) -- both slots prove the same statements and must agree"""
+    import ctypes as C
+    import torch
+    circ = wl.circuit
+    B = inp_np["entropy"].shape[0]
+    d = {k: torch.from_numpy(a).to(dev) for k, a in inp_np.items()}
+    outs = [(torch.empty((B, circ.m, 32), dtype=torch.uint8, device=dev), torch.empty((B, circ.proof_len), dtype=torch.uint8, device=dev),
+             torch.zeros(B, dtype=torch.int32, device=dev)) for _ in range(2)]
+    lbuf = api._buf(wl.label)
+
+    def begin(slot):
+        o = outs[slot]
+        rc = lib.bp_prove_stream_begin(gens._h, circ._h, C.c_int32(slot), C.c_uint32(B), lbuf, C.c_size_t(len(wl.label)), _ptr(d["v"]), _ptr(d["v_blinding"]),
+                                       _ptr(d["entropy"]), _ptr(d.get("aux")), _ptr(d.get("pub")), None, None, None, _ptr(o[0]), _ptr(o[1]), _ptr(o[2]),
+                                       C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0, rc
+
+    def finish(slot):
+        rc = lib.bp_prove_stream_finish(gens._h, circ._h, C.c_int32(slot), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0, rc
+    k = 0
+    begin(0)
+    for _ in range(warm):
+        begin((k + 1) % 2); finish(k % 2); k += 1
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        begin((k + 1) % 2); finish(k % 2); k += 1
+    e1.record()
+    torch.cuda.synchronize()
+    finish(k % 2)
+    torch.cuda.synchronize()
+    for o in outs:
+        assert not o[2].cpu().numpy().any()
+    assert torch.equal(outs[0][1], outs[1][1]), "the two stream slots disagree"
+    return e0.elapsed_time(e1) / steps, outs[0][0], outs[0][1]
+
+
 def combined_verify_device(lib, api, gens, circ, label, dV, dP, dE, dPub, dev, piece=2048):
     """cross-proof combined verification of device-resident proofs in pieces that fit one device chunk: (all combined verdicts 0, structural statuses all 0)"""
     import ctypes as C
@@ -270,15 +311,28 @@ def extra_configs(args, lib, api, workloads, parallel, gens32k, wl5, dev, world,
     # (shift table only), m = 511; byte parity with the C oracle is tests/test_gpu.py::test_vsmt2_depth253_reference_configuration
     g18 = api.Gens(1 << 18)
     wl253 = workloads.Vsmt2(g18, depth=253)
-    Bd = 64
+    # No 8-bit direct tables at this capacity: four rounds over the shift table, then the level-4 generators from 5-bit fold tables
+    # (41 GB, built on the first call; csrc/engine.cu ensure_fold_table).  512 proofs per batch in device chunks of 128, two batches in
+    # flight like the headline: the MSM phase of a batch covers the first phase of the next (253 sequential Poseidon hashes per proof
+    # in the witness program and 287k sequential RNG draws: ~2.7 s of latency whatever the batch size).  The depth-32 workspace
+    # (120 GB with both stream slots) is released first.
+    wl5.circuit.release_workspace()
+    Bd, ch = 512, 128
     inp = wl253.inputs(0, Bd, with_root=False)
-    ms, dV, dP = timed_device_batches(lib, api, g18, wl253, {k: inp[k] for k in ("v", "v_blinding", "entropy")}, 1, dev, warm=1)
-    pub = torch.from_numpy(wl253.roots_batch(inp["v"])).to(dev)
-    okc, oks = combined_verify_device(lib, api, g18, wl253.circuit, wl253.label, dV, dP, torch.from_numpy(inp["entropy"]).to(dev), pub, dev, piece=Bd)
-    out["vsmt2_depth253_reference_config"] = {"proofs_per_s": Bd / ms * 1e3, "ms_per_step": ms, "batch": Bd, "n": wl253.circuit.n, "N": 1 << 18, "m": wl253.circuit.m,
-                                               "proof_bytes": wl253.circuit.proof_len, "verified_combined": bool(okc and oks),
-                                               "note": "one plain call of 64 proofs next to the resident depth-32 workspace: the call is bound by its exposed first phase "
-                                                       "(253 sequential Poseidon hashes per proof in the witness program, 287k sequential RNG draws), not by the MSMs"}
+    os.environ["BP_B200_CHUNK"] = str(ch)
+    try:
+        ms, dV, dP = streamed_device_batches(lib, api, g18, wl253, {k: inp[k] for k in ("v", "v_blinding", "entropy")}, 2, dev, warm=1)
+        ms1, _, dP1 = timed_device_batches(lib, api, g18, wl253, {k: inp[k][:ch] for k in ("v", "v_blinding", "entropy")}, 1, dev, warm=0)
+        assert torch.equal(dP1, dP[:ch]), "streamed and plain calls disagree"
+        pub = torch.from_numpy(wl253.roots_batch(inp["v"])).to(dev)
+        okc, oks = combined_verify_device(lib, api, g18, wl253.circuit, wl253.label, dV, dP, torch.from_numpy(inp["entropy"]).to(dev), pub, dev, piece=ch)
+    finally:
+        del os.environ["BP_B200_CHUNK"]
+    out["vsmt2_depth253_reference_config"] = {"proofs_per_s": Bd / ms * 1e3, "ms_per_step": ms, "batch": Bd, "device_chunk": ch, "n": wl253.circuit.n, "N": 1 << 18,
+                                               "m": wl253.circuit.m, "proof_bytes": wl253.circuit.proof_len, "verified_combined": bool(okc and oks),
+                                               "single_call_of_%d" % ch: {"proofs_per_s": ch / ms1 * 1e3, "ms": ms1,
+                                                                     "note": "one plain call: bound by its exposed first phase, not by the MSMs"}}
+    del dP1
     del g18, wl253, dV, dP, pub
     # config 3: ristretto MSM microbenchmark, one instance over the first 2^k generators of chain G, uniform scalars
     import hashlib
@@ -500,7 +554,7 @@ def main():
     # ---- the other BASELINE configs and the verifier (all ranks take part in the sharded MiMC run) ----
     configs = None
     if not args.no_extras:
-        # release the prover's per-chunk workspace first?  It stays: 72 GB of 180, the extras need < 40 GB
+        # the depth-32 workspace stays until the depth-253 configuration needs the room (extra_configs releases it there)
         configs = extra_configs(args, lib, api, workloads, parallel, gens, wl, dev, world, rank, dist, hbm_peak)
         if world > 1:
             dist.barrier()

@@ -492,6 +492,10 @@ class Circuit:
             _lib.bp_circuit_free(self._h)
             self._h = None
 
+    def release_workspace(self):
+        """frees the device workspace kept between batch calls (the next call allocates it again)"""
+        _check(load().bp_circuit_release_workspace(self._h), "circuit_release_workspace")
+
     def prove_batch(self, gens, label, v, v_blinding, entropy, aux=None, pub=None, witness=None):
         """v, v_blinding: uint8 [B][m][32]; entropy [B][32]; aux [B][num_aux][32]; pub [B][num_public][32]; witness = (aL,aR,aO) each [B][n][32] or None.
         Returns (V [B][m][32], proofs [B][proof_len], status [B]).  Host buffers in, host buffers out."""

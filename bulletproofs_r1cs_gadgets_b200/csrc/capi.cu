@@ -392,6 +392,13 @@ int32_t bp_circuit_from_arrays(uint32_t n, uint32_t m, uint32_t q, const uint32_
   return BP_OK;
 }
 void bp_circuit_free(bp_circuit *c) { if (c) { c->stage[0].release(); c->stage[1].release(); circuit_free(c->c); delete c; } }
+int32_t bp_circuit_release_workspace(bp_circuit *c) {
+  if (!c) return BP_ERR_INVALID_ARGUMENT;
+  int rc = circuit_release_workspace(c->c);
+  if (rc) return rc;
+  c->stage[0].release(); c->stage[1].release();
+  return BP_OK;
+}
 uint32_t bp_circuit_num_multipliers(const bp_circuit *c) { return c ? c->c->n : 0; }
 uint32_t bp_circuit_num_constraints(const bp_circuit *c) { return c ? c->c->q : 0; }
 uint32_t bp_circuit_num_commitments(const bp_circuit *c) { return c ? c->c->m : 0; }

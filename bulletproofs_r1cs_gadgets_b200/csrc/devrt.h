@@ -65,11 +65,15 @@ inline int dev_sync(dev_stream s) {
   if (e != cudaSuccess) { fprintf(stderr, "bp_b200: stream sync failed: %s\n", cudaGetErrorString(e)); return 1; }
   return 0;
 }
+inline int dev_sync_device() { return cudaDeviceSynchronize() != cudaSuccess; }
 #else
 typedef int dev_stream;
 extern long g_launch_count;
+extern int g_profile_on;
+void profile_note(const char *name, long threads);
 template <class K>
 int launch(long n, dev_stream, const K &k) {
+  if (g_profile_on) profile_note(K::kName, n);
   for (long t = 0; t < n; t++) k(t);
   g_launch_count++;
   return 0;
@@ -86,4 +90,5 @@ inline void dev_side_free(dev_side &) {}
 inline dev_stream dev_side_fork(dev_side &, dev_stream main) { return main; }
 inline void dev_side_join(dev_side &, dev_stream) {}
 inline int dev_sync(dev_stream) { return 0; }
+inline int dev_sync_device() { return 0; }
 #endif

@@ -63,8 +63,23 @@ int engine_profile_report(char *buf, size_t cap) {
   return (int)off;
 }
 #else
-void engine_profile_enable(int) {}
-int engine_profile_report(char *buf, size_t cap) { if (cap) buf[0] = 0; return 0; }
+// host emulation (tests): no timing, but the same report lists which kernel bodies ran and how often
+#include <map>
+#include <string>
+int g_profile_on = 0;
+static std::map<std::string, std::pair<long, double>> g_prof;
+void profile_note(const char *name, long threads) { auto &r = g_prof[name]; r.first++; r.second += (double)threads; }
+void engine_profile_enable(int on) { g_profile_on = on; }
+int engine_profile_report(char *buf, size_t cap) {
+  size_t off = 0;
+  for (auto &kv : g_prof) {
+    int w = snprintf(buf + off, off < cap ? cap - off : 0, "%s %ld 0.000000 %.0f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+    if (w < 0 || off + (size_t)w >= cap) break;
+    off += (size_t)w;
+  }
+  g_prof.clear();
+  return (int)off;
+}
 #endif
 
 #define CK(x) do { int _e = (x); if (_e) { fprintf(stderr, "bp_b200: %s failed at %s:%d\n", #x, __FILE__, __LINE__); return BP_ERR_CUDA; } } while (0)
@@ -119,9 +134,10 @@ struct Workspace {
   uint32_t *rg_ai = 0; uint8_t *skip_ai = 0; long rg_ai_cap = -1;  // A_I row map / skip flags with the merged S-box rows
   uint32_t *rg_ver = 0; long rg_ver_cap = -1, rg_ver_N = -1;
   uint32_t *items = 0, *boff = 0, *soff = 0; size_t items_cap = 0, slices_cap = 0; ge_p3 *seg = 0;
+  scm *flat_parts = 0;  // partial sums of the long slots (KFlattenParts)
   void release() {
     for (auto &fs : fronts) { for (Front &f : fs) f.release(); fs.clear(); }
-    void *ps[] = {items, boff, soff, seg, rg_ver, utab, rg_as, rg_ai, skip_ai, vpub, uj, w_all, zpow, ypow, yinvpow, a, b, chal, t, tb, clr, part, dig, buckets, wsum, Q, Gt, Ht, pts, naf, naf_top};
+    void *ps[] = {flat_parts, items, boff, soff, seg, rg_ver, utab, rg_as, rg_ai, skip_ai, vpub, uj, w_all, zpow, ypow, yinvpow, a, b, chal, t, tb, clr, part, dig, buckets, wsum, Q, Gt, Ht, pts, naf, naf_top};
     for (void *p : ps) dev_free(p);
     *this = Workspace();
   }
@@ -182,7 +198,7 @@ int gens_create(uint32_t capacity, BpGens **out) {
 void gens_free(BpGens *g) {
   if (!g) return;
   if (g->msm_ws) { g->msm_ws->release(); delete g->msm_ws; }
-  dev_free(g->G_p3); dev_free(g->H_p3); dev_free(g->G_n); dev_free(g->H_n); dev_free(g->pc); dev_free(g->pc_niels); dev_free(g->pc_table); dev_free(g->table); dev_free(g->sg);
+  dev_free(g->G_p3); dev_free(g->H_p3); dev_free(g->G_n); dev_free(g->H_n); dev_free(g->pc); dev_free(g->pc_niels); dev_free(g->pc_table); dev_free(g->table); dev_free(g->ftable); dev_free(g->sg);
   delete g;
 }
 int gens_export(const BpGens *g, int which, uint32_t count, uint8_t *out) {
@@ -242,6 +258,25 @@ int circuit_create(uint32_t n, uint32_t m, uint32_t npub, uint32_t q, const uint
   CKC(dev_h2d(c->d_slot_ptr, slot_cnt.data(), (c->nslots + 1) * sizeof(uint32_t), s));
   CKC(dev_h2d(c->d_tq, tq.data(), tq.size() * sizeof(uint32_t), s));
   CKC(dev_h2d(c->d_tcoeff, tc.data(), tc.size() * sizeof(scm), s));
+  {  // long slots -> parts of FLATTEN_PART terms
+    std::vector<uint32_t> pbeg, pend, lslot, lfirst;
+    for (uint32_t sl = 0; sl < c->nslots; sl++) {
+      const uint32_t t0 = slot_cnt[sl], t1 = slot_cnt[sl + 1];
+      if (t1 - t0 <= 2 * FLATTEN_PART) continue;
+      lslot.push_back(sl); lfirst.push_back((uint32_t)pbeg.size());
+      for (uint32_t t = t0; t < t1; t += FLATTEN_PART) { pbeg.push_back(t); pend.push_back(std::min(t + FLATTEN_PART, t1)); }
+    }
+    lfirst.push_back((uint32_t)pbeg.size());
+    c->nlong = (uint32_t)lslot.size(); c->nparts = (uint32_t)pbeg.size();
+    if (c->nlong) {
+      if (dalloc(&c->d_part_beg, pbeg.size()) || dalloc(&c->d_part_end, pend.size()) || dalloc(&c->d_long_slot, lslot.size()) || dalloc(&c->d_long_first, lfirst.size())) {
+        circuit_free(c); return BP_ERR_OOM;
+      }
+      CKC(dev_h2d(c->d_part_beg, pbeg.data(), pbeg.size() * sizeof(uint32_t), s)); CKC(dev_h2d(c->d_part_end, pend.data(), pend.size() * sizeof(uint32_t), s));
+      CKC(dev_h2d(c->d_long_slot, lslot.data(), lslot.size() * sizeof(uint32_t), s)); CKC(dev_h2d(c->d_long_first, lfirst.data(), lfirst.size() * sizeof(uint32_t), s));
+      CKC(dev_sync(s));  // the host vectors go out of scope
+    }
+  }
   if (tape) {
     c->has_tape = 1;
     uint32_t wn = wlc_ptr[nwlc];
@@ -312,11 +347,21 @@ int circuit_set_fixed_commitments(BpCircuit *c, uint32_t n, const uint32_t *idx,
 void circuit_free(BpCircuit *c) {
   if (!c) return;
   dev_free(c->d_fixed_idx); dev_free(c->d_fixed_V);
+  dev_free(c->d_part_beg); dev_free(c->d_part_end); dev_free(c->d_long_slot); dev_free(c->d_long_first);
   dev_free(c->d_slot_ptr); dev_free(c->d_tq); dev_free(c->d_tcoeff); dev_free(c->d_tape); dev_free(c->d_wptr); dev_free(c->d_wkind);
   dev_free(c->d_widx); dev_free(c->d_wcoeff); dev_free(c->d_pblocks); dev_free(c->d_pos_rk); dev_free(c->d_pos_mds);
   delete c->merge_src;
   if (c->ws) { c->ws->release(); delete c->ws; }
   delete c;
+}
+
+// frees the per-batch device workspace (tens of GB for a large batch); the next call allocates it again
+int circuit_release_workspace(BpCircuit *c) {
+  if (!c || !c->ws) return BP_OK;
+  if (c->ws->pending[0].active || c->ws->pending[1].active) return BP_ERR_INVALID_ARGUMENT;  // a batch is between begin and finish
+  if (dev_sync_device()) return BP_ERR_CUDA;  // work of earlier calls may still be running on the caller's streams
+  c->ws->release();
+  return BP_OK;
 }
 
 // the sorted-bucket path pays ~54k additions per instance for its 16384-bucket reduction: below this many rows per instance the
@@ -342,12 +387,24 @@ double engine_workspace_bytes_per_proof(const BpCircuit *c) {
   const double items = std::max(2 * n + 1, N + 2) * SB_WINDOWS, slices = std::max(SB_BUCKETS + items / SB_SEG + 2, items * 4 / sizeof(ge_p3) + 1);
   const double nch = std::max(n, N) / CH_DOT + 2;
   double b = 0;
-  b += sizeof(scm) * ((double)c->nslots + (q + 1) + 4 * N + (2 * k + 2) + 40 + nch * 6 + (c->npub + 1));  // w_all, zpow, ypow, yinvpow, a, b, ...
-  b += rows * SB_ROW_BYTES;                                                      // digit rows
+  b += sizeof(scm) * ((double)c->nslots + c->nparts + 1 + (q + 1) + 4 * N + (2 * k + 2) + 40 + nch * 6 + (c->npub + 1));  // w_all, zpow, ypow, yinvpow, a, b, ...
+  b += std::max(rows * SB_ROW_BYTES, 2 * N * 64);                                // digit rows
   b += sizeof(ge_p3) * (slices + 2 * (N / 2 + 1) + (m + 12 + 2 * k) + 2 * SB_SEGS + 1 + 2 * MSM_WINDOWS);  // partial sums, folded generators, ...
   b += 4 * items + 8 * (SB_BUCKETS + 1) + 8 * 256 + 32;                          // sorted items, offsets, NAFs
   b += sizeof(scm) * (2 * (m + 1) + (c->naux + 1) + (c->npub + 1) + 3 * (n + 1) + (3 + 2 * n)) + 2 * sizeof(strobe128);  // front
   return b;
+}
+
+// flattened constraint weights of a chunk: one thread per (slot, proof); slots with very many terms in parts (KFlattenParts)
+static int run_flatten(const BpCircuit *c, Workspace *w, int B, dev_stream s) {
+  KFlatten kf{c->d_slot_ptr, c->d_tq, c->d_tcoeff, w->zpow, w->w_all, B};
+  kf.split = c->nlong ? 2 * FLATTEN_PART : 0;
+  CK(launch((long)c->nslots * B, s, kf));
+  if (c->nlong) {
+    CK(launch((long)c->nparts * B, s, KFlattenParts{c->d_part_beg, c->d_part_end, c->d_tq, c->d_tcoeff, w->zpow, w->flat_parts, B}));
+    CK(launch((long)c->nlong * B, s, KFlattenSum{c->d_long_slot, c->d_long_first, w->flat_parts, w->w_all, B}));
+  }
+  return BP_OK;
 }
 
 static int ensure_workspace(BpCircuit *c, int B) {
@@ -360,6 +417,7 @@ static int ensure_workspace(BpCircuit *c, int B) {
   size_t nchunks = (std::max(n, N) + CH_DOT - 1) / CH_DOT + 1;
   size_t rows_as = (2 * n + 1) + (n + 1) + (2 * n + 1), rows_ipa = 2 * (N + 2), rows_ver = 2 * N + m + 13 + 2 * k + 2;
   w->dig_bytes = std::max(std::max(rows_as, rows_ipa), rows_ver) * SB_ROW_BYTES * Bz;  // sized for the wider 13-bit rows
+  w->dig_bytes = std::max(w->dig_bytes, 2 * N * (size_t)64 * Bz);  // 2N 64-byte rows of narrow-window digits (KRecodeFoldTable with fold tables)
   // bucket slots: enough for one MSM launch at the largest split the launcher will pick
   size_t max_warps = (size_t)std::max<long>(msm_target_warps(), 2L * B) + B;
   w->items_cap = (size_t)std::max(2 * n + 1, N + 2) * SB_WINDOWS;  // items of one instance
@@ -369,7 +427,7 @@ static int ensure_workspace(BpCircuit *c, int B) {
   w->bucket_slots = std::max(w->bucket_slots, Bz * ((w->items_cap * sizeof(uint32_t) + sizeof(ge_p3) - 1) / sizeof(ge_p3)));
   int bad = 0;
   bad |= dalloc(&w->vpub, (size_t)(c->npub + 1) * Bz); bad |= dalloc(&w->uj, (2 * k + 2) * Bz);
-  bad |= dalloc(&w->w_all, (size_t)c->nslots * Bz);
+  bad |= dalloc(&w->w_all, (size_t)c->nslots * Bz); bad |= dalloc(&w->flat_parts, (size_t)(c->nparts + 1) * Bz);
   bad |= dalloc(&w->zpow, (q + 1) * Bz); bad |= dalloc(&w->ypow, N * Bz); bad |= dalloc(&w->yinvpow, N * Bz);
   bad |= dalloc(&w->a, N * Bz); bad |= dalloc(&w->b, N * Bz); bad |= dalloc(&w->chal, 16 * Bz);
   bad |= dalloc(&w->t, 6 * Bz); bad |= dalloc(&w->tb, 5 * Bz); bad |= dalloc(&w->clr, 2 * Bz); bad |= dalloc(&w->part, nchunks * 6 * Bz);
@@ -493,6 +551,44 @@ static long ensure_pad_generator(BpGens *g, long n, long N, dev_stream s) {
   if (bad) return -1;
   g->pad_n[k] = n; g->pad_N[k] = N; g->pad_count = k + 1;
   return 2L * g->capacity + 2 + k;
+}
+
+// Fold tables.  KFoldTable materialises the level-J generators of a proof from fixed-base tables (2^J terms per output, no
+// doublings); the first J rounds then never fold generators.  Up to ~61k generators those are the 8-bit direct tables (26 GB at
+// capacity 32768).  Above, the direct tables do not fit, but a table with NARROWER windows over the first N generators of each chain
+// does: 2 N ceil(253/b) 2^(b-1) 96 B  =  41 GB for b = 5 at N = 262144 (the reference's own depth-253 configuration), and a term
+// costs 51 additions instead of 32 -- against folding 2^18 generators with two scalar multiplications per output from round 0.
+// Built on first use for the circuit's N (a generator set can serve smaller circuits; capacity itself may be much larger than
+// any N: the reference asks for BulletproofGens::new(819200, 1), src/gadget_vsmt_2.rs:290).  BP_B200_FOLD_TABLE_GB: budget
+// (default 48, 0 disables); BP_B200_FOLD_BITS: force the window width (tests).
+struct FoldTableView { const ge_niels *table; long cap; int bits, W, E, rb; };
+static bool fold_table_view(const BpGens *g, long N, FoldTableView &v) {
+  if (g->table) { v = {g->table, (long)g->capacity, 8, TBL_W, TBL_E, 32}; return true; }
+  if (g->ftable && g->ft_cap >= N) { v = {g->ftable, g->ft_cap, g->ft_bits, (253 + g->ft_bits - 1) / g->ft_bits, 1 << (g->ft_bits - 1), 64}; return true; }
+  return false;
+}
+static int ensure_fold_table(BpGens *g, long N, dev_stream s) {
+  const char *force = getenv("BP_B200_FOLD_BITS");
+  if (g->table || (g->ftable && g->ft_cap >= N && !(force && atoi(force) != g->ft_bits))) return BP_OK;
+  if (getenv("BP_B200_NO_TABLE") || !g->sg || N > (long)g->capacity) return BP_OK;  // the unfolded rounds themselves need the shift table
+  double budget = 48.0;
+  if (const char *e = getenv("BP_B200_FOLD_TABLE_GB")) budget = atof(e);
+  int bits = 0;
+  for (int b = 7; b >= 4 && !bits; b--) {
+    const double bytes = 2.0 * (double)N * ((253 + b - 1) / b) * (double)(1 << (b - 1)) * sizeof(ge_niels);
+    if (bytes <= budget * 1073741824.0) bits = b;
+  }
+  if (force) { const int b = atoi(force); if (b >= 4 && b <= 7 && budget > 0) bits = b; }
+  dev_free(g->ftable); g->ftable = nullptr; g->ft_cap = 0;
+  if (!bits) return BP_OK;  // no table: the rounds fold generators from round 0
+  const int W = (253 + bits - 1) / bits, E = 1 << (bits - 1);
+  if (dalloc(&g->ftable, (size_t)2 * N * W * E)) { g->ftable = nullptr; return BP_OK; }  // not enough memory left: same fallback
+  KTableBuild kb{g->G_p3, g->H_p3, g->pc, N, g->ftable};
+  kb.bits = bits; kb.W = W; kb.E = E;
+  CK(launch(2 * N * W, s, kb));
+  CK(dev_sync(s));
+  g->ft_bits = bits; g->ft_cap = N;
+  return BP_OK;
 }
 
 // A_I with merged rows: builds (once per generators / circuit pair) the generator sums of the circuit's equal-scalar groups in
@@ -655,8 +751,13 @@ static int prove_phase_b(const BpGens *g, BpCircuit *c, Front &f, const ProveArg
       CK(launch(B, s, KRecode13{i_b, nullptr, 1, B, dI, rowsI * rb, 0, nullptr}));
       CK(launch(n * B, s, KRecode13{aL, nullptr, (int)n, B, dI, rowsI * rb, 1, skipI}));
       CK(launch(n * B, s, KRecode13{aR, nullptr, (int)n, B, dI, rowsI * rb, (int)(1 + n), skipI}));
-      CK(launch(B, s, KRecode{i_b + B, nullptr, 1, B, dO, rowsO * 32, 0}));   // A_O stays on the direct tables: its scalars are 0/1
-      CK(launch(n * B, s, KRecode{aO, nullptr, (int)n, B, dO, rowsO * 32, 1}));
+      if (g->table) {  // A_O stays on the direct tables: with inverse S-boxes its scalars are 0/1 (one addition per row, no bucket reduction)
+        CK(launch(B, s, KRecode{i_b + B, nullptr, 1, B, dO, rowsO * 32, 0}));
+        CK(launch(n * B, s, KRecode{aO, nullptr, (int)n, B, dO, rowsO * 32, 1}));
+      } else {
+        CK(launch(B, s, KRecode13{i_b + B, nullptr, 1, B, dO, rowsO * rb, 0, nullptr}));
+        CK(launch(n * B, s, KRecode13{aO, nullptr, (int)n, B, dO, rowsO * rb, 1, nullptr}));
+      }
       CK(launch(B, s, KRecode13{i_b + 2L * B, nullptr, 1, B, dS, rowsI * rb, 0, nullptr}));
       CK(launch(n * B, s, KRecode13{sL, nullptr, (int)n, B, dS, rowsI * rb, 1, nullptr}));
       CK(launch(n * B, s, KRecode13{sR, nullptr, (int)n, B, dS, rowsI * rb, (int)(1 + n), nullptr}));
@@ -683,12 +784,7 @@ static int prove_phase_b(const BpGens *g, BpCircuit *c, Front &f, const ProveArg
         RowMap rmI{0, merged ? w->rg_ai : w->rg_as, (long)g->capacity, 0, 0, 0};
         rc = run_msm_sorted(g, w, rmI, rowsI, B, dI, rowsI * rb, A.proofs + 0, plen, s); if (rc) return rc;
         if (g->table) { rc = run_msm_table(g, w, rm, rowsO, B, dO, rowsO * 32, A.proofs + 32, plen, s); if (rc) return rc; }
-        else {
-          // no direct tables (capacities above ~65k generators): A_O through the bucket method on the generators themselves
-          // (its scalars are 0 / 1: one non-zero digit per row)
-          MsmSeg segsO[2] = {{g->pc_niels + 1, 0, 0, 1}, {g->G_n, 0, 0, (int)n}};
-          rc = run_msm(w, segsO, 2, B, dO, rowsO * 32, A.proofs + 32, plen, 0, nullptr, s); if (rc) return rc;
-        }
+        else { rc = run_msm_sorted(g, w, rm, rowsO, B, dO, rowsO * rb, A.proofs + 32, plen, s); if (rc) return rc; }  // no direct tables: shift table
         rc = run_msm_sorted(g, w, rm, rowsI, B, dS, rowsI * rb, A.proofs + 64, plen, s); if (rc) return rc;
       } else {
         rc = run_msm_table(g, w, rm, rowsI, B, dI, rowsI * rb, A.proofs + 0, plen, s); if (rc) return rc;
@@ -707,7 +803,7 @@ static int prove_phase_b(const BpGens *g, BpCircuit *c, Front &f, const ProveArg
   CK(launch(((q + CH_POW - 1) / CH_POW) * B, s, KPowers{ch_z, w->zpow, (int)q, B, 1, CH_POW}));
   CK(launch(((N + CH_POW - 1) / CH_POW) * B, s, KPowers{ch_y, w->ypow, (int)N, B, 0, CH_POW}));
   CK(launch(((N + CH_POW - 1) / CH_POW) * B, s, KPowers{ch_yinv, w->yinvpow, (int)N, B, 0, CH_POW}));
-  CK(launch((long)c->nslots * B, s, KFlatten{c->d_slot_ptr, c->d_tq, c->d_tcoeff, w->zpow, w->w_all, B}));
+  rc = run_flatten(c, w, B, s); if (rc) return rc;
   // 6. t(x) coefficients, T commitments (A.3 steps 8-10)
   PolyIn pin{aL, aR, aO, sL, sR, wL, wR, wO, w->ypow, w->yinvpow};
   {
@@ -733,7 +829,10 @@ static int prove_phase_b(const BpGens *g, BpCircuit *c, Front &f, const ProveArg
   // multiscalar multiplications over the ORIGINAL generators with scalars a_i * prod u_t^(+-1); the folded generators are then
   // materialised once (KFoldTable) and the remaining, short rounds run on per-proof points (bucket method + NAF fold).
   CK(launch(2L * B, s, KFillScalar{alpha, sc_one()}));  // alpha, beta are adjacent
-  const int J = g->table ? (int)std::min<long>(unfold_rounds(), k) : 0;
+  FoldTableView ft{};
+  const bool can_unfold = g->table || (g->sg != nullptr && N + 1 >= SORTED_MIN_ROWS);  // L_j, R_j over the original generators: direct or shift tables
+  if (can_unfold && !g->table && k > 1 && unfold_rounds() > 0) { rc = ensure_fold_table(const_cast<BpGens *>(g), N, s); if (rc) return rc; }
+  const int J = can_unfold && fold_table_view(g, N, ft) ? (int)std::min<long>(unfold_rounds(), k) : 0;
   scm *UG[2] = {w->utab, w->utab + ((size_t)1 << UNFOLD_MAX) * B}, *UH[2] = {w->utab + 2 * ((size_t)1 << UNFOLD_MAX) * B, w->utab + 3 * ((size_t)1 << UNFOLD_MAX) * B};
   if (J > 0) { CK(launch(B, s, KFillScalar{UG[0], sc_one()})); CK(launch(B, s, KFillScalar{UH[0], sc_one()})); }
   int yfree = 0;
@@ -773,8 +872,13 @@ static int prove_phase_b(const BpGens *g, BpCircuit *c, Front &f, const ProveArg
       if (round == J - 1 && h > 1) {
         // folded generators of level J straight from the tables: H side true (beta = 1, the y^-i factors are inside), G side
         // divided by UG[0] so that the first of its 2^J terms is the generator itself; alpha = UG[0] carries the factor
-        CK(launch(N * B, s, KRecodeFoldTable{UG[cur ^ 1], UH[cur ^ 1], w->yinvpow, ch_u, N, h, n, B, w->dig, 2 * N * 32}));
-        CK(launch(2 * h * B, s, KFoldTable{g->table, (long)g->capacity, N, h, w->dig, 2 * N * 32, w->Gt, w->Ht, gs, g->G_p3}));
+        if ((size_t)2 * N * ft.rb * B > w->dig_bytes) return BP_ERR_OOM;
+        KRecodeFoldTable kr{UG[cur ^ 1], UH[cur ^ 1], w->yinvpow, ch_u, N, h, n, B, w->dig, 2 * N * ft.rb};
+        kr.bits = ft.bits; kr.W = ft.W; kr.rb = ft.rb;
+        CK(launch(N * B, s, kr));
+        KFoldTable kf{ft.table, ft.cap, N, h, w->dig, 2 * N * ft.rb, w->Gt, w->Ht, gs, g->G_p3};
+        kf.W = ft.W; kf.E = ft.E; kf.rb = ft.rb;
+        CK(launch(2 * h * B, s, kf));
         CK(dev_d2d(alpha, UG[cur ^ 1], sizeof(scm) * B, s));
         yfree = 1;
       }
@@ -955,7 +1059,7 @@ int engine_verify_combined(BpGens *g, BpCircuit *c, const VerifyArgs &A, int *d_
   CK(launch(B, s, KVerifyRho{seed, A.status, rho}));
   CK(launch(((q + CH_POW - 1) / CH_POW) * B, s, KPowers{ch_z, w->zpow, (int)q, B, 1, CH_POW}));
   CK(launch(((N + CH_POW - 1) / CH_POW) * B, s, KPowers{ch_yinv, w->yinvpow, (int)N, B, 0, CH_POW}));
-  CK(launch((long)c->nslots * B, s, KFlatten{c->d_slot_ptr, c->d_tq, c->d_tcoeff, w->zpow, w->w_all, B}));
+  rc = run_flatten(c, w, B, s); if (rc) return rc;
   if (c->npub) CK(launch((long)c->npub * B, s, KLoadScalars{A.pub, w->vpub, (int)c->npub, B}));
   CK(launch(N * B, s, KVerifyS{uj, ujinv, (int)k, B, w->a}));
   {
@@ -1007,7 +1111,7 @@ int engine_verify(const BpGens *g, BpCircuit *c, const VerifyArgs &A, dev_stream
   CK(launch(B, s, KTsVerify{base, A.V, (int)m, B, (int)k, (unsigned)N, A.proofs, plen, A.entropy, w->chal, uj, ujinv, A.status, nullptr, nullptr, 0}));
   CK(launch(((q + CH_POW - 1) / CH_POW) * B, s, KPowers{ch_z, w->zpow, (int)q, B, 1, CH_POW}));
   CK(launch(((N + CH_POW - 1) / CH_POW) * B, s, KPowers{ch_yinv, w->yinvpow, (int)N, B, 0, CH_POW}));
-  CK(launch((long)c->nslots * B, s, KFlatten{c->d_slot_ptr, c->d_tq, c->d_tcoeff, w->zpow, w->w_all, B}));
+  rc = run_flatten(c, w, B, s); if (rc) return rc;
   if (c->npub) CK(launch((long)c->npub * B, s, KLoadScalars{A.pub, w->vpub, (int)c->npub, B}));
   CK(launch(N * B, s, KVerifyS{uj, ujinv, (int)k, B, w->a}));
   {

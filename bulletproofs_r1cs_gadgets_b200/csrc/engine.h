@@ -19,6 +19,10 @@ struct BpGens {
   long pad_n[8], pad_N[8]; int pad_count;
   long merge_slots; uint64_t merge_owner;  // slots after the spare ones hold the generator sums of ONE circuit at a time (KMergeGens)  // spare shift-table slots holding sum_{i=n-N/2}^{N/2-1} H_i of the circuits seen (see engine.cu)
   ge_niels *table;      // fixed-base tables [(2cap+2)][32][128] (see KTableBuild); NULL when disabled
+  // fold tables: what KFoldTable materialises the level-J generators from when the 8-bit direct tables do not exist (capacities
+  // above ~65k generators).  Same layout with narrower windows, [2][ft_cap][ft_w][2^(ft_bits-1)], built on first use for the
+  // first ft_cap generators of each chain (ensure_fold_table); NULL until then
+  ge_niels *ftable; int ft_bits; long ft_cap;
   uint8_t pc_c[64];     // compressed B, B_blinding (host copy)
   struct Workspace *msm_ws; uint32_t msm_ws_n;  // scratch of the MSM microbenchmark entry
 };
@@ -31,6 +35,7 @@ struct Workspace;
 struct BpCircuit {
   uint32_t n, N, k, m, q, nnz, nslots, naux, npub;
   uint32_t *d_slot_ptr, *d_tq; scm *d_tcoeff;
+  uint32_t nlong, nparts; uint32_t *d_part_beg, *d_part_end, *d_long_slot, *d_long_first;  // slots cut into parts for KFlattenParts (see kernels.h)
   int has_tape;
   TapeOp *d_tape; uint32_t *d_wptr; uint8_t *d_wkind; uint32_t *d_widx; scm *d_wcoeff;
   PoseidonBlock *d_pblocks; scm *d_pos_rk, *d_pos_mds; PoseidonDev pos;
@@ -53,6 +58,7 @@ int circuit_create(uint32_t n, uint32_t m, uint32_t npub, uint32_t q, const uint
 // commitment slots whose compressed value is fixed by the circuit (idx[n], V[n][32], host pointers); checked by the verifiers
 int circuit_set_fixed_commitments(BpCircuit *c, uint32_t n, const uint32_t *idx, const uint8_t *V);
 void circuit_free(BpCircuit *c);
+int circuit_release_workspace(BpCircuit *c);
 size_t circuit_proof_len(const BpCircuit *c);
 double engine_workspace_bytes_per_proof(const BpCircuit *c);
 

@@ -154,8 +154,8 @@ __global__ void __launch_bounds__(SORT_THREADS, 1) sort_buckets_direct_kernel(Ro
 // sectors reach.  Here pass 1 partitions the items of an instance into SORT_GROUPS coarse groups of SORT_FINE buckets (runs
 // of ~70 items per group and tile leave shared memory as whole lines) and pass 2 sorts one coarse group per block inside
 // shared memory and writes it back linearly.  Every global access is coalesced; items cross HBM three times instead of
-// being read-modified-written sector by sector.  The low bucket bits ride in bits 22..28 of the intermediate item, so
-// generator slot * SB_WINDOWS must stay below 2^22 (the launcher falls back to the staged kernel otherwise).
+// being read-modified-written sector by sector.  The low bucket bits ride in bits 24..30 of the intermediate item, so
+// generator slot * SB_WINDOWS must stay below 2^24 (the launcher falls back to the staged kernel otherwise).
 #define SORT2_THREADS 512
 #define SORT2_WARPS (SORT2_THREADS / 32)
 #define SORT_FINE_BITS 7
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 1) sort_buckets_direct_kernel(Ro
 #define SORT2_WC_PER ((SORT_GROUPS * SORT2_WC_STRIDE + SORT2_THREADS - 1) / SORT2_THREADS)
 #define SORT2_WC_WORDS (SORT2_WC_PER * SORT2_THREADS)
 #define SORT2_SMEM_BYTES ((SORT2_BUF_WORDS + SORT2_WC_WORDS + SORT_GROUPS + 8) * 4)
-#define SORT_ITEM_BITS 22
+#define SORT_ITEM_BITS 24   // bits 24..30 carry the fine bucket bits, bit 31 the sign: up to 986k generator slots (capacity ~493k)
 #define SORT_ITEM_MASK (0x80000000u | ((1u << SORT_ITEM_BITS) - 1))
 #define SORT_FINE_CAP 6016   // items of one coarse group sorted inside shared memory (larger groups scatter directly)
 

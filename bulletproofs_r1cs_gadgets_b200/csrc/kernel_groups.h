@@ -10,7 +10,7 @@
 #define KGROUP_TABLE(X) X(KTableBuild) X(KMsmTable) X(KMsmTableFinish) X(KVerifyCheck) X(KMsmTableReduce) X(KVerifyProofPoint) X(KSumPointsStrided) X(KVerifyCombinedCheck)
 #define KGROUP_POINTS(X) X(KCommit) X(KGensFromUniform) X(KPcBases) X(KPcTable) X(KEncodePoints) X(KVerifyDecompress)
 #define KGROUP_TRANSCRIPT(X) X(KTsStart) X(KRngDraw) X(KTsPhase2) X(KTsPhase3) X(KTsPhase4) X(KTsIpaRound) X(KSelfTest) X(KTsVerify) X(KBatchSeed) X(KVerifyRho)
-#define KGROUP_SCALAR(X) X(KLoadScalars) X(KRecode) X(KPowers) X(KFillScalar) X(KFlatten) X(KPolyT) X(KSumPartials) X(KPolyEval) \
+#define KGROUP_SCALAR(X) X(KLoadScalars) X(KRecode) X(KPowers) X(KFillScalar) X(KFlatten) X(KFlattenParts) X(KFlattenSum) X(KPolyT) X(KSumPartials) X(KPolyEval) \
   X(KProverScalars) X(KIpaDots) X(KRecodeIpa) X(KFoldAB) X(KStoreAB) X(KWitnessTape) X(KVerifyS) X(KVerifyDelta) X(KVerifyGH) X(KVerifyScalars) X(KVerifyCombineRows) X(KCheckFixedCommitments) X(KIpaUTable) X(KRecodeUnfolded) X(KRecodeFoldTable)
 
 #define KGROUP_SORTED(X) X(KShiftTableBuild) X(KShiftTableOne) X(KMergeGens) X(KRecode13) X(KRecodeUnfolded13) X(KSortBucketsSerial) X(KBucketAccumulate) X(KBucketReduce) X(KBucketFinish) X(KSumPointsEncode)

@@ -101,6 +101,21 @@ HD void sc_recode_bytes(int8_t dig[32], const scm &s) {
     dig[i] = (int8_t)d;
   }
 }
+// signed radix-2^bits digits (bits in 4..8) of a canonical scalar: W = ceil(253 / bits) digits in [-2^(bits-1), 2^(bits-1))
+HD void sc_recode_win(int8_t *dig, const scm &s, int bits, int W) {
+  uint64_t w[4]; sc_to_canonical(w, s);
+  const int mask = (1 << bits) - 1, half = 1 << (bits - 1);
+  int carry = 0;
+  for (int i = 0; i < W; i++) {
+    const int bit = bits * i, word = bit >> 6, off = bit & 63;
+    uint64_t v = word < 4 ? (w[word] >> off) : 0;
+    if (off + bits > 64 && word + 1 < 4) v |= w[word + 1] << (64 - off);
+    int d = (int)(v & (uint64_t)mask) + carry;
+    carry = d >= half;
+    d -= carry << bits;
+    dig[i] = (int8_t)d;
+  }
+}
 HD void store_digits(int8_t *dst, const int8_t dig[32]) {
 #if defined(__CUDA_ARCH__)
   uint4 a, b;
@@ -534,11 +549,40 @@ struct KFlatten {
   static constexpr int kBlock = 128, kMinBlocks = 1;
   static constexpr const char *kName = "KFlatten";
   const uint32_t *slot_ptr; const uint32_t *t_q; const scm *t_coeff; const scm *zpow; scm *w; int B;
+  uint32_t split = 0;  // slots with more terms than this are left to KFlattenParts / KFlattenSum (0: none are)
   HD void operator()(long tid) const {
     int p = (int)(tid % B); long s = tid / B;
+    const uint32_t t0 = slot_ptr[s], t1 = slot_ptr[s + 1];
+    if (split && t1 - t0 > split) return;
     scm acc = sc_zero();
-    for (uint32_t t = slot_ptr[s]; t < slot_ptr[s + 1]; t++) acc = sc_add(acc, sc_mul(t_coeff[t], zpow[(long)t_q[t] * B + p]));
+    for (uint32_t t = t0; t < t1; t++) acc = sc_add(acc, sc_mul(t_coeff[t], zpow[(long)t_q[t] * B + p]));
     w[s * B + p] = acc;
+  }
+};
+// A slot with very many terms -- the constant slot wc carries one term per constraint with a constant (every Poseidon round
+// key: 42k terms at depth 32, 340k at depth 253) -- would be one thread's sequential chain per proof; the circuit cuts such slots
+// into parts of FLATTEN_PART terms (circuit_create), summed per part here and per slot in KFlattenSum.
+#define FLATTEN_PART 256
+struct KFlattenParts {
+  static constexpr int kBlock = 128, kMinBlocks = 1;
+  static constexpr const char *kName = "KFlattenParts";
+  const uint32_t *part_beg, *part_end; const uint32_t *t_q; const scm *t_coeff; const scm *zpow; scm *parts; int B;
+  HD void operator()(long tid) const {
+    int p = (int)(tid % B); long part = tid / B;
+    scm acc = sc_zero();
+    for (uint32_t t = part_beg[part]; t < part_end[part]; t++) acc = sc_add(acc, sc_mul(t_coeff[t], zpow[(long)t_q[t] * B + p]));
+    parts[part * B + p] = acc;
+  }
+};
+struct KFlattenSum {
+  static constexpr int kBlock = 128, kMinBlocks = 1;
+  static constexpr const char *kName = "KFlattenSum";
+  const uint32_t *long_slot, *long_first; const scm *parts; scm *w; int B;  // parts long_first[l] .. long_first[l+1] belong to slot long_slot[l]
+  HD void operator()(long tid) const {
+    int p = (int)(tid % B); long l = tid / B;
+    scm acc = sc_zero();
+    for (uint32_t j = long_first[l]; j < long_first[l + 1]; j++) acc = sc_add(acc, parts[(long)j * B + p]);
+    w[(long)long_slot[l] * B + p] = acc;
   }
 };
 
@@ -1260,26 +1304,27 @@ struct KTableBuild {
   static constexpr int kBlock = 64, kMinBlocks = 1;
   static constexpr const char *kName = "KTableBuild";
   const ge_p3 *G, *H, *pc; long cap; ge_niels *table;
+  int bits = 8, W = TBL_W, E = TBL_E;  // window width, windows per generator, entries per window (the fold tables of large capacities use narrower windows)
   HD void operator()(long tid) const {
-    long gen = tid / TBL_W; int w = (int)(tid % TBL_W);
+    long gen = tid / W; int w = (int)(tid % W);
     ge_p3 P;
     if (gen < cap) load_struct(P, &G[gen]); else if (gen < 2 * cap) load_struct(P, &H[gen - cap]); else load_struct(P, &pc[gen - 2 * cap]);
-    for (int i = 0; i < 8 * w; i++) ge_dbl(P, P);
-    ge_niels *slot = table + tid * TBL_E;
+    for (int i = 0; i < bits * w; i++) ge_dbl(P, P);
+    ge_niels *slot = table + tid * E;
     // pass 1: multiples in projective form parked in the slots, prefix products of Z kept locally
     fe pre[TBL_E];
     ge_p3 acc = P;
     fe run; fe_1(run);
-    for (int e = 0; e < TBL_E; e++) {
+    for (int e = 0; e < E; e++) {
       ge_niels tmp; tmp.ypx = acc.X; tmp.ymx = acc.Y; tmp.xy2d = acc.Z;
       store_struct(&slot[e], tmp);
       pre[e] = run;
       fe_mul(run, run, acc.Z);
       ge_add(acc, acc, P);
     }
-    // pass 2: one inversion for all 128 Z (Montgomery's trick), then normalise to affine Niels
+    // pass 2: one inversion for all Z (Montgomery's trick), then normalise to affine Niels
     fe inv, d2; fe_invert(inv, run); FE_2D(d2);
-    for (int e = TBL_E - 1; e >= 0; e--) {
+    for (int e = E - 1; e >= 0; e--) {
       ge_niels t; load_struct(t, &slot[e]);
       fe zi, x, y;
       fe_mul(zi, inv, pre[e]); fe_mul(inv, inv, t.xy2d);
@@ -1469,37 +1514,47 @@ struct KRecodeFoldTable {
   static constexpr int kBlock = 128, kMinBlocks = 1;
   static constexpr const char *kName = "KRecodeFoldTable";
   const scm *UG, *UH, *yinvpow, *ufac; long N, nJ, n; int B; int8_t *dig; long inst_stride;
+  int bits = 8, W = TBL_W, rb = 32;  // window width, digits per row, bytes per digit row (multiple of 16)
+  HD void put(int8_t *dst, const scm &v) const {
+    if (bits == 8) { int8_t d[32]; sc_recode_bytes(d, v); store_digits(dst, d); return; }
+    int8_t d[64];
+    sc_recode_win(d, v, bits, W);
+    for (int i = W; i < rb; i++) d[i] = 0;
+    for (int i = 0; i < rb; i += 32) store_digits(dst + i, d + i);
+  }
   HD void operator()(long tid) const {
     int p = (int)(tid % B); long idx = tid / B;
     const long blk = idx / nJ;
     scm gf = idx >= n ? ufac[p] : sc_one();
-    int8_t d[32];
     int8_t *row = dig + (long)p * inst_stride;
-    sc_recode_bytes(d, blk == 0 ? sc_zero() : sc_mul(sc_mul(UG[blk * B + p], gf), UH[p])); store_digits(row + idx * 32, d);
-    sc_recode_bytes(d, sc_mul(sc_mul(UH[blk * B + p], yinvpow[idx * B + p]), gf)); store_digits(row + (N + idx) * 32, d);
+    put(row + idx * rb, blk == 0 ? sc_zero() : sc_mul(sc_mul(UG[blk * B + p], gf), UH[p]));
+    put(row + (N + idx) * rb, sc_mul(sc_mul(UH[blk * B + p], yinvpow[idx * B + p]), gf));
   }
 };
 // G_J[i] = G_i + sum_{b>0} (row b*nJ+i) * G_{b*nJ+i} (un-normalised, see KRecodeFoldTable), H_J[i] = sum_b (row N+b*nJ+i) * H_{b*nJ+i}:
-// the folded generators after J rounds, straight from the tables
+// the folded generators after J rounds, straight from the tables.  table[((which*cap + idx) * W + w) * E + e] = (e+1) * 2^(bits*w) * P
+// (the 8-bit direct tables of a generator set, or its narrower fold tables when those do not fit: ensure_fold_table in engine.cu)
 struct KFoldTable {
   static constexpr int kBlock = 128, kMinBlocks = BP_OCC_TABLE;
   static constexpr const char *kName = "KFoldTable";
   const ge_niels *table; long cap, N, nJ; const int8_t *dig; long dig_inst_stride; ge_p3 *dstG, *dstH; long dst_stride; const ge_p3 *G;
+  int W = TBL_W, E = TBL_E, rb = 32;
   HD void operator()(long tid) const {
     long p = tid / (2 * nJ); long r = tid % (2 * nJ); int which = (int)(r / nJ); long i = r % nJ;
-    const int8_t *drow = dig + p * dig_inst_stride + (which ? N * 32 : 0);
+    const int8_t *drow = dig + p * dig_inst_stride + (which ? N * (long)rb : 0);
     ge_p3 acc;
     if (which) ge_identity(acc); else load_struct(acc, &G[i]);  // G side: block 0 carries the scalar 1 (see KRecodeFoldTable)
-    const long terms = (N / nJ) * TBL_W;
+    const long terms = (N / nJ) * W;
+    long idx = i; int w = 0;
 #pragma unroll 1
     for (long t = 0; t < terms; t++) {  // one flat loop over (block, window): ONE addition site, field multiplications expanded in place
-      const long idx = (t / TBL_W) * nJ + i; const int w = (int)(t % TBL_W);
-      const int dv = drow[idx * 32 + w];
+      const int dv = drow[idx * rb + w];
       if (dv != 0) {
         int neg = dv < 0; int e = (neg ? -dv : dv) - 1;
-        ge_niels q; load_struct(q, &table[(((which ? cap : 0) + idx) * TBL_W + w) * (long)TBL_E + e]);
+        ge_niels q; load_struct(q, &table[(((which ? cap : 0) + idx) * W + w) * (long)E + e]);
         ge_madd<true>(acc, acc, q, neg);
       }
+      if (++w == W) { w = 0; idx += nJ; }
     }
     store_struct(&(which ? dstH : dstG)[p * dst_stride + i], acc);
   }

@@ -171,6 +171,10 @@ int32_t bp_circuit_compile(const bp_cs *recorded, bp_circuit **out);
 int32_t bp_circuit_from_arrays(uint32_t n_multipliers, uint32_t n_commitments, uint32_t n_constraints, const uint32_t *cons_ptr,
                                const uint8_t *kind, const uint32_t *idx, const uint8_t *coeff, bp_circuit **out);
 void bp_circuit_free(bp_circuit *c);
+/* Frees the device workspace the batch calls keep between calls (sized by the largest chunk proved or verified so far: ~26 MB per
+ * proof of a chunk at depth 32, 72 GB budget); the next batch call allocates it again.  InvalidArgument while a batch is
+ * between bp_prove_stream_begin and _finish. */
+int32_t bp_circuit_release_workspace(bp_circuit *c);
 uint32_t bp_circuit_num_multipliers(const bp_circuit *c);
 uint32_t bp_circuit_num_constraints(const bp_circuit *c);
 uint32_t bp_circuit_num_commitments(const bp_circuit *c);

@@ -58,10 +58,12 @@ def test_verifier_rejects_tampering(api, gens): E.test_verifier_rejects_tamperin
 def test_batch_witness_program_and_public_inputs(api, gens): E.test_batch_witness_program_and_public_inputs(api, gens)
 def test_batch_aux_inputs_bound_check(api, gens): E.test_batch_aux_inputs_bound_check(api, gens)
 def test_explicit_witness_equals_witness_program(api, gens, oracle_lib): E.test_explicit_witness_equals_witness_program(api, gens, oracle_lib)
+def test_slots_with_very_many_terms(api, gens, oracle_lib): E.test_slots_with_very_many_terms(api, gens, oracle_lib)
 def test_chunking_is_invisible(api, gens, monkeypatch): E.test_chunking_is_invisible(api, gens, monkeypatch)
 def test_msm_path_choice_is_invisible(api, gens, monkeypatch): E.test_msm_path_choice_is_invisible(api, gens, monkeypatch)
 def test_combined_verification(api, gens): E.test_combined_verification(api, gens)
 def test_shift_table_only_generators(api, gens, monkeypatch): E.test_shift_table_only_generators(api, gens, monkeypatch)
+def test_fold_tables_of_large_capacities(api, gens, monkeypatch): E.test_fold_tables_of_large_capacities(api, gens, monkeypatch)
 def test_wire_format(api, gens): E.test_wire_format(api, gens)
 def test_static_commitments_are_checked_by_the_batch_verifiers(api, gens): E.test_static_commitments_are_checked_by_the_batch_verifiers(api, gens)
 def test_vsmt4_membership_small(api, gens): E.test_vsmt4_membership(api, gens)

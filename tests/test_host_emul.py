@@ -393,6 +393,39 @@ def test_skewed_digit_distributions(api, gens, oracle_lib, n=100, cap=256):
         assert rc == 0 and oV.tobytes() == V[i].tobytes() and oP == P[i].tobytes(), i
 
 
+def test_slots_with_very_many_terms(api, gens, oracle_lib, n=20, cap=256):
+    """variables that appear in hundreds of constraints (the constant slot of a Poseidon circuit holds one term per round key): their
+    flattened weights are summed in parts of 256 terms (KFlattenParts / KFlattenSum); proof bytes against the C oracle's prover, and
+    the verifiers (which flatten the same way) accept"""
+    q = 1300
+    rng = np.random.RandomState(5)
+    kind, idx, co, cons_ptr = [], [], [], [0]
+    for k in range(q):  # constraint k:  c1 * V_0 + c2 * (constant) + c3 * aL[k % n]  (+ c4 * aO[3] in every other one)
+        kind += [0, 4, 1]; idx += [0, 0, k % n]; co += [int(x) for x in rng.randint(1, 2 ** 31, 3)]
+        if k % 2:
+            kind.append(3); idx.append(3); co.append(L - 1 - k)
+        cons_ptr.append(len(kind))
+    coeff = api.scalars_to_array(co)
+    circ = api.Circuit.from_arrays(n, 1, cons_ptr, kind, idx, coeff)
+    oc = CO.Circuit(n, 1, cons_ptr, kind, idx, coeff)
+    B = 3
+    wit = [np.stack([api.scalars_to_array(H.rand_scalars(40 + 3 * i + j, n)) for i in range(B)]) for j in range(3)]
+    v = api.scalars_to_array(H.rand_scalars(31, B)).reshape(B, 1, 32)
+    vb = api.scalars_to_array(H.rand_scalars(32, B)).reshape(B, 1, 32)
+    ent = np.frombuffer(bytes(range(50, 50 + 32 * B)), dtype=np.uint8).reshape(B, 32)
+    api.profile_enable(1)
+    V, P, st = circ.prove_batch(gens, b"long", v, vb, ent, witness=tuple(wit))
+    api.profile_enable(0)
+    assert "KFlattenParts" in api.profile_report()
+    assert not st.any()
+    for i in range(B):
+        rc, oV, oP = CO.prove(oc, wit[0][i], wit[1][i], wit[2][i], v[i], vb[i], b"long", ent[i].tobytes(), cap)
+        assert rc == 0 and oV.tobytes() == V[i].tobytes() and oP == P[i].tobytes(), i
+    # (the circuit is not satisfied by random wires: the verifiers must reject, identically, after flattening the same weights)
+    assert circ.verify_batch(gens, b"long", V, P, ent).tolist() == [3] * B
+    assert [CO.verify(oc, V[i], P[i].tobytes(), b"long", ent[i].tobytes(), cap) for i in range(B)] == [3] * B
+
+
 def test_chunking_is_invisible(api, gens, monkeypatch):
     from bulletproofs_r1cs_gadgets_b200 import workloads
     wl = workloads.Mimc(gens, rounds=3)
@@ -452,6 +485,50 @@ def test_shift_table_only_generators(api, gens, monkeypatch):
             bad = inp["pub"].copy(); bad[2, 0, 1] ^= 2
             assert wl.circuit.verify_batch(lean, wl.label, V, P, inp["entropy"], pub=bad).tolist() == [0, 0, 3]
         monkeypatch.delenv("BP_B200_SORTED_MIN_ROWS")
+
+
+def test_fold_tables_of_large_capacities(api, gens, monkeypatch):
+    """Without the 8-bit direct tables the level-4 generators are materialised from FOLD tables with narrower windows (4..7 bits,
+    chosen by a memory budget; built on first use for the circuit's N) after four rounds over the shift table -- the path of the
+    reference's own configuration (N = 262144, src/gadget_vsmt_2.rs:23,290).  Every window width must give the bytes the fully
+    tabulated generators produce; a zero budget falls back to folding from round 0."""
+    from bulletproofs_r1cs_gadgets_b200 import workloads
+    monkeypatch.setenv("BP_B200_NO_DIRECT_TABLE", "1")
+    lean = api.Gens(256)
+    monkeypatch.delenv("BP_B200_NO_DIRECT_TABLE")
+    monkeypatch.setenv("BP_B200_SORTED_MIN_ROWS", "0")
+    wls = (workloads.Mimc(gens, rounds=5), workloads.Vsmt2(gens, depth=2, params=api.PoseidonParams(6, 2, 2, 3)))
+    for wl in wls:
+        inp = wl.inputs(0, 3)
+        want = wl.circuit.prove_batch(gens, wl.label, inp["v"], inp["v_blinding"], inp["entropy"], pub=inp["pub"])
+        for bits in ("4", "5", "6", "7", None):
+            if bits is None:  # budget 0 on generators that have no fold table yet
+                monkeypatch.delenv("BP_B200_FOLD_BITS")
+                monkeypatch.setenv("BP_B200_FOLD_TABLE_GB", "0")
+                monkeypatch.setenv("BP_B200_NO_DIRECT_TABLE", "1")
+                target = api.Gens(256)
+                monkeypatch.delenv("BP_B200_NO_DIRECT_TABLE")
+            else:
+                monkeypatch.setenv("BP_B200_FOLD_BITS", bits)
+                target = lean
+            api.profile_enable(1)
+            V, P, st = wl.circuit.prove_batch(target, wl.label, inp["v"], inp["v_blinding"], inp["entropy"], pub=inp["pub"])
+            api.profile_enable(0)
+            ran = api.profile_report()
+            if wl.circuit.n > 16:  # (the 5-round MiMC circuit has four rounds in all: nothing left to materialise)
+                assert ("KFoldTable" in ran) == (bits is not None), (bits, sorted(ran))
+            assert not st.any() and V.tobytes() == want[0].tobytes() and P.tobytes() == want[1].tobytes(), (wl.name, bits)
+        monkeypatch.delenv("BP_B200_FOLD_TABLE_GB")
+    # the workspace can be dropped between batches and comes back on the next call
+    wl = wls[0]
+    wl.circuit.release_workspace()
+    inp = wl.inputs(0, 3)
+    V, P, st = wl.circuit.prove_batch(lean, wl.label, inp["v"], inp["v_blinding"], inp["entropy"], pub=inp["pub"])
+    assert not st.any() and P.tobytes() == want_first(wl, gens, inp)
+
+
+def want_first(wl, gens, inp):
+    return wl.circuit.prove_batch(gens, wl.label, inp["v"], inp["v_blinding"], inp["entropy"], pub=inp["pub"])[1].tobytes()
 
 
 def test_combined_verification(api, gens):
