@@ -37,7 +37,12 @@ int launch(long n, dev_stream s, const K &k) {
   if (e != cudaSuccess) { fprintf(stderr, "bp_b200: launch failed: %s\n", cudaGetErrorString(e)); return 1; }
   return 0;
 }
-inline int dev_malloc(void **p, size_t n) { return cudaMalloc(p, n ? n : 16) != cudaSuccess; }
+inline int dev_malloc(void **p, size_t n) {
+  if (cudaMalloc(p, n ? n : 16) == cudaSuccess) return 0;
+  cudaGetLastError();  // an allocation failure is reported to the caller (BP_ERR_OOM or a fallback); it must not surface again at the next launch check
+  *p = nullptr;
+  return 1;
+}
 inline void dev_free(void *p) { if (p) cudaFree(p); }
 inline int dev_h2d(void *d, const void *h, size_t n, dev_stream s) { return n ? cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s) != cudaSuccess : 0; }
 inline int dev_d2h(void *h, const void *d, size_t n, dev_stream s) { return n ? cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s) != cudaSuccess : 0; }

@@ -556,11 +556,11 @@ static long ensure_pad_generator(BpGens *g, long n, long N, dev_stream s) {
 // Fold tables.  KFoldTable materialises the level-J generators of a proof from fixed-base tables (2^J terms per output, no
 // doublings); the first J rounds then never fold generators.  Up to ~61k generators those are the 8-bit direct tables (26 GB at
 // capacity 32768).  Above, the direct tables do not fit, but a table with NARROWER windows over the first N generators of each chain
-// does: 2 N ceil(253/b) 2^(b-1) 96 B  =  41 GB for b = 5 at N = 262144 (the reference's own depth-253 configuration), and a term
-// costs 51 additions instead of 32 -- against folding 2^18 generators with two scalar multiplications per output from round 0.
+// does: 2 N ceil(253/b) 2^(b-1) 96 B  =  69 GB for b = 6 (41 GB for b = 5) at N = 262144, the reference's own depth-253
+// configuration, and a term costs 43 (51) additions instead of 32 -- against folding 2^18 generators with two scalar multiplications per output from round 0.
 // Built on first use for the circuit's N (a generator set can serve smaller circuits; capacity itself may be much larger than
 // any N: the reference asks for BulletproofGens::new(819200, 1), src/gadget_vsmt_2.rs:290).  BP_B200_FOLD_TABLE_GB: budget
-// (default 48, 0 disables); BP_B200_FOLD_BITS: force the window width (tests).
+// (default 72, 0 disables); BP_B200_FOLD_BITS: force the window width (tests).
 struct FoldTableView { const ge_niels *table; long cap; int bits, W, E, rb; };
 static bool fold_table_view(const BpGens *g, long N, FoldTableView &v) {
   if (g->table) { v = {g->table, (long)g->capacity, 8, TBL_W, TBL_E, 32}; return true; }
@@ -571,7 +571,7 @@ static int ensure_fold_table(BpGens *g, long N, dev_stream s) {
   const char *force = getenv("BP_B200_FOLD_BITS");
   if (g->table || (g->ftable && g->ft_cap >= N && !(force && atoi(force) != g->ft_bits))) return BP_OK;
   if (getenv("BP_B200_NO_TABLE") || !g->sg || N > (long)g->capacity) return BP_OK;  // the unfolded rounds themselves need the shift table
-  double budget = 48.0;
+  double budget = 72.0;
   if (const char *e = getenv("BP_B200_FOLD_TABLE_GB")) budget = atof(e);
   int bits = 0;
   for (int b = 7; b >= 4 && !bits; b--) {
@@ -581,8 +581,10 @@ static int ensure_fold_table(BpGens *g, long N, dev_stream s) {
   if (force) { const int b = atoi(force); if (b >= 4 && b <= 7 && budget > 0) bits = b; }
   dev_free(g->ftable); g->ftable = nullptr; g->ft_cap = 0;
   if (!bits) return BP_OK;  // no table: the rounds fold generators from round 0
+  // narrower windows when the device has less room left than the budget (the workspace of a large chunk is allocated first)
+  while (bits >= 4 && dalloc(&g->ftable, (size_t)2 * N * ((253 + bits - 1) / bits) * ((size_t)1 << (bits - 1)))) { g->ftable = nullptr; bits = force ? 0 : bits - 1; }
+  if (bits < 4) return BP_OK;  // not even the 4-bit table fits: same fallback
   const int W = (253 + bits - 1) / bits, E = 1 << (bits - 1);
-  if (dalloc(&g->ftable, (size_t)2 * N * W * E)) { g->ftable = nullptr; return BP_OK; }  // not enough memory left: same fallback
   KTableBuild kb{g->G_p3, g->H_p3, g->pc, N, g->ftable};
   kb.bits = bits; kb.W = W; kb.E = E;
   CK(launch(2 * N * W, s, kb));

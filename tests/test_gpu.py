@@ -313,12 +313,13 @@ def test_vsmt2_depth32_chunk_border_vs_c_oracle(api, gens_big, oracle_lib, monke
 
 def test_vsmt2_depth253_reference_configuration(api, oracle_lib):
     """The reference's own test configuration (src/gadget_vsmt_2.rs:23,262-399): TreeDepth = 253, inverse S-box, 4+140+4 rounds,
-    n = 143704 multipliers -> N = 262144 generators (shift table only, no direct tables), m = 511 commitments, label b"VSMT".
+    n = 143704 multipliers -> N = 262144 of 819200 generators (shift table + 6-bit fold tables, no direct tables), m = 511 commitments,
+    label b"VSMT".
     Two proofs, byte-equal to the C oracle's; both verifiers accept them and reject a wrong root."""
     from bulletproofs_r1cs_gadgets_b200 import workloads
     oracle_lib.poseidon_set_params(H.POSEIDON_BLOB)
     depth, B, cap = 253, 2, 1 << 18
-    g = api.Gens(cap)
+    g = api.Gens(819200)  # BulletproofGens::new(819200, 1), src/gadget_vsmt_2.rs:290: capacity well above the N = 2^18 the proof uses (the C oracle builds the first 2^18)
     wl = workloads.Vsmt2(g, depth=depth)
     assert (wl.circuit.n, wl.circuit.q, wl.circuit.m, wl.circuit.proof_len) == (143704, 334973, 511, 1664)  # SURVEY section 8 table
     inp = wl.inputs(7000, B, with_root=False)
