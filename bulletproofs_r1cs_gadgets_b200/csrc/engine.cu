@@ -133,7 +133,7 @@ struct Workspace {
   scm *utab = 0; uint32_t *rg_as = 0; long rg_cap = -1;
   uint32_t *rg_ai = 0; uint8_t *skip_ai = 0; long rg_ai_cap = -1;  // A_I row map / skip flags with the merged S-box rows
   uint32_t *rg_ver = 0; long rg_ver_cap = -1, rg_ver_N = -1;
-  uint32_t *items = 0, *boff = 0, *soff = 0; size_t items_cap = 0, slices_cap = 0; ge_p3 *seg = 0;
+  uint32_t *items = 0, *boff = 0, *soff = 0; size_t items_cap = 0, slices_cap = 0; ge_p3 *seg = 0; size_t seg_cap = 0;
   scm *flat_parts = 0;  // partial sums of the long slots (KFlattenParts)
   void release() {
     for (auto &fs : fronts) { for (Front &f : fs) f.release(); fs.clear(); }
@@ -389,7 +389,7 @@ double engine_workspace_bytes_per_proof(const BpCircuit *c) {
   double b = 0;
   b += sizeof(scm) * ((double)c->nslots + c->nparts + 1 + (q + 1) + 4 * N + (2 * k + 2) + 40 + nch * 6 + (c->npub + 1));  // w_all, zpow, ypow, yinvpow, a, b, ...
   b += std::max(rows * SB_ROW_BYTES, 2 * N * 64);                                // digit rows
-  b += sizeof(ge_p3) * (slices + 2 * (N / 2 + 1) + (m + 12 + 2 * k) + 2 * SB_SEGS + 1 + 2 * MSM_WINDOWS);  // partial sums, folded generators, ...
+  b += sizeof(ge_p3) * (slices + 2 * (N / 2 + 1) + (m + 12 + 2 * k) + 2 * SB_SEGS + 3 * SB_FIN_GROUPS + 1 + 2 * MSM_WINDOWS);  // partial sums, folded generators, ...
   b += 4 * items + 8 * (SB_BUCKETS + 1) + 8 * 256 + 32;                          // sorted items, offsets, NAFs
   b += sizeof(scm) * (2 * (m + 1) + (c->naux + 1) + (c->npub + 1) + 3 * (n + 1) + (3 + 2 * n)) + 2 * sizeof(strobe128);  // front
   return b;
@@ -436,7 +436,7 @@ static int ensure_workspace(BpCircuit *c, int B) {
   bad |= dalloc(&w->pts, (m + 11 + 2 * k + 1) * Bz);
   bad |= dalloc(&w->naf, 8 * 256 * Bz); bad |= dalloc(&w->naf_top, 8 * Bz);
   bad |= dalloc(&w->items, w->items_cap * Bz); bad |= dalloc(&w->boff, (size_t)(SB_BUCKETS + 1) * Bz); bad |= dalloc(&w->soff, (size_t)(SB_BUCKETS + 1) * Bz);
-  bad |= dalloc(&w->seg, (size_t)SB_SEGS * 2 * Bz);
+  bad |= dalloc(&w->seg, ((size_t)SB_SEGS * 2 + SB_FIN_GROUPS * 3) * Bz);
   bad |= dalloc(&w->utab, 4 * (size_t)(1 << UNFOLD_MAX) * Bz + 4 * Bz); bad |= dalloc(&w->rg_as, 2 * n + 2); bad |= dalloc(&w->rg_ai, 2 * n + 2); bad |= dalloc(&w->skip_ai, 2 * n + 2);
   if (bad) { w->release(); return BP_ERR_OOM; }
   w->B = B;
@@ -489,12 +489,26 @@ static int run_msm(Workspace *w, const MsmSeg *segs, int nseg, long ninst, const
 static int run_msm_table(const BpGens *g, Workspace *w, const RowMap &rmap, long rows, long ninst, const int8_t *dig, long dig_inst_stride,
                          uint8_t *out, long out_stride, dev_stream s) {
   long S = 262144 / (ninst > 0 ? ninst : 1);
-  if (S > rows / 16) S = rows / 16;
-  if (S > 1024) S = 1024;
+  // a handful of instances (the MSM entry point, single proofs): the launch is a latency chain, not a throughput problem -- down to one
+  // row (32 additions) per thread, partial sums combined 16 to 1 per stage
+  const bool few = ninst <= 8;
+  const long min_rows = few ? 1 : 16;
+  if (S > rows / min_rows) S = rows / min_rows;
+  if (S > (few ? 32768 : 1024)) S = few ? 32768 : 1024;
   if (S < 1) S = 1;
   while ((size_t)(ninst * S) > w->bucket_slots && S > 1) S--;
   CK(launch(ninst * S, s, KMsmTable{g->table, rmap, dig, dig_inst_stride, rows, (int)S, w->buckets}));
-  if (S > 64 && ninst < 4096) {  // two-stage reduction of the per-thread partial sums
+  if (few) {
+    ge_p3 *cur = w->buckets, *stage = w->buckets + (size_t)ninst * S;
+    long count = S;
+    while (count > 16) {
+      const long R = (count + 15) / 16;
+      if ((size_t)(stage - w->buckets) + (size_t)ninst * R > w->bucket_slots) return BP_ERR_OOM;
+      CK(launch(ninst * R, s, KMsmTableReduce{cur, (int)count, (int)R, stage}));
+      cur = stage; stage += ninst * R; count = R;
+    }
+    CK(launch(ninst, s, KMsmTableFinish{cur, (int)count, out, out_stride}));
+  } else if (S > 64 && ninst < 4096) {  // two-stage reduction of the per-thread partial sums
     const int R = 32;
     ge_p3 *stage = w->buckets + (size_t)ninst * S;
     if ((size_t)ninst * (S + R) > w->bucket_slots) return BP_ERR_OOM;
@@ -520,7 +534,9 @@ static int run_msm_sorted(const BpGens *g, Workspace *w, const RowMap &rmap, lon
 #endif
   CK(launch(ninst * segs, s, KBucketAccumulate{g->sg, sv, w->buckets, segs}));
   CK(launch(ninst * SB_SEGS, s, KBucketReduce{w->buckets, sv, w->seg}));
-  CK(launch(ninst, s, KBucketFinish{w->seg, out, out_stride, nullptr}));
+  ge_p3 *grp = w->seg + (size_t)ninst * SB_SEGS * 2;  // behind the segment sums (ensure_workspace sizes the buffer for both)
+  CK(launch(ninst * SB_FIN_GROUPS, s, KBucketFinishA{w->seg, grp}));
+  CK(launch(ninst, s, KBucketFinishB{grp, out, out_stride, nullptr}));
   return BP_OK;
 }
 
@@ -949,6 +965,10 @@ int engine_commit(const BpGens *g, int count, const uint8_t *v, const uint8_t *r
 // batched sorted-bucket kernels (sort, accumulate, reduce) like the proofs of a batch do; their partial results are summed.
 // scalars: d_bytes (canonical 32-byte scalars) or d_scm (Montgomery form already on the device); result encoded to d_out or
 // kept as a point in out_p3.  Uses the generator set's own scratch workspace.
+// buckets per thread of KBucketReduceW: short segments while the sub-instances are few (latency), longer ones once there are
+// enough threads to fill the device anyway (the weight's double-and-add is paid once per segment)
+static int split_seg_len(long S) { int L = 8; while (L < 128 && (long)L * 8 <= S) L *= 2; return L; }
+static const int SPLIT_SEG_LEN = 8;  // the shortest: sizes the buffers
 static int sorted_split_msm(BpGens *g, long nrows, const uint8_t *d_bytes, const scm *d_scm, int mode, long mapN, uint8_t *d_out, ge_p3 *out_p3,
                             dev_stream s) {
   long R = nrows / 64; if (R < 8192) R = 8192; if (R > 32768) R = 32768; if (R > nrows) R = nrows;
@@ -959,15 +979,19 @@ static int sorted_split_msm(BpGens *g, long nrows, const uint8_t *d_bytes, const
     w->items_cap = (size_t)R * SB_WINDOWS;
     w->slices_cap = SB_BUCKETS + w->items_cap / SB_SEG + 2;
     w->bucket_slots = (size_t)S * w->slices_cap + S + 1;
+    // the partial-sum buffer doubles as the scratch of the two-pass sort (one 4-byte item per digit)
+    w->bucket_slots = std::max(w->bucket_slots, (size_t)S * ((w->items_cap * sizeof(uint32_t) + sizeof(ge_p3) - 1) / sizeof(ge_p3)));
     w->dig_bytes = (size_t)S * R * SB_ROW_BYTES;
+    const size_t tree = (size_t)S * (SB_BUCKETS / SPLIT_SEG_LEN);  // one point per segment, then the stages of the plain sum
     if (dalloc(&w->a, (size_t)S * R) || dalloc(&w->dig, w->dig_bytes) || dalloc(&w->buckets, w->bucket_slots) || dalloc(&w->items, w->items_cap * S) ||
-        dalloc(&w->boff, (size_t)(SB_BUCKETS + 1) * S) || dalloc(&w->soff, (size_t)(SB_BUCKETS + 1) * S) || dalloc(&w->seg, (size_t)SB_SEGS * 2 * S)) {
+        dalloc(&w->boff, (size_t)(SB_BUCKETS + 1) * S) || dalloc(&w->soff, (size_t)(SB_BUCKETS + 1) * S) || dalloc(&w->seg, tree + tree / 8 + 64)) {
       w->release(); delete w; g->msm_ws = nullptr; return BP_ERR_OOM;
     }
+    w->seg_cap = tree + tree / 8 + 64;
     g->msm_ws_n = (uint32_t)nrows;
   }
   Workspace *w = g->msm_ws;
-  if ((size_t)S * R * SB_ROW_BYTES > w->dig_bytes || (size_t)R * SB_WINDOWS > w->items_cap || (size_t)S * w->slices_cap + S + 1 > w->bucket_slots) {
+  if ((size_t)S * (SB_BUCKETS / SPLIT_SEG_LEN) * 9 / 8 + 64 > w->seg_cap || (size_t)S * R * SB_ROW_BYTES > w->dig_bytes || (size_t)R * SB_WINDOWS > w->items_cap || (size_t)S * w->slices_cap + S + 1 > w->bucket_slots) {
     g->msm_ws_n = 0;  // geometry of an earlier, different size: rebuild
     return sorted_split_msm(g, nrows, d_bytes, d_scm, mode, mapN, d_out, out_p3, s);
   }
@@ -975,15 +999,29 @@ static int sorted_split_msm(BpGens *g, long nrows, const uint8_t *d_bytes, const
   if (d_bytes) { CK(launch(nrows, s, KLoadScalars{d_bytes, w->a, (int)nrows, 1})); d_scm = w->a; }
   CK(launch(nrows, s, KRecode13{d_scm, nullptr, (int)nrows, 1, w->dig, 0, 0, nullptr}));  // B = 1: row i at dig + i * SB_ROW_BYTES = sub-instance i / R, row i % R
   RowMap rm{mode, nullptr, (long)g->capacity, mapN, 0, 0, R};
-  CK(launch_sort_buckets(rm, w->dig, R * SB_ROW_BYTES, R, S, w->items, (long)w->items_cap, w->boff, w->soff, nullptr, 0, 0, s));
+  // chain G in order (mode 3): items carry the generator index relative to the sub-instance's first row, so 2^22 rows still sort in two passes
+  rm.rel = mode == 3 && !getenv("BP_B200_NO_REL");
+  const long gen_slots = rm.rel ? R : 2L * g->capacity + 2 + SG_SPARE + g->merge_slots;
+  CK(launch_sort_buckets(rm, w->dig, R * SB_ROW_BYTES, R, S, w->items, (long)w->items_cap, w->boff, w->soff, (uint32_t *)w->buckets,
+                         w->bucket_slots * sizeof(ge_p3), gen_slots, s));
   SortedView sv{w->items, w->boff, w->soff, (long)w->items_cap, (long)w->slices_cap};
+  sv.base_stride = rm.rel ? R * SB_WINDOWS : 0;
   const long segs = (R * SB_WINDOWS + SB_SEG - 1) / SB_SEG;
-  ge_p3 *partial = w->buckets + (size_t)S * w->slices_cap;
-  CK(launch(S * segs, s, KBucketAccumulate{g->sg, sv, w->buckets, segs}));
-  CK(launch(S * SB_SEGS, s, KBucketReduce{w->buckets, sv, w->seg}));
-  CK(launch(S, s, KBucketFinish{w->seg, nullptr, 0, partial}));
-  if (out_p3) CK(launch(1, s, KSumPointsStrided{partial, S, 1, out_p3}));
-  else CK(launch(1, s, KSumPointsEncode{partial, (int)S, d_out}));
+  if (rm.rel) CK(launch(S * segs, s, KBucketAccumulateRel{g->sg, sv, w->buckets, segs}));
+  else CK(launch(S * segs, s, KBucketAccumulate{g->sg, sv, w->buckets, segs}));
+  // at most 128 sub-instances: short segments with their weights applied in place, then a plain sum over all of them (see KBucketReduceW)
+  const int L = split_seg_len(S);
+  long count = S * (SB_BUCKETS / L);
+  ge_p3 *bufA = w->seg, *bufB = w->seg + count, *cur = bufA;  // stage outputs shrink 16x: ping-pong between the two
+  CK(launch(count, s, KBucketReduceW{w->buckets, sv, cur, L}));
+  while (count > 16) {
+    const long T = (count + 15) / 16;
+    ge_p3 *dst = cur == bufA ? bufB : bufA;
+    CK(launch(T, s, KSumPointsStrided{cur, count, T, dst}));
+    cur = dst; count = T;
+  }
+  if (out_p3) CK(launch(1, s, KSumPointsStrided{cur, count, 1, out_p3}));
+  else CK(launch(1, s, KSumPointsEncode{cur, (int)count, d_out}));
   return BP_OK;
 }
 static int msm_gens_sorted(BpGens *g, uint32_t n, const uint8_t *d_scalars, uint8_t *d_out, dev_stream s) {
@@ -1149,7 +1187,9 @@ int engine_verify(const BpGens *g, BpCircuit *c, const VerifyArgs &A, dev_stream
       const long segs = ((N + 1) * SB_WINDOWS + SB_SEG - 1) / SB_SEG;
       CK(launch(B * segs, s, KBucketAccumulate{g->sg, sv, w->buckets, segs}));
       CK(launch((long)B * SB_SEGS, s, KBucketReduce{w->buckets, sv, w->seg}));
-      CK(launch(B, s, KBucketFinish{w->seg, nullptr, 0, tpart + (size_t)half * B}));
+      ge_p3 *grp = w->seg + (size_t)B * SB_SEGS * 2;
+      CK(launch((long)B * SB_FIN_GROUPS, s, KBucketFinishA{w->seg, grp}));
+      CK(launch(B, s, KBucketFinishB{grp, nullptr, 0, tpart + (size_t)half * B}));
     }
     CK(launch(B, s, KVerifyCheck{w->wsum, tpart, 2, A.status, (long)B}));
     return BP_OK;

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 1) sort_buckets_kernel(RowMap rm
     const uint32_t ttotal = sort_block_scan(tcnt, warp_tot);
     if (tid == 0) tcnt[SB_BUCKETS] = ttotal;
     if (r < rows) {
-      const uint32_t g = (uint32_t)row_gen(rmap, r + inst * rmap.inst_off) * SB_WINDOWS;
+      const uint32_t g = (uint32_t)row_gen_item(rmap, r, inst) * SB_WINDOWS;
 #pragma unroll
       for (int w = 0; w < SB_WINDOWS; w++) if (code[w] != 0xffffffffu) {
         const uint32_t b = (code[w] >> 16) & 0x7fffu;
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 1) sort_buckets_direct_kernel(Ro
   __syncthreads();
   for (long r = tid; r < rows; r += SORT_THREADS) {
     int16_t d[24]; load_digits13(d, drow + r * SB_ROW_BYTES);
-    const uint32_t g = (uint32_t)row_gen(rmap, r + inst * rmap.inst_off) * SB_WINDOWS;
+    const uint32_t g = (uint32_t)row_gen_item(rmap, r, inst) * SB_WINDOWS;
 #pragma unroll
     for (int w = 0; w < SB_WINDOWS; w++) if (d[w]) {
       const uint32_t neg = d[w] < 0; const uint32_t b = (uint32_t)(neg ? -d[w] : d[w]) - 1;
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(SORT2_THREADS, 2) sort_coarse_kernel(RowMap rm
     if (tid == 0 && t0 + SORT2_THREADS < rows) { fence_proxy_async_smem(); fetch_tile(t0 + SORT2_THREADS); }
     const uint32_t ttotal = block_scan_excl<SORT2_WC_PER, SORT2_THREADS>(wc, warp_tot);
     if (r < rows) {
-      const uint32_t g = (uint32_t)row_gen(rmap, r + inst * rmap.inst_off) * SB_WINDOWS;
+      const uint32_t g = (uint32_t)row_gen_item(rmap, r, inst) * SB_WINDOWS;
 #pragma unroll
       for (int w = 0; w < SB_WINDOWS; w++) if (code[w] != 0xffffffffu) {
         const uint32_t b = (code[w] >> 16) & 0x7fffu;

@@ -1339,7 +1339,7 @@ struct KTableBuild {
 
 // row -> generator index.  mode 0: explicit map; 1/2: the L / R multiscalar multiplication of an UNFOLDED inner-product
 // round over the original generators (nj = current vector length, h = nj/2, N rows of G then H, last row = B).
-struct RowMap { int mode; const uint32_t *map; long cap, N, nj, h; long inst_off; long pad_gen; };  // inst_off: generator offset per instance (split MSM); pad_gen: generator index of row N + 1 (modes 1, 2)
+struct RowMap { int mode; const uint32_t *map; long cap, N, nj, h; long inst_off; long pad_gen; int rel = 0; };  // inst_off: generator offset per instance (split MSM); pad_gen: generator index of row N + 1 (modes 1, 2)
 HD long row_gen(const RowMap &m, long r) {
   if (m.mode == 0) return m.map[r];
   if (m.mode == 3) return r;  // (global) row r is generator r; sub-instance `inst` of a split MSM covers rows inst * inst_off ..
@@ -1354,6 +1354,10 @@ HD long row_gen(const RowMap &m, long r) {
   const bool hi = (m.mode == 1) != isH;
   return (isH ? m.cap : 0) + blk * m.nj + (hi ? m.h : 0) + i;
 }
+// generator index the sort writes into the items of instance `inst`, row r.  rel (mode 3 only, split MSM): relative to the
+// instance's first generator inst * inst_off -- KBucketAccumulate adds the base back (SortedView::base_stride) -- so that the items of
+// a 2^22-row MSM still fit the 24 index bits of the two-pass sort
+HD long row_gen_item(const RowMap &m, long r, long inst) { return m.rel ? r : row_gen(m, r + inst * m.inst_off); }
 // table-driven multiscalar multiplication: one thread per (instance, split); partial[tid] = sum over its rows
 struct KMsmTable {
   static constexpr int kBlock = 128, kMinBlocks = BP_OCC_TABLE;
@@ -1673,7 +1677,7 @@ struct KRecodeUnfolded13 {
 // ceil(c / SB_SLICE) slices so that no thread adds more than SB_SLICE points: padded circuits put thousands of identical
 // scalars -- hence identical digits -- into a handful of buckets)
 #define SB_SLICE 256
-struct SortedView { const uint32_t *items; const uint32_t *boff; const uint32_t *soff; long items_stride; long slices_cap; };
+struct SortedView { const uint32_t *items; const uint32_t *boff; const uint32_t *soff; long items_stride; long slices_cap; long base_stride = 0; };  // base_stride: shift-table entries between the first generators of consecutive instances (RowMap::rel)
 // reference (one thread per instance) counting sort: used by the emulation build and as the fallback for tiny launches
 struct KSortBucketsSerial {
   static constexpr int kBlock = 32, kMinBlocks = 1;
@@ -1692,7 +1696,7 @@ struct KSortBucketsSerial {
     uint32_t *it = items + inst * items_stride;
     for (long r = 0; r < rows; r++) {
       int16_t d[24]; load_digits13(d, drow + r * SB_ROW_BYTES);
-      const uint32_t g = (uint32_t)row_gen(rmap, r + inst * rmap.inst_off) * SB_WINDOWS;
+      const uint32_t g = (uint32_t)row_gen_item(rmap, r, inst) * SB_WINDOWS;
       for (int w = 0; w < SB_WINDOWS; w++) if (d[w]) {
         int neg = d[w] < 0; int b = (neg ? -d[w] : d[w]) - 1;
         it[off[b]++] = (g + w) | ((uint32_t)neg << 31);
@@ -1723,12 +1727,14 @@ struct KSortBucketsSerial {
 // where one thread moves a whole tile (the digit tiles of the bucket sort, k_sorted.cu).
 #define BP_TMA_STAGE 0
 #endif
-struct KBucketAccumulate {
+template <bool REL>  // REL: item indices are relative to the instance's first generator (split MSM over chain G; a pointer held in registers)
+struct KBucketAccumulateT {
   static constexpr int kBlock = 128, kMinBlocks = BP_OCC_SORTED;
-  static constexpr const char *kName = "KBucketAccumulate";
-  const ge_niels *sg; SortedView sv; ge_p3 *psum; long segs_cap;  // psum[inst*slices_cap + b + s]
+  static constexpr const char *kName = REL ? "KBucketAccumulateRel" : "KBucketAccumulate";
+  const ge_niels *sg0; SortedView sv; ge_p3 *psum; long segs_cap;  // psum[inst*slices_cap + b + s]
   HD void operator()(long tid) const {
     const long inst = tid / segs_cap; const uint32_t s = (uint32_t)(tid % segs_cap);
+    const ge_niels *sg = REL ? sg0 + inst * sv.base_stride : sg0;
     const uint32_t *off = sv.boff + inst * (SB_BUCKETS + 1);
     const uint32_t total = off[SB_BUCKETS];
     const uint32_t k0 = s * SB_SEG;
@@ -1766,6 +1772,7 @@ struct KBucketAccumulate {
   // of one, and the LSU issues one bulk request per entry instead of six 16-byte loads.  Every lane of a warp makes exactly
   // SB_SEG passes (lanes past the end of their list only arrive at the barriers), so barrier phases stay in step.
   __device__ __forceinline__ void staged(long inst, uint32_t s, const uint32_t *off, uint32_t total, uint32_t k0) const {
+    const ge_niels *sg = REL ? sg0 + inst * sv.base_stride : sg0;
     __shared__ alignas(128) ge_niels stage[2][kBlock];
     __shared__ alignas(8) uint64_t bars[2][kBlock / 32];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1819,6 +1826,8 @@ struct KBucketAccumulate {
   }
 #endif
 };
+using KBucketAccumulate = KBucketAccumulateT<false>;
+using KBucketAccumulateRel = KBucketAccumulateT<true>;
 // per group of 128 buckets: S = sum b_i, W = sum (local index + 1) * b_i   (running-sum trick); b_i = sum of its partials
 struct KBucketReduce {
   static constexpr int kBlock = 64, kMinBlocks = 1;
@@ -1854,6 +1863,83 @@ struct KBucketFinish {
     for (int s = 0; s < SB_SEGS; s++) { ge_p3 t; load_struct(t, &sgp[s * 2 + 1]); ge_add(Wsum, Wsum, t); }
     ge_add(T, T, Wsum);
     if (out_p3) store_struct(&out_p3[inst], T); else ristretto_encode(out + inst * out_stride, T);
+  }
+};
+// KBucketFinish in two steps (what the batch paths launch): one thread per instance runs 380 point operations one after the other,
+// and with a few thousand instances per launch that chain is the launch's whole duration.  Step A: thread (inst, h) folds 16
+// segments into Sum_h = sum S, Floc_h = sum j * S_{16h+j}, Wsum_h = sum W; step B: result = sum_h Wsum_h + 128 * (sum_h Floc_h +
+// 16 * sum_h h * Sum_h) -- ~50 + ~45 operations deep.
+#define SB_FIN_GROUP 16
+#define SB_FIN_GROUPS (SB_SEGS / SB_FIN_GROUP)
+struct KBucketFinishA {
+  static constexpr int kBlock = 64, kMinBlocks = 1;
+  static constexpr const char *kName = "KBucketFinishA";
+  const ge_p3 *seg; ge_p3 *grp;  // grp[(inst*SB_FIN_GROUPS + h)*3 + {0: Sum, 1: Floc, 2: Wsum}]
+  HD void operator()(long tid) const {
+    const long inst = tid / SB_FIN_GROUPS; const int h = (int)(tid % SB_FIN_GROUPS);
+    const ge_p3 *sgp = seg + (inst * SB_SEGS + (long)h * SB_FIN_GROUP) * 2;
+    ge_p3 run, tot, ws; ge_identity(run); ge_identity(tot); ge_identity(ws);
+    for (int j = SB_FIN_GROUP - 1; j >= 0; j--) {
+      ge_p3 t; load_struct(t, &sgp[j * 2]); ge_add_f(run, run, t);
+      if (j > 0) ge_add_f(tot, tot, run);
+      load_struct(t, &sgp[j * 2 + 1]); ge_add_f(ws, ws, t);
+    }
+    store_struct(&grp[tid * 3], run); store_struct(&grp[tid * 3 + 1], tot); store_struct(&grp[tid * 3 + 2], ws);
+  }
+};
+struct KBucketFinishB {
+  static constexpr int kBlock = 64, kMinBlocks = 1;
+  static constexpr const char *kName = "KBucketFinishB";
+  const ge_p3 *grp; uint8_t *out; long out_stride; ge_p3 *out_p3;  // out_p3 != NULL: keep the point
+  HD void operator()(long inst) const {
+    const ge_p3 *gp = grp + inst * SB_FIN_GROUPS * 3;
+    ge_p3 run, T, fl, ws; ge_identity(run); ge_identity(T); ge_identity(fl); ge_identity(ws);
+    for (int h = SB_FIN_GROUPS - 1; h >= 0; h--) {
+      ge_p3 t;
+      if (h > 0) { load_struct(t, &gp[h * 3]); ge_add_f(run, run, t); ge_add_f(T, T, run); }
+      load_struct(t, &gp[h * 3 + 1]); ge_add_f(fl, fl, t);
+      load_struct(t, &gp[h * 3 + 2]); ge_add_f(ws, ws, t);
+    }
+    for (int i = 0; i < 4; i++) ge_dbl_f(T, T);  // * SB_FIN_GROUP (16)
+    ge_add_f(T, T, fl);
+    for (int i = 0; i < 7; i++) ge_dbl_f(T, T);  // * SB_SEG_LEN (128)
+    ge_add_f(T, T, ws);
+    if (out_p3) store_struct(&out_p3[inst], T); else ristretto_encode(out + inst * out_stride, T);
+  }
+};
+// Few instances (one large MSM split into at most 128 sub-instances): the two kernels above are latency chains -- 128 buckets x 2
+// additions per thread, then 380 sequential point operations per instance -- and cost 2.4 ms whatever the size.  Here a thread
+// reduces only L buckets and applies its segment's weight by a short double-and-add, so that every segment yields ONE point
+//   out[inst*(SB_BUCKETS/L) + s] = sum_{j<L} (s*L + j + 1) * bucket_{s*L+j}
+// and the rest is a plain sum (KSumPointsStrided stages) over all segments of all sub-instances: ~10x the additions, spread over
+// 16384/L threads per instance, ~100 operations deep in all.
+struct KBucketReduceW {
+  static constexpr int kBlock = 64, kMinBlocks = 1;
+  static constexpr const char *kName = "KBucketReduceW";
+  const ge_p3 *psum; SortedView sv; ge_p3 *out; int L;
+  HD void operator()(long tid) const {
+    const long nseg = SB_BUCKETS / L;
+    long inst = tid / nseg; int sgm = (int)(tid % nseg);
+    const uint32_t *off = sv.boff + inst * (SB_BUCKETS + 1);
+    const ge_p3 *ps = psum + inst * sv.slices_cap;
+    ge_p3 run, tot; ge_identity(run); ge_identity(tot);
+    for (int i = L - 1; i >= 0; i--) {
+      const int b = sgm * L + i;
+      const uint32_t o0 = off[b], o1 = off[b + 1];
+      if (o1 > o0) {
+        const uint32_t s0 = o0 / SB_SEG, s1 = (o1 - 1) / SB_SEG;
+        for (uint32_t sj = s0; sj <= s1; sj++) { ge_p3 t; load_struct(t, &ps[b + sj]); ge_add_f(run, run, t); }
+      }
+      ge_add_f(tot, tot, run);
+    }
+    const uint32_t k = (uint32_t)sgm * (uint32_t)L;  // + k * (sum of the segment's buckets)
+    if (k) {
+      int top = 31; while (!((k >> top) & 1)) top--;
+      ge_p3 acc = run;
+      for (int bit = top - 1; bit >= 0; bit--) { ge_dbl_f(acc, acc); if ((k >> bit) & 1) ge_add_f(acc, acc, run); }
+      ge_add_f(tot, tot, acc);
+    }
+    store_struct(&out[tid], tot);
   }
 };
 // sum of `count` points -> ristretto encoding (last step of a split MSM; one thread)
