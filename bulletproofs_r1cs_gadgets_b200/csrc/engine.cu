@@ -1182,7 +1182,9 @@ int engine_verify(const BpGens *g, BpCircuit *c, const VerifyArgs &A, dev_stream
     for (int half = 0; half < 2; half++) {
       RowMap rm{4, nullptr, (long)g->capacity, 0, half, 0, 0};
       const int8_t *dg = half ? wideH : wideG;
-      CK(launch_sort_buckets(rm, dg, (N + 1) * SB_ROW_BYTES, N + 1, B, w->items, (long)w->items_cap, w->boff, w->soff, nullptr, 0, 0, s));
+      // (the bucket area is idle between KMsmAccumulate above, which leaves its window sums in wsum, and KBucketAccumulate below: sort scratch)
+      CK(launch_sort_buckets(rm, dg, (N + 1) * SB_ROW_BYTES, N + 1, B, w->items, (long)w->items_cap, w->boff, w->soff, (uint32_t *)w->buckets,
+                             w->bucket_slots * sizeof(ge_p3), 2L * g->capacity + 2 + SG_SPARE + g->merge_slots, s));
       SortedView sv{w->items, w->boff, w->soff, (long)w->items_cap, (long)w->slices_cap};
       const long segs = ((N + 1) * SB_WINDOWS + SB_SEG - 1) / SB_SEG;
       CK(launch(B * segs, s, KBucketAccumulate{g->sg, sv, w->buckets, segs}));
