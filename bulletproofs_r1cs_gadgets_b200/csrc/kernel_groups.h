@@ -13,7 +13,7 @@
 #define KGROUP_SCALAR(X) X(KLoadScalars) X(KRecode) X(KPowers) X(KFillScalar) X(KFlatten) X(KFlattenParts) X(KFlattenSum) X(KPolyT) X(KSumPartials) X(KPolyEval) \
   X(KProverScalars) X(KIpaDots) X(KRecodeIpa) X(KFoldAB) X(KStoreAB) X(KWitnessTape) X(KVerifyS) X(KVerifyDelta) X(KVerifyGH) X(KVerifyScalars) X(KVerifyCombineRows) X(KCheckFixedCommitments) X(KIpaUTable) X(KRecodeUnfolded) X(KRecodeFoldTable)
 
-#define KGROUP_SORTED(X) X(KShiftTableBuild) X(KShiftTableOne) X(KMergeGens) X(KRecode13) X(KRecodeUnfolded13) X(KSortBucketsSerial) X(KBucketAccumulate) X(KBucketAccumulateRel) X(KBucketReduce) X(KBucketReduceW) X(KBucketFinish) X(KBucketFinishA) X(KBucketFinishB) X(KSumPointsEncode)
+#define KGROUP_SORTED(X) X(KShiftTableBuild) X(KShiftTableOne) X(KMergeGens) X(KRecode13) X(KRecodeUnfolded13) X(KSortBucketsSerial) X(KBucketAccumulate) X(KBucketAccumulateRel) X(KBucketReduce) X(KBucketReduceW) X(KBucketFinishA) X(KBucketFinishB) X(KSumPointsEncode)
 
 #define KDECL_EXTERN(K) extern template int launch<K>(long, dev_stream, const K &);
 #define KDEFINE(K) template int launch<K>(long, dev_stream, const K &);

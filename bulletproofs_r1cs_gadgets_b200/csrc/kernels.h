@@ -1571,7 +1571,7 @@ struct KFoldTable {
 // with the 8-bit direct tables, and one running-sum reduction per instance instead of one per window.  Per launch:
 //   sort_buckets (block per instance, counting sort in shared memory)  ->  item list grouped by bucket
 //   KBucketAccumulate (thread per 128-item segment of the sorted list: register accumulator, partial sums at bucket borders)
-//   KBucketReduce (groups of 128 buckets: plain and weighted sums)  ->  KBucketFinish (combine, encode)
+//   KBucketReduce (groups of 128 buckets: plain and weighted sums)  ->  KBucketFinishA / B (combine, encode)
 // ------------------------------------------------------------------------------------------------
 // shift table: sg[gen*20 + w] = 2^(13w) * P_gen in affine Niels form
 struct KShiftTableBuild {
@@ -1850,23 +1850,8 @@ struct KBucketReduce {
     store_struct(&seg[tid * 2], run); store_struct(&seg[tid * 2 + 1], tot);
   }
 };
-// result = sum_s W_s + 128 * sum_s s * S_s
-struct KBucketFinish {
-  static constexpr int kBlock = 64, kMinBlocks = 1;
-  static constexpr const char *kName = "KBucketFinish";
-  const ge_p3 *seg; uint8_t *out; long out_stride; ge_p3 *out_p3;  // out_p3 != NULL: keep the point (partial result of a split MSM)
-  HD void operator()(long inst) const {
-    const ge_p3 *sgp = seg + inst * SB_SEGS * 2;
-    ge_p3 run, T, Wsum; ge_identity(run); ge_identity(T); ge_identity(Wsum);
-    for (int s = SB_SEGS - 1; s >= 1; s--) { ge_p3 t; load_struct(t, &sgp[s * 2]); ge_add(run, run, t); ge_add(T, T, run); }
-    for (int i = 0; i < 7; i++) ge_dbl(T, T);  // * SB_SEG_LEN (128)
-    for (int s = 0; s < SB_SEGS; s++) { ge_p3 t; load_struct(t, &sgp[s * 2 + 1]); ge_add(Wsum, Wsum, t); }
-    ge_add(T, T, Wsum);
-    if (out_p3) store_struct(&out_p3[inst], T); else ristretto_encode(out + inst * out_stride, T);
-  }
-};
-// KBucketFinish in two steps (what the batch paths launch): one thread per instance runs 380 point operations one after the other,
-// and with a few thousand instances per launch that chain is the launch's whole duration.  Step A: thread (inst, h) folds 16
+// result = sum_s W_s + 128 * sum_s s * S_s, in two steps: one thread per instance would run 380 point operations one after the
+// other, and with a few thousand instances per launch that chain is the launch's whole duration (round 1's KBucketFinish).  Step A: thread (inst, h) folds 16
 // segments into Sum_h = sum S, Floc_h = sum j * S_{16h+j}, Wsum_h = sum W; step B: result = sum_h Wsum_h + 128 * (sum_h Floc_h +
 // 16 * sum_h h * Sum_h) -- ~50 + ~45 operations deep.
 #define SB_FIN_GROUP 16
