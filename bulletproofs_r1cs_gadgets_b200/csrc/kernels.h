@@ -1829,8 +1829,11 @@ struct KBucketAccumulateT {
 using KBucketAccumulate = KBucketAccumulateT<false>;
 using KBucketAccumulateRel = KBucketAccumulateT<true>;
 // per group of 128 buckets: S = sum b_i, W = sum (local index + 1) * b_i   (running-sum trick); b_i = sum of its partials
+#ifndef BP_OCC_REDUCE
+#define BP_OCC_REDUCE 8   // 128 registers (292 B of spills) against 176: 16 warps per SM instead of 10 hide the chain of dependent additions (430 -> 384 ms per step)
+#endif
 struct KBucketReduce {
-  static constexpr int kBlock = 64, kMinBlocks = 1;
+  static constexpr int kBlock = 64, kMinBlocks = BP_OCC_REDUCE;
   static constexpr const char *kName = "KBucketReduce";
   const ge_p3 *psum; SortedView sv; ge_p3 *seg;  // seg[(inst*32 + s)*2 + {0: S, 1: W}]
   HD void operator()(long tid) const {
