@@ -136,7 +136,8 @@ def run_reference(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 (F_l, GF(2^255-19))",
             "data": "synthetic", "impl": "reference",
-            "config": {"workload": "gadget_vsmt_2 depth-%d membership proofs, inverse S-box (n=%d, m=%d)" % (args.depth, circ.n, circ.m),
+            "config": {"workload": "gadget_vsmt_2 depth-%d membership proofs, inverse S-box (n=%d, N=%d, m=%d, q=%d)"
+                                   % (args.depth, circ.n, 1 << (circ.n - 1).bit_length(), circ.m, circ.q),  # the product arm's workload string
                        "proofs_per_step": sample, "note": "C port of the reference algorithm (oracle/bp_oracle.c); curve25519-dalek itself is not buildable here"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": "%d proofs per step, one thread per proof" % sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
