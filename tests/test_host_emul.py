@@ -519,6 +519,20 @@ def test_fold_tables_of_large_capacities(api, gens, monkeypatch):
                 assert ("KFoldTable" in ran) == (bits is not None), (bits, sorted(ran))
             assert not st.any() and V.tobytes() == want[0].tobytes() and P.tobytes() == want[1].tobytes(), (wl.name, bits)
         monkeypatch.delenv("BP_B200_FOLD_TABLE_GB")
+    # a smaller circuit on the same generators reads the table that was built for the larger one (table capacity > its N)
+    small = workloads.Mimc(gens, rounds=20)
+    assert small.circuit.n == 40 and wls[1].circuit.n > 64
+    inp = small.inputs(0, 2)
+    want = small.circuit.prove_batch(gens, small.label, inp["v"], inp["v_blinding"], inp["entropy"], pub=inp["pub"])
+    monkeypatch.setenv("BP_B200_FOLD_BITS", "5")
+    wls[1].circuit.prove_batch(lean, wls[1].label, *[wls[1].inputs(0, 1)[k] for k in ("v", "v_blinding", "entropy")], pub=wls[1].inputs(0, 1)["pub"])
+    api.profile_enable(1)
+    V, P, st = small.circuit.prove_batch(lean, small.label, inp["v"], inp["v_blinding"], inp["entropy"], pub=inp["pub"])
+    api.profile_enable(0)
+    ran = api.profile_report()
+    assert "KFoldTable" in ran and "KTableBuild" not in ran, sorted(ran)
+    assert not st.any() and V.tobytes() == want[0].tobytes() and P.tobytes() == want[1].tobytes()
+    monkeypatch.delenv("BP_B200_FOLD_BITS")
     # the workspace can be dropped between batches and comes back on the next call
     wl = wls[0]
     wl.circuit.release_workspace()
